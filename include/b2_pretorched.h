@@ -1,0 +1,141 @@
+/* b2_pretorched.h -- C ABI of the B200-native forward engine for pretorched-x's video-ConvNet hot path.
+ *
+ * The reference (alexandonian/pretorched-x @ 36a5754) has no FFI layer of its own: every FLOP of
+ * its hot path is a torch.nn call inside a Python `forward` body.  Each entry point below therefore
+ * cites the reference *operator call site(s)* it replaces (file:line under /root/reference).  The
+ * Python host side (pretorched_x_b200/) binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers owned by the caller.  The library never allocates, frees
+ *     or retains them; work is enqueued on `stream` (a cudaStream_t passed as void*) and the call
+ *     returns immediately.  Safe under CUDA-graph capture (no syncs, no allocations).
+ *   - Activations are fp16 NDHWC ("channels last"), i.e. a dense matrix [N*T*H*W][ld] with channel
+ *     pitch `ld` (elements) a multiple of 8.  Channels in [C, ld) must be zero.
+ *   - Returns 0 on success, a negative B2_ERR_* code otherwise; b2_last_error() returns a
+ *     thread-local message.  No C++ exception crosses the ABI.
+ *   - There is NO CPU fallback: on a machine without an sm_100 GPU every compute call fails with
+ *     B2_ERR_CUDA / B2_ERR_UNSUPPORTED.
+ */
+#ifndef B2_PRETORCHED_H_
+#define B2_PRETORCHED_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
+#define B2_ERR_CUDA (-2)        /* a CUDA runtime / driver call failed */
+#define B2_ERR_UNSUPPORTED (-3) /* valid request the engine does not implement */
+
+#define B2_CONV_AUTO 0  /* generic implicit GEMM: x has channel pitch C (multiple of 8)            */
+#define B2_CONV_STEM7 1 /* kw == 7, sw == 2, pw == 3, Cin <= 4 stored as NDHWC4 (stem convolutions) */
+
+int b2_version(void);
+const char* b2_last_error(void);
+/* number of kernels this library has launched from the calling process so far (bench bookkeeping) */
+uint64_t b2_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution as implicit GEMM on tcgen05 tensor cores, with the eval-mode BatchNorm affine
+ * (scale/shift), the residual add and the ReLU fused into the epilogue:
+ *     y[m, k] = act( scale[k] * sum_{tap,c} x[m @ tap, c] * w[k, tap, c] + shift[k] + residual[m, k] )
+ * Replaces nn.Conv3d -> nn.BatchNorm3d -> (+=residual) -> nn.ReLU chains at
+ *   resnet3D.py:91-106 (BasicBlock.forward), resnet3D.py:125-143 (Bottleneck.forward),
+ *   resnet3D.py:176-185 (type-B shortcut), r2plus1d.py:85-88 (SpatioTemporalConv.forward),
+ *   nonlocalnet.py:143-166 (theta/phi/g/W 1x1x1 convs), torchvision_models.py:448-452 (stem).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b2_conv_args {
+  const void* x;        /* fp16 [N,T,H,W,C]; C is the channel pitch                               */
+  const void* w;        /* fp16 packed [K][taps][C] (b2_pack_conv_weight), taps = kt*kh*kw        */
+  const float* scale;   /* fp32 [K]                                                                */
+  const float* shift;   /* fp32 [K]                                                                */
+  const void* residual; /* nullable; fp16 [M][ldr], M = N*To*Ho*Wo                                 */
+  void* y;              /* fp16 [M][ldy]  (fp32 when out_f32)                                      */
+  int32_t N, T, H, W, C;
+  int32_t K;            /* logical output channels; columns [K, ldy) of y are written as zero      */
+  int32_t ldy, ldr;
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;
+  int32_t pt, ph, pw;
+  int32_t relu;
+  int32_t out_f32;      /* y is fp32 (direct-store epilogue)                                       */
+  int32_t accumulate;   /* out_f32 only: y += result                                               */
+  int32_t mode;         /* B2_CONV_AUTO | B2_CONV_STEM7                                            */
+} b2_conv_args;
+
+int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream);
+/* Same contract on plain CUDA cores (one thread per output element, fp32 accumulate).  A debugging
+ * cross-check for the tensor-core path; never used by the model forward. */
+int b2_conv_ndhwc_fprop_simt(const b2_conv_args* a, void* stream);
+
+/* fp32 [K][Cin][kt][kh][kw] (nn.Conv3d.weight layout, resnet3D.py:60,115-119) -> fp16 packed
+ * [K][taps][C] with zero padding of channels [Cin, C).  mode B2_CONV_STEM7: [K][kt*kh (padded to even)]
+ * [8 px][4 ch] with px 0 and ch >= Cin zero (see DESIGN.md "stem"). */
+size_t b2_pack_conv_weight_elems(int K, int Cin, int kt, int kh, int kw, int C, int mode);
+int b2_pack_conv_weight(const float* w_oidhw, void* w_packed, int K, int Cin, int kt, int kh, int kw, int C,
+                        int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layer / 1x1x1 convolution as a plain GEMM:  D[M][N] = act(scale * (A[M][Kd] . B[N][Kd]^T) + shift
+ * + residual).  scale/shift index the N dimension, or the M dimension when per_row != 0 (used to
+ * produce the transposed g projection for the non-local block).  Replaces nn.Linear at
+ * resnet3D.py:162 / torchvision_models.py:460-464 (head), trn.py:39-49 (Relation MLP).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b2_gemm_args {
+  const void* a; /* fp16 [M][lda] */
+  const void* b; /* fp16 [N][ldb] */
+  const float* scale;
+  const float* shift;
+  const void* residual; /* nullable fp16 [M][ldr] */
+  void* d;              /* fp16 [M][ldd] or fp32 when out_f32 */
+  int32_t M, N, Kd;
+  int32_t lda, ldb, ldd, ldr;
+  int32_t per_row;
+  int32_t relu;
+  int32_t out_f32;
+  int32_t accumulate;
+} b2_gemm_args;
+int b2_gemm_f16(const b2_gemm_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Non-local block core (nonlocalnet.py:143-166, `_embedded_gaussian`):
+ *     O[b] = softmax_rows(Q[b] . K[b]^T) . V[b]        (unscaled logits, softmax over keys)
+ * Q, K: fp16 [B*Npos][ld] (d columns used); Vt: fp16 [dv][B*Npos] (V transposed, produced by
+ * b2_gemm_f16 with per_row); O: fp16 [B*Npos][ldo].  One fused kernel, the Npos x Npos matrix is
+ * never materialised.
+ * ------------------------------------------------------------------------------------------- */
+int b2_nonlocal_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* o,
+                          int ldo, int B, int Npos, int d, int dv, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooling / layout / elementwise helpers (all HBM-bound, 128-bit accesses)
+ * ------------------------------------------------------------------------------------------- */
+/* nn.MaxPool3d (resnet3D.py:156): padding taps are skipped (== -inf padding). */
+int b2_maxpool3d_ndhwc(const void* x, void* y, int N, int T, int H, int W, int C, int kt, int kh, int kw,
+                       int st, int sh, int sw, int pt, int ph, int pw, void* stream);
+/* nn.AdaptiveAvgPool3d(1) (resnet3D.py:161): x fp16 [N][S][C] -> y fp16 [N][C], fp32 accumulation. */
+int b2_avgpool_global_ndhwc(const void* x, void* y, int N, int S, int C, void* stream);
+/* fp32 NCDHW (the reference's input layout) -> fp16 NDHWC with channel pitch Cp (zero padded). */
+int b2_ncdhw_f32_to_ndhwc_f16(const float* x, void* y, int N, int C, int T, int H, int W, int Cp, void* stream);
+/* fp16 NDHWC (pitch Cp) -> fp32 NCDHW, for `features()` callers that want the reference layout. */
+int b2_ndhwc_f16_to_ncdhw_f32(const void* x, float* y, int N, int C, int T, int H, int W, int Cp, void* stream);
+/* y[r][c] = (relu ? max(x,0) : x) as fp16, rows x cols with pitches ldx / ldy; columns [cols, ldy) zeroed.
+ * Used for the leading nn.ReLU of the TRN relation MLP (trn.py:40-41). */
+int b2_cast_f32_to_f16(const float* x, int ldx, void* y, int ldy, int rows, int cols, int relu, void* stream);
+/* Parameter-free type-A shortcut (resnet3D.py:65-74, nonlocalnet.py:322-332): spatial/temporal
+ * subsampling by `stride` and zero-padding of channels [C, Cout). */
+int b2_shortcut_a_ndhwc(const void* x, void* y, int N, int T, int H, int W, int C, int stride, int Cout,
+                        void* stream);
+/* y[n][j*F + f] = x[n][idx[j]][f]: frame-tuple gather of MultiScaleRelation (trn.py:108), fp16. */
+int b2_gather_frames(const void* x, void* y, const int32_t* idx_dev, int N, int T, int F, int n_idx,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2_PRETORCHED_H_ */

@@ -1,0 +1,251 @@
+"""CPU restatement of the reference's hot-path forward passes -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this package.  The product path (``pretorched_x_b200``) never does.
+
+Every function restates, in plain functional PyTorch on CPU fp32 tensors, what one reference ``forward`` body
+computes from a ``state_dict`` (citations: file:line under /root/reference).  The reference's arithmetic itself
+lives in third-party torch (unpinned in requirements.txt:1; installed here: 2.11.0+cu128, oneDNN CPU backend),
+which is why the restatement also calls torch.nn.functional: it is the same library the reference calls, minus
+the reference's nn.Module graph.
+
+Pinning: the reference ships no golden vectors and no tests for this path, so the oracle is
+pinned against *outputs of the reference itself run in the build container*: ``oracle/make_golden.py`` imports
+the unmodified reference from /root/reference, checks these functions against it bit-for-bit on seeded inputs,
+and stores the reference's outputs under ``tests/golden/``.  ``tests/test_oracle_golden.py`` re-checks the
+restatement against those fixtures wherever the test-suite runs.
+"""
+import itertools
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # nn.BatchNorm3d default, used by every BN on the path (resnet3D.py:84)
+
+
+# ---------------------------------------------------------------------------------------------
+# architecture table (what the reference's factories instantiate)
+# ---------------------------------------------------------------------------------------------
+ARCHS = {
+    # resnet3D.py:242-308
+    'resnet3d10': dict(family='resnet3d', block='basic', layers=[1, 1, 1, 1], shortcut='B'),
+    'resnet3d18': dict(family='resnet3d', block='basic', layers=[2, 2, 2, 2], shortcut='A'),
+    'resnet3d34': dict(family='resnet3d', block='basic', layers=[3, 4, 6, 3], shortcut='A'),
+    'resnet3d50': dict(family='resnet3d', block='bottleneck', layers=[3, 4, 6, 3], shortcut='B'),
+    'resnet3d101': dict(family='resnet3d', block='bottleneck', layers=[3, 4, 23, 3], shortcut='B'),
+    # r2plus1d.py:113-152
+    'r2plus1d10': dict(family='r2plus1d', block='basic', layers=[1, 1, 1, 1], shortcut='B'),
+    'r2plus1d18': dict(family='r2plus1d', block='basic', layers=[2, 2, 2, 2], shortcut='B'),
+    'r2plus1d34': dict(family='r2plus1d', block='basic', layers=[3, 4, 6, 3], shortcut='B'),
+    'r2plus1d50': dict(family='r2plus1d', block='bottleneck', layers=[3, 4, 6, 3], shortcut='B'),
+    # nonlocalnet.py:553-570 (5 non-local blocks: nonlocal_blocks=[0,2,3,0], shortcut A)
+    'nonlocalresnet3d50': dict(family='nonlocal', block='bottleneck', layers=[3, 4, 6, 3], shortcut='A',
+                               nonlocal_blocks=[0, 2, 3, 0]),
+    # torchvision_models.py:484-492 (torchvision BasicBlock body)
+    'resnet18': dict(family='resnet2d', block='basic', layers=[2, 2, 2, 2], shortcut='B'),
+}
+
+
+def nonlocal_positions(layers, nonlocal_blocks):
+    """Blocks that carry a non-local block: i % (blocks // n) == 0 (nonlocalnet.py:474-479)."""
+    out = []
+    for li, (nb, nn_) in enumerate(zip(layers, nonlocal_blocks)):
+        freq = nb // nn_ if nn_ != 0 else -1
+        out.append([i for i in range(nb) if freq > 0 and i % freq == 0])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# primitives
+# ---------------------------------------------------------------------------------------------
+def _bn(x, sd, p):
+    """Eval-mode BatchNorm: (x - mean) / sqrt(var + eps) * gamma + beta."""
+    return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'], sd[p + '.bias'],
+                        False, 0.0, BN_EPS)
+
+
+def _conv(x, sd, p, stride=1, padding=0):
+    w = sd[p + '.weight']
+    fn = F.conv2d if w.dim() == 4 else F.conv3d
+    return fn(x, w, sd.get(p + '.bias'), stride, padding)
+
+
+def spatio_temporal_conv(x, sd, p, kernel, stride, padding):
+    """SpatioTemporalConv.forward (r2plus1d.py:85-88): (1,k,k) conv -> BN -> ReLU -> (k,1,1) conv."""
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = padding
+    x = _conv(x, sd, p + '.spatial_conv', (1, sh, sw), (0, ph, pw))
+    x = F.relu(_bn(x, sd, p + '.bn'))
+    return _conv(x, sd, p + '.temporal_conv', (st, 1, 1), (pt, 0, 0))
+
+
+def _block_conv(x, sd, p, family, k, stride, padding):
+    """A block-level "Conv3d": plain nn.Conv3d, or SpatioTemporalConv for R(2+1)D (r2plus1d.py:91-96)."""
+    if family == 'r2plus1d':
+        return spatio_temporal_conv(x, sd, p, (k, k, k), (stride,) * 3, (padding,) * 3)
+    return _conv(x, sd, p, stride, padding)
+
+
+def shortcut_a(x, planes, stride):
+    """downsample_basic_block (resnet3D.py:65-74 / nonlocalnet.py:322-332)."""
+    out = F.avg_pool3d(x, kernel_size=1, stride=stride)
+    pad = torch.zeros(out.size(0), planes - out.size(1), out.size(2), out.size(3), out.size(4), dtype=out.dtype)
+    return torch.cat([out, pad], dim=1)
+
+
+def _residual(x, sd, p, family, shortcut, planes_out, stride, has_downsample):
+    if not has_downsample:
+        return x
+    if shortcut == 'A':
+        return shortcut_a(x, planes_out, stride)
+    # type B: 1x1x1 conv (stride s) + BN (resnet3D.py:176-185)
+    y = _block_conv(x, sd, p + '.downsample.0', family, 1, stride, 0)
+    return _bn(y, sd, p + '.downsample.1')
+
+
+def basic_block(x, sd, p, family, shortcut, planes, stride, has_downsample):
+    """BasicBlock.forward (resnet3D.py:91-106; torchvision resnet.py BasicBlock for the 2-D net)."""
+    out = F.relu(_bn(_block_conv(x, sd, p + '.conv1', family, 3, stride, 1), sd, p + '.bn1'))
+    out = _bn(_block_conv(out, sd, p + '.conv2', family, 3, 1, 1), sd, p + '.bn2')
+    out = out + _residual(x, sd, p, family, shortcut, planes, stride, has_downsample)
+    return F.relu(out)
+
+
+def bottleneck(x, sd, p, family, shortcut, planes, stride, has_downsample):
+    """Bottleneck.forward (resnet3D.py:125-143)."""
+    out = F.relu(_bn(_block_conv(x, sd, p + '.conv1', family, 1, 1, 0), sd, p + '.bn1'))
+    out = F.relu(_bn(_block_conv(out, sd, p + '.conv2', family, 3, stride, 1), sd, p + '.bn2'))
+    out = _bn(_block_conv(out, sd, p + '.conv3', family, 1, 1, 0), sd, p + '.bn3')
+    out = out + _residual(x, sd, p, family, shortcut, planes * 4, stride, has_downsample)
+    return F.relu(out)
+
+
+def nonlocal_block(x, sd, p):
+    """_NonLocalBlockND._embedded_gaussian (nonlocalnet.py:143-166), 3-D, no sub-sampling."""
+    b, c = x.shape[0], x.shape[1]
+    d = sd[p + '.g.weight'].shape[0]
+    g_x = _conv(x, sd, p + '.g').view(b, d, -1).permute(0, 2, 1)
+    theta_x = _conv(x, sd, p + '.theta').view(b, d, -1).permute(0, 2, 1)
+    phi_x = _conv(x, sd, p + '.phi').view(b, d, -1)
+    f = torch.matmul(theta_x, phi_x)                 # unscaled logits
+    f_div_c = F.softmax(f, dim=-1)                   # over keys
+    y = torch.matmul(f_div_c, g_x).permute(0, 2, 1).contiguous().view(b, d, *x.shape[2:])
+    w_y = _bn(_conv(y, sd, p + '.W.0'), sd, p + '.W.1')
+    return w_y + x
+
+
+# ---------------------------------------------------------------------------------------------
+# whole networks
+# ---------------------------------------------------------------------------------------------
+def stem(x, sd, family):
+    """conv1 -> bn1 -> relu -> maxpool (torchvision_models.py:449-452; modules resnet3D.py:153-156)."""
+    if family == 'resnet2d':
+        x = F.relu(_bn(_conv(x, sd, 'conv1', 2, 3), sd, 'bn1'))
+        return F.max_pool2d(x, 3, 2, 1)
+    if family == 'r2plus1d':
+        x = spatio_temporal_conv(x, sd, 'conv1', (7, 7, 7), (1, 2, 2), (3, 3, 3))
+    else:
+        x = _conv(x, sd, 'conv1', (1, 2, 2), (3, 3, 3))
+    x = F.relu(_bn(x, sd, 'bn1'))
+    return F.max_pool3d(x, kernel_size=(3, 3, 3), stride=2, padding=1)
+
+
+def trunk(x, sd, arch, stages=None):
+    """``features`` (torchvision_models.py:448-458).  If ``stages`` is a dict it receives every stage output."""
+    spec = ARCHS[arch] if isinstance(arch, str) else arch
+    family, shortcut = spec['family'], spec['shortcut']
+    block_fn = bottleneck if spec['block'] == 'bottleneck' else basic_block
+    expansion = 4 if spec['block'] == 'bottleneck' else 1
+    nl = nonlocal_positions(spec['layers'], spec['nonlocal_blocks']) if 'nonlocal_blocks' in spec else [[]] * 4
+    x = stem(x, sd, family)
+    if stages is not None:
+        stages['maxpool'] = x
+    inplanes = 64
+    for li, (planes, nblocks) in enumerate(zip((64, 128, 256, 512), spec['layers'])):
+        for bi in range(nblocks):
+            stride = 2 if (li > 0 and bi == 0) else 1
+            has_ds = bi == 0 and (stride != 1 or inplanes != planes * expansion)
+            p = 'layer%d.%d' % (li + 1, bi)
+            x = block_fn(x, sd, p, 'resnet3d' if family in ('nonlocal', 'resnet2d') else family, shortcut, planes,
+                         stride, has_ds)
+            if bi in nl[li]:
+                x = nonlocal_block(x, sd, p + '.nonlocalblock')
+            inplanes = planes * expansion
+        if stages is not None:
+            stages['layer%d' % (li + 1)] = x
+    return x
+
+
+def head(feat, sd, name=None):
+    """avgpool -> view -> last_linear / fc (torchvision_models.py:460-464)."""
+    if name is None:
+        name = 'last_linear' if 'last_linear.weight' in sd else 'fc'
+    pooled = feat.mean(dim=tuple(range(2, feat.dim())))
+    return F.linear(pooled, sd[name + '.weight'], sd[name + '.bias'])
+
+
+def forward(x, sd, arch, stages=None):
+    """``model(x)`` = logits(features(x)) (torchvision_models.py:466-469)."""
+    feat = trunk(x, sd, arch, stages)
+    out = head(feat, sd)
+    if stages is not None:
+        stages['logits'] = out
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# TRN relation heads
+# ---------------------------------------------------------------------------------------------
+def relation(x, sd, p, num_inputs, in_features):
+    """Relation.func (trn.py:47-49): view(-1, T*F) -> ReLU -> Linear -> ReLU -> Linear -> view(B, -1, out)."""
+    flat = x.contiguous().view(-1, num_inputs * in_features)
+    h = F.relu(F.linear(F.relu(flat), sd[p + 'relate.1.weight'], sd[p + 'relate.1.bias']))
+    out = F.linear(h, sd[p + 'relate.3.weight'], sd[p + 'relate.3.bias'])
+    return out.view(x.size(0), -1, out.shape[-1])
+
+
+def multiscale_relation(x, sd, num_input, in_features, num_relations=3, tuples=None):
+    """MultiScaleRelation.forward (trn.py:100-110).  ``tuples`` (per scale) overrides the np.random.choice draw;
+    when None the draw is made exactly as the reference does, from NumPy's global RNG."""
+    scales = list(range(num_input, 1, -1))
+    sets = [list(itertools.combinations(range(num_input), s)) for s in scales]
+    outs = []
+    for si, s in enumerate(scales):
+        if tuples is None:
+            idx = np.random.choice(len(sets[si]), min(num_relations, len(sets[si])), replace=False)
+            chosen = [sets[si][i] for i in idx]
+        else:
+            chosen = tuples[si]
+        for tup in chosen:
+            outs.append(relation(x[..., list(tup), :], sd, 'relations.%d.' % si, s, in_features))
+    total = torch.stack(outs).sum(0)
+    return total.view(x.size(0), -1, total.shape[-1])
+
+
+# ---------------------------------------------------------------------------------------------
+# deterministic test conditioning shared by the golden generator and the tests
+# ---------------------------------------------------------------------------------------------
+def randomize_bn_(module, seed):
+    """Give every BatchNorm non-trivial affine + running stats so that BN folding bugs
+    cannot hide behind identity statistics.  Walks ``named_modules()`` in order; works on the reference's
+    modules and on pretorched_x_b200's alike (same tree => same values)."""
+    g = torch.Generator().manual_seed(seed)
+    for _, m in module.named_modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            n = m.num_features
+            m.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(n, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(n, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(n, generator=g) * 0.1)
+    return module
+
+
+def seeded_input(shape, seed):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def state_digest(sd):
+    """Per-tensor (sum, abs-sum) in float64 -- a cheap fingerprint to prove two inits are identical."""
+    return {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in sd.items()}

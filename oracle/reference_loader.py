@@ -1,0 +1,74 @@
+"""Import the UNMODIFIED reference from /root/reference (build container only) -- TEST INFRASTRUCTURE.
+
+/root/reference does not exist on the GPU box; nothing that runs there may call this.  It is used by
+``oracle/make_golden.py`` (fixture generation), by CPU tests that skip when the tree is absent, and by
+``bench.py --impl reference`` when available.
+
+Work-arounds for upstream import defects:
+  * r2plus1d.py:10 does ``import resnet3D`` (absolute)      -> alias ``sys.modules['resnet3D']``
+  * trn.py:8 does ``import pretrainedmodels`` (missing dep)  -> alias to the ``pretorched`` package
+The reference tree is read-only, so bytecode writing is disabled around the import.
+"""
+import importlib
+import os
+import sys
+import warnings
+
+REFERENCE_ROOT = os.environ.get("B2_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "pretorched"))
+
+
+def load():
+    """Returns the reference's top-level ``pretorched`` package."""
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    old = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return importlib.import_module("pretorched")
+    finally:
+        sys.dont_write_bytecode = old
+
+
+def load_r2plus1d():
+    """pretorched.models.r2plus1d.  NOTE: R2Plus1D.forward breaks once any resnet3d*
+    factory has run in the process (class-level patch by modify_resnets); build R(2+1)D first or use
+    ``ResNet3D.forward`` explicitly as ``reference_forward`` below does."""
+    pt = load()
+    sys.modules.setdefault("resnet3D", pt.models.resnet3D)
+    old = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        return importlib.import_module("pretorched.models.r2plus1d")
+    finally:
+        sys.dont_write_bytecode = old
+
+
+def load_trn():
+    pt = load()
+    sys.modules.setdefault("pretrainedmodels", pt)
+    old = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return importlib.import_module("pretorched.models.trn")
+    finally:
+        sys.dont_write_bytecode = old
+
+
+def build(arch, **kwargs):
+    """Instantiate a reference model with ``pretrained=None`` (URLs are unreachable offline)."""
+    pt = load()
+    if arch.startswith("r2plus1d"):
+        return getattr(load_r2plus1d(), arch)(**kwargs)
+    if arch.startswith("nonlocal"):
+        return getattr(pt.models.nonlocalnet, arch)(pretrained=None, **kwargs)
+    return getattr(pt, arch)(pretrained=None, **kwargs)

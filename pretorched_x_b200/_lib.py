@@ -1,0 +1,106 @@
+"""ctypes binding of libb2pretorched.so -- the C-ABI boundary declared in include/b2_pretorched.h.
+
+This is the only place Python touches native code.  There is deliberately no fallback: if the shared
+library is missing it is built with nvcc (sm_100a); if that is impossible, or a compute entry point
+is called without a B200, a RuntimeError carrying b2_last_error() is raised.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "csrc", "libb2pretorched.so")
+_lock = threading.Lock()
+_lib = None
+
+B2_OK = 0
+B2_CONV_AUTO = 0
+B2_CONV_STEM7 = 1
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_i32 = ctypes.c_int32
+
+
+class ConvArgs(ctypes.Structure):
+    """Mirror of `struct b2_conv_args` (include/b2_pretorched.h)."""
+    _fields_ = [
+        ("x", c_void_p), ("w", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+        ("residual", c_void_p), ("y", c_void_p),
+        ("N", c_i32), ("T", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32),
+        ("K", c_i32), ("ldy", c_i32), ("ldr", c_i32),
+        ("kt", c_i32), ("kh", c_i32), ("kw", c_i32),
+        ("st", c_i32), ("sh", c_i32), ("sw", c_i32),
+        ("pt", c_i32), ("ph", c_i32), ("pw", c_i32),
+        ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32),
+    ]
+
+
+class GemmArgs(ctypes.Structure):
+    """Mirror of `struct b2_gemm_args`."""
+    _fields_ = [
+        ("a", c_void_p), ("b", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+        ("residual", c_void_p), ("d", c_void_p),
+        ("M", c_i32), ("N", c_i32), ("Kd", c_i32),
+        ("lda", c_i32), ("ldb", c_i32), ("ldd", c_i32), ("ldr", c_i32),
+        ("per_row", c_i32), ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/b2_pretorched.h declares
+SYMBOLS = {
+    "b2_version": (c_int, []),
+    "b2_last_error": (ctypes.c_char_p, []),
+    "b2_launch_count": (ctypes.c_uint64, []),
+    "b2_conv_ndhwc_fprop": (c_int, [ctypes.POINTER(ConvArgs), c_void_p]),
+    "b2_conv_ndhwc_fprop_simt": (c_int, [ctypes.POINTER(ConvArgs), c_void_p]),
+    "b2_pack_conv_weight_elems": (ctypes.c_size_t, [c_int] * 7),
+    "b2_pack_conv_weight": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "b2_gemm_f16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "b2_nonlocal_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                      c_int, c_int, c_int, c_int, c_void_p]),
+    "b2_maxpool3d_ndhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 14 + [c_void_p]),
+    "b2_avgpool_global_ndhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b2_ncdhw_f32_to_ndhwc_f16": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "b2_ndhwc_f16_to_ncdhw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
+    "b2_cast_f32_to_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2_shortcut_a_ndhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "b2_gather_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Return the loaded shared library, building it first if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            from .csrc.build import build
+            build()  # raises if nvcc is missing: the product path must not degrade silently
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().b2_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != B2_OK:
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, last_error()))
+
+
+def launch_count():
+    return int(load().b2_launch_count())

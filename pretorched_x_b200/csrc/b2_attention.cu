@@ -1,0 +1,301 @@
+// b2_attention.cu -- fused QK^T -> softmax -> .V kernel for the non-local block
+// (reference: nonlocalnet.py:143-166, `_embedded_gaussian`: f = theta^T phi (unscaled), softmax over
+// keys, y = f . g).  The Npos x Npos matrix never leaves the SM: logits are produced by tcgen05.mma
+// into TMEM, each of 128 softmax threads owns one query row (= one TMEM lane), probabilities go back
+// to shared memory as the fp16 A operand of the second MMA, and the output accumulates in TMEM.
+//
+// Two passes over the keys (exact softmax, no accumulator rescaling):
+//   pass 1: S = Q K^T per 64-key block -> running row max m and row sum l (fp32 registers)
+//   pass 2: S again -> P = exp(S - m) / l (fp16, smem) -> O += P . V   (O in TMEM, DVT fp32 columns)
+//
+// CTA = (128 query rows, sample b, DVT-wide slice of the value channels).  6 warps: 0-3 softmax +
+// output epilogue, 4 TMA producer, 5 MMA issuer / TMEM owner.  All operands are K-major 128B-swizzled
+// tiles; V arrives transposed ([dv][positions]) so that keys are its contiguous (K) dimension.
+#include "b2_host.h"
+#include "b2_ptx.cuh"
+
+#include <math.h>
+#include <string.h>
+
+namespace b2 {
+
+constexpr int kAttThreads = 192;
+constexpr int kAttBM = 128;        // queries per CTA
+constexpr int kAttBKV = 64;        // keys per block
+constexpr int kAttSlots = 4;       // smem ring slots
+constexpr int kAttSlotBytes = 32768;
+
+struct AttParams {
+  int Npos;       // positions per sample (queries == keys)
+  int nkb;        // d / 64
+  int nkv;        // ceil(Npos / 64)
+  __half* o;
+  int ldo;
+};
+
+template <int DVT>
+struct AttSmem {
+  static constexpr int kRing = kAttSlots * kAttSlotBytes;        // 128 KB
+  static constexpr int kPBytes = kAttBM * kAttBKV * 2;           // 16 KB
+  static constexpr int kPOff = kRing;
+  static constexpr int kBarOff = kRing + 2 * kPBytes;
+  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static_assert(DVT * 128 <= kAttSlotBytes, "V tile must fit a ring slot");
+};
+
+template <int DVT>
+__global__ void __launch_bounds__(kAttThreads, 1)
+nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  using S = AttSmem<DVT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);   // [4]
+  uint64_t* empty_bar = full_bar + kAttSlots;                            // [4]
+  uint64_t* s_full = empty_bar + kAttSlots;                              // [2]
+  uint64_t* s_empty = s_full + 2;                                        // [2]
+  uint64_t* p_full = s_empty + 2;                                        // [2]
+  uint64_t* p_empty = p_full + 2;                                        // [2]
+  uint64_t* o_full = p_empty + 2;                                        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * kAttBM;            // first query row of this CTA within the sample
+  const int b = blockIdx.y;
+  const int dv0 = blockIdx.z * DVT;
+  const int row_base = b * p.Npos;               // first global row of the sample
+
+  if (tid == 128) {
+    for (int s = 0; s < kAttSlots; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;             // 2 x 64 columns
+  const uint32_t tmem_O = tmem_base + 128;       // DVT columns
+
+  if (warp < 4) {
+    // =========================== softmax + epilogue =====================================
+    const int r = tid;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float L2E = 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint32_t v[32];
+    int g = 0;
+    // ---- pass 1: row max and row sum ----
+    for (int kvb = 0; kvb < p.nkv; ++kvb, ++g) {
+      const int buf = g & 1;
+      mbar_wait(&s_full[buf], (g >> 1) & 1);
+      tc_fence_after();
+      const int nvalid = p.Npos - kvb * kAttBKV;    // keys >= nvalid belong to the next sample / OOB
+      float sv[64];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        tmem_ld32(tmem_S + lane_off + buf * 64 + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sv[h * 32 + i] = (h * 32 + i < nvalid) ? __uint_as_float(v[i]) : -INFINITY;
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[buf]);
+      float mx = m_run;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, sv[i]);
+      float sum = 0.f;
+      const float mb = mx * L2E;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sum += exp2f(sv[i] * L2E - mb);
+      l_run = l_run * exp2f((m_run - mx) * L2E) + sum;
+      m_run = mx;
+    }
+    const float inv_l = 1.f / l_run;
+    const float mb = m_run * L2E;
+    // ---- pass 2: probabilities -> smem (A operand of P.V) ----
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    for (int j = 0; j < p.nkv; ++j, ++g) {
+      const int buf = g & 1;
+      const int pb = j & 1;
+      mbar_wait(&s_full[buf], (g >> 1) & 1);
+      tc_fence_after();
+      const int nvalid = p.Npos - j * kAttBKV;
+      mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
+      uint8_t* prow = smem + S::kPOff + pb * S::kPBytes + r * 128;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        tmem_ld32(tmem_S + lane_off + buf * 64 + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = c * 8 + e * 2;
+            const int key = h * 32 + i;
+            const float p0 = (key < nvalid) ? exp2f(__uint_as_float(v[i]) * L2E - mb) * inv_l : 0.f;
+            const float p1 = (key + 1 < nvalid) ? exp2f(__uint_as_float(v[i + 1]) * L2E - mb) * inv_l : 0.f;
+            o4[e] = pack_half2(p0, p1);
+          }
+          const uint32_t chunk = static_cast<uint32_t>(h * 4 + c);
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ swz) << 4)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_empty[buf]);
+      fence_proxy_async();
+      mbar_arrive(&p_full[pb]);
+    }
+    // ---- epilogue: O (TMEM) -> fp16 global ----
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const bool row_ok = (q0 + r) < p.Npos;
+    __half* orow = p.o + (size_t)(row_base + q0 + r) * p.ldo + dv0;
+#pragma unroll 1
+    for (int jc = 0; jc < DVT / 32; ++jc) {
+      tmem_ld32(tmem_O + lane_off + jc * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o4[e] = pack_half2(__uint_as_float(v[c * 8 + e * 2]), __uint_as_float(v[c * 8 + e * 2 + 1]));
+          *reinterpret_cast<uint4*>(orow + jc * 32 + c * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =========================== TMA producer ===========================================
+    if (lane == 0) {
+      int it = 0;
+      auto acquire = [&](uint32_t bytes) -> uint8_t* {
+        const int s = it % kAttSlots;
+        mbar_wait(&empty_bar[s], ((it / kAttSlots) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], bytes);
+        return smem + s * kAttSlotBytes;
+      };
+      auto load_qk = [&](int kvb) {
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          uint8_t* dst = acquire(kAttBM * 128 + kAttBKV * 128);
+          const int s = it % kAttSlots;
+          tma_load_2d(dst, &tmQ, &full_bar[s], kb * 64, row_base + q0);
+          tma_load_2d(dst + kAttBM * 128, &tmK, &full_bar[s], kb * 64, row_base + kvb * kAttBKV);
+          ++it;
+        }
+      };
+      for (int kvb = 0; kvb < p.nkv; ++kvb) load_qk(kvb);           // pass 1
+      load_qk(0);                                                   // pass 2 prologue
+      for (int j = 0; j < p.nkv; ++j) {
+        if (j + 1 < p.nkv) load_qk(j + 1);
+        uint8_t* dst = acquire(DVT * 128);
+        const int s = it % kAttSlots;
+        tma_load_2d(dst, &tmV, &full_bar[s], row_base + j * kAttBKV, dv0);
+        ++it;
+      }
+    }
+  } else {
+    // =========================== MMA issuer =============================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(kAttBM, kAttBKV, 0);
+      constexpr uint32_t idesc_pv = make_idesc_f16(kAttBM, DVT, 0);
+      int it = 0;
+      int g = 0;
+      auto issue_qk = [&]() {       // S[g&1] = Q . K_block^T
+        const int buf = g & 1;
+        mbar_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          const int s = it % kAttSlots;
+          mbar_wait(&full_bar[s], (it / kAttSlots) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * kAttSlotBytes);
+          const uint32_t b_addr = a_addr + kAttBM * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_S + buf * 64, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32),
+                     idesc_qk, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          ++it;
+        }
+        umma_commit(&s_full[buf]);
+        ++g;
+      };
+      for (int kvb = 0; kvb < p.nkv; ++kvb) issue_qk();             // pass 1
+      issue_qk();                                                   // pass 2 prologue: S for block 0
+      for (int j = 0; j < p.nkv; ++j) {
+        if (j + 1 < p.nkv) issue_qk();                              // overlap softmax(j) with QK(j+1)
+        const int pb = j & 1;
+        mbar_wait(&p_full[pb], (j >> 1) & 1);
+        const int s = it % kAttSlots;
+        mbar_wait(&full_bar[s], (it / kAttSlots) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + S::kPOff + pb * S::kPBytes);
+        const uint32_t b_addr = smem_u32(smem + s * kAttSlotBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_O, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32), idesc_pv,
+                   (j | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        umma_commit(&p_empty[pb]);
+        ++it;
+      }
+      umma_commit(o_full);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+template <int DVT>
+static int launch_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* o, int ldo,
+                            int B, int Npos, int d, int dv, cudaStream_t stream) {
+  using S = AttSmem<DVT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(nonlocal_attention_kernel<DVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  const uint64_t rows = (uint64_t)B * Npos;
+  if ((rc = make_tmap_2d_f16(&tmQ, q, (uint64_t)d, rows, (uint64_t)ldq, 64, kAttBM, true)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmK, k, (uint64_t)d, rows, (uint64_t)ldk, 64, kAttBKV, true)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmV, vt, rows, (uint64_t)dv, (uint64_t)ldvt, 64, DVT, true)) != B2_OK) return rc;
+  AttParams p;
+  p.Npos = Npos; p.nkb = d / 64; p.nkv = (Npos + kAttBKV - 1) / kAttBKV;
+  p.o = reinterpret_cast<__half*>(o); p.ldo = ldo;
+  dim3 grid((Npos + kAttBM - 1) / kAttBM, B, dv / DVT);
+  nonlocal_attention_kernel<DVT><<<grid, kAttThreads, S::kTotal, stream>>>(tmQ, tmK, tmV, p);
+  B2_CHECK_LAUNCH("nonlocal_attention_kernel");
+  return B2_OK;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_nonlocal_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* o,
+                                     int ldo, int B, int Npos, int d, int dv, void* stream) {
+  B2_CHECK_ARG(q && k && vt && o, "null pointer");
+  B2_CHECK_ARG(B > 0 && Npos > 0 && d > 0 && dv > 0, "non-positive dimension");
+  B2_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && ldo % 8 == 0, "pitches must be multiples of 8");
+  B2_CHECK_ARG(ldq >= d && ldk >= d && ldo >= dv && ldvt >= B * Npos, "pitch smaller than extent");
+  if (d % 64 != 0 || dv % 64 != 0)
+    return set_error(B2_ERR_UNSUPPORTED, "non-local attention needs d and dv multiples of 64 (got %d, %d)", d, dv);
+  int rc;
+  if ((rc = require_sm100()) != B2_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dv % 256 == 0) return launch_attention<256>(q, ldq, k, ldk, vt, ldvt, o, ldo, B, Npos, d, dv, st);
+  if (dv % 128 == 0) return launch_attention<128>(q, ldq, k, ldk, vt, ldvt, o, ldo, B, Npos, d, dv, st);
+  return launch_attention<64>(q, ldq, k, ldk, vt, ldvt, o, ldo, B, Npos, d, dv, st);
+}

@@ -1,0 +1,264 @@
+// b2_conv_api.cu -- C-ABI entry points for the tcgen05 implicit-GEMM convolution and the dense GEMM,
+// plus library-wide error/launch bookkeeping and the CUtensorMap builder.
+#include <atomic>
+#include <mutex>
+#include <string.h>
+
+#include "b2_host.h"
+#include "b2_igemm.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------
+// error + launch bookkeeping
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+int require_sm100() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(B2_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return set_error(B2_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+  if (major != 10)
+    return set_error(B2_ERR_UNSUPPORTED, "this library targets sm_100a (B200); device is sm_%d0 and there is no fallback",
+                     major);
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                     uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(B2_ERR_INVALID, "tensor base not 16-byte aligned");
+  if ((pitch_elems * 2) % 16 != 0) return set_error(B2_ERR_INVALID, "row pitch %llu elements is not a multiple of 8",
+                                                    (unsigned long long)pitch_elems);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu pitch=%llu box=%ux%u", (int)r,
+                     (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems, box_inner,
+                     box_outer);
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// launcher shared by conv and gemm
+// ------------------------------------------------------------------------------------------
+struct IgemmLaunch {
+  IgemmParams p;
+  const void* a_mat;      // AMODE_TMA: A as [M][lda]
+  int lda;
+  int a_cols;             // logical K extent of A (columns readable)
+  const void* w;          // B as [Ncols][ldb]
+  int ldb;
+  int b_cols;             // logical K extent of B
+};
+
+template <int BN>
+static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
+  using S = IgemmSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
+    attr_set = true;
+  }
+  const IgemmParams& p = L.p;
+  CUtensorMap tmA, tmB, tmC, tmR;
+  memset(&tmA, 0, sizeof(tmA)); memset(&tmC, 0, sizeof(tmC)); memset(&tmR, 0, sizeof(tmR));
+  int rc;
+  if ((rc = make_tmap_2d_f16(&tmB, L.w, (uint64_t)L.b_cols, (uint64_t)p.Ncols, (uint64_t)L.ldb, kBK, BN, true)) != B2_OK)
+    return rc;
+  if (p.amode == AMODE_TMA) {
+    if ((rc = make_tmap_2d_f16(&tmA, L.a_mat, (uint64_t)L.a_cols, (uint64_t)p.M_total, (uint64_t)L.lda, kBK, kBM, true)) != B2_OK)
+      return rc;
+  } else {
+    tmA = tmB;
+  }
+  if (p.epi == EPI_TMA_F16) {
+    if ((rc = make_tmap_2d_f16(&tmC, p.y, (uint64_t)p.ldy, (uint64_t)p.M_total, (uint64_t)p.ldy, 64, kBM, true)) != B2_OK)
+      return rc;
+    if (p.residual) {
+      if ((rc = make_tmap_2d_f16(&tmR, p.residual, (uint64_t)p.ldr, (uint64_t)p.M_total, (uint64_t)p.ldr, 64, kBM, true)) != B2_OK)
+        return rc;
+    } else {
+      tmR = tmC;
+    }
+  } else {
+    tmC = tmB; tmR = tmB;
+  }
+  dim3 grid((p.epi == EPI_TMA_F16 ? (p.ldy + BN - 1) / BN : (p.Ncols + BN - 1) / BN), (p.M_total + kBM - 1) / kBM, 1);
+  igemm_kernel<BN><<<grid, kThreads, S::kTotalBytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  B2_CHECK_LAUNCH("igemm_kernel");
+  return B2_OK;
+}
+
+static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
+  // 64-wide tiles for narrow outputs, 128 otherwise
+  const int width = (L.p.epi == EPI_TMA_F16) ? L.p.ldy : L.p.Ncols;
+  if (width <= 64) return launch_igemm<64>(L, stream);
+  return launch_igemm<128>(L, stream);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+int b2_version(void) { return 100; }
+const char* b2_last_error(void) { return g_err; }
+uint64_t b2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+static int conv_out_dim(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+static int validate_conv(const b2_conv_args* a) {
+  B2_CHECK_ARG(a != nullptr, "null args");
+  B2_CHECK_ARG(a->x && a->w && a->scale && a->shift && a->y, "null tensor pointer");
+  B2_CHECK_ARG(a->N > 0 && a->T > 0 && a->H > 0 && a->W > 0 && a->C > 0 && a->K > 0, "non-positive dimension");
+  B2_CHECK_ARG(a->kt > 0 && a->kh > 0 && a->kw > 0 && a->st > 0 && a->sh > 0 && a->sw > 0, "bad kernel/stride");
+  B2_CHECK_ARG(a->pt >= 0 && a->ph >= 0 && a->pw >= 0, "negative padding");
+  B2_CHECK_ARG(a->ldy >= a->K, "ldy < K");
+  B2_CHECK_ARG(a->residual == nullptr || a->ldr >= a->K, "ldr < K");
+  B2_CHECK_ARG(conv_out_dim(a->T, a->kt, a->st, a->pt) > 0 && conv_out_dim(a->H, a->kh, a->sh, a->ph) > 0 &&
+                   conv_out_dim(a->W, a->kw, a->sw, a->pw) > 0,
+               "empty output");
+  if (a->mode == B2_CONV_STEM7) {
+    B2_CHECK_ARG(a->C == 4, "STEM7 needs NDHWC4 input (C == 4), got %d", a->C);
+    B2_CHECK_ARG(a->kw == 7 && a->sw == 2 && a->pw == 3, "STEM7 needs kw=7, sw=2, pw=3");
+    B2_CHECK_ARG(a->W % 2 == 0, "STEM7 needs an even input width, got %d", a->W);
+  } else {
+    B2_CHECK_ARG(a->mode == B2_CONV_AUTO, "unknown conv mode %d", a->mode);
+    B2_CHECK_ARG(a->C % 8 == 0, "channel pitch %d is not a multiple of 8", a->C);
+  }
+  if (!a->out_f32) {
+    B2_CHECK_ARG(a->ldy % 8 == 0, "ldy %d is not a multiple of 8", a->ldy);
+    B2_CHECK_ARG(a->residual == nullptr || a->ldr % 8 == 0, "ldr %d is not a multiple of 8", a->ldr);
+    B2_CHECK_ARG(!a->accumulate, "accumulate requires out_f32");
+  }
+  return B2_OK;
+}
+
+int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
+  int rc = validate_conv(a);
+  if (rc != B2_OK) return rc;
+  if ((rc = require_sm100()) != B2_OK) return rc;
+
+  IgemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  IgemmParams& p = L.p;
+  p.x = reinterpret_cast<const __half*>(a->x);
+  p.N = a->N; p.T = a->T; p.H = a->H; p.W = a->W; p.C = a->C;
+  p.To = conv_out_dim(a->T, a->kt, a->st, a->pt);
+  p.Ho = conv_out_dim(a->H, a->kh, a->sh, a->ph);
+  p.Wo = conv_out_dim(a->W, a->kw, a->sw, a->pw);
+  p.kt = a->kt; p.kh = a->kh; p.kw = a->kw;
+  p.st = a->st; p.sh = a->sh; p.sw = a->sw;
+  p.pt = a->pt; p.ph = a->ph; p.pw = a->pw;
+  const long long M = (long long)a->N * p.To * p.Ho * p.Wo;
+  B2_CHECK_ARG(M < (1ll << 31), "output too large");
+  p.M_total = (int)M;
+  p.Ncols = a->K;
+  p.scale = a->scale; p.shift = a->shift;
+  p.residual = reinterpret_cast<const __half*>(a->residual);
+  p.ldr = a->ldr;
+  p.y = a->y; p.ldy = a->ldy;
+  p.relu = a->relu; p.per_row = 0; p.accumulate = a->accumulate;
+  p.epi = a->out_f32 ? EPI_DIRECT_F32 : EPI_TMA_F16;
+  L.w = a->w;
+
+  const int taps = a->kt * a->kh * a->kw;
+  if (a->mode == B2_CONV_STEM7) {
+    p.amode = AMODE_STEM7;
+    p.npairs = a->kt * a->kh;
+    p.nkb = (p.npairs + 1) / 2;
+    L.ldb = p.nkb * 64;
+    L.b_cols = L.ldb;
+  } else if (taps == 1 && a->st == 1 && a->sh == 1 && a->sw == 1 && a->pt == 0 && a->ph == 0 && a->pw == 0) {
+    // 1x1x1 stride-1: A is literally the [M][C] activation matrix -> TMA on both operands
+    p.amode = AMODE_TMA;
+    p.nkb = (a->C + kBK - 1) / kBK;
+    L.a_mat = a->x; L.lda = a->C; L.a_cols = a->C;
+    L.ldb = a->C; L.b_cols = a->C;
+  } else {
+    p.amode = AMODE_GATHER;
+    p.cchunks = (a->C + kBK - 1) / kBK;
+    p.nkb = taps * p.cchunks;
+    L.ldb = taps * a->C;
+    L.b_cols = L.ldb;
+    // When C % 64 != 0 the last K block of a tap also covers the first columns of the next tap's
+    // weights; the activation side zero-fills channels >= C, so those products vanish.
+  }
+  return dispatch_igemm(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int b2_gemm_f16(const b2_gemm_args* g, void* stream) {
+  B2_CHECK_ARG(g != nullptr, "null args");
+  B2_CHECK_ARG(g->a && g->b && g->scale && g->shift && g->d, "null tensor pointer");
+  B2_CHECK_ARG(g->M > 0 && g->N > 0 && g->Kd > 0, "non-positive dimension");
+  B2_CHECK_ARG(g->lda % 8 == 0 && g->ldb % 8 == 0 && g->lda >= g->Kd && g->ldb >= g->Kd, "bad operand pitch");
+  B2_CHECK_ARG(g->ldd >= g->N, "ldd < N");
+  if (!g->out_f32) {
+    B2_CHECK_ARG(g->ldd % 8 == 0, "ldd not a multiple of 8");
+    B2_CHECK_ARG(!g->accumulate, "accumulate requires out_f32");
+    B2_CHECK_ARG(g->residual == nullptr || (g->ldr % 8 == 0 && g->ldr >= g->N), "bad residual pitch");
+  }
+  int rc;
+  if ((rc = require_sm100()) != B2_OK) return rc;
+
+  IgemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  IgemmParams& p = L.p;
+  p.amode = AMODE_TMA;
+  p.M_total = g->M;
+  p.Ncols = g->N;
+  p.nkb = (g->Kd + kBK - 1) / kBK;
+  p.scale = g->scale; p.shift = g->shift;
+  p.residual = reinterpret_cast<const __half*>(g->residual);
+  p.ldr = g->ldr;
+  p.y = g->d; p.ldy = g->ldd;
+  p.relu = g->relu; p.per_row = g->per_row; p.accumulate = g->accumulate;
+  p.epi = g->out_f32 ? EPI_DIRECT_F32 : EPI_TMA_F16;
+  p.x = reinterpret_cast<const __half*>(g->a);
+  L.a_mat = g->a; L.lda = g->lda; L.a_cols = g->Kd;
+  L.w = g->b; L.ldb = g->ldb; L.b_cols = g->Kd;
+  return dispatch_igemm(L, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// b2_host.h -- host-side helpers shared by the C-ABI translation units: error reporting, launch
+// accounting and CUtensorMap construction through the driver entry point (no -lcuda link needed).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b2_pretorched.h"
+
+namespace b2 {
+
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define B2_CHECK_ARG(cond, ...)                                   \
+  do {                                                            \
+    if (!(cond)) return ::b2::set_error(B2_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define B2_CHECK_CUDA(expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return ::b2::set_error(B2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                                   \
+  } while (0)
+
+// after a kernel launch: picks up launch-configuration errors without synchronising
+#define B2_CHECK_LAUNCH(name)                                                                        \
+  do {                                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                            \
+    if (e__ != cudaSuccess)                                                                          \
+      return ::b2::set_error(B2_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+    ::b2::count_launch();                                                                            \
+  } while (0)
+
+// 2-D fp16 tensor map: `inner` contiguous elements per row, `outer` rows of pitch `pitch_elems`;
+// box = [box_inner x box_outer]; swizzle128 selects CU_TENSOR_MAP_SWIZZLE_128B (box_inner must be 64).
+// Out-of-bounds elements read as zero and are dropped on store.
+int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                     uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+
+int require_sm100();   // B2_OK when the current device is compute capability 10.x
+
+}  // namespace b2

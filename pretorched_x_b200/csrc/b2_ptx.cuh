@@ -1,0 +1,225 @@
+// b2_ptx.cuh -- thin inline-PTX wrappers for the sm_100a features the hot path uses:
+// mbarrier, TMA (cp.async.bulk.tensor), cp.async, tcgen05 (alloc / mma / commit / ld) and the
+// shared-memory / instruction descriptors that tcgen05.mma consumes.
+//
+// Everything here is device-side and header-only.  No CUTLASS/CuTe is used; the bit layouts
+// follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------
+// address helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Blocking wait with a watchdog: a pipeline bug traps (surfacing as a CUDA error in the caller)
+// instead of hanging the GPU.  try_wait suspends in hardware, so the loop count is small in
+// the normal case.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifndef B2_NO_WATCHDOG
+  uint32_t spins = 0;
+#endif
+  while (!mbar_try_wait(bar, parity)) {
+#ifndef B2_NO_WATCHDOG
+    if (++spins > (1u << 24)) __trap();
+#endif
+  }
+}
+
+// generic-proxy writes (st.shared / cp.async) -> async-proxy readers (TMA store, tcgen05.mma)
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA (tiled mode).  Coordinates are innermost-first, in elements.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// cp.async (LDGSTS): 16-byte gather with zero fill (src_bytes == 0 writes 16 zero bytes)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16_ca(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_16_cg(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+// arrive on `bar` once every cp.async this thread issued so far has landed (counts against the
+// barrier's expected arrival count: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05: tensor memory + 5th-gen tensor core MMA
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {  // whole warp
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16/bf16 inputs, fp32 accumulate; single thread issues.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// TMEM -> registers: warp w reads lanes [32*(w%4), +32); thread = one lane (one accumulator row),
+// 32 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (64 bit):
+//   [ 0,14) start address >> 4        [16,30) leading-dim byte offset >> 4
+//   [32,46) stride-dim byte offset>>4 [46,48) version (1 on sm_100)
+//   [49,52) base offset               [61,64) layout: 0 none, 2 = 128B swizzle, 4 = 64B, 6 = 32B
+//
+// K-major, 128B swizzle (what TMA SWIZZLE_128B writes for a [rows][64 x fp16] box): rows are 128 B
+// apart, 8-row groups are SBO = 1024 B apart, the 16 B chunk index is XORed with (row & 7).
+// Advancing K by 16 elements inside the 64-element swizzle row = +32 B on the start address.
+__device__ __forceinline__ uint64_t make_desc_sw128_kmajor(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;            // LBO (unused for swizzled K-major; 1 like CuTe)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO
+  d |= static_cast<uint64_t>(1) << 46;            // version
+  d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+  return d;
+}
+// K-major, no swizzle ("interleave"): core matrix = 8 rows x 16 B with rows 16 B apart;
+// LBO = byte distance between K-adjacent core matrices, SBO = between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_noswz_kmajor(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                           uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 (32 bit):
+//   [4,6) D format (1 = f32)  [7,10) A format (0 = f16, 1 = bf16)  [10,13) B format
+//   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, uint32_t ab_fmt /*0 f16, 1 bf16*/) {
+  return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// small numeric helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+
+}  // namespace b2

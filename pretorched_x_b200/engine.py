@@ -1,0 +1,217 @@
+"""Forward engine: walks a (reference-layout) module tree and replaces the bodies of its hot blocks by
+fused sm_100a kernels.
+
+The nn.Modules in ``models/`` are *parameter containers* that keep the reference's ``state_dict``
+layout; nothing in them computes.  This file holds the block bodies:
+
+* ``conv_bn_act``        Conv3d/Conv2d/SpatioTemporalConv + BatchNorm (+residual) (+ReLU) -> one or two
+                         implicit-GEMM launches                      (resnet3D.py:91-106, 125-143)
+* ``run_basic/run_bottleneck``  residual blocks incl. type-A/B shortcuts (resnet3D.py:65-74, 176-185)
+* ``run_nonlocal``       theta/phi/g projections, fused attention, W+BN+residual (nonlocalnet.py:143-166)
+* ``run_stem`` / ``run_head``   stem conv+BN+ReLU+maxpool, global average + last_linear
+                         (torchvision_models.py:448-464)
+
+Packed fp16 filters and folded BN affines are cached on the owning module and rebuilt whenever a
+source tensor changes (``load_state_dict``, in-place edits), so checkpoints stay drop-in.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import Act
+
+
+# ---------------------------------------------------------------------------------------------
+# packed-parameter cache
+# ---------------------------------------------------------------------------------------------
+def _sig(*tensors):
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None for t in tensors)
+
+
+def _bn_tensors(bn):
+    if bn is None:
+        return ()
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+
+
+def _cached(owner, slot, sig, build):
+    cache = owner.__dict__.setdefault("_b2_cache", {})
+    hit = cache.get(slot)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    val = build()
+    cache[slot] = (sig, val)
+    return val
+
+
+def _triple(v):
+    if isinstance(v, (tuple, list)):
+        v = tuple(int(i) for i in v)
+        return (1,) + v if len(v) == 2 else v
+    return (int(v),) * 3
+
+
+def _conv_geometry(conv):
+    if isinstance(conv, nn.Conv2d):
+        s, p = conv.stride, conv.padding
+        return (1, int(s[0]), int(s[1])), (0, int(p[0]), int(p[1]))
+    return _triple(conv.stride), _triple(conv.padding)
+
+
+def packed_conv(conv, bn, in_pitch, stem=False):
+    """PackedConv for a plain nn.Conv3d / nn.Conv2d followed (optionally) by BatchNorm ``bn``."""
+    if conv.groups != 1 or any(d != 1 for d in conv.dilation):
+        raise NotImplementedError("grouped / dilated convolutions are outside the engine's scope")
+    sig = _sig(conv.weight, conv.bias, *_bn_tensors(bn)) + (in_pitch, stem, id(bn))
+    stride, padding = _conv_geometry(conv)
+    return _cached(conv, "pc", sig,
+                   lambda: ops.PackedConv(conv.weight, conv.bias, bn, stride, padding, in_pitch=in_pitch, stem=stem))
+
+
+def _is_stem_shape(conv):
+    w = conv.weight
+    kw = w.shape[-1]
+    stride, padding = _conv_geometry(conv)
+    return w.shape[1] <= 4 and kw == 7 and stride[2] == 2 and padding[2] == 3
+
+
+def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False):
+    """Run ``conv`` (Conv3d / Conv2d / SpatioTemporalConv-like) -> ``bn`` -> (+residual) -> (ReLU)."""
+    if hasattr(conv, "spatial_conv") and hasattr(conv, "temporal_conv"):
+        # (2+1)D factorised conv (r2plus1d.py:85-88): spatial conv + its own BN + ReLU, then the temporal
+        # conv whose epilogue carries the *outer* BN / residual / ReLU.
+        mid = conv_bn_act(conv.spatial_conv, conv.bn, a, relu=True, simt=simt)
+        return conv_bn_act(conv.temporal_conv, bn, mid, residual=residual, relu=relu, simt=simt)
+    stem = a.ld == 4
+    if stem and not _is_stem_shape(conv):
+        raise NotImplementedError("NDHWC4 inputs are only supported by 7-wide stride-2 stem convolutions")
+    pc = packed_conv(conv, bn, a.ld, stem=stem)
+    if a.W % 2 != 0 and stem:
+        raise ValueError("stem convolution needs an even input width (got %d)" % a.W)
+    return ops.conv(a, pc, residual=residual, relu=relu, simt=simt)
+
+
+# ---------------------------------------------------------------------------------------------
+# residual blocks
+# ---------------------------------------------------------------------------------------------
+def _shortcut(block, a, simt):
+    ds = block.downsample
+    if ds is None:
+        return a
+    if isinstance(ds, nn.Sequential):          # type B: 1x1x1 conv (stride s) + BN
+        return conv_bn_act(ds[0], ds[1], a, relu=False, simt=simt)
+    if hasattr(ds, "planes") and hasattr(ds, "stride"):   # type A (ShortcutA)
+        return ops.shortcut_a(a, ds.stride, ds.planes)
+    raise NotImplementedError("unsupported downsample %r" % (ds,))
+
+
+def run_basic(block, a, simt=False):
+    """conv-BN-ReLU-conv-BN-(+shortcut)-ReLU (resnet3D.py:91-106)."""
+    res = _shortcut(block, a, simt)
+    out = conv_bn_act(block.conv1, block.bn1, a, relu=True, simt=simt)
+    out = conv_bn_act(block.conv2, block.bn2, out, residual=res, relu=True, simt=simt)
+    return out
+
+
+def run_bottleneck(block, a, simt=False):
+    """1x1x1-BN-ReLU, 3x3x3(stride)-BN-ReLU, 1x1x1-BN-(+shortcut)-ReLU (resnet3D.py:125-143)."""
+    res = _shortcut(block, a, simt)
+    out = conv_bn_act(block.conv1, block.bn1, a, relu=True, simt=simt)
+    out = conv_bn_act(block.conv2, block.bn2, out, relu=True, simt=simt)
+    out = conv_bn_act(block.conv3, block.bn3, out, residual=res, relu=True, simt=simt)
+    return out
+
+
+def run_block(block, a, simt=False):
+    out = run_bottleneck(block, a, simt) if hasattr(block, "conv3") else run_basic(block, a, simt)
+    nl = getattr(block, "nonlocalblock", None)
+    if nl is not None and getattr(block, "nonlocal_layer", True):
+        out = run_nonlocal(nl, out, simt=simt)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# non-local block (embedded gaussian, no sub-sampling)
+# ---------------------------------------------------------------------------------------------
+def _conv1x1_matrix(conv):
+    return conv.weight.detach().reshape(conv.weight.shape[0], -1)
+
+
+def run_nonlocal(nl, a, simt=False):
+    """z = BN(W(softmax(theta(x)^T phi(x)) g(x))) + x   (nonlocalnet.py:143-166)."""
+    if nl.mode != "embedded_gaussian" or nl.sub_sample or nl.dimension != 3:
+        raise NotImplementedError("engine implements the 3-D embedded-gaussian non-local block without sub-sampling")
+    d = nl.inter_channels
+    C = nl.in_channels
+    dev = a.data.device
+    Wseq = nl.W
+    w_conv, w_bn = (Wseq[0], Wseq[1]) if isinstance(Wseq, nn.Sequential) else (Wseq, None)
+
+    def build():
+        # theta|phi concatenated along the output dim -> one projection GEMM for both
+        wqk = torch.zeros((2 * d, a.ld), dtype=torch.float16, device=dev)
+        wqk[:d, :C] = _conv1x1_matrix(nl.theta).to(torch.float16)
+        wqk[d:, :C] = _conv1x1_matrix(nl.phi).to(torch.float16)
+        bqk = torch.cat([nl.theta.bias.detach(), nl.phi.bias.detach()]).float().contiguous()
+        wg = torch.zeros((d, a.ld), dtype=torch.float16, device=dev)
+        wg[:, :C] = _conv1x1_matrix(nl.g).to(torch.float16)
+        bg = nl.g.bias.detach().float().contiguous()
+        ones_qk = torch.ones(2 * d, dtype=torch.float32, device=dev)
+        ones_g = torch.ones(d, dtype=torch.float32, device=dev)
+        return wqk, bqk, ones_qk, wg, bg, ones_g
+
+    sig = _sig(nl.theta.weight, nl.theta.bias, nl.phi.weight, nl.phi.bias, nl.g.weight, nl.g.bias) + (a.ld,)
+    wqk, bqk, ones_qk, wg, bg, ones_g = _cached(nl, "proj", sig, build)
+
+    M = a.M
+    Npos = a.positions
+    # theta|phi: [M][2d]
+    qk = ops.gemm(a.data, wqk, ones_qk, bqk, M, 2 * d, a.ld)
+    # g transposed (swap-AB): Vt[dv][M] = Wg . x^T, bias per row -> keys become the contiguous (K) dim
+    Mp = ops._round_up(M, 8)
+    vt = torch.empty((d, Mp), dtype=torch.float16, device=dev)
+    if Mp != M:
+        vt.zero_()
+    ops.gemm(wg, a.data, ones_g, bg, d, M, a.ld, per_row=True, out=vt)
+    y = ops.nonlocal_attention(qk, d, vt, d, a.N, Npos)
+    ya = Act(y, a.N, a.T, a.H, a.W, d)
+    # W (1x1x1 conv with bias) + BN + residual x, no ReLU
+    return conv_bn_act(w_conv, w_bn, ya, residual=a, relu=False, simt=simt)
+
+
+# ---------------------------------------------------------------------------------------------
+# stem / trunk / head
+# ---------------------------------------------------------------------------------------------
+def _pool_args(mp):
+    if isinstance(mp, nn.MaxPool2d):
+        k, s, p = mp.kernel_size, mp.stride, mp.padding
+        two = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+        k, s, p = two(k), two(s), two(p)
+        return (1, k[0], k[1]), (1, s[0], s[1]), (0, p[0], p[1])
+    return _triple(mp.kernel_size), _triple(mp.stride), _triple(mp.padding)
+
+
+def run_stem(model, x, simt=False):
+    """conv1 -> bn1 -> relu -> maxpool (torchvision_models.py:449-452)."""
+    a = x if isinstance(x, Act) else ops.from_ncdhw(x)
+    a = conv_bn_act(model.conv1, model.bn1, a, relu=True, simt=simt)
+    k, s, p = _pool_args(model.maxpool)
+    return ops.maxpool3d(a, k, s, p)
+
+
+def run_trunk(model, x, simt=False):
+    a = run_stem(model, x, simt=simt)
+    for name in ("layer1", "layer2", "layer3", "layer4"):
+        for block in getattr(model, name):
+            a = run_block(block, a, simt=simt)
+    return a
+
+
+def run_head(model, a, head):
+    """avgpool -> view(B,-1) -> last_linear (torchvision_models.py:460-464).  Returns fp32 [N][classes]."""
+    pooled = ops.avgpool_global(a)                     # fp16 [N][ld]
+    if isinstance(head, nn.Linear):
+        pl = _cached(head, "pl", _sig(head.weight, head.bias), lambda: ops.PackedLinear(head.weight, head.bias))
+        return ops.linear(pooled, pl, out_f32=True)
+    # user-swapped head (Identity, Dropout, custom module): hand it the pooled features like the reference does
+    return head(pooled[:, :a.C].float())

@@ -1,0 +1,283 @@
+"""Host-side operator layer: torch tensors in, C-ABI calls out.
+
+Activations travel between kernels as :class:`Act` -- an fp16 NDHWC matrix ``[N*T*H*W, ld]`` plus its
+logical dims -- so that every convolution is an (implicit) GEMM over dense rows and every epilogue
+writes full 128-byte lines.  The functions here mirror, one for one, the torch.nn calls on the
+reference's hot path (file:line given per function); the arithmetic happens in
+``csrc/*.cu`` behind ``include/b2_pretorched.h``.  There is no CPU implementation.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, GemmArgs, B2_CONV_AUTO, B2_CONV_STEM7
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError("%s must live on a CUDA (sm_100a) device: this engine has no CPU path" % what)
+
+
+class Act:
+    """fp16 channels-last activation: ``data`` is ``[N*T*H*W, ld]`` with channels ``[C, ld)`` zero."""
+    __slots__ = ("data", "N", "T", "H", "W", "C")
+
+    def __init__(self, data, N, T, H, W, C):
+        self.data, self.N, self.T, self.H, self.W, self.C = data, N, T, H, W, C
+
+    @property
+    def ld(self):
+        return self.data.shape[1]
+
+    @property
+    def M(self):
+        return self.data.shape[0]
+
+    @property
+    def positions(self):
+        return self.T * self.H * self.W
+
+    def __repr__(self):
+        return "Act(N=%d,T=%d,H=%d,W=%d,C=%d,ld=%d)" % (self.N, self.T, self.H, self.W, self.C, self.ld)
+
+
+# ---------------------------------------------------------------------------------------------
+# layout
+# ---------------------------------------------------------------------------------------------
+def from_ncdhw(x, pitch=None):
+    """fp32 NCDHW (or NCHW) tensor -> Act.  ``pitch`` = channel pitch (4 for stem inputs)."""
+    _require_cuda(x, "input")
+    if x.dim() == 4:
+        x = x.unsqueeze(2)
+    if x.dim() != 5:
+        raise ValueError("expected a [N,C,T,H,W] or [N,C,H,W] tensor, got %s" % (tuple(x.shape),))
+    x = x.contiguous().float()
+    N, C, T, H, W = x.shape
+    if pitch is None:
+        pitch = 4 if C <= 4 else _round_up(C, 8)
+    y = torch.empty((N * T * H * W, pitch), dtype=torch.float16, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.b2_ncdhw_f32_to_ndhwc_f16(_ptr(x), _ptr(y), N, C, T, H, W, pitch, _stream()), "b2_ncdhw_f32_to_ndhwc_f16")
+    return Act(y, N, T, H, W, C)
+
+
+def to_ncdhw(a):
+    """Act -> fp32 NCDHW tensor (the layout/dtype the reference's ``features`` returns)."""
+    y = torch.empty((a.N, a.C, a.T, a.H, a.W), dtype=torch.float32, device=a.data.device)
+    lib = _lib.load()
+    _lib.check(lib.b2_ndhwc_f16_to_ncdhw_f32(_ptr(a.data), _ptr(y), a.N, a.C, a.T, a.H, a.W, a.ld, _stream()),
+               "b2_ndhwc_f16_to_ncdhw_f32")
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
+# packed convolution parameters
+# ---------------------------------------------------------------------------------------------
+class PackedConv:
+    """fp16 filter in the engine's [K][taps][C] layout + the folded per-channel affine.
+
+    ``scale``/``shift`` fold the conv bias and the eval-mode BatchNorm that follows the convolution in
+    the reference (y = (conv + bias - mean) / sqrt(var + eps) * gamma + beta).
+    """
+    __slots__ = ("w", "scale", "shift", "K", "Cin", "C", "k", "s", "p", "mode")
+
+    def __init__(self, weight, bias=None, bn=None, stride=(1, 1, 1), padding=(0, 0, 0), in_pitch=None, stem=False):
+        _require_cuda(weight, "conv weight")
+        if weight.dim() == 4:       # Conv2d weight -> T = 1
+            weight = weight.unsqueeze(2)
+        K, Cin, kt, kh, kw = weight.shape
+        self.K, self.Cin = K, Cin
+        self.k = (kt, kh, kw)
+        self.s = tuple(int(v) for v in stride)
+        self.p = tuple(int(v) for v in padding)
+        self.mode = B2_CONV_STEM7 if stem else B2_CONV_AUTO
+        self.C = 4 if stem else (in_pitch if in_pitch is not None else _round_up(Cin, 8))
+        lib = _lib.load()
+        n = lib.b2_pack_conv_weight_elems(K, Cin, kt, kh, kw, self.C, self.mode)
+        self.w = torch.empty(n, dtype=torch.float16, device=weight.device)
+        w32 = weight.detach().contiguous().float()
+        _lib.check(lib.b2_pack_conv_weight(_ptr(w32), _ptr(self.w), K, Cin, kt, kh, kw, self.C, self.mode, _stream()),
+                   "b2_pack_conv_weight")
+        self.scale, self.shift = fold_affine(K, bias, bn, weight.device)
+
+
+def fold_affine(K, bias, bn, device):
+    """Per-output-channel (scale, shift) in fp32 for conv(+bias) followed by eval-mode BatchNorm."""
+    if bn is not None:
+        if bn.training:
+            raise RuntimeError("the forward engine is inference-only: call model.eval() (BatchNorm uses running stats)")
+        g = bn.weight.detach().double() if bn.weight is not None else torch.ones(K, dtype=torch.float64, device=device)
+        b = bn.bias.detach().double() if bn.bias is not None else torch.zeros(K, dtype=torch.float64, device=device)
+        inv = torch.rsqrt(bn.running_var.detach().double() + bn.eps)
+        scale = g * inv
+        shift = b - bn.running_mean.detach().double() * scale
+        if bias is not None:
+            shift = shift + bias.detach().double() * scale
+    else:
+        scale = torch.ones(K, dtype=torch.float64, device=device)
+        shift = bias.detach().double() if bias is not None else torch.zeros(K, dtype=torch.float64, device=device)
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def _out_dim(i, k, s, p):
+    return (i + 2 * p - k) // s + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# convolution / dense
+# ---------------------------------------------------------------------------------------------
+def conv(a, pc, residual=None, relu=False, simt=False):
+    """nn.Conv3d -> BatchNorm3d -> (+residual) -> ReLU in one kernel
+    (resnet3D.py:91-106, 125-143, 176-185; r2plus1d.py:85-88; torchvision_models.py:449-451)."""
+    if a.ld != pc.C:
+        raise ValueError("activation pitch %d != packed filter pitch %d" % (a.ld, pc.C))
+    kt, kh, kw = pc.k
+    To, Ho, Wo = (_out_dim(a.T, kt, pc.s[0], pc.p[0]), _out_dim(a.H, kh, pc.s[1], pc.p[1]),
+                  _out_dim(a.W, kw, pc.s[2], pc.p[2]))
+    M = a.N * To * Ho * Wo
+    ldy = _round_up(pc.K, 8)
+    y = torch.empty((M, ldy), dtype=torch.float16, device=a.data.device)
+    args = ConvArgs()
+    args.x, args.w, args.scale, args.shift = _ptr(a.data), _ptr(pc.w), _ptr(pc.scale), _ptr(pc.shift)
+    args.residual = _ptr(residual.data if residual is not None else None)
+    args.y = _ptr(y)
+    args.N, args.T, args.H, args.W, args.C = a.N, a.T, a.H, a.W, a.ld
+    args.K, args.ldy = pc.K, ldy
+    args.ldr = residual.ld if residual is not None else 0
+    if residual is not None and residual.M != M:
+        raise ValueError("residual rows %d != output rows %d" % (residual.M, M))
+    args.kt, args.kh, args.kw = kt, kh, kw
+    args.st, args.sh, args.sw = pc.s
+    args.pt, args.ph, args.pw = pc.p
+    args.relu, args.out_f32, args.accumulate, args.mode = int(relu), 0, 0, pc.mode
+    lib = _lib.load()
+    fn = lib.b2_conv_ndhwc_fprop_simt if simt else lib.b2_conv_ndhwc_fprop
+    _lib.check(fn(ctypes.byref(args), _stream()), "b2_conv_ndhwc_fprop")
+    return Act(y, a.N, To, Ho, Wo, pc.K)
+
+
+def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=False, out=None, out_f32=False,
+         accumulate=False):
+    """D[M][N] = act(scale * A[M][Kd] . B[N][Kd]^T + shift + residual) on tcgen05 (b2_gemm_f16)."""
+    dev = a2d.device
+    if out is None:
+        ldd = N if out_f32 else _round_up(N, 8)
+        out = torch.empty((M, ldd), dtype=torch.float32 if out_f32 else torch.float16, device=dev)
+    g = GemmArgs()
+    g.a, g.b, g.scale, g.shift = _ptr(a2d), _ptr(b2d), _ptr(scale), _ptr(shift)
+    g.residual = _ptr(residual)
+    g.d = _ptr(out)
+    g.M, g.N, g.Kd = M, N, Kd
+    g.lda, g.ldb, g.ldd = a2d.stride(0), b2d.stride(0), out.stride(0)
+    g.ldr = residual.stride(0) if residual is not None else 0
+    g.per_row, g.relu, g.out_f32, g.accumulate = int(per_row), int(relu), int(out_f32), int(accumulate)
+    _lib.check(_lib.load().b2_gemm_f16(ctypes.byref(g), _stream()), "b2_gemm_f16")
+    return out
+
+
+class PackedLinear:
+    """nn.Linear weights as an fp16 [out][in_pitch] matrix + fp32 bias (resnet3D.py:162, trn.py:42-44)."""
+    __slots__ = ("w", "scale", "shift", "out_features", "in_features", "in_pitch")
+
+    def __init__(self, weight, bias=None):
+        _require_cuda(weight, "linear weight")
+        out_f, in_f = weight.shape
+        self.out_features, self.in_features = out_f, in_f
+        self.in_pitch = _round_up(in_f, 8)
+        w = torch.zeros((out_f, self.in_pitch), dtype=torch.float16, device=weight.device)
+        w[:, :in_f] = weight.detach().to(torch.float16)
+        self.w = w
+        self.scale, self.shift = fold_affine(out_f, bias, None, weight.device)
+
+
+def linear(x2d, pl, relu=False, out_f32=False, out=None, accumulate=False):
+    """x2d: fp16 [M][in_pitch]  ->  [M][out] (fp16, or fp32 when out_f32)."""
+    if x2d.shape[1] < pl.in_features:
+        raise ValueError("input has %d features, layer needs %d" % (x2d.shape[1], pl.in_features))
+    return gemm(x2d, pl.w, pl.scale, pl.shift, x2d.shape[0], pl.out_features, pl.in_features, relu=relu,
+                out_f32=out_f32, out=out, accumulate=accumulate)
+
+
+# ---------------------------------------------------------------------------------------------
+# pooling / shortcuts / casts
+# ---------------------------------------------------------------------------------------------
+def maxpool3d(a, kernel, stride, padding):
+    """nn.MaxPool3d (resnet3D.py:156; executed at torchvision_models.py:452)."""
+    kt, kh, kw = kernel
+    st, sh, sw = stride
+    pt, ph, pw = padding
+    To, Ho, Wo = _out_dim(a.T, kt, st, pt), _out_dim(a.H, kh, sh, ph), _out_dim(a.W, kw, sw, pw)
+    y = torch.empty((a.N * To * Ho * Wo, a.ld), dtype=torch.float16, device=a.data.device)
+    _lib.check(_lib.load().b2_maxpool3d_ndhwc(_ptr(a.data), _ptr(y), a.N, a.T, a.H, a.W, a.ld, kt, kh, kw, st, sh, sw,
+                                             pt, ph, pw, _stream()), "b2_maxpool3d_ndhwc")
+    return Act(y, a.N, To, Ho, Wo, a.C)
+
+
+def avgpool_global(a):
+    """nn.AdaptiveAvgPool3d(1) + view(B, -1) (torchvision_models.py:460-463): -> fp16 [N][ld]."""
+    y = torch.empty((a.N, a.ld), dtype=torch.float16, device=a.data.device)
+    _lib.check(_lib.load().b2_avgpool_global_ndhwc(_ptr(a.data), _ptr(y), a.N, a.positions, a.ld, _stream()),
+               "b2_avgpool_global_ndhwc")
+    return y
+
+
+def shortcut_a(a, stride, out_channels):
+    """Type-A shortcut: F.avg_pool3d(k=1, stride) + zero channel padding (resnet3D.py:65-74)."""
+    To, Ho, Wo = (a.T - 1) // stride + 1, (a.H - 1) // stride + 1, (a.W - 1) // stride + 1
+    ldo = _round_up(out_channels, 8)
+    y = torch.empty((a.N * To * Ho * Wo, ldo), dtype=torch.float16, device=a.data.device)
+    _lib.check(_lib.load().b2_shortcut_a_ndhwc(_ptr(a.data), _ptr(y), a.N, a.T, a.H, a.W, a.ld, stride, ldo, _stream()),
+               "b2_shortcut_a_ndhwc")
+    return Act(y, a.N, To, Ho, Wo, out_channels)
+
+
+def cast_rows(x2d, relu=False):
+    """fp32 [rows][cols] -> fp16 [rows][round_up(cols, 8)], optional ReLU (trn.py:40-41)."""
+    _require_cuda(x2d, "input")
+    x2d = x2d.contiguous().float()
+    rows, cols = x2d.shape
+    y = torch.empty((rows, _round_up(cols, 8)), dtype=torch.float16, device=x2d.device)
+    _lib.check(_lib.load().b2_cast_f32_to_f16(_ptr(x2d), x2d.stride(0), _ptr(y), y.stride(0), rows, cols, int(relu),
+                                             _stream()), "b2_cast_f32_to_f16")
+    return y
+
+
+def gather_frames(x3d, idx_dev):
+    """x3d fp16 [N][T][F], idx int32[n] on device -> [N][n*F] (trn.py:108)."""
+    N, T, F = x3d.shape
+    n = idx_dev.numel()
+    y = torch.empty((N, n * F), dtype=torch.float16, device=x3d.device)
+    _lib.check(_lib.load().b2_gather_frames(_ptr(x3d), _ptr(y), _ptr(idx_dev), N, T, F, n, _stream()), "b2_gather_frames")
+    return y
+
+
+# ---------------------------------------------------------------------------------------------
+# non-local attention
+# ---------------------------------------------------------------------------------------------
+def nonlocal_attention(qk, d, vt, dv, B, Npos):
+    """softmax(theta^T phi) . g  (nonlocalnet.py:150-160).
+
+    qk: fp16 [B*Npos][>=2d] with theta in columns [0,d) and phi in [d,2d); vt: fp16 [dv][B*Npos pitch].
+    Returns fp16 [B*Npos][dv].
+    """
+    o = torch.empty((B * Npos, _round_up(dv, 8)), dtype=torch.float16, device=qk.device)
+    q = qk
+    k = qk[:, d:]
+    _lib.check(_lib.load().b2_nonlocal_attention(_ptr(q), q.stride(0), ctypes.c_void_p(k.data_ptr()), k.stride(0),
+                                                _ptr(vt), vt.stride(0), _ptr(o), o.stride(0), B, Npos, d, dv, _stream()),
+               "b2_nonlocal_attention")
+    return o

@@ -1,0 +1,103 @@
+"""CPU: pin oracle/functional.py and the package's seeded init against fixtures produced by the unmodified
+reference (oracle/make_golden.py).  SURVEY.md section 8c: the reference has no golden vectors of its own."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import functional as OF
+from oracle import reference_loader as RL
+import pretorched_x_b200 as P
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+MODEL_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "model"]
+
+
+def build_ours(fx):
+    torch.manual_seed(fx["seeds"]["init"])
+    arch = fx["arch"]
+    if arch.startswith("r2plus1d"):
+        m = getattr(P, arch)(**fx["kwargs"])
+    else:
+        m = getattr(P, arch)(pretrained=None, **fx["kwargs"])
+    OF.randomize_bn_(m, fx["seeds"]["bn"])
+    return m.eval()
+
+
+def test_fixtures_present():
+    assert len(MODEL_FIX) >= 5 and len(GOLDEN) >= 8
+
+
+@pytest.mark.parametrize("path", MODEL_FIX, ids=[os.path.basename(p)[:-3] for p in MODEL_FIX])
+def test_seeded_init_matches_reference_digest(path):
+    fx = torch.load(path, weights_only=False)
+    sd = build_ours(fx).state_dict()
+    assert len(sd) == fx["n_state"]
+    assert list(sd) == list(fx["weight_digest"])          # same keys, same order as the reference's state_dict
+    got = OF.state_digest(sd)
+    for k, (s, a) in fx["weight_digest"].items():
+        assert got[k] == (s, a), k
+
+
+@pytest.mark.parametrize("path", MODEL_FIX, ids=[os.path.basename(p)[:-3] for p in MODEL_FIX])
+def test_oracle_reproduces_reference_outputs(path):
+    fx = torch.load(path, weights_only=False)
+    sd = build_ours(fx).state_dict()
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"])
+    stages = {}
+    with torch.no_grad():
+        out = OF.forward(x, sd, fx["arch"], stages)
+    scale = fx["logits"].abs().max().item()
+    assert (out - fx["logits"]).abs().max().item() <= 1e-5 * scale
+    for name, ref in fx["stages"].items():
+        got = stages[name]
+        assert tuple(got.shape) == ref["shape"]
+        samp = got.reshape(-1)[::ref["step"]][:ref["sample"].numel()]
+        assert (samp - ref["sample"]).abs().max().item() <= 1e-5 * max(ref["absmax"], 1e-6), name
+
+
+def test_relation_fixtures():
+    for name in ("relation_small", "relation_htrn"):
+        fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", name + ".pt"), weights_only=False)
+        torch.manual_seed(fx["seeds"]["init"])
+        ours = P.Relation(fx["T"], fx["F"], fx["out"], bottleneck_dim=fx["bottleneck"])
+        assert OF.state_digest(ours.state_dict()) == fx["weight_digest"]
+        x = OF.seeded_input((fx["B"], fx["T"], fx["F"]), fx["seeds"]["input"])
+        with torch.no_grad():
+            y = OF.relation(x, ours.state_dict(), "", fx["T"], fx["F"])
+        assert (y - fx["output"]).abs().max().item() <= 1e-5 * fx["output"].abs().max().item()
+
+
+def test_multiscale_relation_fixture():
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "msrelation_small.pt"), weights_only=False)
+    torch.manual_seed(fx["seeds"]["init"])
+    ours = P.MultiScaleRelation(fx["T"], fx["F"], fx["out"], bottleneck_dim=fx["bottleneck"])
+    assert OF.state_digest(ours.state_dict()) == fx["weight_digest"]
+    x = OF.seeded_input((fx["B"], fx["T"], fx["F"]), fx["seeds"]["input"])
+    np.random.seed(fx["np_seed"])
+    with torch.no_grad():
+        y = OF.multiscale_relation(x, ours.state_dict(), fx["T"], fx["F"])
+    assert (y - fx["output"]).abs().max().item() <= 1e-5 * fx["output"].abs().max().item()
+    # the package draws the same tuples from the same NumPy seed as the reference (trn.py:103-106)
+    np.random.seed(fx["np_seed"])
+    picks = ours.sample_tuples()
+    np.random.seed(fx["np_seed"])
+    y2 = OF.multiscale_relation(x, ours.state_dict(), fx["T"], fx["F"], tuples=picks)
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.skipif(not RL.available(), reason="/root/reference not present (GPU box)")
+def test_state_dict_identical_to_live_reference():
+    RL.load(); RL.load_r2plus1d()
+    for arch, kw in [("r2plus1d18", dict(num_classes=400)), ("resnet3d50", dict(num_classes=400)),
+                     ("nonlocalresnet3d50", dict())]:
+        torch.manual_seed(3)
+        ref = RL.build(arch, **kw)
+        torch.manual_seed(3)
+        ours = getattr(P, arch)(**kw) if arch.startswith("r2") else getattr(P, arch)(pretrained=None, **kw)
+        a, b = ref.state_dict(), ours.state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (arch, k)
