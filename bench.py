@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- clips/sec of the resnet3d50 forward (B=32 clips of 16x224x224 per GPU), BASELINE.json config[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one forward pass of the hot path over one batch of synthetic clips per GPU (weak scaling: every rank
+runs B=32; clips shard with no data-path collective, one all-gather of the [B,400] logits per step).  Prints ONE
+JSON line (rank 0).  ``value`` times CUDA-graph replays with the input resident in HBM; ``e2e`` times the same
+forward through the public API with pinned HOST input (H2D inside) and a D2H read of the logits every step.
+
+``--impl reference`` times the reference's CPU fp32 forward (the oracle port of it; /root/reference itself when
+the tree is present) on the box's host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ARCH = "resnet3d50"
+NUM_CLASSES = 400
+CLIP = (3, 16, 224, 224)
+BATCH_PER_GPU = 32
+GFLOP_PER_CLIP = 79.69          # algorithmic, padding taps included (SURVEY.md section 8a / BASELINE.md section 2)
+METRIC = "clips/sec resnet3d50 16x224x224 forward"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            pk = json.load(fh)
+        return dict(hbm_gbs=pk["hbm_gbs"], tflops=pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                    tflops_burst=pk["bf16_tflops"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=10)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (reference's own implementation of the path on host cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_forward_fn():
+    """Returns (callable(x) -> logits, kind).  Uses the unmodified reference when /root/reference exists (build
+    container), else the oracle port of it (GPU box)."""
+    import torch
+    from oracle import functional as OF
+    from oracle import reference_loader as RL
+    torch.set_num_threads(os.cpu_count() or 1)
+    if RL.available():
+        RL.load()
+        torch.manual_seed(0)
+        model = RL.build(ARCH, num_classes=NUM_CLASSES)
+        OF.randomize_bn_(model, 1)
+        model.eval()
+        return (lambda x: model(x)), "reference"
+    import pretorched_x_b200 as P
+    torch.manual_seed(0)
+    sd = OF.randomize_bn_(P.resnet3d50(num_classes=NUM_CLASSES, pretrained=None), 1).state_dict()
+    return (lambda x: OF.forward(x, sd, ARCH)), "port"
+
+
+def time_cpu(steps, warmup, sample_clips=2):
+    import torch
+    from oracle import functional as OF
+    fn, kind = cpu_forward_fn()
+    x = OF.seeded_input((sample_clips,) + CLIP, 2)
+    with torch.no_grad():
+        for _ in range(warmup):
+            fn(x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn(x)
+        dt = time.perf_counter() - t0
+    return dict(value=sample_clips * steps / dt, unit="clips/s", cores=torch.get_num_threads(), kind=kind,
+                sample="%d steps x %d clips of %s fp32 on %d host threads (torch %s)" % (
+                    steps, sample_clips, "x".join(map(str, CLIP)), torch.get_num_threads(), torch.__version__),
+                ms_per_step=dt / steps * 1e3)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 6))
+    cb = time_cpu(steps, max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded randn clips, random-init weights)",
+        "config": {"workload": "resnet3d50 forward, clips of 16x224x224 (bounded CPU sample: 2 clips per step)",
+                   "parallelism": "cpu"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import pretorched_x_b200 as P
+    from pretorched_x_b200 import ops, parallel, _lib
+    from pretorched_x_b200.graph import GraphedForward
+    from oracle import functional as OF           # BN conditioning + cpu_baseline leg only
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+    torch.manual_seed(0)
+    model = P.resnet3d50(num_classes=NUM_CLASSES, pretrained=None)
+    OF.randomize_bn_(model, 1)
+    model = model.eval().to(dev)
+    if world > 1:
+        parallel.broadcast_parameters(model)
+
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_in = [torch.randn((B,) + CLIP, generator=g).pin_memory() for _ in range(2)]   # fp32 NCDHW, as the reference takes
+    x_dev = host_in[0].to(dev)
+    h2d_bytes = host_in[0].numel() * 4
+    host_out = torch.empty((B, NUM_CLASSES), dtype=torch.float32).pin_memory()
+    d2h_bytes = host_out.numel() * 4
+
+    # launches per forward, counted on one eager pass (graph replays re-issue exactly these kernels)
+    with torch.no_grad():
+        model(x_dev)
+        torch.cuda.synchronize()
+        c0 = _lib.launch_count()
+        model(x_dev)
+        torch.cuda.synchronize()
+        launches_per_fwd = _lib.launch_count() - c0
+
+    graphed = GraphedForward(model, x_dev, warmup=2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(args.warmup):
+        graphed()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = graphed()
+        if world > 1:
+            gathered = parallel.gather_logits(out, B * world)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = B * world * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end: pinned host input -> H2D -> forward -> D2H logits, every step ----
+    for i in range(2):
+        graphed(host_in[i % 2])
+        host_out.copy_(graphed.static_out, non_blocking=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = graphed(host_in[i % 2])                 # static_in.copy_(pinned host) + graph replay
+        if world > 1:
+            out = parallel.gather_logits(out, B * world)[rank * B:(rank + 1) * B]
+        host_out.copy_(out, non_blocking=True)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / (float(t.item()) / 1e3)
+
+    if rank != 0:
+        return
+
+    # ---- per-launch profile (eager, CUDA events on the launching stream) -> roofline of the dominant kernel ----
+    peaks = load_peaks()
+    with torch.no_grad():
+        model(x_dev)
+        with ops.profile() as prof:
+            for _ in range(2):
+                model(x_dev)
+    rows = prof.rows
+    nrep = 2
+    conv_rows = [r for r in rows if r["kind"] in ("conv", "gemm")]
+    conv_ms = sum(r["ms"] for r in conv_rows) / nrep
+    conv_flops = sum(r["flops"] for r in conv_rows) / nrep
+    all_ms = sum(r["ms"] for r in rows) / nrep
+    achieved_tflops = conv_flops / (conv_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "b2::igemm_kernel (all %d conv/linear launches of one forward)" % (len(conv_rows) // nrep),
+        "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"],
+        "traffic": None, "peak_source": peaks["source"] + ", sustained bf16/fp16 GEMM",
+        "share_of_step": conv_ms / all_ms,
+        "whole_step_tflops": GFLOP_PER_CLIP * 1e9 * value / world / 1e12,
+        "whole_step_frac": GFLOP_PER_CLIP * 1e9 * value / world / 1e12 / peaks["tflops"],
+    }
+    if args.layers:
+        agg = {}
+        for r in rows:
+            a = agg.setdefault(r["desc"], dict(kind=r["kind"], ms=0.0, flops=0.0, bytes=0.0, n=0))
+            a["ms"] += r["ms"] / nrep; a["flops"] += r["flops"] / nrep; a["bytes"] += r["bytes"] / nrep; a["n"] += 1
+        print("%-52s %4s %9s %9s %8s %8s" % ("layer", "n", "ms", "TFLOP/s", "GB/s", "%step"), file=sys.stderr)
+        for d, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            print("%-52s %4d %9.3f %9.1f %8.0f %7.1f%%" % (d, a["n"] // nrep, a["ms"], a["flops"] / a["ms"] / 1e9 if a["ms"] else 0,
+                                                          a["bytes"] / a["ms"] / 1e6 if a["ms"] else 0, 100 * a["ms"] / all_ms), file=sys.stderr)
+        print("eager per-launch total %.3f ms/forward (graph replay: %.3f ms)" % (all_ms, ms_total / args.steps), file=sys.stderr)
+
+    cpu = None
+    if not args.no_cpu:
+        cb = time_cpu(steps=3, warmup=1)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic (seeded randn clips, random-init weights, randomised BN statistics)",
+        "config": {"workload": "resnet3d50 forward, B=%d clips of 16x224x224 per GPU (BASELINE.json configs[1])" % B,
+                   "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "l2": "inputs (%.0f MB fp32 clips, %.0f MB of activations per step) exceed the 126 MB L2; no flush needed"
+                         % (h2d_bytes / 1e6, 127.9e6 * 2 * B / 1e6),
+                   "timing": "CUDA events around %d CUDA-graph replays, max over ranks" % args.steps},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world},
+        "gpu_launches": int(launches_per_fwd * args.steps),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: the BASELINE config)")
+    ap.add_argument("--layers", action="store_true", help="print the per-layer table to stderr")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world > 1:
+        from pretorched_x_b200 import parallel
+        parallel.init_from_env(backend="nccl")
+    run_ours(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,48 @@ def _require_cuda(t, what):
         raise RuntimeError("%s must live on a CUDA (sm_100a) device: this engine has no CPU path" % what)
 
 
+# ---------------------------------------------------------------------------------------------
+# optional per-launch profiling (bench.py / tools): CUDA events on the launching stream + algorithmic work
+# ---------------------------------------------------------------------------------------------
+_PROFILE = None
+
+
+class profile:
+    """``with ops.profile() as prof: model(x)`` -> prof.rows = [dict(kind, desc, ms, flops, bytes)] per launch."""
+
+    def __enter__(self):
+        global _PROFILE
+        self.records = []
+        _PROFILE = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        _PROFILE = None
+        torch.cuda.synchronize()
+        self.rows = [dict(kind=k, desc=d, ms=e0.elapsed_time(e1), flops=f, bytes=b) for (k, d, e0, e1, f, b) in self.records]
+        return False
+
+
+class _timed:
+    def __init__(self, kind, desc, flops, nbytes):
+        self.meta = (kind, desc, flops, nbytes)
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.e1.record()
+            k, d, f, b = self.meta
+            _PROFILE.append((k, d, self.e0, self.e1, f, b))
+        return False
+
+
 class Act:
     """fp16 channels-last activation: ``data`` is ``[N*T*H*W, ld]`` with channels ``[C, ld)`` zero."""
     __slots__ = ("data", "N", "T", "H", "W", "C")
@@ -71,7 +113,8 @@ def from_ncdhw(x, pitch=None):
         pitch = 4 if C <= 4 else _round_up(C, 8)
     y = torch.empty((N * T * H * W, pitch), dtype=torch.float16, device=x.device)
     lib = _lib.load()
-    _lib.check(lib.b2_ncdhw_f32_to_ndhwc_f16(_ptr(x), _ptr(y), N, C, T, H, W, pitch, _stream()), "b2_ncdhw_f32_to_ndhwc_f16")
+    with _timed("layout", "ncdhw_f32->ndhwc_f16 C%d px=%d" % (C, N * T * H * W), 0.0, N * T * H * W * (4.0 * C + 2.0 * pitch)):
+        _lib.check(lib.b2_ncdhw_f32_to_ndhwc_f16(_ptr(x), _ptr(y), N, C, T, H, W, pitch, _stream()), "b2_ncdhw_f32_to_ndhwc_f16")
     return Act(y, N, T, H, W, C)
 
 
@@ -166,7 +209,12 @@ def conv(a, pc, residual=None, relu=False, simt=False):
     args.relu, args.out_f32, args.accumulate, args.mode = int(relu), 0, 0, pc.mode
     lib = _lib.load()
     fn = lib.b2_conv_ndhwc_fprop_simt if simt else lib.b2_conv_ndhwc_fprop
-    _lib.check(fn(ctypes.byref(args), _stream()), "b2_conv_ndhwc_fprop")
+    taps = kt * kh * kw
+    flops = 2.0 * M * pc.K * pc.Cin * taps                     # algorithmic (padding taps included)
+    nbytes = 2.0 * (a.M * a.C + M * pc.K * (2 if residual is not None else 1) + pc.K * pc.Cin * taps)
+    desc = "conv %dx%dx%d s%s C%d->%d M=%d" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, M)
+    with _timed("conv", desc, flops, nbytes):
+        _lib.check(fn(ctypes.byref(args), _stream()), "b2_conv_ndhwc_fprop")
     return Act(y, a.N, To, Ho, Wo, pc.K)
 
 
@@ -185,7 +233,9 @@ def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=Fa
     g.lda, g.ldb, g.ldd = a2d.stride(0), b2d.stride(0), out.stride(0)
     g.ldr = residual.stride(0) if residual is not None else 0
     g.per_row, g.relu, g.out_f32, g.accumulate = int(per_row), int(relu), int(out_f32), int(accumulate)
-    _lib.check(_lib.load().b2_gemm_f16(ctypes.byref(g), _stream()), "b2_gemm_f16")
+    with _timed("gemm", "gemm M=%d N=%d K=%d" % (M, N, Kd), 2.0 * M * N * Kd,
+                2.0 * (M * Kd + N * Kd) + out.element_size() * M * N):
+        _lib.check(_lib.load().b2_gemm_f16(ctypes.byref(g), _stream()), "b2_gemm_f16")
     return out
 
 
@@ -222,16 +272,18 @@ def maxpool3d(a, kernel, stride, padding):
     pt, ph, pw = padding
     To, Ho, Wo = _out_dim(a.T, kt, st, pt), _out_dim(a.H, kh, sh, ph), _out_dim(a.W, kw, sw, pw)
     y = torch.empty((a.N * To * Ho * Wo, a.ld), dtype=torch.float16, device=a.data.device)
-    _lib.check(_lib.load().b2_maxpool3d_ndhwc(_ptr(a.data), _ptr(y), a.N, a.T, a.H, a.W, a.ld, kt, kh, kw, st, sh, sw,
-                                             pt, ph, pw, _stream()), "b2_maxpool3d_ndhwc")
+    with _timed("maxpool", "maxpool C%d M=%d->%d" % (a.C, a.M, y.shape[0]), 0.0, 2.0 * a.C * (a.M + y.shape[0])):
+        _lib.check(_lib.load().b2_maxpool3d_ndhwc(_ptr(a.data), _ptr(y), a.N, a.T, a.H, a.W, a.ld, kt, kh, kw, st, sh, sw,
+                                                 pt, ph, pw, _stream()), "b2_maxpool3d_ndhwc")
     return Act(y, a.N, To, Ho, Wo, a.C)
 
 
 def avgpool_global(a):
     """nn.AdaptiveAvgPool3d(1) + view(B, -1) (torchvision_models.py:460-463): -> fp16 [N][ld]."""
     y = torch.empty((a.N, a.ld), dtype=torch.float16, device=a.data.device)
-    _lib.check(_lib.load().b2_avgpool_global_ndhwc(_ptr(a.data), _ptr(y), a.N, a.positions, a.ld, _stream()),
-               "b2_avgpool_global_ndhwc")
+    with _timed("avgpool", "avgpool C%d M=%d" % (a.C, a.M), 0.0, 2.0 * a.C * (a.M + a.N)):
+        _lib.check(_lib.load().b2_avgpool_global_ndhwc(_ptr(a.data), _ptr(y), a.N, a.positions, a.ld, _stream()),
+                   "b2_avgpool_global_ndhwc")
     return y
 
 
@@ -277,7 +329,9 @@ def nonlocal_attention(qk, d, vt, dv, B, Npos):
     o = torch.empty((B * Npos, _round_up(dv, 8)), dtype=torch.float16, device=qk.device)
     q = qk
     k = qk[:, d:]
-    _lib.check(_lib.load().b2_nonlocal_attention(_ptr(q), q.stride(0), ctypes.c_void_p(k.data_ptr()), k.stride(0),
-                                                _ptr(vt), vt.stride(0), _ptr(o), o.stride(0), B, Npos, d, dv, _stream()),
-               "b2_nonlocal_attention")
+    with _timed("attention", "attention B=%d N=%d d=%d dv=%d" % (B, Npos, d, dv), 2.0 * B * Npos * Npos * (d + dv),
+                2.0 * B * Npos * (2 * d + 2 * dv)):
+        _lib.check(_lib.load().b2_nonlocal_attention(_ptr(q), q.stride(0), ctypes.c_void_p(k.data_ptr()), k.stride(0),
+                                                    _ptr(vt), vt.stride(0), _ptr(o), o.stride(0), B, Npos, d, dv, _stream()),
+                   "b2_nonlocal_attention")
     return o

@@ -1,0 +1,190 @@
+"""GPU (-m gpu): kernel-level parity of the C-ABI entry points against the CPU oracle (torch fp32 on the same
+fp16-rounded operands).  Tolerances are relative to max|reference|: 2e-3 for fp16 outputs (fp32 accumulate,
+one fp16 rounding of the result = 2^-11), 1e-4 for fp32 outputs."""
+import zlib
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import functional as OF
+
+pytestmark = pytest.mark.gpu
+
+TOL_F16 = 2e-3
+TOL_F32 = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from pretorched_x_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def h(x):
+    return x.half().float()
+
+
+def rel(got, ref):
+    return (got.double().cpu() - ref.double()).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+
+
+def seed_of(name):
+    return zlib.crc32(name.encode()) % 100000
+
+
+CONV_CASES = [
+    # name, N, Cin, T, H, W, K, kernel, stride, padding, residual, relu, bias, bn
+    ("1x1x1_tma", 2, 64, 4, 8, 8, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0), True, True, False, True),
+    ("1x1x1_reduce", 1, 256, 4, 8, 8, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), False, True, False, True),
+    ("3x3x3_s1", 1, 64, 4, 8, 8, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    ("3x3x3_s1_ragged_rows", 1, 64, 3, 7, 5, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), True, True, False, True),
+    ("3x3x3_s2", 1, 128, 4, 8, 8, 128, (3, 3, 3), (2, 2, 2), (1, 1, 1), False, True, False, True),
+    ("3x3x3_T1_all_temporal_padding", 2, 128, 1, 7, 7, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    ("shortcutB_1x1x1_s2", 1, 256, 4, 8, 8, 512, (1, 1, 1), (2, 2, 2), (0, 0, 0), False, False, False, True),
+    ("r2p1d_spatial_144", 1, 64, 4, 8, 8, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False, True),
+    ("r2p1d_temporal_from_144", 1, 144, 4, 8, 8, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
+    ("r2p1d_temporal7_from_110", 1, 110, 8, 8, 8, 64, (7, 1, 1), (1, 1, 1), (3, 0, 0), False, False, False, True),
+    ("r2p1d_spatial_s2_odd_230", 1, 64, 4, 8, 8, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1), False, True, False, True),
+    ("r2p1d_temporal_s2_from_230", 1, 230, 4, 4, 4, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0), False, True, False, True),
+    ("nonlocal_theta_bias_no_bn", 1, 128, 2, 4, 4, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), False, False, True, False),
+    ("stem_7x7x7", 1, 3, 4, 32, 32, 64, (7, 7, 7), (1, 2, 2), (3, 3, 3), False, True, False, True),
+    ("stem_r2p1d_1x7x7_to_110", 1, 3, 4, 32, 32, 110, (1, 7, 7), (1, 2, 2), (0, 3, 3), False, True, False, True),
+    ("single_output_pixel", 1, 64, 1, 1, 1, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "simt_crosscheck"])
+def test_conv_bn_act_matches_oracle(dev, case, simt):
+    from pretorched_x_b200 import ops, engine
+    name, N, Cin, T, H, W, K, k, s, p, res, relu, bias, bn = case
+    g = torch.Generator().manual_seed(seed_of(name))
+    x = h(torch.randn(N, Cin, T, H, W, generator=g))
+    conv = nn.Conv3d(Cin, K, k, stride=s, padding=p, bias=bias)
+    with torch.no_grad():
+        conv.weight.copy_(h(torch.randn(conv.weight.shape, generator=g) / (Cin * k[0] * k[1] * k[2]) ** 0.5))
+        if bias:
+            conv.bias.copy_(torch.randn(K, generator=g))
+    bnm = OF.randomize_bn_(nn.BatchNorm3d(K), 7).eval() if bn else None
+    with torch.no_grad():
+        y = conv(x)
+        y = bnm(y) if bnm is not None else y
+        r = h(torch.randn(y.shape, generator=g)) if res else None
+        y = y + r if res else y
+        y = F.relu(y) if relu else y
+    a = ops.from_ncdhw(x.to(dev))
+    ra = ops.from_ncdhw(r.to(dev), pitch=ops._round_up(K, 8)) if res else None
+    out = engine.conv_bn_act(conv.to(dev), bnm.to(dev) if bnm is not None else None, a, residual=ra, relu=relu, simt=simt)
+    assert (out.N, out.T, out.H, out.W, out.C) == (y.shape[0], y.shape[2], y.shape[3], y.shape[4], K)
+    assert rel(ops.to_ncdhw(out), y) <= TOL_F16
+    if out.ld > out.C:                                     # channel padding must stay exactly zero
+        assert float(out.data[:, out.C:].abs().max()) == 0.0
+
+
+GEMM_CASES = [
+    ("one_tile", 128, 64, 64, False, False, False, False, False),
+    ("bn128", 256, 128, 128, False, True, False, False, False),
+    ("ragged_everything", 300, 200, 192, True, True, False, False, False),
+    ("deep_k", 1000, 512, 512, True, False, False, False, False),
+    ("head_fp32", 64, 400, 2048, False, False, False, True, False),
+    ("tiny_m_fp32", 3, 339, 2048, False, False, False, True, False),
+    ("swap_ab_per_row", 256, 136, 96, False, False, True, False, False),
+    ("fp32_accumulate", 20, 64, 128, False, False, False, True, True),
+    ("k_not_multiple_of_64", 130, 72, 200, False, True, False, False, False),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=[c[0] for c in GEMM_CASES])
+def test_gemm_matches_oracle(dev, case):
+    from pretorched_x_b200 import ops
+    name, M, N, Kd, res, relu, per_row, f32, acc = case
+    g = torch.Generator().manual_seed(seed_of(name))
+    A, B = h(torch.randn(M, Kd, generator=g)), h(torch.randn(N, Kd, generator=g) / Kd ** 0.5)
+    nsc = M if per_row else N
+    sc, sh = torch.rand(nsc, generator=g) + 0.5, torch.randn(nsc, generator=g)
+    D = A @ B.t()
+    D = D * (sc.view(-1, 1) if per_row else sc.view(1, -1)) + (sh.view(-1, 1) if per_row else sh.view(1, -1))
+    R = h(torch.randn(M, N, generator=g)) if res else None
+    D = D + R if res else D
+    D = F.relu(D) if relu else D
+    Kp, Np = ops._round_up(Kd, 8), ops._round_up(N, 8)
+    Ad = torch.zeros(M, Kp, dtype=torch.float16, device=dev); Ad[:, :Kd] = A.half().to(dev)
+    Bd = torch.zeros(N, Kp, dtype=torch.float16, device=dev); Bd[:, :Kd] = B.half().to(dev)
+    Rd = None
+    if res:
+        Rd = torch.zeros(M, Np, dtype=torch.float16, device=dev); Rd[:, :N] = R.half().to(dev)
+    out = None
+    if acc:
+        base = torch.randn(M, N, generator=g)
+        out, D = base.clone().to(dev), D + base
+    got = ops.gemm(Ad, Bd, sc.to(dev), sh.to(dev), M, N, Kd, residual=Rd, relu=relu, per_row=per_row, out_f32=f32,
+                   out=out, accumulate=acc)
+    assert rel(got[:, :N].float(), D) <= (TOL_F32 if f32 else TOL_F16)
+    if not f32 and Np > N:
+        assert float(got[:, N:].abs().max()) == 0.0
+
+
+ATT_CASES = [("one_block", 1, 128, 64, 64), ("ragged_keys_and_queries", 2, 200, 128, 128),
+             ("layer2_like", 1, 576, 256, 256), ("layer3_like_dv_split", 2, 72, 512, 512), ("n_lt_64", 1, 16, 64, 64)]
+
+
+@pytest.mark.parametrize("case", ATT_CASES, ids=[c[0] for c in ATT_CASES])
+def test_nonlocal_attention_matches_oracle(dev, case):
+    from pretorched_x_b200 import ops
+    name, B, Npos, d, dv = case
+    g = torch.Generator().manual_seed(seed_of(name))
+    q, k = h(torch.randn(B, Npos, d, generator=g) * 0.3), h(torch.randn(B, Npos, d, generator=g) * 0.3)
+    v = h(torch.randn(B, Npos, dv, generator=g))
+    ref = torch.softmax(q @ k.transpose(1, 2), dim=-1) @ v            # nonlocalnet.py:156-160, unscaled
+    qk = torch.cat([q, k], dim=2).reshape(B * Npos, 2 * d).half().to(dev).contiguous()
+    vt = torch.zeros(dv, ops._round_up(B * Npos, 8), dtype=torch.float16, device=dev)
+    vt[:, :B * Npos] = v.reshape(B * Npos, dv).t().half().to(dev)
+    o = ops.nonlocal_attention(qk, d, vt, dv, B, Npos)
+    assert rel(o[:, :dv].float().view(B, Npos, dv), ref) <= 4e-3
+
+
+def test_attention_rows_are_convex_combinations(dev):
+    """Size-independent property: with V == 1 every output must be exactly 1 (softmax rows sum to one)."""
+    from pretorched_x_b200 import ops
+    B, Npos, d, dv = 2, 1000, 64, 64
+    g = torch.Generator().manual_seed(5)
+    qk = (torch.randn(B * Npos, 2 * d, generator=g) * 0.5).half().to(dev)
+    vt = torch.ones(dv, B * Npos, dtype=torch.float16, device=dev)
+    o = ops.nonlocal_attention(qk, d, vt, dv, B, Npos)
+    assert (o[:, :dv].float() - 1.0).abs().max().item() <= 2e-3
+
+
+def test_pooling_layout_and_helpers(dev):
+    from pretorched_x_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 24, 5, 12, 10, generator=g)
+    a = ops.from_ncdhw(x.to(dev))
+    assert torch.equal(ops.to_ncdhw(a).cpu(), h(x))
+    assert torch.equal(ops.to_ncdhw(ops.maxpool3d(a, (3, 3, 3), (2, 2, 2), (1, 1, 1))).cpu(), F.max_pool3d(h(x), 3, 2, 1))
+    assert rel(ops.avgpool_global(a)[:, :24].float(), h(x).mean(dim=(2, 3, 4))) <= 1e-3
+    assert torch.equal(ops.to_ncdhw(ops.shortcut_a(a, 2, 40)).cpu(), OF.shortcut_a(h(x), 40, 2))
+    x3 = torch.randn(1, 3, 2, 6, 6, generator=g)
+    a3 = ops.from_ncdhw(x3.to(dev))
+    assert a3.ld == 4 and torch.equal(ops.to_ncdhw(a3).cpu(), h(x3))
+    assert float(a3.data[:, 3].abs().max()) == 0.0
+
+
+def test_conv_linearity_at_full_layer_size(dev):
+    """Size-independent property at a BASELINE-sized layer (layer1 conv2 of resnet3d50, 4 clips of 8x56x56):
+    with identity BN, no ReLU:  conv(a) + conv(b) == conv(a + b) up to fp16 rounding of the three outputs."""
+    from pretorched_x_b200 import ops, engine
+    g = torch.Generator().manual_seed(3)
+    conv = nn.Conv3d(64, 64, 3, padding=1, bias=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (64 * 27) ** 0.5)
+    conv = conv.to(dev)
+    xa = torch.randn(4, 64, 8, 56, 56, generator=g).half().float()
+    xb = torch.randn(4, 64, 8, 56, 56, generator=g).half().float()
+    xs = (xa + xb).half().float()
+    ya, yb, ys = (engine.conv_bn_act(conv, None, ops.from_ncdhw(t.to(dev))).data.float() for t in (xa, xb, xs))
+    scale = ys.abs().max().item()
+    assert (ya + yb - ys).abs().max().item() <= 4e-3 * scale
