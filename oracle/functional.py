@@ -249,3 +249,15 @@ def seeded_input(shape, seed):
 def state_digest(sd):
     """Per-tensor (sum, abs-sum) in float64 -- a cheap fingerprint to prove two inits are identical."""
     return {k: (float(v.double().sum()), float(v.double().abs().sum())) for k, v in sd.items()}
+
+
+def digests_match(a, b, rtol=1e-9):
+    """Compare two ``state_digest`` results.  The float64 sums are reduced by the host CPU's vector units, whose
+    summation order differs between machines, so equality is up to a few ulps rather than bit-exact."""
+    if list(a) != list(b):
+        return False
+    for k in a:
+        for u, v in zip(a[k], b[k]):
+            if abs(u - v) > rtol * max(abs(u), abs(v), 1e-30):
+                return False
+    return True

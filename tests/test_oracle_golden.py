@@ -36,9 +36,7 @@ def test_seeded_init_matches_reference_digest(path):
     sd = build_ours(fx).state_dict()
     assert len(sd) == fx["n_state"]
     assert list(sd) == list(fx["weight_digest"])          # same keys, same order as the reference's state_dict
-    got = OF.state_digest(sd)
-    for k, (s, a) in fx["weight_digest"].items():
-        assert got[k] == (s, a), k
+    assert OF.digests_match(OF.state_digest(sd), fx["weight_digest"])
 
 
 @pytest.mark.parametrize("path", MODEL_FIX, ids=[os.path.basename(p)[:-3] for p in MODEL_FIX])
@@ -63,7 +61,7 @@ def test_relation_fixtures():
         fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", name + ".pt"), weights_only=False)
         torch.manual_seed(fx["seeds"]["init"])
         ours = P.Relation(fx["T"], fx["F"], fx["out"], bottleneck_dim=fx["bottleneck"])
-        assert OF.state_digest(ours.state_dict()) == fx["weight_digest"]
+        assert OF.digests_match(OF.state_digest(ours.state_dict()), fx["weight_digest"])
         x = OF.seeded_input((fx["B"], fx["T"], fx["F"]), fx["seeds"]["input"])
         with torch.no_grad():
             y = OF.relation(x, ours.state_dict(), "", fx["T"], fx["F"])
@@ -74,7 +72,7 @@ def test_multiscale_relation_fixture():
     fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "msrelation_small.pt"), weights_only=False)
     torch.manual_seed(fx["seeds"]["init"])
     ours = P.MultiScaleRelation(fx["T"], fx["F"], fx["out"], bottleneck_dim=fx["bottleneck"])
-    assert OF.state_digest(ours.state_dict()) == fx["weight_digest"]
+    assert OF.digests_match(OF.state_digest(ours.state_dict()), fx["weight_digest"])
     x = OF.seeded_input((fx["B"], fx["T"], fx["F"]), fx["seeds"]["input"])
     np.random.seed(fx["np_seed"])
     with torch.no_grad():
