@@ -32,6 +32,8 @@ MODEL_CASES = {
     "r2plus1d34_b1_t8_64": ("r2plus1d34", dict(num_classes=400), (1, 3, 8, 64, 64)),
     "nonlocalresnet3d50_b1_t16_96": ("nonlocalresnet3d50", dict(), (1, 3, 16, 96, 96)),
     "resnet18_b2_64": ("resnet18", dict(num_classes=1000), (2, 3, 64, 64)),
+    # same net with theta/phi rescaled into a trained-like logit regime (oracle.functional.calibrate_nonlocal_)
+    "nonlocalresnet3d50_tamed_b1_t16_96": ("nonlocalresnet3d50", dict(), (1, 3, 16, 96, 96)),
 }
 SEED_INIT, SEED_BN, SEED_INPUT = 0, 1, 2
 
@@ -57,6 +59,7 @@ def run_model_case(name, arch, kwargs, shape):
     OF.randomize_bn_(ref, SEED_BN)
     ref.eval()
     x = OF.seeded_input(shape, SEED_INPUT)
+    nl_factors = OF.calibrate_nonlocal_(ref, x) if "tamed" in name else None
 
     hooked = {}
     handles = []
@@ -84,7 +87,7 @@ def run_model_case(name, arch, kwargs, shape):
     assert torch.equal(out, logits)
 
     fixture = dict(
-        kind="model", arch=arch, kwargs=kwargs, input_shape=tuple(shape),
+        kind="model", arch=arch, kwargs=kwargs, input_shape=tuple(shape), nl_factors=nl_factors,
         seeds=dict(init=SEED_INIT, bn=SEED_BN, input=SEED_INPUT),
         logits=logits.clone(), stages={k: summarize(v) for k, v in hooked.items()},
         weight_digest=OF.state_digest(sd), n_state=len(sd),

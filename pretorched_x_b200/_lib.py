@@ -89,6 +89,11 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
             fn.restype = res
             fn.argtypes = args
+        algo = os.environ.get("B2_CONV_ALGO")          # debug: "gather" disables the slab kernel (A/B timing)
+        if algo:
+            lib.b2_debug_set_conv_algo.restype = c_int
+            lib.b2_debug_set_conv_algo.argtypes = [c_int]
+            lib.b2_debug_set_conv_algo(1 if algo == "gather" else 0)
         _lib = lib
     return _lib
 

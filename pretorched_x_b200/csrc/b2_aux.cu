@@ -28,20 +28,27 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restri
   out[i] = __float2half_rn(v);
 }
 
-// STEM7 layout: [K][pairs_padded][8 px][4 ch]; pair = dt*kh + dh; px 0 is the alignment pixel (zero),
-// px 1..7 <-> kw index 0..6; channels >= Cin zero; padded pairs zero.
+// STEM7 weight image (consumed by b2_stemconv.cuh): [ntile][pair = dt*kh + dh][n/8][j = 16-byte K chunk (4)]
+// [n%8][e (8)] with K element index k = j*8 + e = px*4 + c, px 0 = zero alignment pixel, px 1..7 <-> kw tap 0..6,
+// channels >= Cin zero, output channels >= K zero.  This is the canonical SWIZZLE_NONE K-major smem layout of a
+// [BN x 32] B operand (LBO = 128 B, SBO = 512 B), so a tap pair is one contiguous BN*64-byte block.
 __global__ void pack_weight_stem7_kernel(const float* __restrict__ w, __half* __restrict__ out, int K, int Cin,
-                                         int kt, int kh, int pairs_pad, long long total) {
+                                         int kt, int kh, int BN, long long total) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i & 3);
-  int px = (int)((i >> 2) & 7);
-  long long q = i >> 5;
-  int pr = (int)(q % pairs_pad);
-  int k = (int)(q / pairs_pad);
+  const int e = (int)(i & 7);
+  const int nn = (int)((i >> 3) & 7);
+  const int j = (int)((i >> 6) & 3);
+  long long q = i >> 8;
+  const int n8 = (int)(q % (BN / 8)); q /= (BN / 8);
+  const int pairs = kt * kh;
+  const int pr = (int)(q % pairs);
+  const int ntile = (int)(q / pairs);
+  const int k = ntile * BN + n8 * 8 + nn;
+  const int px = j * 2 + (e >> 2), c = e & 3;
   float v = 0.f;
-  if (pr < kt * kh && px >= 1 && c < Cin) {
-    int dt = pr / kh, dh = pr % kh, dw = px - 1;
+  if (k < K && px >= 1 && c < Cin) {
+    const int dt = pr / kh, dh = pr % kh, dw = px - 1;
     v = w[((((long long)k * Cin + c) * kt + dt) * kh + dh) * 7 + dw];
   }
   out[i] = __float2half_rn(v);
@@ -79,9 +86,16 @@ __global__ void conv_simt_kernel(SimtConvParams p, long long total) {
           if ((unsigned)wi >= (unsigned)p.W) continue;
           const __half* xp = p.x + ((((size_t)n * p.T + ti) * p.H + hi) * p.W + wi) * (size_t)p.C;
           const __half* wp;
-          if (p.stem7) wp = p.w + (size_t)k * p.ldw + ((size_t)(dt * p.kh + dh) * 8 + (dw + 1)) * 4;
-          else wp = p.w + (size_t)k * p.ldw + (size_t)((dt * p.kh + dh) * p.kw + dw) * p.C;
-          for (int c = 0; c < p.C; ++c) acc += __half2float(xp[c]) * __half2float(wp[c]);
+          if (p.stem7) {
+            // weight image [ntile][pair][n/8][j][n%8][e], BN = p.ldw
+            const int BN = p.ldw, px = dw + 1;
+            const size_t base = ((((size_t)(k / BN) * (p.kt * p.kh) + (dt * p.kh + dh)) * (BN / 8) + (k % BN) / 8) * 4 + px / 2) * 64 +
+                                (size_t)(k % 8) * 8 + (px & 1) * 4;
+            for (int c = 0; c < p.C; ++c) acc += __half2float(xp[c]) * __half2float(p.w[base + c]);
+          } else {
+            wp = p.w + (size_t)k * p.ldw + (size_t)((dt * p.kh + dh) * p.kw + dw) * p.C;
+            for (int c = 0; c < p.C; ++c) acc += __half2float(xp[c]) * __half2float(wp[c]);
+          }
         }
       }
     }
@@ -255,9 +269,14 @@ extern "C" {
 
 static int odim(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
 
+static int stem_bn(int K) { return K <= 64 ? 64 : 128; }
+
 size_t b2_pack_conv_weight_elems(int K, int Cin, int kt, int kh, int kw, int C, int mode) {
   (void)Cin;
-  if (mode == B2_CONV_STEM7) return (size_t)K * (size_t)(((kt * kh + 1) / 2) * 2) * 32;
+  if (mode == B2_CONV_STEM7) {
+    const int BN = stem_bn(K);
+    return (size_t)((K + BN - 1) / BN) * kt * kh * BN * 32;
+  }
   return (size_t)K * kt * kh * kw * C;
 }
 
@@ -270,7 +289,7 @@ int b2_pack_conv_weight(const float* w, void* out, int K, int Cin, int kt, int k
   if (mode == B2_CONV_STEM7) {
     B2_CHECK_ARG(kw == 7 && Cin <= 4, "STEM7 packing needs kw == 7 and Cin <= 4");
     pack_weight_stem7_kernel<<<div_up(total, 256), 256, 0, st>>>(w, reinterpret_cast<__half*>(out), K, Cin, kt, kh,
-                                                                 ((kt * kh + 1) / 2) * 2, total);
+                                                                 stem_bn(K), total);
   } else {
     B2_CHECK_ARG(C >= Cin && C % 8 == 0, "packed channel pitch %d must be >= Cin and a multiple of 8", C);
     pack_weight_kernel<<<div_up(total, 256), 256, 0, st>>>(w, reinterpret_cast<__half*>(out), K, Cin, kt, kh, kw, C, total);
@@ -290,7 +309,7 @@ int b2_conv_ndhwc_fprop_simt(const b2_conv_args* a, void* stream) {
   p.To = odim(a->T, a->kt, a->st, a->pt); p.Ho = odim(a->H, a->kh, a->sh, a->ph); p.Wo = odim(a->W, a->kw, a->sw, a->pw);
   p.relu = a->relu; p.out_f32 = a->out_f32; p.accumulate = a->accumulate;
   p.stem7 = (a->mode == B2_CONV_STEM7);
-  p.ldw = p.stem7 ? (((a->kt * a->kh + 1) / 2) * 64) : a->kt * a->kh * a->kw * a->C;
+  p.ldw = p.stem7 ? stem_bn(a->K) : a->kt * a->kh * a->kw * a->C;
   const long long total = (long long)a->N * p.To * p.Ho * p.Wo * a->ldy;
   conv_simt_kernel<<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, total);
   B2_CHECK_LAUNCH("conv_simt");

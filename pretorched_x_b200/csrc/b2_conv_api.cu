@@ -6,6 +6,8 @@
 
 #include "b2_host.h"
 #include "b2_igemm.cuh"
+#include "b2_slabconv.cuh"
+#include "b2_stemconv.cuh"
 
 namespace b2 {
 
@@ -78,6 +80,162 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return B2_OK;
 }
 
+int make_tmap_ndhwc_slab(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t planes,
+                         uint32_t box_w, uint32_t box_h) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(B2_ERR_INVALID, "tensor base not 16-byte aligned");
+  cuuint64_t dims[4] = {C, W, H, planes};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d) C=%llu W=%llu H=%llu planes=%llu box=%ux%u", (int)r,
+                     (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)planes, box_w, box_h);
+  return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// slab convolution launcher (stride 1, "same" padding)
+// ------------------------------------------------------------------------------------------
+static int g_conv_algo = 0;   // 0 auto, 1 force gather (debug / A-B comparisons)
+
+static int slab_rows(int MT, int PW, int reach, int P) {
+  int R = 0;
+  for (int q0 = 0; q0 < P; q0 += MT * 128) {
+    int lo = q0 - reach;
+    lo = (lo >= 0) ? lo / PW : -((-lo + PW - 1) / PW);
+    const int hi = (q0 + MT * 128 - 1 + reach) / PW;
+    R = (hi - lo + 1) > R ? (hi - lo + 1) : R;
+  }
+  return R;
+}
+
+template <int BN>
+static int launch_slab(const b2_conv_args* a, int MT, int R, cudaStream_t stream) {
+  SlabParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = a->T; p.H = a->H; p.W = a->W; p.C = a->C;
+  p.kt = a->kt; p.kh = a->kh; p.kw = a->kw;
+  p.cchunks = (a->C + 63) / 64;
+  p.PW = a->W + (a->kw - 1);
+  p.R = R;
+  p.slab_bytes = ((R * p.PW * 128) + 1023) / 1024 * 1024;
+  p.MT = MT;
+  p.P = a->H * p.PW;
+  p.Ncols = a->K;
+  p.scale = a->scale; p.shift = a->shift;
+  p.residual = reinterpret_cast<const __half*>(a->residual);
+  p.ldr = a->ldr;
+  p.y = reinterpret_cast<__half*>(a->y);
+  p.ldy = a->ldy;
+  p.relu = a->relu;
+  const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * BN * 128 + 128 + 2 * BN * 4 + 1024;
+  static int attr_bytes = 0;
+  if (smem_bytes > attr_bytes) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(slabconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_bytes = 227 * 1024;
+  }
+  CUtensorMap tmX, tmB;
+  int rc;
+  const int taps = a->kt * a->kh * a->kw;
+  if ((rc = make_tmap_ndhwc_slab(&tmX, a->x, (uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N * a->T,
+                                 (uint32_t)p.PW, (uint32_t)R)) != B2_OK)
+    return rc;
+  if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)taps * a->C, (uint64_t)a->K, (uint64_t)taps * a->C, 64, BN, true)) != B2_OK)
+    return rc;
+  dim3 grid((a->ldy + BN - 1) / BN, (p.P + MT * 128 - 1) / (MT * 128), a->N * a->T);
+  slabconv_kernel<BN><<<grid, kSlabThreads, smem_bytes, stream>>>(tmX, tmB, p);
+  B2_CHECK_LAUNCH("slabconv_kernel");
+  return B2_OK;
+}
+
+// returns 1 when the slab kernel took the convolution, 0 when it does not apply, <0 on error
+static int try_slab(const b2_conv_args* a, cudaStream_t stream) {
+  if (g_conv_algo == 1 || a->mode != B2_CONV_AUTO || a->out_f32) return 0;
+  if (a->st != 1 || a->sh != 1 || a->sw != 1) return 0;
+  if ((a->kt & 1) == 0 || (a->kh & 1) == 0 || (a->kw & 1) == 0) return 0;
+  if (a->pt != (a->kt - 1) / 2 || a->ph != (a->kh - 1) / 2 || a->pw != (a->kw - 1) / 2) return 0;
+  if (a->kt * a->kh * a->kw == 1) return 0;                 // 1x1x1: plain GEMM path
+  const int PW = a->W + a->kw - 1;
+  if (PW > 256) return 0;
+  const int BN = (a->ldy <= 64) ? 64 : 128;
+  const int P = a->H * PW;
+  const int reach = ((a->kh - 1) / 2) * PW + (a->kw - 1) / 2;
+  const int planes = a->N * a->T;
+  const int ntn = (a->ldy + BN - 1) / BN;
+  int best_mt = 0, best_R = 0;
+  for (int MT = 512 / BN > 4 ? 4 : 512 / BN; MT >= 1; MT >>= 1) {
+    const int R = slab_rows(MT, PW, reach, P);
+    if (R > 256) continue;
+    const long long smem = 2ll * (((long long)R * PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * BN * 128 + 128 + 2 * BN * 4 + 1024;
+    if (smem > 227 * 1024) continue;
+    if (best_mt == 0) { best_mt = MT; best_R = R; }
+    const long long ctas = (long long)ntn * ((P + MT * 128 - 1) / (MT * 128)) * planes;
+    best_mt = MT; best_R = R;
+    if (ctas >= 2 * 148) break;      // enough CTAs for two waves: keep the largest MT that achieves it
+  }
+  if (best_mt == 0) return 0;
+  int rc = (BN == 64) ? launch_slab<64>(a, best_mt, best_R, stream) : launch_slab<128>(a, best_mt, best_R, stream);
+  return rc == B2_OK ? 1 : rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// stem convolution launcher (Toeplitz-descriptor kernel)
+// ------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  StemParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = a->T; p.H = a->H; p.W = a->W;
+  p.To = (a->T + 2 * a->pt - a->kt) / a->st + 1;
+  p.Ho = (a->H + 2 * a->ph - a->kh) / a->sh + 1;
+  p.Wo = (a->W + 6 - 7) / 2 + 1;
+  p.kt = a->kt; p.kh = a->kh; p.sh = a->sh; p.pt = a->pt; p.ph = a->ph;
+  p.G = 512 / BN;
+  if (p.G > p.Ho) p.G = p.Ho;
+  p.rows = a->sh * (p.G - 1) + a->kh;
+  p.w_bytes = a->kh * BN * 64;
+  p.stage_bytes = ((p.rows * kStemPitch + p.w_bytes) + 127) / 128 * 128;
+  const int budget = 227 * 1024 - 2048;
+  p.nstages = budget / p.stage_bytes;
+  if (p.nstages > 3) p.nstages = 3;
+  if (p.nstages > a->kt) p.nstages = a->kt;
+  if (p.nstages < 1) return set_error(B2_ERR_UNSUPPORTED, "stem slab does not fit in shared memory (kh=%d sh=%d)", a->kh, a->sh);
+  p.Ncols = a->K;
+  p.wimg = reinterpret_cast<const __half*>(a->w);
+  p.scale = a->scale; p.shift = a->shift;
+  p.y = reinterpret_cast<__half*>(a->y);
+  p.ldy = a->ldy;
+  p.relu = a->relu;
+  const int smem_bytes = p.nstages * p.stage_bytes + 128 + 2 * BN * 4 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(stemconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  // input viewed as (8 = 2 pixels x 4 channels, W/2, H, N*T); box (8, 132, rows, 1); no swizzle -> dense rows
+  CUtensorMap tmX;
+  cuuint64_t dims[4] = {8, (cuuint64_t)a->W / 2, (cuuint64_t)a->H, (cuuint64_t)a->N * a->T};
+  cuuint64_t strides[3] = {16, (cuuint64_t)a->W * 8, (cuuint64_t)a->H * a->W * 8};
+  cuuint32_t box[4] = {8, (cuuint32_t)kStemPairs, (cuuint32_t)p.rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a->x), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled(stem) failed (%d)", (int)r);
+  const int ntiles = (a->ldy + BN - 1) / BN;
+  dim3 grid((p.Wo + 127) / 128, (p.Ho + p.G - 1) / p.G, a->N * p.To * ntiles);
+  stemconv_kernel<BN><<<grid, kStemThreads, smem_bytes, stream>>>(tmX, p);
+  B2_CHECK_LAUNCH("stemconv_kernel");
+  return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // launcher shared by conv and gemm
 // ------------------------------------------------------------------------------------------
@@ -142,7 +300,9 @@ using namespace b2;
 
 extern "C" {
 
-int b2_version(void) { return 100; }
+int b2_version(void) { return 101; }
+/* debug knob (not in the public header): 0 = auto, 1 = never use the slab kernel */
+int b2_debug_set_conv_algo(int algo) { g_conv_algo = algo; return B2_OK; }
 const char* b2_last_error(void) { return g_err; }
 uint64_t b2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -179,6 +339,8 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   int rc = validate_conv(a);
   if (rc != B2_OK) return rc;
   if ((rc = require_sm100()) != B2_OK) return rc;
+  rc = try_slab(a, reinterpret_cast<cudaStream_t>(stream));
+  if (rc != 0) return rc < 0 ? rc : B2_OK;
 
   IgemmLaunch L;
   memset(&L, 0, sizeof(L));
@@ -205,11 +367,10 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
 
   const int taps = a->kt * a->kh * a->kw;
   if (a->mode == B2_CONV_STEM7) {
-    p.amode = AMODE_STEM7;
-    p.npairs = a->kt * a->kh;
-    p.nkb = (p.npairs + 1) / 2;
-    L.ldb = p.nkb * 64;
-    L.b_cols = L.ldb;
+    B2_CHECK_ARG(!a->out_f32 && a->residual == nullptr, "stem convolution has no residual / fp32 output");
+    B2_CHECK_ARG(a->st == 1, "stem convolution needs temporal stride 1");
+    const cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return a->K <= 64 ? launch_stem<64>(a, st) : launch_stem<128>(a, st);
   } else if (taps == 1 && a->st == 1 && a->sh == 1 && a->sw == 1 && a->pt == 0 && a->ph == 0 && a->pw == 0) {
     // 1x1x1 stride-1: A is literally the [M][C] activation matrix -> TMA on both operands
     p.amode = AMODE_TMA;

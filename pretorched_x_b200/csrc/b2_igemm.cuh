@@ -3,7 +3,7 @@
 //   D[M][N] = act( scale * (A_im2col[M][Ktot] . W[N][Ktot]^T) + shift + residual )
 //
 // One CTA computes one 128 x BN output tile.  6 warps:
-//   warps 0-3  A producers in the gather modes (cp.async im2col, one output row per thread), then
+//   warps 0-3  A producers in gather mode (cp.async im2col, one output row per thread), then
 //              the epilogue (thread = accumulator row = TMEM lane)
 //   warp  4    TMA producer (weights always; activations too in AMODE_TMA)
 //   warp  5    TMEM allocation + the single MMA-issuing thread
@@ -24,7 +24,7 @@ constexpr int kBK = 64;      // K elements per pipeline stage
 constexpr int kStages = 3;   // smem ring depth
 constexpr int kThreads = 192;
 
-enum : int { AMODE_TMA = 0, AMODE_GATHER = 1, AMODE_STEM7 = 2 };
+enum : int { AMODE_TMA = 0, AMODE_GATHER = 1 };
 enum : int { EPI_TMA_F16 = 0, EPI_DIRECT_F16 = 1, EPI_DIRECT_F32 = 2 };
 
 struct IgemmParams {
@@ -34,7 +34,6 @@ struct IgemmParams {
   int To, Ho, Wo;
   int kt, kh, kw, st, sh, sw, pt, ph, pw;
   int cchunks;             // ceil(C / 64): K blocks per filter tap      (AMODE_GATHER)
-  int npairs;              // kt*kh                                       (AMODE_STEM7)
   // problem
   int M_total;             // rows of D
   int Ncols;               // logical columns of D (Cout)
@@ -147,7 +146,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA,   // activations as [M][C]
       const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
       const uint32_t swz = static_cast<uint32_t>(r & 7);
 
-      if (p.amode == AMODE_GATHER) {
+      {
         const int wi0 = wo * p.sw - p.pw;
         int dt = 0, dh = 0, dw = 0, cc = 0;
         for (int kb = 0; kb < p.nkb; ++kb) {
@@ -176,36 +175,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA,   // activations as [M][C]
               if (++dh == p.kh) { dh = 0; ++dt; }
             }
           }
-        }
-      } else {
-        // AMODE_STEM7: input is NDHWC4 (8 B per pixel).  One K block = two (dt,dh) "pairs"; a pair
-        // contributes the 8 consecutive pixels [2*wo-4, 2*wo+4) x 4 channels = 64 contiguous bytes
-        // (pixel 2*wo-4 carries a zero weight: it only exists to keep the run 16-byte aligned).
-        const int wi0 = wo * 2 - 4;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const int s = kb % kStages;
-          const uint32_t par = (kb / kStages) & 1;
-          mbar_wait(&empty_bar[s], par ^ 1);
-          const uint32_t dst = smem_u32(smem + s * S::kStageBytes) + row_off;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int pr = kb * 2 + half;
-            const int dt = pr / p.kh, dh = pr - dt * p.kh;
-            const int ti = ti0 + dt, hi = hi0 + dh;
-            const bool ok = row_ok && pr < p.npairs && (unsigned)ti < (unsigned)p.T &&
-                            (unsigned)hi < (unsigned)p.H;
-            const __half* src = p.x;
-            if (ok) src = p.x + ((((size_t)n * p.T + ti) * p.H + hi) * p.W) * 4;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int px = wi0 + 2 * q;   // even; W is even, so a 2-pixel chunk is all-in or all-out
-              const bool okq = ok && px >= 0 && px + 1 < p.W;
-              const int j = half * 4 + q;
-              cp_async_16_ca(dst + ((static_cast<uint32_t>(j) ^ swz) << 4), okq ? (src + (size_t)px * 4) : p.x,
-                             okq ? 16u : 0u);
-            }
-          }
-          cp_async_mbar_arrive_noinc(&full_bar[s]);
         }
       }
     }

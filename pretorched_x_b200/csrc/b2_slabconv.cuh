@@ -1,0 +1,211 @@
+// b2_slabconv.cuh -- stride-1 "same"-padded convolution (3x3x3, 1x3x3, 3x1x1, 7x1x1 ...) as an implicit GEMM
+// whose A operand is never re-fetched per filter tap.
+//
+// The generic gather kernel (b2_igemm.cuh) moves 16 KB of activations from L2 for every (tap, 64-channel)
+// K block: 27 x for a 3x3x3 filter, which makes those layers L2-bandwidth bound at ~20% of tensor peak.
+// Here one TMA box load brings a *slab* -- R input rows x (W + 2*pw) pixels x 64 channels, halo columns and
+// out-of-range rows zero-filled by the TMA unit -- into shared memory once per (temporal tap, channel chunk).
+// Pixels of the slab are 128-byte rows of a K-major SWIZZLE_128B tile, so the A operand of tap (dh, dw) is
+// simply the same tile with its descriptor start address advanced by (dh*(W+2pw) + dw) * 128 bytes (the
+// swizzle is a function of absolute smem address bits, verified by tools/probe_umma.py).  All kh*kw in-plane
+// taps therefore run out of one slab: L2 traffic for activations drops by ~kh*kw.
+//
+// Output positions are enumerated in *padded-row* coordinates q = h*(W+2pw) + w' of one (n,t) plane; a CTA owns
+// MT consecutive 128-position M tiles (MT accumulators in TMEM share every weight tile) and discards the
+// positions that fall on halo columns.
+#pragma once
+
+#include "b2_ptx.cuh"
+
+namespace b2 {
+
+constexpr int kSlabThreads = 192;
+constexpr int kSlabWStages = 4;     // weight-tile ring depth
+constexpr int kSlabSStages = 2;     // slab ring depth
+
+struct SlabParams {
+  int T, H, W, C;          // input dims per clip, C = channel pitch
+  int kt, kh, kw;          // filter (odd), stride 1, padding (k-1)/2
+  int cchunks;             // ceil(C / 64)
+  int PW;                  // W + 2*pw: padded row length
+  int R;                   // slab rows (TMA box height)
+  int slab_bytes;          // R * PW * 128, rounded up to 1024
+  int MT;                  // M tiles per CTA (MT * BN <= 512)
+  int P;                   // H * PW: padded positions per plane
+  int Ncols;               // logical output channels
+  const float* scale;
+  const float* shift;
+  const __half* residual;  // nullable, dense [M][ldr]
+  int ldr;
+  __half* y;               // dense [M][ldy]
+  int ldy;
+  int relu;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kSlabThreads, 1)
+slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H, N*T), box (64, PW, R, 1)
+                const __grid_constant__ CUtensorMap tmB,   // weights [Ncols][taps*C], box (64, BN)
+                const SlabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kWBytes = BN * 128;
+  uint8_t* slab_base = smem;
+  uint8_t* w_base = smem + kSlabSStages * p.slab_bytes;
+  uint8_t* tail = w_base + kSlabWStages * kWBytes;
+  uint64_t* slab_full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* slab_empty = slab_full + kSlabSStages;
+  uint64_t* w_full = slab_empty + kSlabSStages;
+  uint64_t* w_empty = w_full + kSlabWStages;
+  uint64_t* tmem_full = w_empty + kSlabWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_scale = reinterpret_cast<float*>(tail + 128);
+  float* s_shift = s_scale + BN;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN;
+  const int q0 = blockIdx.y * (p.MT * 128);          // first padded position of this CTA within the plane
+  const int plane = blockIdx.z;                      // n*T + t
+  const int t = plane % p.T;
+  const int pt = (p.kt - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+  // slab row origin: the lowest input row any tap of any tile of this CTA touches
+  const int reach = ph * p.PW + pw;
+  int r_lo = (q0 - reach);
+  r_lo = (r_lo >= 0) ? r_lo / p.PW : -((-r_lo + p.PW - 1) / p.PW);
+  // temporal taps that stay inside the clip
+  const int dt_lo = max(0, pt - t), dt_hi = min(p.kt - 1, p.T - 1 - t + pt);
+  const int n_dt = dt_hi - dt_lo + 1;
+  const int taps_hw = p.kh * p.kw;
+  const int n_slabs = p.cchunks * n_dt;
+  // M tiles of this CTA that contain at least one position of the plane
+  int mt_valid = (p.P - q0 + 127) / 128;
+  mt_valid = mt_valid > p.MT ? p.MT : mt_valid;
+
+  if (tid == 128) {
+    for (int s = 0; s < kSlabSStages; ++s) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
+    for (int s = 0; s < kSlabWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  for (int i = tid; i < BN; i += kSlabThreads) {
+    const int c = n0 + i;
+    s_scale[i] = (c < p.Ncols) ? __ldg(&p.scale[c]) : 0.f;
+    s_shift[i] = (c < p.Ncols) ? __ldg(&p.shift[c]) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================ TMA producer ======================================
+    if (lane == 0) {
+      int wit = 0;
+      auto load_slab = [&](int si) {
+        const int cc = si / n_dt, dt = dt_lo + (si - cc * n_dt);
+        const int s = si % kSlabSStages;
+        mbar_wait(&slab_empty[s], ((si / kSlabSStages) & 1) ^ 1);
+        mbar_expect_tx(&slab_full[s], static_cast<uint32_t>(p.R * p.PW * 128));
+        tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64, -pw, r_lo, plane + dt - pt);
+      };
+      load_slab(0);
+      // The next slab is requested once the weight ring (kSlabWStages deep) guarantees the MMA thread has
+      // already retired the slab that occupied the target slot, so this wait never stalls weight issue.
+      const int pf = min(kSlabWStages, taps_hw - 1);
+      for (int si = 0; si < n_slabs; ++si) {
+        const int cc = si / n_dt, dt = dt_lo + (si - cc * n_dt);
+        for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
+          if (thw == pf && si + 1 < n_slabs) load_slab(si + 1);
+          const int ws = wit % kSlabWStages;
+          mbar_wait(&w_empty[ws], ((wit / kSlabWStages) & 1) ^ 1);
+          mbar_expect_tx(&w_full[ws], kWBytes);
+          const int tap = dt * taps_hw + thw;
+          tma_load_2d(w_base + ws * kWBytes, &tmB, &w_full[ws], tap * p.C + cc * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
+      int wit = 0;
+      for (int si = 0; si < n_slabs; ++si) {
+        const int s = si % kSlabSStages;
+        mbar_wait(&slab_full[s], (si / kSlabSStages) & 1);
+        tc_fence_after();
+        const uint32_t slab_addr = smem_u32(slab_base + s * p.slab_bytes);
+        for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
+          const int dh = thw / p.kw, dw = thw - dh * p.kw;
+          const int ws = wit % kSlabWStages;
+          mbar_wait(&w_full[ws], (wit / kSlabWStages) & 1);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(w_base + ws * kWBytes);
+          // slab-local pixel index of padded position q0 under tap (dh, dw)
+          const int pix0 = q0 + (dh - ph) * p.PW + (dw - pw) - r_lo * p.PW;
+          for (int j = 0; j < mt_valid; ++j) {
+            const uint32_t a_addr = slab_addr + static_cast<uint32_t>(pix0 + j * 128) * 128u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + j * BN, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32),
+                       idesc, (wit | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&w_empty[ws]);
+        }
+        umma_commit(&slab_empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ================================ epilogue ==========================================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int ncols_here = min(BN, p.ldy - n0);     // columns of this tile that exist in y (incl. zero padding)
+    for (int j = 0; j < mt_valid; ++j) {
+      const int q = q0 + j * 128 + tid;
+      const int h = q / p.PW, wp = q - h * p.PW;
+      const bool ok = (q < p.P) && (wp >= pw) && (wp < pw + p.W);
+      const size_t row = (static_cast<size_t>(plane) * p.H + h) * p.W + (wp - pw);
+      __half* yrow = p.y + row * p.ldy + n0;
+      const __half* rrow = p.residual ? p.residual + row * p.ldr + n0 : nullptr;
+#pragma unroll 1
+      for (int jc = 0; jc < BN / 32; ++jc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + j * BN + jc * 32, v);     // warp-collective: outside the `ok` branch
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8) {
+            const int col = jc * 32 + c8 * 8;
+            if (col < ncols_here) {
+              uint4 rv = make_uint4(0, 0, 0, 0);
+              if (rrow) rv = __ldg(reinterpret_cast<const uint4*>(rrow + col));
+              const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int ci = col + e * 2;
+                float a0 = __uint_as_float(v[c8 * 8 + e * 2]) * s_scale[ci] + s_shift[ci];
+                float a1 = __uint_as_float(v[c8 * 8 + e * 2 + 1]) * s_scale[ci + 1] + s_shift[ci + 1];
+                const float2 rf = unpack_half2(rr[e]);
+                a0 += rf.x; a1 += rf.y;
+                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                o[e] = pack_half2(a0, a1);
+              }
+              *reinterpret_cast<uint4*>(yrow + col) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace b2

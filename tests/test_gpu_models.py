@@ -3,10 +3,12 @@ reference) and against the CPU oracle, plus size-independent properties at the B
 
 Stated tolerances (fp16 activations, fp32 accumulation; relative to max|reference| of the tensor):
   * per-stage samples <= 1e-2, logits <= 5e-3, arg-max must agree            
-  * non-local net: layer1/layer2 as above; from the first layer3 non-local block on, the reference's unscaled
-    softmax over random-init logits (|f| ~ 1e5) is an arg-max whose top-2 gaps are below fp16 resolution for some
-    rows, so max-norm parity is not meaningful there; the test checks the median error instead
-    (see DESIGN.md "non-local numerics").
+  * non-local net at raw random init: the reference's unscaled softmax sees logits of 1e4..1e8, i.e. an arg-max
+    whose top-2 gaps fall below fp16 resolution for some rows; one flipped row is then amplified by every later
+    non-local block, so whole-network max-norm parity past layer2 is chaotic (DESIGN.md "non-local numerics").
+    That fixture is therefore checked end-to-end up to layer2 and block-by-block (teacher-forced: each block gets
+    OUR input, the oracle recomputes it in fp32) for the rest; the "tamed" fixture (theta/phi scaled into a
+    trained-like regime, same transform on the reference) is checked end-to-end at the normal tolerances.
 """
 import glob
 import os
@@ -35,6 +37,8 @@ def build(fx, dev):
     arch = fx["arch"]
     m = getattr(P, arch)(**fx["kwargs"]) if arch.startswith("r2") else getattr(P, arch)(pretrained=None, **fx["kwargs"])
     OF.randomize_bn_(m, fx["seeds"]["bn"])
+    if fx.get("nl_factors"):
+        OF.apply_nonlocal_factors_(m, fx["nl_factors"])
     return m.eval().to(dev)
 
 
@@ -67,19 +71,50 @@ def test_forward_matches_reference_golden(dev, path):
     assert OF.digests_match(OF.state_digest({k: v.cpu() for k, v in m.state_dict().items()}), fx["weight_digest"])
     x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"]).to(dev)
     errs, logits = stage_errors(m, x, fx)
-    nonlocal_net = "nonlocal" in fx["arch"]
+    chaotic = "nonlocal" in fx["arch"] and not fx.get("nl_factors")
     for name, (emax, emed) in errs.items():
-        if nonlocal_net and name in ("layer3", "layer4", "logits"):
-            assert emed <= 1e-2, (name, emax, emed)
-        elif name == "logits":
-            assert emax <= 5e-3, (name, emax)
-        else:
-            assert emax <= 1e-2, (name, emax)
-    if not nonlocal_net:
+        if chaotic and name in ("layer3", "layer4", "logits"):
+            continue      # arg-max regime: see module docstring; covered block-by-block by the teacher-forced test below
+        assert emax <= (5e-3 if name == "logits" else 1e-2), (name, emax, emed)
+    if not chaotic:
         assert torch.equal(logits.argmax(1).cpu(), fx["logits"].argmax(1))
     # public API path gives the same numbers as the staged walk
     with torch.no_grad():
         assert torch.equal(m(x), logits)
+
+
+def test_nonlocal_net_block_by_block_teacher_forced(dev):
+    """Every residual / non-local block of the raw random-init non-local net against the CPU oracle on the SAME
+    (our) block input: isolates each block's arithmetic from upstream drift."""
+    from pretorched_x_b200 import engine, ops
+    fx = torch.load([p for p in MODEL_FIX if p.endswith("nonlocalresnet3d50_b1_t16_96.pt")][0], weights_only=False)
+    m = build(fx, torch.device("cpu"))
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(dev)
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"]).to(dev)
+    nlpos = OF.nonlocal_positions([3, 4, 6, 3], [0, 2, 3, 0])
+    with torch.no_grad():
+        a = engine.run_stem(m, x)
+        inplanes = 64
+        for li, ln in enumerate(("layer1", "layer2", "layer3", "layer4")):
+            planes = (64, 128, 256, 512)[li]
+            for bi, blk in enumerate(getattr(m, ln)):
+                stride = 2 if (li > 0 and bi == 0) else 1
+                has_ds = bi == 0 and (stride != 1 or inplanes != planes * 4)
+                pfx = "%s.%d" % (ln, bi)
+                want = OF.bottleneck(ops.to_ncdhw(a).cpu(), sd, pfx, "resnet3d", "A", planes, stride, has_ds)
+                a = engine.run_bottleneck(blk, a)
+                got = ops.to_ncdhw(a).cpu()
+                assert (got - want).abs().max().item() <= 3e-3 * want.abs().max().item(), pfx
+                if bi in nlpos[li]:
+                    want = OF.nonlocal_block(got, sd, pfx + ".nonlocalblock")
+                    a = engine.run_nonlocal(blk.nonlocalblock, a)
+                    d = (ops.to_ncdhw(a).cpu() - want).abs() / want.abs().max().item()
+                    per_position = d.amax(dim=1).reshape(-1)
+                    # near-tied arg-max rows may legitimately flip under fp16 theta/phi; they must stay rare
+                    assert float((per_position > 1e-2).double().mean()) <= 0.02, pfx
+                    assert d.median().item() <= 1e-3, pfx
+                inplanes = planes * 4
 
 
 def test_features_logits_api_and_identity_head(dev):

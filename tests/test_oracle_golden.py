@@ -23,6 +23,8 @@ def build_ours(fx):
     else:
         m = getattr(P, arch)(pretrained=None, **fx["kwargs"])
     OF.randomize_bn_(m, fx["seeds"]["bn"])
+    if fx.get("nl_factors"):
+        OF.apply_nonlocal_factors_(m, fx["nl_factors"])
     return m.eval()
 
 

@@ -173,6 +173,16 @@ def run_group(group):
         conv_case("1x1x1 bias no-bn 128->64 (theta)", 1, 128, 2, 4, 4, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0), bias=True, bn=False, relu=False)
         conv_case("3x3x3 s1 512->512 T=1 (layer4)", 2, 512, 1, 7, 7, 512, (3, 3, 3), (1, 1, 1), (1, 1, 1))
         conv_case("3x3x3 s1 64->64 big M", 2, 64, 8, 28, 28, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        conv_case("slab 3x3x3 64->64 56x56 T=4 (layer1)", 2, 64, 4, 56, 56, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        conv_case("slab 3x3x3 128->128 28x28 T=3 +res", 2, 128, 3, 28, 28, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), res=True)
+        conv_case("slab 3x3x3 256->256 14x14 T=2", 3, 256, 2, 14, 14, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        conv_case("slab 3x3x3 512->512 7x7 T=1", 3, 512, 1, 7, 7, 512, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        conv_case("slab 3x3x3 64->200 odd sizes 13x11 T=5", 1, 64, 5, 13, 11, 200, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+        conv_case("slab (1,3,3) 64->144 28x28", 1, 64, 4, 28, 28, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+        conv_case("slab (3,1,1) 144->64 28x28", 1, 144, 6, 28, 28, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), res=True)
+        conv_case("slab (7,1,1) 110->64 56x56", 1, 110, 8, 56, 56, 64, (7, 1, 1), (1, 1, 1), (3, 0, 0))
+        conv_case("slab 3x3 2-D 64->64 56x56 (resnet18)", 2, 64, 1, 56, 56, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), res=True)
+        conv_case("slab 3x3x3 64->64 112x112 T=2 (wide)", 1, 64, 2, 112, 112, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1))
 
     elif group == "stem":
         conv_case("stem 7x7x7 s(1,2,2) 3->64", 1, 3, 4, 32, 32, 64, (7, 7, 7), (1, 2, 2), (3, 3, 3))
@@ -217,6 +227,8 @@ def run_group(group):
             arch = fx["arch"]
             m = getattr(P, arch)(**fx["kwargs"]) if arch.startswith("r2") else getattr(P, arch)(pretrained=None, **fx["kwargs"])
             OF.randomize_bn_(m, fx["seeds"]["bn"])
+            if fx.get("nl_factors"):
+                OF.apply_nonlocal_factors_(m, fx["nl_factors"])
             m = m.eval().to(dev)
             x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"]).to(dev)
             t0 = time.time()
