@@ -94,6 +94,10 @@ def load():
             lib.b2_debug_set_conv_algo.restype = c_int
             lib.b2_debug_set_conv_algo.argtypes = [c_int]
             lib.b2_debug_set_conv_algo(1 if algo == "gather" else 0)
+        if os.environ.get("B2_GEMM_ALGO"):             # debug: "tile" disables the persistent GEMM kernel
+            lib.b2_debug_set_gemm_algo.restype = c_int
+            lib.b2_debug_set_gemm_algo.argtypes = [c_int]
+            lib.b2_debug_set_gemm_algo(1 if os.environ["B2_GEMM_ALGO"] == "tile" else 0)
         _lib = lib
     return _lib
 

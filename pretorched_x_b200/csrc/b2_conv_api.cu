@@ -6,6 +6,7 @@
 
 #include "b2_host.h"
 #include "b2_igemm.cuh"
+#include "b2_pgemm.cuh"
 #include "b2_slabconv.cuh"
 #include "b2_stemconv.cuh"
 
@@ -219,18 +220,18 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(stemconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  // input viewed as (8 = 2 pixels x 4 channels, W/2, H, N*T); box (8, 132, rows, 1); no swizzle -> dense rows
+  // input viewed as 8-byte pixels (W, H, N*T); box (256, rows, 1); no swizzle -> dense 2 KB rows in smem
   CUtensorMap tmX;
-  cuuint64_t dims[4] = {8, (cuuint64_t)a->W / 2, (cuuint64_t)a->H, (cuuint64_t)a->N * a->T};
-  cuuint64_t strides[3] = {16, (cuuint64_t)a->W * 8, (cuuint64_t)a->H * a->W * 8};
-  cuuint32_t box[4] = {8, (cuuint32_t)kStemPairs, (cuuint32_t)p.rows, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(a->x), dims, strides, box, estr,
+  cuuint64_t dims[3] = {(cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N * a->T};
+  cuuint64_t strides[2] = {(cuuint64_t)a->W * 8, (cuuint64_t)a->H * a->W * 8};
+  cuuint32_t box[3] = {(cuuint32_t)kStemRowPx, (cuuint32_t)p.rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(a->x), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled(stem) failed (%d)", (int)r);
   const int ntiles = (a->ldy + BN - 1) / BN;
-  dim3 grid((p.Wo + 127) / 128, (p.Ho + p.G - 1) / p.G, a->N * p.To * ntiles);
+  dim3 grid((p.Wo + kStemTileW - 1) / kStemTileW, (p.Ho + p.G - 1) / p.G, a->N * p.To * ntiles);
   stemconv_kernel<BN><<<grid, kStemThreads, smem_bytes, stream>>>(tmX, p);
   B2_CHECK_LAUNCH("stemconv_kernel");
   return B2_OK;
@@ -287,7 +288,54 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   return B2_OK;
 }
 
+static int g_gemm_algo = 0;   // 0 auto (persistent kernel where it applies), 1 force the per-tile kernel
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
+  using S = PgemmSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(pgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  const IgemmParams& ip = L.p;
+  CUtensorMap tmA, tmB, tmC, tmR;
+  int rc;
+  if ((rc = make_tmap_2d_f16(&tmA, L.a_mat, (uint64_t)L.a_cols, (uint64_t)ip.M_total, (uint64_t)L.lda, 64, 128, true)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmB, L.w, (uint64_t)L.b_cols, (uint64_t)ip.Ncols, (uint64_t)L.ldb, 64, BN, true)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmC, ip.y, (uint64_t)ip.ldy, (uint64_t)ip.M_total, (uint64_t)ip.ldy, 64, 128, true)) != B2_OK) return rc;
+  if (ip.residual) {
+    if ((rc = make_tmap_2d_f16(&tmR, ip.residual, (uint64_t)ip.ldr, (uint64_t)ip.M_total, (uint64_t)ip.ldr, 64, 128, true)) != B2_OK) return rc;
+  } else {
+    tmR = tmC;
+  }
+  PgemmParams p;
+  p.M = ip.M_total; p.Ncols = ip.Ncols; p.ldy = ip.ldy; p.nkb = ip.nkb;
+  p.tiles_n = (ip.ldy + BN - 1) / BN;
+  p.tiles_total = p.tiles_n * ((ip.M_total + 127) / 128);
+  p.scale = ip.scale; p.shift = ip.shift;
+  p.has_residual = ip.residual != nullptr;
+  p.relu = ip.relu;
+  const int grid = p.tiles_total < sm_count() ? p.tiles_total : sm_count();
+  pgemm_kernel<BN><<<grid, kPgThreads, S::kTotal, stream>>>(tmA, tmB, tmC, tmR, p);
+  B2_CHECK_LAUNCH("pgemm_kernel");
+  return B2_OK;
+}
+
 static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
+  if (g_gemm_algo == 0 && L.p.amode == AMODE_TMA && L.p.epi == EPI_TMA_F16 && !L.p.per_row) {
+    return L.p.ldy <= 64 ? launch_pgemm<64>(L, stream) : launch_pgemm<128>(L, stream);
+  }
   // 64-wide tiles for narrow outputs, 128 otherwise
   const int width = (L.p.epi == EPI_TMA_F16) ? L.p.ldy : L.p.Ncols;
   if (width <= 64) return launch_igemm<64>(L, stream);
@@ -303,6 +351,7 @@ extern "C" {
 int b2_version(void) { return 101; }
 /* debug knob (not in the public header): 0 = auto, 1 = never use the slab kernel */
 int b2_debug_set_conv_algo(int algo) { g_conv_algo = algo; return B2_OK; }
+int b2_debug_set_gemm_algo(int algo) { g_gemm_algo = algo; return B2_OK; }
 const char* b2_last_error(void) { return g_err; }
 uint64_t b2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -1,0 +1,203 @@
+// b2_pgemm.cuh -- persistent, warp-specialised GEMM for the 1x1x1 convolutions and dense layers:
+//
+//     D[M][N] = act( scale[n] * (A[M][K] . B[N][K]^T) + shift[n] + residual[M][N] )      (fp16 in/out, fp32 accumulate)
+//
+// These layers are HBM-bound (K is 64..2048 while every output element is written once and, for the block-closing
+// conv3, a residual element is read once), so the kernel is organised around keeping the memory system busy rather
+// than the tensor core: one CTA per SM loops over output tiles, and the three stages of a tile -- TMA loads of A/B
+// (and of the residual tile), the tcgen05 MMAs, and the epilogue (TMEM -> registers -> BN/residual/ReLU -> smem ->
+// TMA store) -- belong to different warps and overlap across consecutive tiles through double-buffered TMEM
+// accumulators, a double-buffered residual tile and an smem operand ring.  The non-persistent igemm_kernel pays the
+// TMEM allocation, barrier set-up and a cold pipeline for every 128 x 128 tile; with K = 64 that prologue dominates.
+//
+//   warp 4   producer: residual tile of tile i, then its K blocks (A and B boxes, 128B-swizzled)
+//   warp 5   MMA issuer: accumulates tile i into TMEM buffer i & 1
+//   warps 0-3 epilogue of tile i (thread = accumulator row), TMA store from a staging tile
+#pragma once
+
+#include "b2_ptx.cuh"
+
+namespace b2 {
+
+constexpr int kPgThreads = 192;
+constexpr int kPgStages = 3;
+
+struct PgemmParams {
+  int M, Ncols, ldy;        // rows, logical columns, output pitch (columns [Ncols, ldy) are written as zero)
+  int nkb;                  // K blocks of 64
+  int tiles_n, tiles_total;
+  const float* scale;
+  const float* shift;
+  int has_residual;
+  int relu;
+};
+
+template <int BN>
+struct PgemmSmem {
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kTile = 128 * BN * 2;                 // one C / residual staging tile
+  static constexpr int kRing = kPgStages * kStage;
+  static constexpr int kResOff = kRing;                      // 2 residual tiles
+  static constexpr int kCOff = kResOff + 2 * kTile;          // 1 C tile
+  static constexpr int kBarOff = kCOff + kTile;
+  static constexpr int kAffOff = kBarOff + 256;              // scale[BN], shift[BN] of the current tile
+  static constexpr int kTotal = kAffOff + 2 * BN * 4 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kPgThreads, 1)
+pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const PgemmParams p) {
+  using S = PgemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);   // [3]
+  uint64_t* empty = full + kPgStages;                                // [3]
+  uint64_t* acc_full = empty + kPgStages;                            // [2]
+  uint64_t* acc_empty = acc_full + 2;                                // [2]
+  uint64_t* res_full = acc_empty + 2;                                // [2]
+  uint64_t* res_empty = res_full + 2;                                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 128) {
+    for (int s = 0; s < kPgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128);
+      mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================ producer ==========================================
+    if (lane == 0) {
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
+        const int m0 = (tile / p.tiles_n) * 128, n0 = (tile % p.tiles_n) * BN;
+        if (p.has_residual) {
+          const int rb = lt & 1;
+          mbar_wait(&res_empty[rb], ((lt >> 1) & 1) ^ 1);
+          mbar_expect_tx(&res_full[rb], S::kTile);
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_2d(smem + S::kResOff + rb * S::kTile + b * (128 * 128), &tmR, &res_full[rb], n0 + b * 64, m0);
+        }
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % kPgStages;
+          mbar_wait(&empty[s], ((it / kPgStages) & 1) ^ 1);
+          mbar_expect_tx(&full[s], S::kStage);
+          uint8_t* dst = smem + s * S::kStage;
+          tma_load_2d(dst, &tmA, &full[s], kb * 64, m0);
+          tma_load_2d(dst + S::kABytes, &tmB, &full[s], kb * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
+        const int ab = lt & 1;
+        mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+          const int s = it % kPgStages;
+          mbar_wait(&full[s], (it / kPgStages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * S::kStage);
+          const uint32_t b_addr = a_addr + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + ab * BN, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32),
+                     idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[ab]);
+      }
+    }
+  } else {
+    // ================================ epilogue ==========================================
+    float* s_scale = reinterpret_cast<float*>(smem + S::kAffOff);
+    float* s_shift = s_scale + BN;
+    const int r = tid;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    uint8_t* c_stage = smem + S::kCOff;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / p.tiles_n) * 128, n0 = (tile % p.tiles_n) * BN;
+      const int ab = lt & 1;
+      mbar_wait(&acc_full[ab], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint8_t* r_stage = smem + S::kResOff + ab * S::kTile;
+      if (p.has_residual) mbar_wait(&res_full[ab], (lt >> 1) & 1);
+      // the previous tile's TMA store must have finished reading the staging tile before we overwrite it
+      if (tid == 0) tma_store_wait_read0();
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // (also: everyone is done with the previous tile's affine)
+      if (tid < BN) {
+        const int c = n0 + tid;
+        s_scale[tid] = (c < p.Ncols) ? __ldg(&p.scale[c]) : 0.f;
+        s_shift[tid] = (c < p.Ncols) ? __ldg(&p.shift[c]) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_off + ab * BN + j * 32, v);
+        tmem_ld_wait();
+        const int box = j >> 1, chunk0 = (j & 1) * 4;
+        uint8_t* crow = c_stage + box * (128 * 128) + r * 128;
+        const uint8_t* rrow = r_stage + box * (128 * 128) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t coff = (static_cast<uint32_t>(chunk0 + q) ^ swz) << 4;
+          uint4 rv = make_uint4(0, 0, 0, 0);
+          if (p.has_residual) rv = *reinterpret_cast<const uint4*>(rrow + coff);
+          const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+          uint32_t out[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int ci = j * 32 + q * 8 + e * 2;
+            float a0 = __uint_as_float(v[q * 8 + e * 2]) * s_scale[ci] + s_shift[ci];
+            float a1 = __uint_as_float(v[q * 8 + e * 2 + 1]) * s_scale[ci + 1] + s_shift[ci + 1];
+            const float2 rf = unpack_half2(rr[e]);
+            a0 += rf.x; a1 += rf.y;
+            if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            out[e] = pack_half2(a0, a1);
+          }
+          *reinterpret_cast<uint4*>(crow + coff) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+      }
+      // accumulator and residual buffers are free for tile lt + 2
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+      if (p.has_residual) mbar_arrive(&res_empty[ab]);
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b)
+          if (n0 + b * 64 < p.ldy) tma_store_2d(&tmC, c_stage + b * (128 * 128), n0 + b * 64, m0);
+        tma_store_commit();
+      }
+    }
+    if (tid == 0) tma_store_wait_read0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+}  // namespace b2

@@ -8,11 +8,12 @@
 //     byte(row r, 16-byte chunk j) = start + (r % 8) * 16 + (r / 8) * SBO + j * LBO,
 // so with LBO = 16 and SBO = 128 the 128 x 32 im2col tile of one (dt, dh) tap pair is an overlapping (Toeplitz)
 // view of the raw input row sitting in shared memory (verified by tools/probe_umma.py, mode 1).  One TMA box per
-// temporal tap brings 2G+5 input rows (zero-filled outside the image) for G output rows; every (dt, dh) tap is then
+// temporal tap brings 2G+5 input rows (zero-filled outside the image) for G output rows -- the tensor map treats a
+// pixel as one 8-byte element so that a box row is a single 2 KB run (16-byte-wide boxes starve the TMA unit); every (dt, dh) tap is then
 // two K=16 MMAs per output row straight out of that slab.  Activation traffic from L2 drops ~4.4x versus
 // gathering 64 bytes per output pixel per tap, and no thread touches the data on its way to the tensor core.
 //
-// CTA = G output rows x 128 output columns x BN output channels (G accumulators of BN fp32 columns in TMEM).
+// CTA = G output rows x 120 output columns x BN output channels (G accumulators of BN fp32 columns in TMEM).
 // Warps 0-3: epilogue (BN + ReLU -> fp16 NDHWC), warp 4: TMA/bulk-copy producer, warp 5: MMA issuer.
 #pragma once
 
@@ -21,8 +22,9 @@
 namespace b2 {
 
 constexpr int kStemThreads = 192;
-constexpr int kStemPitch = 2112;        // bytes per slab row: 132 pixel pairs = pixels [2*w0-4, 2*w0+260)
-constexpr int kStemPairs = 132;
+constexpr int kStemPitch = 2048;        // bytes per slab row: 256 pixels [2*w0-4, 2*w0+252) of 8 bytes
+constexpr int kStemRowPx = 256;         // TMA box width (the maximum box extent), one 8-byte element per pixel
+constexpr int kStemTileW = 120;         // output columns per CTA: rows r < 124 of the 128-row MMA tile see complete runs
 
 struct StemParams {
   int T, H, W;             // input dims per clip (W even)
@@ -53,7 +55,7 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 
 template <int BN>
 __global__ void __launch_bounds__(kStemThreads, 1)
-stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (8 = 2px*4ch, W/2, H, N*T), box (8, 132, rows, 1), no swizzle
+stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pixels (W, H, N*T), box (256, rows, 1), no swizzle
                 const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -66,7 +68,7 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (8 = 2px*
   float* s_shift = s_scale + BN;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int w0 = blockIdx.x * 128;                    // first output column of the tile
+  const int w0 = blockIdx.x * kStemTileW;             // first output column of the tile
   const int ho0 = blockIdx.y * p.G;
   const int ntile = blockIdx.z % ((p.ldy + BN - 1) / BN);
   const int plane_o = blockIdx.z / ((p.ldy + BN - 1) / BN);     // n*To + to   (temporal stride 1 => To == T)
@@ -102,7 +104,7 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (8 = 2px*
         mbar_wait(&empty[s], ((i / p.nstages) & 1) ^ 1);
         mbar_expect_tx(&full[s], static_cast<uint32_t>(slab_bytes + p.w_bytes));
         uint8_t* dst = smem + s * p.stage_bytes;
-        tma_load_4d(dst, &tmX, &full[s], 0, w0 - 2, p.sh * ho0 - p.ph, n * p.T + to + dt - p.pt);
+        tma_load_3d(dst, &tmX, &full[s], 2 * w0 - 4, p.sh * ho0 - p.ph, n * p.T + to + dt - p.pt);
         const __half* wsrc = p.wimg + (static_cast<size_t>(ntile) * p.kt + dt) * (p.w_bytes / 2);
         bulk_load_1d(dst + slab_bytes, wsrc, static_cast<uint32_t>(p.w_bytes), &full[s]);
       }
@@ -136,7 +138,7 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (8 = 2px*
     tc_fence_after();
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     const int wo = w0 + tid;
-    const bool col_ok = wo < p.Wo;
+    const bool col_ok = (tid < kStemTileW) && (wo < p.Wo);
     const int ncols_here = min(BN, p.ldy - n0);
     for (int g = 0; g < g_valid; ++g) {
       const size_t row = (static_cast<size_t>(plane_o) * p.Ho + (ho0 + g)) * p.Wo + wo;

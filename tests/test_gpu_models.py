@@ -145,8 +145,7 @@ def test_nonlocal_block_teacher_forced(dev):
     blk.eval()
     x = OF.seeded_input((2, 256, 2, 7, 7), 4).half().float()
     with torch.no_grad():
-        want = OF.nonlocal_block(x, blk.state_dict(), "")[:, :, :, :, :]
-        sd = blk.state_dict()
+        want = OF.nonlocal_block(x, {"nl." + k: v for k, v in blk.state_dict().items()}, "nl")
     with torch.no_grad():
         got = blk.to(dev)(x.to(dev))
     assert (got.cpu() - want).abs().max().item() <= 5e-3 * want.abs().max().item()
