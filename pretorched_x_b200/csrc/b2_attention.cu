@@ -174,80 +174,87 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     }
   } else if (warp == 4) {
     // =========================== TMA producer ===========================================
-    if (lane == 0) {
-      int it = 0;
-      auto acquire = [&](uint32_t bytes) -> uint8_t* {
+    // whole warp, warp-uniform operands; one elected lane issues (see elect_one() in b2_ptx.cuh)
+    int it = 0;
+    auto load_qk = [&](int kvb) {
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
         const int s = it % kAttSlots;
         mbar_wait(&empty_bar[s], ((it / kAttSlots) & 1) ^ 1);
-        mbar_expect_tx(&full_bar[s], bytes);
-        return smem + s * kAttSlotBytes;
-      };
-      auto load_qk = [&](int kvb) {
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          uint8_t* dst = acquire(kAttBM * 128 + kAttBKV * 128);
-          const int s = it % kAttSlots;
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[s], kAttBM * 128 + kAttBKV * 128);
+          uint8_t* dst = smem + s * kAttSlotBytes;
           tma_load_2d(dst, &tmQ, &full_bar[s], kb * 64, row_base + q0);
           tma_load_2d(dst + kAttBM * 128, &tmK, &full_bar[s], kb * 64, row_base + kvb * kAttBKV);
-          ++it;
         }
-      };
-      for (int kvb = 0; kvb < p.nkv; ++kvb) load_qk(kvb);           // pass 1
-      load_qk(0);                                                   // pass 2 prologue
-      for (int j = 0; j < p.nkv; ++j) {
-        if (j + 1 < p.nkv) load_qk(j + 1);
-        uint8_t* dst = acquire(DVT * 128);
-        const int s = it % kAttSlots;
-        tma_load_2d(dst, &tmV, &full_bar[s], row_base + j * kAttBKV, dv0);
-        ++it;
+        __syncwarp();
       }
+    };
+    for (int kvb = 0; kvb < p.nkv; ++kvb) load_qk(kvb);           // pass 1
+    load_qk(0);                                                   // pass 2 prologue
+    for (int j = 0; j < p.nkv; ++j) {
+      if (j + 1 < p.nkv) load_qk(j + 1);
+      const int s = it % kAttSlots;
+      mbar_wait(&empty_bar[s], ((it / kAttSlots) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full_bar[s], DVT * 128);
+        tma_load_2d(smem + s * kAttSlotBytes, &tmV, &full_bar[s], row_base + j * kAttBKV, dv0);
+      }
+      __syncwarp();
+      ++it;
     }
   } else {
     // =========================== MMA issuer =============================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(kAttBM, kAttBKV, 0);
-      constexpr uint32_t idesc_pv = make_idesc_f16(kAttBM, DVT, 0);
-      int it = 0;
-      int g = 0;
-      auto issue_qk = [&]() {       // S[g&1] = Q . K_block^T
-        const int buf = g & 1;
-        mbar_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const int s = it % kAttSlots;
-          mbar_wait(&full_bar[s], (it / kAttSlots) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * kAttSlotBytes);
-          const uint32_t b_addr = a_addr + kAttBM * 128;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_S + buf * 64, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32),
-                     idesc_qk, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
-          ++it;
-        }
-        umma_commit(&s_full[buf]);
-        ++g;
-      };
-      for (int kvb = 0; kvb < p.nkv; ++kvb) issue_qk();             // pass 1
-      issue_qk();                                                   // pass 2 prologue: S for block 0
-      for (int j = 0; j < p.nkv; ++j) {
-        if (j + 1 < p.nkv) issue_qk();                              // overlap softmax(j) with QK(j+1)
-        const int pb = j & 1;
-        mbar_wait(&p_full[pb], (j >> 1) & 1);
+    constexpr uint32_t idesc_qk = make_idesc_f16(kAttBM, kAttBKV, 0);
+    constexpr uint32_t idesc_pv = make_idesc_f16(kAttBM, DVT, 0);
+    const uint32_t tmS = warp_uniform(tmem_S), tmO = warp_uniform(tmem_O);
+    const uint32_t ring = smem_u32(smem);
+    int it = 0;
+    int g = 0;
+    auto issue_qk = [&]() {       // S[g&1] = Q . K_block^T
+      const int buf = g & 1;
+      mbar_wait(&s_empty[buf], ((g >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
         const int s = it % kAttSlots;
         mbar_wait(&full_bar[s], (it / kAttSlots) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + S::kPOff + pb * S::kPBytes);
-        const uint32_t b_addr = smem_u32(smem + s * kAttSlotBytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_O, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32), idesc_pv,
-                   (j | k) != 0 ? 1u : 0u);
+        const uint32_t a_lo = sw128_desc_lo(ring + s * kAttSlotBytes);
+        const uint32_t b_lo = sw128_desc_lo(ring + s * kAttSlotBytes + kAttBM * 128);
+        const uint32_t d = tmS + buf * 64;
+        if (elect_one()) {
+          umma_f16(d, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc_qk, kb != 0 ? 1u : 0u);
+          umma_f16(d, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc_qk, 1u);
+          umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc_qk, 1u);
+          umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc_qk, 1u);
+          umma_commit(&empty_bar[s]);
+          if (kb == p.nkb - 1) umma_commit(&s_full[buf]);
+        }
+        __syncwarp();
+      }
+      ++g;
+    };
+    for (int kvb = 0; kvb < p.nkv; ++kvb) issue_qk();             // pass 1
+    issue_qk();                                                   // pass 2 prologue: S for block 0
+    for (int j = 0; j < p.nkv; ++j) {
+      if (j + 1 < p.nkv) issue_qk();                              // overlap softmax(j) with QK(j+1)
+      const int pb = j & 1;
+      mbar_wait(&p_full[pb], (j >> 1) & 1);
+      const int s = it % kAttSlots;
+      mbar_wait(&full_bar[s], (it / kAttSlots) & 1);
+      tc_fence_after();
+      const uint32_t a_lo = sw128_desc_lo(ring + S::kPOff + pb * S::kPBytes);
+      const uint32_t b_lo = sw128_desc_lo(ring + s * kAttSlotBytes);
+      if (elect_one()) {
+        umma_f16(tmO, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc_pv, j != 0 ? 1u : 0u);
+        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc_pv, 1u);
+        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc_pv, 1u);
+        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc_pv, 1u);
         umma_commit(&empty_bar[s]);
         umma_commit(&p_empty[pb]);
-        ++it;
+        if (j == p.nkv - 1) umma_commit(o_full);
       }
-      umma_commit(o_full);
+      __syncwarp();
+      ++it;
     }
   }
 

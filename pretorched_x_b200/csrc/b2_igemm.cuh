@@ -278,44 +278,47 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA,   // activations as [M][C]
     }
   } else if (warp == 4) {
     // ================================ TMA producer ======================================
-    if (lane == 0) {
-      const uint32_t tx = S::kBBytes + (gather ? 0 : S::kABytes);
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t par = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[s], par ^ 1);
+    // (whole warp with warp-uniform operands; one elected lane issues -- see elect_one())
+    const uint32_t tx = S::kBBytes + (gather ? 0 : S::kABytes);
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t par = (kb / kStages) & 1;
+      mbar_wait(&empty_bar[s], par ^ 1);
+      int kcol = kb * kBK;
+      if (p.amode == AMODE_GATHER) {          // weight columns are [tap][C]: block (tap, cc) starts at tap*C + cc*64
+        const int tap = kb / p.cchunks;
+        kcol = tap * p.C + (kb - tap * p.cchunks) * kBK;
+      }
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[s], tx);
         uint8_t* a_dst = smem + s * S::kStageBytes;
-        uint8_t* b_dst = a_dst + S::kABytes;
-        int kcol = kb * kBK;
-        if (p.amode == AMODE_GATHER) {          // weight columns are [tap][C]: block (tap, cc) starts at tap*C + cc*64
-          const int tap = kb / p.cchunks;
-          kcol = tap * p.C + (kb - tap * p.cchunks) * kBK;
-        }
-        tma_load_2d(b_dst, &tmB, &full_bar[s], kcol, n0);
+        tma_load_2d(a_dst + S::kABytes, &tmB, &full_bar[s], kcol, n0);
         if (!gather) tma_load_2d(a_dst, &tmA, &full_bar[s], kb * kBK, m0);
       }
+      __syncwarp();
     }
   } else {
     // ================================ MMA issuer ========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(kBM, BN, 0);
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t par = (kb / kStages) & 1;
-        mbar_wait(&full_bar[s], par);
-        tc_fence_after();
-        if (gather) fence_proxy_async();
-        const uint32_t a_addr = smem_u32(smem + s * S::kStageBytes);
-        const uint32_t b_addr = a_addr + S::kABytes;
-#pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          umma_f16(tmem_base, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32),
-                   idesc, (kb | k) != 0 ? 1u : 0u);
-        }
+    constexpr uint32_t idesc = make_idesc_f16(kBM, BN, 0);
+    const uint32_t tm = warp_uniform(tmem_base);
+    const uint32_t ring = smem_u32(smem);
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t par = (kb / kStages) & 1;
+      mbar_wait(&full_bar[s], par);
+      tc_fence_after();
+      if (gather) fence_proxy_async();
+      const uint32_t a_lo = sw128_desc_lo(ring + s * S::kStageBytes);
+      const uint32_t b_lo = sw128_desc_lo(ring + s * S::kStageBytes + S::kABytes);
+      if (elect_one()) {
+        umma_f16(tm, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc, kb != 0 ? 1u : 0u);
+        umma_f16(tm, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc, 1u);
+        umma_f16(tm, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
+        umma_f16(tm, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
         umma_commit(&empty_bar[s]);            // frees the smem slot once these MMAs retire
+        if (kb == p.nkb - 1) umma_commit(tmem_full_bar);   // accumulator complete -> epilogue
       }
-      umma_commit(tmem_full_bar);              // accumulator complete -> epilogue
+      __syncwarp();
     }
   }
 

@@ -80,50 +80,58 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 4) {
     // ================================ producer ==========================================
-    if (lane == 0) {
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
-        const int m0 = (tile / p.tiles_n) * 128, n0 = (tile % p.tiles_n) * BN;
-        if (p.has_residual) {
-          const int rb = lt & 1;
-          mbar_wait(&res_empty[rb], ((lt >> 1) & 1) ^ 1);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / p.tiles_n) * 128, n0 = (tile % p.tiles_n) * BN;
+      if (p.has_residual) {
+        const int rb = lt & 1;
+        mbar_wait(&res_empty[rb], ((lt >> 1) & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&res_full[rb], S::kTile);
 #pragma unroll
           for (int b = 0; b < BN / 64; ++b)
             tma_load_2d(smem + S::kResOff + rb * S::kTile + b * (128 * 128), &tmR, &res_full[rb], n0 + b * 64, m0);
         }
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % kPgStages;
-          mbar_wait(&empty[s], ((it / kPgStages) & 1) ^ 1);
+        __syncwarp();
+      }
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        const int s = it % kPgStages;
+        mbar_wait(&empty[s], ((it / kPgStages) & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full[s], S::kStage);
           uint8_t* dst = smem + s * S::kStage;
           tma_load_2d(dst, &tmA, &full[s], kb * 64, m0);
           tma_load_2d(dst + S::kABytes, &tmB, &full[s], kb * 64, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
     // ================================ MMA issuer ========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
-        const int ab = lt & 1;
-        mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+    constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
+    const uint32_t tm = warp_uniform(tmem_base);
+    const uint32_t ring = smem_u32(smem);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d = tm + ab * BN;
+      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+        const int s = it % kPgStages;
+        mbar_wait(&full[s], (it / kPgStages) & 1);
         tc_fence_after();
-        for (int kb = 0; kb < p.nkb; ++kb, ++it) {
-          const int s = it % kPgStages;
-          mbar_wait(&full[s], (it / kPgStages) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * S::kStage);
-          const uint32_t b_addr = a_addr + S::kABytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + ab * BN, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32),
-                     idesc, (kb | k) != 0 ? 1u : 0u);
+        const uint32_t a_lo = sw128_desc_lo(ring + s * S::kStage);
+        const uint32_t b_lo = sw128_desc_lo(ring + s * S::kStage + S::kABytes);
+        if (elect_one()) {
+          umma_f16(d, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc, kb != 0 ? 1u : 0u);
+          umma_f16(d, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc, 1u);
+          umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
+          umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
           umma_commit(&empty[s]);
+          if (kb == p.nkb - 1) umma_commit(&acc_full[ab]);
         }
-        umma_commit(&acc_full[ab]);
+        __syncwarp();
       }
     }
   } else {

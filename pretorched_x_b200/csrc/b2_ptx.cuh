@@ -219,6 +219,32 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, ui
   return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// Cheap descriptor arithmetic for issue loops: the high word of a K-major SWIZZLE_128B descriptor is a
+// constant, the low word is (addr >> 4) | LBO; stepping K by 16 elements (+32 B) is "+2" on the low word.
+constexpr uint32_t kSw128DescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t desc_from(uint32_t hi, uint32_t lo) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// One lane of a fully converged warp.  Issue loops run on the whole warp with warp-uniform operands and wrap only
+// the tcgen05 / TMA instructions in `if (elect_one())`: that keeps descriptors in uniform registers (a loop nested
+// under `if (lane == 0)` makes ptxas emit an ELECT/R2UR "waterfall" around every UTCHMMA, ~100 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ------------------------------------------------------------------------------------------
 // small numeric helpers
 // ------------------------------------------------------------------------------------------

@@ -102,61 +102,70 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
 
   if (warp == 4) {
     // ================================ TMA producer ======================================
-    if (lane == 0) {
-      int wit = 0;
-      auto load_slab = [&](int si) {
-        const int cc = si / n_dt, dt = dt_lo + (si - cc * n_dt);
-        const int s = si % kSlabSStages;
-        mbar_wait(&slab_empty[s], ((si / kSlabSStages) & 1) ^ 1);
+    int wit = 0;
+    auto load_slab = [&](int si) {
+      const int cc = si / n_dt, dt = dt_lo + (si - cc * n_dt);
+      const int s = si % kSlabSStages;
+      mbar_wait(&slab_empty[s], ((si / kSlabSStages) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&slab_full[s], static_cast<uint32_t>(p.R * p.PW * 128));
         tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64, -pw, r_lo, plane + dt - pt);
-      };
-      load_slab(0);
-      // The next slab is requested once the weight ring (kSlabWStages deep) guarantees the MMA thread has
-      // already retired the slab that occupied the target slot, so this wait never stalls weight issue.
-      const int pf = min(kSlabWStages, taps_hw - 1);
-      for (int si = 0; si < n_slabs; ++si) {
-        const int cc = si / n_dt, dt = dt_lo + (si - cc * n_dt);
-        for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
-          if (thw == pf && si + 1 < n_slabs) load_slab(si + 1);
-          const int ws = wit % kSlabWStages;
-          mbar_wait(&w_empty[ws], ((wit / kSlabWStages) & 1) ^ 1);
+      }
+      __syncwarp();
+    };
+    load_slab(0);
+    // The next slab is requested once the weight ring (kSlabWStages deep) guarantees the MMA thread has
+    // already retired the slab that occupied the target slot, so this wait never stalls weight issue.
+    const int pf = min(kSlabWStages, taps_hw - 1);
+    for (int si = 0; si < n_slabs; ++si) {
+      const int cc = si / n_dt, dt = dt_lo + (si - cc * n_dt);
+      for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
+        if (thw == pf && si + 1 < n_slabs) load_slab(si + 1);
+        const int ws = wit % kSlabWStages;
+        mbar_wait(&w_empty[ws], ((wit / kSlabWStages) & 1) ^ 1);
+        const int tap = dt * taps_hw + thw;
+        if (elect_one()) {
           mbar_expect_tx(&w_full[ws], kWBytes);
-          const int tap = dt * taps_hw + thw;
           tma_load_2d(w_base + ws * kWBytes, &tmB, &w_full[ws], tap * p.C + cc * 64, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
     // ================================ MMA issuer ========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
-      int wit = 0;
-      for (int si = 0; si < n_slabs; ++si) {
-        const int s = si % kSlabSStages;
-        mbar_wait(&slab_full[s], (si / kSlabSStages) & 1);
+    // whole warp, warp-uniform operands; one elected lane issues (see elect_one())
+    constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
+    const uint32_t tm = warp_uniform(tmem_base);
+    const uint32_t slab0 = smem_u32(slab_base), w0s = smem_u32(w_base);
+    int wit = 0;
+    for (int si = 0; si < n_slabs; ++si) {
+      const int s = si % kSlabSStages;
+      mbar_wait(&slab_full[s], (si / kSlabSStages) & 1);
+      const uint32_t slab_addr = slab0 + s * p.slab_bytes;
+      for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
+        const int dh = thw / p.kw, dw = thw - dh * p.kw;
+        const int ws = wit % kSlabWStages;
+        mbar_wait(&w_full[ws], (wit / kSlabWStages) & 1);
         tc_fence_after();
-        const uint32_t slab_addr = smem_u32(slab_base + s * p.slab_bytes);
-        for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
-          const int dh = thw / p.kw, dw = thw - dh * p.kw;
-          const int ws = wit % kSlabWStages;
-          mbar_wait(&w_full[ws], (wit / kSlabWStages) & 1);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(w_base + ws * kWBytes);
-          // slab-local pixel index of padded position q0 under tap (dh, dw)
-          const int pix0 = q0 + (dh - ph) * p.PW + (dw - pw) - r_lo * p.PW;
+        // slab-local pixel index of padded position q0 under tap (dh, dw)
+        const int pix0 = q0 + (dh - ph) * p.PW + (dw - pw) - r_lo * p.PW;
+        const uint32_t b_lo = sw128_desc_lo(w0s + ws * kWBytes);
+        const uint32_t a_lo0 = sw128_desc_lo(slab_addr + static_cast<uint32_t>(pix0) * 128u);
+        if (elect_one()) {
           for (int j = 0; j < mt_valid; ++j) {
-            const uint32_t a_addr = slab_addr + static_cast<uint32_t>(pix0 + j * 128) * 128u;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_base + j * BN, make_desc_sw128_kmajor(a_addr + k * 32), make_desc_sw128_kmajor(b_addr + k * 32),
-                       idesc, (wit | k) != 0 ? 1u : 0u);
+            const uint32_t a_lo = a_lo0 + j * (128u * 128u >> 4);
+            const uint32_t d = tm + j * BN;
+            umma_f16(d, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc, wit != 0 ? 1u : 0u);
+            umma_f16(d, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc, 1u);
+            umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
+            umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
           }
           umma_commit(&w_empty[ws]);
+          if (thw == taps_hw - 1) umma_commit(&slab_empty[s]);
+          if (thw == taps_hw - 1 && si == n_slabs - 1) umma_commit(tmem_full);
         }
-        umma_commit(&slab_empty[s]);
+        __syncwarp();
       }
-      umma_commit(tmem_full);
     }
   } else {
     // ================================ epilogue ==========================================

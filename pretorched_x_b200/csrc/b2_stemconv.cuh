@@ -97,41 +97,45 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
-      for (int i = 0; i < n_dt; ++i) {
-        const int dt = dt_lo + i;
-        const int s = i % p.nstages;
-        mbar_wait(&empty[s], ((i / p.nstages) & 1) ^ 1);
+    for (int i = 0; i < n_dt; ++i) {
+      const int dt = dt_lo + i;
+      const int s = i % p.nstages;
+      mbar_wait(&empty[s], ((i / p.nstages) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&full[s], static_cast<uint32_t>(slab_bytes + p.w_bytes));
         uint8_t* dst = smem + s * p.stage_bytes;
         tma_load_3d(dst, &tmX, &full[s], 2 * w0 - 4, p.sh * ho0 - p.ph, n * p.T + to + dt - p.pt);
         const __half* wsrc = p.wimg + (static_cast<size_t>(ntile) * p.kt + dt) * (p.w_bytes / 2);
         bulk_load_1d(dst + slab_bytes, wsrc, static_cast<uint32_t>(p.w_bytes), &full[s]);
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
-      constexpr uint32_t kPairBytes = BN * 64;           // weight image of one (dt, dh) pair: BN rows x 32 k
-      for (int i = 0; i < n_dt; ++i) {
-        const int s = i % p.nstages;
-        mbar_wait(&full[s], (i / p.nstages) & 1);
-        tc_fence_after();
-        const uint32_t slab = smem_u32(smem + s * p.stage_bytes);
-        const uint32_t wbase = slab + slab_bytes;
+    constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
+    constexpr uint32_t kPairBytes = BN * 64;           // weight image of one (dt, dh) pair: BN rows x 32 k
+    // SWIZZLE_NONE K-major descriptors: hi = SBO >> 4 | version; lo = addr >> 4 | (LBO >> 4) << 16
+    constexpr uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (512u >> 4) | (1u << 14);
+    const uint32_t tm = warp_uniform(tmem_base);
+    const uint32_t base = smem_u32(smem);
+    for (int i = 0; i < n_dt; ++i) {
+      const int s = i % p.nstages;
+      mbar_wait(&full[s], (i / p.nstages) & 1);
+      tc_fence_after();
+      const uint32_t slab = base + s * p.stage_bytes;
+      const uint32_t wbase = slab + slab_bytes;
+      if (elect_one()) {
         for (int dh = 0; dh < p.kh; ++dh) {
-          const uint32_t b_addr = wbase + dh * kPairBytes;
+          const uint32_t b_lo = ((wbase + dh * kPairBytes) >> 4) | ((128u >> 4) << 16);
           for (int g = 0; g < g_valid; ++g) {
-            const uint32_t a_addr = slab + static_cast<uint32_t>(p.sh * g + dh) * kStemPitch;
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              umma_f16(tmem_base + g * BN, make_desc_noswz_kmajor(a_addr + k * 32, 16, 128),
-                       make_desc_noswz_kmajor(b_addr + k * 256, 128, 512), idesc, (i | dh | k) != 0 ? 1u : 0u);
+            const uint32_t a_lo = ((slab + static_cast<uint32_t>(p.sh * g + dh) * kStemPitch) >> 4) | ((16u >> 4) << 16);
+            umma_f16(tm + g * BN, desc_from(a_hi, a_lo), desc_from(b_hi, b_lo), idesc, (i | dh) != 0 ? 1u : 0u);
+            umma_f16(tm + g * BN, desc_from(a_hi, a_lo + 2), desc_from(b_hi, b_lo + 16), idesc, 1u);
           }
         }
         umma_commit(&empty[s]);
+        if (i == n_dt - 1) umma_commit(tmem_full);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
     }
   } else {
     mbar_wait(tmem_full, 0);
