@@ -28,10 +28,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __half* __restri
   out[i] = __float2half_rn(v);
 }
 
-// STEM7 weight image (consumed by b2_stemconv.cuh): [ntile][pair = dt*kh + dh][n/8][j = 16-byte K chunk (4)]
-// [n%8][e (8)] with K element index k = j*8 + e = px*4 + c, px 0 = zero alignment pixel, px 1..7 <-> kw tap 0..6,
-// channels >= Cin zero, output channels >= K zero.  This is the canonical SWIZZLE_NONE K-major smem layout of a
-// [BN x 32] B operand (LBO = 128 B, SBO = 512 B), so a tap pair is one contiguous BN*64-byte block.
+// STEM7 weight image (consumed by b2_stemconv.cuh): [ntile][dt][slot][n/8][j = 16-byte K chunk (4)][n%8][e (8)]
+// with K element index k = j*8 + e = px*4 + c, px 0 = zero alignment pixel, px 1..7 <-> kw tap 0..6, channels >= Cin
+// zero, output channels >= K zero.  `slot` orders the vertical taps of one temporal tap as: even dh in decreasing
+// order, then odd dh in decreasing order (stem_slot()), so that the taps feeding consecutive output rows from one
+// input row are adjacent.  Each tap is the canonical SWIZZLE_NONE K-major smem layout of a [BN x 32] B operand
+// (LBO = 128 B, SBO = 512 B): one contiguous BN*64-byte block, and consecutive taps concatenate to a taller B.
 __global__ void pack_weight_stem7_kernel(const float* __restrict__ w, __half* __restrict__ out, int K, int Cin,
                                          int kt, int kh, int BN, long long total) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -48,7 +50,9 @@ __global__ void pack_weight_stem7_kernel(const float* __restrict__ w, __half* __
   const int px = j * 2 + (e >> 2), c = e & 3;
   float v = 0.f;
   if (k < K && px >= 1 && c < Cin) {
-    const int dt = pr / kh, dh = pr % kh, dw = px - 1;
+    const int dt = pr / kh, slot = pr % kh, dw = px - 1;
+    const int emax = ((kh - 1) / 2) * 2, n_even = emax / 2 + 1, omax = (kh >= 2) ? ((kh - 2) / 2) * 2 + 1 : -1;
+    const int dh = (slot < n_even) ? emax - 2 * slot : omax - 2 * (slot - n_even);
     v = w[((((long long)k * Cin + c) * kt + dt) * kh + dh) * 7 + dw];
   }
   out[i] = __float2half_rn(v);
@@ -89,7 +93,9 @@ __global__ void conv_simt_kernel(SimtConvParams p, long long total) {
           if (p.stem7) {
             // weight image [ntile][pair][n/8][j][n%8][e], BN = p.ldw
             const int BN = p.ldw, px = dw + 1;
-            const size_t base = ((((size_t)(k / BN) * (p.kt * p.kh) + (dt * p.kh + dh)) * (BN / 8) + (k % BN) / 8) * 4 + px / 2) * 64 +
+            const int emax = ((p.kh - 1) / 2) * 2, n_even = emax / 2 + 1, omax = (p.kh >= 2) ? ((p.kh - 2) / 2) * 2 + 1 : -1;
+            const int slot = (dh % 2 == 0) ? (emax - dh) / 2 : n_even + (omax - dh) / 2;
+            const size_t base = ((((size_t)(k / BN) * (p.kt * p.kh) + (dt * p.kh + slot)) * (BN / 8) + (k % BN) / 8) * 4 + px / 2) * 64 +
                                 (size_t)(k % 8) * 8 + (px & 1) * 4;
             for (int c = 0; c < p.C; ++c) acc += __half2float(xp[c]) * __half2float(p.w[base + c]);
           } else {

@@ -184,6 +184,16 @@ static int try_slab(const b2_conv_args* a, cudaStream_t stream) {
   return rc == B2_OK ? 1 : rc;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 // ------------------------------------------------------------------------------------------
 // stem convolution launcher (Toeplitz-descriptor kernel)
 // ------------------------------------------------------------------------------------------
@@ -195,26 +205,41 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   p.T = a->T; p.H = a->H; p.W = a->W;
   p.To = (a->T + 2 * a->pt - a->kt) / a->st + 1;
-  p.Ho = (a->H + 2 * a->ph - a->kh) / a->sh + 1;
+  p.Ho = (a->H + 2 * a->ph - a->kh) / 2 + 1;
   p.Wo = (a->W + 6 - 7) / 2 + 1;
-  p.kt = a->kt; p.kh = a->kh; p.sh = a->sh; p.pt = a->pt; p.ph = a->ph;
-  p.G = 512 / BN;
-  if (p.G > p.Ho) p.G = p.Ho;
-  p.rows = a->sh * (p.G - 1) + a->kh;
+  p.kt = a->kt; p.kh = a->kh; p.pt = a->pt; p.ph = a->ph;
+  p.G = 256 / BN;
+  p.rows = 2 * (p.G - 1) + a->kh;
+  if (p.rows > kStemMaxRows) return set_error(B2_ERR_UNSUPPORTED, "stem kernel height %d too large", a->kh);
+  for (int i = 0; i < p.rows; ++i) {
+    int g_lo = i - (a->kh - 1);
+    g_lo = g_lo > 0 ? (g_lo + 1) / 2 : 0;
+    int g_hi = i / 2;
+    if (g_hi > p.G - 1) g_hi = p.G - 1;
+    p.row_glo[i] = (signed char)g_lo;
+    p.row_ghi[i] = (signed char)g_hi;
+    p.row_slot[i] = (signed char)(g_lo <= g_hi ? stem_slot(i - 2 * g_lo, a->kh) : 0);
+  }
   p.w_bytes = a->kh * BN * 64;
   p.stage_bytes = ((p.rows * kStemPitch + p.w_bytes) + 127) / 128 * 128;
-  const int budget = 227 * 1024 - 2048;
-  p.nstages = budget / p.stage_bytes;
-  if (p.nstages > 3) p.nstages = 3;
-  if (p.nstages > a->kt) p.nstages = a->kt;
-  if (p.nstages < 1) return set_error(B2_ERR_UNSUPPORTED, "stem slab does not fit in shared memory (kh=%d sh=%d)", a->kh, a->sh);
+  const int tail_bytes = 128 + 2048 + 256;
+  p.nstages = (227 * 1024 - tail_bytes) / p.stage_bytes;
+  if (p.nstages > kStemMaxStages) p.nstages = kStemMaxStages;
+  if (p.nstages < 1) return set_error(B2_ERR_UNSUPPORTED, "stem slab does not fit in shared memory (kh=%d)", a->kh);
   p.Ncols = a->K;
+  p.ntiles_n = (a->ldy + BN - 1) / BN;
+  if (p.ntiles_n * BN > 256) return set_error(B2_ERR_UNSUPPORTED, "stem convolution supports at most 256 output channels");
+  p.tiles_w = (p.Wo + kStemTileW - 1) / kStemTileW;
+  p.tiles_h = (p.Ho + p.G - 1) / p.G;
+  const long long items = (long long)p.tiles_w * p.tiles_h * p.ntiles_n * a->N * p.To;
+  if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "stem problem too large");
+  p.items_total = (int)items;
   p.wimg = reinterpret_cast<const __half*>(a->w);
   p.scale = a->scale; p.shift = a->shift;
   p.y = reinterpret_cast<__half*>(a->y);
   p.ldy = a->ldy;
   p.relu = a->relu;
-  const int smem_bytes = p.nstages * p.stage_bytes + 128 + 2 * BN * 4 + 256;
+  const int smem_bytes = p.nstages * p.stage_bytes + tail_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(stemconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -230,8 +255,7 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled(stem) failed (%d)", (int)r);
-  const int ntiles = (a->ldy + BN - 1) / BN;
-  dim3 grid((p.Wo + kStemTileW - 1) / kStemTileW, (p.Ho + p.G - 1) / p.G, a->N * p.To * ntiles);
+  const int grid = p.items_total < sm_count() ? p.items_total : sm_count();
   stemconv_kernel<BN><<<grid, kStemThreads, smem_bytes, stream>>>(tmX, p);
   B2_CHECK_LAUNCH("stemconv_kernel");
   return B2_OK;
@@ -289,16 +313,6 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
 }
 
 static int g_gemm_algo = 0;   // 0 auto (persistent kernel where it applies), 1 force the per-tile kernel
-
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
 
 template <int BN>
 static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
@@ -417,7 +431,7 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   const int taps = a->kt * a->kh * a->kw;
   if (a->mode == B2_CONV_STEM7) {
     B2_CHECK_ARG(!a->out_f32 && a->residual == nullptr, "stem convolution has no residual / fp32 output");
-    B2_CHECK_ARG(a->st == 1, "stem convolution needs temporal stride 1");
+    B2_CHECK_ARG(a->st == 1 && a->sh == 2, "stem convolution needs strides (1, 2, 2)");
     const cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return a->K <= 64 ? launch_stem<64>(a, st) : launch_stem<128>(a, st);
   } else if (taps == 1 && a->st == 1 && a->sh == 1 && a->sw == 1 && a->pt == 0 && a->ph == 0 && a->pw == 0) {

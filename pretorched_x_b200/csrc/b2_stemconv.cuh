@@ -1,4 +1,4 @@
-// b2_stemconv.cuh -- stem convolutions (kt x kh x 7, stride (1, sh, 2), padding (pt, ph, 3), Cin <= 4) as an
+// b2_stemconv.cuh -- stem convolutions (kt x kh x 7, stride (1, 2, 2), padding (pt, ph, 3), Cin <= 4) as an
 // implicit GEMM whose im2col matrix is never built: it is *described*.
 //
 // Input is NDHWC4 (8 bytes per pixel).  For a fixed temporal/vertical tap (dt, dh) the 7 horizontal taps of
@@ -6,15 +6,22 @@
 // the run 16-byte aligned): 32 fp16 = 64 contiguous bytes, and the run of output pixel wo+1 starts exactly
 // 16 bytes later.  A K-major SWIZZLE_NONE tcgen05 operand is addressed as
 //     byte(row r, 16-byte chunk j) = start + (r % 8) * 16 + (r / 8) * SBO + j * LBO,
-// so with LBO = 16 and SBO = 128 the 128 x 32 im2col tile of one (dt, dh) tap pair is an overlapping (Toeplitz)
-// view of the raw input row sitting in shared memory (verified by tools/probe_umma.py, mode 1).  One TMA box per
-// temporal tap brings 2G+5 input rows (zero-filled outside the image) for G output rows -- the tensor map treats a
-// pixel as one 8-byte element so that a box row is a single 2 KB run (16-byte-wide boxes starve the TMA unit); every (dt, dh) tap is then
-// two K=16 MMAs per output row straight out of that slab.  Activation traffic from L2 drops ~4.4x versus
-// gathering 64 bytes per output pixel per tap, and no thread touches the data on its way to the tensor core.
+// so with LBO = 16 and SBO = 128 the 128 x 32 im2col tile of one input row is an overlapping (Toeplitz) view of
+// the raw row sitting in shared memory (verified by tools/probe_umma.py, mode 1): no thread touches the data on
+// its way to the tensor core.
 //
-// CTA = G output rows x 120 output columns x BN output channels (G accumulators of BN fp32 columns in TMEM).
-// Warps 0-3: epilogue (BN + ReLU -> fp16 NDHWC), warp 4: TMA/bulk-copy producer, warp 5: MMA issuer.
+// Input-row-stationary schedule.  Slab row i (input row 2*ho0 - ph + i) feeds local output row g through vertical
+// tap dh = i - 2g, i.e. up to 4 consecutive output rows.  The per-row accumulators sit side by side in TMEM (row g
+// at column BN*g) and the weight image stores the taps of one parity class in *decreasing* dh order, so all of
+// those contributions are ONE MMA: A = the Toeplitz tile of slab row i, B = [W(dh_max); W(dh_max-2); ...]
+// (N = BN x #taps, up to 256), D = the accumulator columns of the touched output rows.  Compared with one N=64
+// MMA per (output row, dh) every A tile is read from shared memory once instead of up to 4 times and 4x fewer
+// instructions are issued: the kernel moves from smem-operand-bound to tensor-bound.  Accumulators start from
+// zero (tcgen05.st by the epilogue warps), so every MMA accumulates.
+//
+// Persistent CTAs (one per SM) walk (plane, row-group, column-tile) work items; TMEM holds two accumulator sets
+// so the epilogue of item i (BN + ReLU -> fp16 NDHWC) overlaps the MMAs of item i+1.
+// Warps 0-3: epilogue, warp 4: TMA/bulk-copy producer, warp 5: MMA issuer.
 #pragma once
 
 #include "b2_ptx.cuh"
@@ -24,21 +31,25 @@ namespace b2 {
 constexpr int kStemThreads = 192;
 constexpr int kStemPitch = 2048;        // bytes per slab row: 256 pixels [2*w0-4, 2*w0+252) of 8 bytes
 constexpr int kStemRowPx = 256;         // TMA box width (the maximum box extent), one 8-byte element per pixel
-constexpr int kStemTileW = 120;         // output columns per CTA: rows r < 124 of the 128-row MMA tile see complete runs
+constexpr int kStemTileW = 120;         // output columns per item: rows r < 124 of the 128-row MMA tile see complete runs
+constexpr int kStemMaxStages = 4;
+constexpr int kStemMaxRows = 16;        // slab rows = 2*(G-1) + kh <= 2*3 + 9
 
 struct StemParams {
   int T, H, W;             // input dims per clip (W even)
   int To, Ho, Wo;
-  int kt, kh;              // kw == 7
-  int sh;                  // vertical stride (horizontal stride is 2, temporal stride 1)
+  int kt, kh;              // kw == 7, strides (1, 2, 2)
   int pt, ph;
-  int G;                   // output rows per CTA
-  int rows;                // slab rows = sh*(G-1) + kh
+  int G;                   // output rows per item (G * BN <= 256)
+  int rows;                // slab rows = 2*(G-1) + kh
   int stage_bytes;         // slab + weights of one temporal tap, multiple of 128
-  int w_bytes;             // kh * BN * 64: weight image of one temporal tap for this N tile
+  int w_bytes;             // kh * BN * 64: weight image of one temporal tap for one N tile
   int nstages;
   int Ncols;
-  const __half* wimg;      // packed weight image [ntile][kt*kh][BN/8][4][8][8]
+  int tiles_w, tiles_h, ntiles_n, items_total;
+  // per slab row: first / last local output row it feeds, and the image slot of the tap used by the first one
+  signed char row_glo[kStemMaxRows], row_ghi[kStemMaxRows], row_slot[kStemMaxRows];
+  const __half* wimg;      // packed weight image, see b2_pack_conv_weight (STEM7)
   const float* scale;
   const float* shift;
   __half* y;               // [N*To*Ho*Wo][ldy]
@@ -46,11 +57,46 @@ struct StemParams {
   int relu;
 };
 
+// slot of vertical tap dh inside one temporal tap of the weight image: even taps in decreasing order, then odd taps
+__host__ __device__ inline int stem_slot(int dh, int kh) {
+  const int emax = ((kh - 1) / 2) * 2;              // largest even tap
+  const int n_even = emax / 2 + 1;
+  const int omax = (kh >= 2) ? ((kh - 2) / 2) * 2 + 1 : -1;
+  return (dh % 2 == 0) ? (emax - dh) / 2 : n_even + (omax - dh) / 2;
+}
+
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// registers -> TMEM: zero 32 consecutive fp32 columns of this thread's lane
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+struct StemItem {
+  int w0, ho0, ntile, plane_o, to, n;
+};
+__device__ __forceinline__ StemItem stem_item(const StemParams& p, int item) {
+  StemItem it;
+  const int tw = item % p.tiles_w; item /= p.tiles_w;
+  const int th = item % p.tiles_h; item /= p.tiles_h;
+  it.ntile = item % p.ntiles_n;
+  it.plane_o = item / p.ntiles_n;
+  it.w0 = tw * kStemTileW;
+  it.ho0 = th * p.G;
+  it.to = it.plane_o % p.To;
+  it.n = it.plane_o / p.To;
+  return it;
 }
 
 template <int BN>
@@ -60,36 +106,28 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* tail = smem + p.nstages * p.stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tail);          // [nstages]
-  uint64_t* empty = full + 4;                                  // [nstages]
-  uint64_t* tmem_full = empty + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* s_scale = reinterpret_cast<float*>(tail + 128);
-  float* s_shift = s_scale + BN;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);          // [kStemMaxStages]
+  uint64_t* empty = full + kStemMaxStages;
+  uint64_t* acc_full = empty + kStemMaxStages;                 // [2]
+  uint64_t* acc_empty = acc_full + 2;                          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_scale = reinterpret_cast<float*>(tail + 128);       // [256] (ntiles_n * BN <= 256 is enforced by the host)
+  float* s_shift = s_scale + 256;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int w0 = blockIdx.x * kStemTileW;             // first output column of the tile
-  const int ho0 = blockIdx.y * p.G;
-  const int ntile = blockIdx.z % ((p.ldy + BN - 1) / BN);
-  const int plane_o = blockIdx.z / ((p.ldy + BN - 1) / BN);     // n*To + to   (temporal stride 1 => To == T)
-  const int n0 = ntile * BN;
-  const int to = plane_o % p.To, n = plane_o / p.To;
-  const int dt_lo = max(0, p.pt - to), dt_hi = min(p.kt - 1, p.T - 1 - to + p.pt);
-  const int n_dt = dt_hi - dt_lo + 1;
-  const int g_valid = min(p.G, p.Ho - ho0);
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int slab_bytes = p.rows * kStemPitch;
+  constexpr int kAccCols = 256;                                // one accumulator set: G * BN <= 256 columns
 
   if (tid == 128) {
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
   }
   if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  for (int i = tid; i < BN; i += kStemThreads) {
-    const int c = n0 + i;
-    s_scale[i] = (c < p.Ncols) ? __ldg(&p.scale[c]) : 0.f;
-    s_shift[i] = (c < p.Ncols) ? __ldg(&p.shift[c]) : 0.f;
+  for (int i = tid; i < 256; i += kStemThreads) {
+    s_scale[i] = (i < p.Ncols) ? __ldg(&p.scale[i]) : 0.f;
+    s_shift[i] = (i < p.Ncols) ? __ldg(&p.shift[i]) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -97,80 +135,116 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    for (int i = 0; i < n_dt; ++i) {
-      const int dt = dt_lo + i;
-      const int s = i % p.nstages;
-      mbar_wait(&empty[s], ((i / p.nstages) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&full[s], static_cast<uint32_t>(slab_bytes + p.w_bytes));
-        uint8_t* dst = smem + s * p.stage_bytes;
-        tma_load_3d(dst, &tmX, &full[s], 2 * w0 - 4, p.sh * ho0 - p.ph, n * p.T + to + dt - p.pt);
-        const __half* wsrc = p.wimg + (static_cast<size_t>(ntile) * p.kt + dt) * (p.w_bytes / 2);
-        bulk_load_1d(dst + slab_bytes, wsrc, static_cast<uint32_t>(p.w_bytes), &full[s]);
+    // ================================ producer ==========================================
+    int it = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
+      const StemItem w = stem_item(p, item);
+      const int dt_lo = max(0, p.pt - w.to), dt_hi = min(p.kt - 1, p.T - 1 - w.to + p.pt);
+      for (int dt = dt_lo; dt <= dt_hi; ++dt, ++it) {
+        const int s = it % p.nstages;
+        mbar_wait(&empty[s], ((it / p.nstages) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full[s], static_cast<uint32_t>(slab_bytes + p.w_bytes));
+          uint8_t* dst = smem + s * p.stage_bytes;
+          tma_load_3d(dst, &tmX, &full[s], 2 * w.w0 - 4, 2 * w.ho0 - p.ph, w.n * p.T + w.to + dt - p.pt);
+          const __half* wsrc = p.wimg + (static_cast<size_t>(w.ntile) * p.kt + dt) * (p.w_bytes / 2);
+          bulk_load_1d(dst + slab_bytes, wsrc, static_cast<uint32_t>(p.w_bytes), &full[s]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp == 5) {
-    constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
-    constexpr uint32_t kPairBytes = BN * 64;           // weight image of one (dt, dh) pair: BN rows x 32 k
+    // ================================ MMA issuer ========================================
     // SWIZZLE_NONE K-major descriptors: hi = SBO >> 4 | version; lo = addr >> 4 | (LBO >> 4) << 16
     constexpr uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = (512u >> 4) | (1u << 14);
+    constexpr uint32_t kTapBytes = BN * 64;            // weight image of one (dt, dh) tap: BN rows x 32 k
     const uint32_t tm = warp_uniform(tmem_base);
     const uint32_t base = smem_u32(smem);
-    for (int i = 0; i < n_dt; ++i) {
-      const int s = i % p.nstages;
-      mbar_wait(&full[s], (i / p.nstages) & 1);
+    int it = 0, lt = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
+      const StemItem w = stem_item(p, item);
+      const int dt_lo = max(0, p.pt - w.to), dt_hi = min(p.kt - 1, p.T - 1 - w.to + p.pt);
+      const int g_valid = min(p.G, p.Ho - w.ho0);
+      const int ab = lt & 1;
+      mbar_wait(&acc_empty[ab], (lt >> 1) & 1);            // the epilogue has drained and re-zeroed this set
       tc_fence_after();
-      const uint32_t slab = base + s * p.stage_bytes;
-      const uint32_t wbase = slab + slab_bytes;
-      if (elect_one()) {
-        for (int dh = 0; dh < p.kh; ++dh) {
-          const uint32_t b_lo = ((wbase + dh * kPairBytes) >> 4) | ((128u >> 4) << 16);
-          for (int g = 0; g < g_valid; ++g) {
-            const uint32_t a_lo = ((slab + static_cast<uint32_t>(p.sh * g + dh) * kStemPitch) >> 4) | ((16u >> 4) << 16);
-            umma_f16(tm + g * BN, desc_from(a_hi, a_lo), desc_from(b_hi, b_lo), idesc, (i | dh) != 0 ? 1u : 0u);
-            umma_f16(tm + g * BN, desc_from(a_hi, a_lo + 2), desc_from(b_hi, b_lo + 16), idesc, 1u);
+      const uint32_t acc = tm + ab * kAccCols;
+      for (int dt = dt_lo; dt <= dt_hi; ++dt, ++it) {
+        const int s = it % p.nstages;
+        mbar_wait(&full[s], (it / p.nstages) & 1);
+        tc_fence_after();
+        const uint32_t slab = base + s * p.stage_bytes;
+        const uint32_t wbase = slab + slab_bytes;
+        if (elect_one()) {
+          for (int i = 0; i < p.rows; ++i) {
+            const int g_lo = p.row_glo[i];
+            const int g_hi = min(static_cast<int>(p.row_ghi[i]), g_valid - 1);
+            if (g_lo > g_hi) continue;
+            const uint32_t idesc = make_idesc_f16(128, static_cast<uint32_t>(g_hi - g_lo + 1) * BN, 0);
+            const uint32_t a_lo = ((slab + static_cast<uint32_t>(i) * kStemPitch) >> 4) | ((16u >> 4) << 16);
+            const uint32_t b_lo = ((wbase + static_cast<uint32_t>(p.row_slot[i]) * kTapBytes) >> 4) | ((128u >> 4) << 16);
+            const uint32_t d = acc + g_lo * BN;
+            umma_f16(d, desc_from(a_hi, a_lo), desc_from(b_hi, b_lo), idesc, 1u);
+            umma_f16(d, desc_from(a_hi, a_lo + 2), desc_from(b_hi, b_lo + 16), idesc, 1u);
           }
+          umma_commit(&empty[s]);
+          if (dt == dt_hi) umma_commit(&acc_full[ab]);
         }
-        umma_commit(&empty[s]);
-        if (i == n_dt - 1) umma_commit(tmem_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+    // ================================ epilogue ==========================================
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const int wo = w0 + tid;
-    const bool col_ok = (tid < kStemTileW) && (wo < p.Wo);
-    const int ncols_here = min(BN, p.ldy - n0);
-    for (int g = 0; g < g_valid; ++g) {
-      const size_t row = (static_cast<size_t>(plane_o) * p.Ho + (ho0 + g)) * p.Wo + wo;
-      __half* yrow = p.y + row * p.ldy + n0;
+    for (int c = 0; c < 512; c += 32) tmem_st32_zero(tmem_base + lane_off + c);   // both accumulator sets start at zero
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&acc_empty[0]);
+    mbar_arrive(&acc_empty[1]);
+    int lt = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
+      const StemItem w = stem_item(p, item);
+      const int g_valid = min(p.G, p.Ho - w.ho0);
+      const int ab = lt & 1;
+      const int n0 = w.ntile * BN;
+      const int ncols_here = min(BN, p.ldy - n0);
+      const int wo = w.w0 + tid;
+      const bool col_ok = (tid < kStemTileW) && (wo < p.Wo);
+      mbar_wait(&acc_full[ab], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + lane_off + ab * kAccCols;
+      for (int g = 0; g < g_valid; ++g) {
+        const size_t row = (static_cast<size_t>(w.plane_o) * p.Ho + (w.ho0 + g)) * p.Wo + wo;
+        __half* yrow = p.y + row * p.ldy + n0;
 #pragma unroll 1
-      for (int jc = 0; jc < BN / 32; ++jc) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + g * BN + jc * 32, v);
-        tmem_ld_wait();
-        if (col_ok) {
+        for (int jc = 0; jc < BN / 32; ++jc) {
+          uint32_t v[32];
+          tmem_ld32(acc + g * BN + jc * 32, v);
+          tmem_ld_wait();
+          if (col_ok) {
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const int col = jc * 32 + c8 * 8;
-            if (col < ncols_here) {
-              uint32_t o[4];
+            for (int c8 = 0; c8 < 4; ++c8) {
+              const int col = jc * 32 + c8 * 8;
+              if (col < ncols_here) {
+                uint32_t o[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int ci = col + e * 2;
-                float a0 = __uint_as_float(v[c8 * 8 + e * 2]) * s_scale[ci] + s_shift[ci];
-                float a1 = __uint_as_float(v[c8 * 8 + e * 2 + 1]) * s_scale[ci + 1] + s_shift[ci + 1];
-                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                o[e] = pack_half2(a0, a1);
+                for (int e = 0; e < 4; ++e) {
+                  const int ci = n0 + col + e * 2;
+                  float a0 = __uint_as_float(v[c8 * 8 + e * 2]) * s_scale[ci] + s_shift[ci];
+                  float a1 = __uint_as_float(v[c8 * 8 + e * 2 + 1]) * s_scale[ci + 1] + s_shift[ci + 1];
+                  if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                  o[e] = pack_half2(a0, a1);
+                }
+                *reinterpret_cast<uint4*>(yrow + col) = make_uint4(o[0], o[1], o[2], o[3]);
               }
-              *reinterpret_cast<uint4*>(yrow + col) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
         }
       }
+      for (int c = 0; c < kAccCols; c += 32) tmem_st32_zero(acc + c);        // hand the set back zeroed
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
     }
   }
 

@@ -212,6 +212,8 @@ def run_group(group):
         att_case("att B2 N72 d512 dv512 (dv split)", 2, 72, 512, 512)
         att_case("att B1 N784 d512 dv512", 1, 784, 512, 512)
         att_case("att peaked logits (scale 3)", 1, 256, 64, 64, scale=3.0, tol=2e-2)
+        for cfg in [(1, 98, 64, 64), (2, 128, 128, 128), (1, 98, 128, 128), (2, 100, 128, 128), (2, 98, 128, 128)]:
+            att_case("att sweep B%d N%d d%d dv%d" % cfg, *cfg)
 
     elif group in ("models", "models_simt"):
         import glob
