@@ -10,16 +10,17 @@
 // accumulators, a double-buffered residual tile and an smem operand ring.  The non-persistent igemm_kernel pays the
 // TMEM allocation, barrier set-up and a cold pipeline for every 128 x 128 tile; with K = 64 that prologue dominates.
 //
-//   warp 4   producer: residual tile of tile i, then its K blocks (A and B boxes, 128B-swizzled)
-//   warp 5   MMA issuer: accumulates tile i into TMEM buffer i & 1
-//   warps 0-3 epilogue of tile i (thread = accumulator row), TMA store from a staging tile
+//   warp 8   producer: residual tile of tile i, then its K blocks (A and B boxes, 128B-swizzled)
+//   warp 9   MMA issuer: accumulates tile i into TMEM buffer i & 1
+//   warps 0-7 epilogue of tile i (thread = accumulator row x one half of the columns), TMA store from a staging tile
 #pragma once
 
 #include "b2_ptx.cuh"
 
 namespace b2 {
 
-constexpr int kPgThreads = 192;
+constexpr int kPgEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kPgThreads = (kPgEpiWarps + 2) * 32;
 constexpr int kPgStages = 3;
 
 struct PgemmParams {
@@ -63,22 +64,22 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (tid == 128) {
+  if (tid == kPgEpiWarps * 32) {
     for (int s = 0; s < kPgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128);
-      mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 128);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPgEpiWarps * 32);
+      mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], kPgEpiWarps * 32);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
   }
-  if (warp == 5) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
+  if (warp == kPgEpiWarps + 1) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kPgEpiWarps) {
     // ================================ producer ==========================================
     int it = 0, lt = 0;
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
@@ -106,7 +107,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kPgEpiWarps + 1) {
     // ================================ MMA issuer ========================================
     constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
     const uint32_t tm = warp_uniform(tmem_base);
@@ -138,8 +139,9 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ================================ epilogue ==========================================
     float* s_scale = reinterpret_cast<float*>(smem + S::kAffOff);
     float* s_shift = s_scale + BN;
-    const int r = tid;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int r = (warp & 3) * 32 + (tid & 31);        // accumulator row == TMEM lane
+    const int half = warp >> 2;                        // which half of the tile's columns this warp handles
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t swz = static_cast<uint32_t>(r & 7);
     uint8_t* c_stage = smem + S::kCOff;
     int lt = 0;
@@ -152,15 +154,15 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (p.has_residual) mbar_wait(&res_full[ab], (lt >> 1) & 1);
       // the previous tile's TMA store must have finished reading the staging tile before we overwrite it
       if (tid == 0) tma_store_wait_read0();
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // (also: everyone is done with the previous tile's affine)
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // (also: everyone is done with the previous tile's affine)
       if (tid < BN) {
         const int c = n0 + tid;
         s_scale[tid] = (c < p.Ncols) ? __ldg(&p.scale[c]) : 0.f;
         s_shift[tid] = (c < p.Ncols) ? __ldg(&p.shift[c]) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = half * (BN / 64); j < (half + 1) * (BN / 64); ++j) {
         uint32_t v[32];
         tmem_ld32(tmem_base + lane_off + ab * BN + j * 32, v);
         tmem_ld_wait();
@@ -192,7 +194,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_arrive(&acc_empty[ab]);
       if (p.has_residual) mbar_arrive(&res_empty[ab]);
       fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b)
@@ -205,7 +207,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == kPgEpiWarps + 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 }  // namespace b2

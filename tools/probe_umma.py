@@ -18,7 +18,7 @@ g = torch.Generator().manual_seed(0)
 
 
 def run(a, b, mode, shift, base_off):
-    out = torch.zeros(128, 64, dtype=torch.float32, device=dev)
+    out = torch.zeros(128, 128 if mode == 2 else 64, dtype=torch.float32, device=dev)
     rc = fn(a.data_ptr(), b.data_ptr(), out.data_ptr(), mode, shift, base_off, None)
     assert rc == 0, _lib.last_error()
     torch.cuda.synchronize()
@@ -43,3 +43,10 @@ want = buf.float()[idx] @ B1.float().t()
 got = run(buf.to(dev), B1.to(dev), 1, 0, 0)
 err = (got - want).abs().max().item() / want.abs().max().item()
 print("mode 1: no-swizzle Toeplitz A (LBO=16, SBO=128): rel err %.3e %s" % (err, "EXACT" if err < 1e-5 else "wrong"))
+
+A2 = torch.randn(128, 64, generator=g).half()
+V2 = (torch.randn(64, 128, generator=g) / 8).half()
+want = A2.float() @ V2.float()
+got = run(A2.to(dev), V2.to(dev), 2, 0, 0)
+err = (got - want).abs().max().item() / want.abs().max().item()
+print("mode 2: MN-major SW128 B (LBO=8192, SBO=1024, K step 2048 B): rel err %.3e %s" % (err, "EXACT" if err < 1e-5 else "wrong"))
