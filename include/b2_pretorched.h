@@ -105,11 +105,10 @@ int b2_gemm_f16(const b2_gemm_args* a, void* stream);
 /* ---------------------------------------------------------------------------------------------
  * Non-local block core (nonlocalnet.py:143-166, `_embedded_gaussian`):
  *     O[b] = softmax_rows(Q[b] . K[b]^T) . V[b]        (unscaled logits, softmax over keys)
- * Q, K: fp16 [B*Npos][ld] (d columns used); Vt: fp16 [dv][B*Npos] (V transposed, produced by
- * b2_gemm_f16 with per_row); O: fp16 [B*Npos][ldo].  One fused kernel, the Npos x Npos matrix is
- * never materialised.
+ * Q, K, V: fp16 [B*Npos][ld] (d resp. dv columns used; typically three column ranges of one projection
+ * output); O: fp16 [B*Npos][ldo].  One fused kernel, the Npos x Npos matrix is never materialised.
  * ------------------------------------------------------------------------------------------- */
-int b2_nonlocal_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* o,
+int b2_nonlocal_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o,
                           int ldo, int B, int Npos, int d, int dv, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

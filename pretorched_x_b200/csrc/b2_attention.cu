@@ -9,8 +9,10 @@
 //   pass 2: S again -> P = exp(S - m) / l (fp16, smem) -> O += P . V   (O in TMEM, DVT fp32 columns)
 //
 // CTA = (128 query rows, sample b, DVT-wide slice of the value channels).  6 warps: 0-3 softmax +
-// output epilogue, 4 TMA producer, 5 MMA issuer / TMEM owner.  All operands are K-major 128B-swizzled
-// tiles; V arrives transposed ([dv][positions]) so that keys are its contiguous (K) dimension.
+// output epilogue, 4 TMA producer, 5 MMA issuer / TMEM owner.  Q, K and P are K-major 128B-swizzled tiles; V stays
+// in its natural [positions][dv] layout and enters the second MMA as an MN-major B operand (64-wide dv blocks of
+// [64 keys x 128 B], LBO = 8 KB between blocks, SBO = 1 KB between 8-key groups; tools/probe_umma.py mode 2), so
+// theta, phi and g come out of ONE projection GEMM and no transposed copy of g is ever made.
 #include "b2_host.h"
 #include "b2_ptx.cuh"
 
@@ -197,7 +199,9 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       mbar_wait(&empty_bar[s], ((it / kAttSlots) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&full_bar[s], DVT * 128);
-        tma_load_2d(smem + s * kAttSlotBytes, &tmV, &full_bar[s], row_base + j * kAttBKV, dv0);
+#pragma unroll
+        for (int blk = 0; blk < DVT / 64; ++blk)      // [64 dv x 64 keys] boxes, 8 KB apart
+          tma_load_2d(smem + s * kAttSlotBytes + blk * 8192, &tmV, &full_bar[s], dv0 + blk * 64, row_base + j * kAttBKV);
       }
       __syncwarp();
       ++it;
@@ -205,7 +209,8 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   } else {
     // =========================== MMA issuer =============================================
     constexpr uint32_t idesc_qk = make_idesc_f16(kAttBM, kAttBKV, 0);
-    constexpr uint32_t idesc_pv = make_idesc_f16(kAttBM, DVT, 0);
+    constexpr uint32_t idesc_pv = make_idesc_f16(kAttBM, DVT, 0) | (1u << 16);   // B (= V) is MN-major
+    constexpr uint32_t v_hi = kSw128DescHi;                                        // SBO 1024, version, 128B swizzle
     const uint32_t tmS = warp_uniform(tmem_S), tmO = warp_uniform(tmem_O);
     const uint32_t ring = smem_u32(smem);
     int it = 0;
@@ -243,12 +248,13 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       mbar_wait(&full_bar[s], (it / kAttSlots) & 1);
       tc_fence_after();
       const uint32_t a_lo = sw128_desc_lo(ring + S::kPOff + pb * S::kPBytes);
-      const uint32_t b_lo = sw128_desc_lo(ring + s * kAttSlotBytes);
+      // V tile: LBO = 8192 B (next 64-wide dv block); stepping K by 16 keys = 16 rows x 128 B = +2048 B
+      const uint32_t b_lo = (((ring + s * kAttSlotBytes) & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16);
       if (elect_one()) {
-        umma_f16(tmO, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc_pv, j != 0 ? 1u : 0u);
-        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc_pv, 1u);
-        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc_pv, 1u);
-        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc_pv, 1u);
+        umma_f16(tmO, desc_from(kSw128DescHi, a_lo), desc_from(v_hi, b_lo), idesc_pv, j != 0 ? 1u : 0u);
+        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 2), desc_from(v_hi, b_lo + 128), idesc_pv, 1u);
+        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 4), desc_from(v_hi, b_lo + 256), idesc_pv, 1u);
+        umma_f16(tmO, desc_from(kSw128DescHi, a_lo + 6), desc_from(v_hi, b_lo + 384), idesc_pv, 1u);
         umma_commit(&empty_bar[s]);
         umma_commit(&p_empty[pb]);
         if (j == p.nkv - 1) umma_commit(o_full);
@@ -264,7 +270,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 }
 
 template <int DVT>
-static int launch_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* o, int ldo,
+static int launch_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                             int B, int Npos, int d, int dv, cudaStream_t stream) {
   using S = AttSmem<DVT>;
   static bool attr_set = false;
@@ -277,7 +283,7 @@ static int launch_attention(const void* q, int ldq, const void* k, int ldk, cons
   const uint64_t rows = (uint64_t)B * Npos;
   if ((rc = make_tmap_2d_f16(&tmQ, q, (uint64_t)d, rows, (uint64_t)ldq, 64, kAttBM, true)) != B2_OK) return rc;
   if ((rc = make_tmap_2d_f16(&tmK, k, (uint64_t)d, rows, (uint64_t)ldk, 64, kAttBKV, true)) != B2_OK) return rc;
-  if ((rc = make_tmap_2d_f16(&tmV, vt, rows, (uint64_t)dv, (uint64_t)ldvt, 64, DVT, true)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmV, v, (uint64_t)dv, rows, (uint64_t)ldv, 64, kAttBKV, true)) != B2_OK) return rc;
   AttParams p;
   p.Npos = Npos; p.nkb = d / 64; p.nkv = (Npos + kAttBKV - 1) / kAttBKV;
   p.o = reinterpret_cast<__half*>(o); p.ldo = ldo;
@@ -291,18 +297,18 @@ static int launch_attention(const void* q, int ldq, const void* k, int ldk, cons
 
 using namespace b2;
 
-extern "C" int b2_nonlocal_attention(const void* q, int ldq, const void* k, int ldk, const void* vt, int ldvt, void* o,
+extern "C" int b2_nonlocal_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o,
                                      int ldo, int B, int Npos, int d, int dv, void* stream) {
-  B2_CHECK_ARG(q && k && vt && o, "null pointer");
+  B2_CHECK_ARG(q && k && v && o, "null pointer");
   B2_CHECK_ARG(B > 0 && Npos > 0 && d > 0 && dv > 0, "non-positive dimension");
-  B2_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldvt % 8 == 0 && ldo % 8 == 0, "pitches must be multiples of 8");
-  B2_CHECK_ARG(ldq >= d && ldk >= d && ldo >= dv && ldvt >= B * Npos, "pitch smaller than extent");
+  B2_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "pitches must be multiples of 8");
+  B2_CHECK_ARG(ldq >= d && ldk >= d && ldo >= dv && ldv >= dv, "pitch smaller than extent");
   if (d % 64 != 0 || dv % 64 != 0)
     return set_error(B2_ERR_UNSUPPORTED, "non-local attention needs d and dv multiples of 64 (got %d, %d)", d, dv);
   int rc;
   if ((rc = require_sm100()) != B2_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dv % 256 == 0) return launch_attention<256>(q, ldq, k, ldk, vt, ldvt, o, ldo, B, Npos, d, dv, st);
-  if (dv % 128 == 0) return launch_attention<128>(q, ldq, k, ldk, vt, ldvt, o, ldo, B, Npos, d, dv, st);
-  return launch_attention<64>(q, ldq, k, ldk, vt, ldvt, o, ldo, B, Npos, d, dv, st);
+  if (dv % 256 == 0) return launch_attention<256>(q, ldq, k, ldk, v, ldv, o, ldo, B, Npos, d, dv, st);
+  if (dv % 128 == 0) return launch_attention<128>(q, ldq, k, ldk, v, ldv, o, ldo, B, Npos, d, dv, st);
+  return launch_attention<64>(q, ldq, k, ldk, v, ldv, o, ldo, B, Npos, d, dv, st);
 }

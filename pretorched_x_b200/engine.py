@@ -7,7 +7,7 @@ layout; nothing in them computes.  This file holds the block bodies:
 * ``conv_bn_act``        Conv3d/Conv2d/SpatioTemporalConv + BatchNorm (+residual) (+ReLU) -> one or two
                          implicit-GEMM launches                      (resnet3D.py:91-106, 125-143)
 * ``run_basic/run_bottleneck``  residual blocks incl. type-A/B shortcuts (resnet3D.py:65-74, 176-185)
-* ``run_nonlocal``       theta/phi/g projections, fused attention, W+BN+residual (nonlocalnet.py:143-166)
+* ``run_nonlocal``       fused theta|phi|g projection, fused attention, W+BN+residual (nonlocalnet.py:143-166)
 * ``run_stem`` / ``run_head``   stem conv+BN+ReLU+maxpool, global average + last_linear
                          (torchvision_models.py:448-464)
 
@@ -148,32 +148,20 @@ def run_nonlocal(nl, a, simt=False):
     w_conv, w_bn = (Wseq[0], Wseq[1]) if isinstance(Wseq, nn.Sequential) else (Wseq, None)
 
     def build():
-        # theta|phi concatenated along the output dim -> one projection GEMM for both
-        wqk = torch.zeros((2 * d, a.ld), dtype=torch.float16, device=dev)
-        wqk[:d, :C] = _conv1x1_matrix(nl.theta).to(torch.float16)
-        wqk[d:, :C] = _conv1x1_matrix(nl.phi).to(torch.float16)
-        bqk = torch.cat([nl.theta.bias.detach(), nl.phi.bias.detach()]).float().contiguous()
-        wg = torch.zeros((d, a.ld), dtype=torch.float16, device=dev)
-        wg[:, :C] = _conv1x1_matrix(nl.g).to(torch.float16)
-        bg = nl.g.bias.detach().float().contiguous()
-        ones_qk = torch.ones(2 * d, dtype=torch.float32, device=dev)
-        ones_g = torch.ones(d, dtype=torch.float32, device=dev)
-        return wqk, bqk, ones_qk, wg, bg, ones_g
+        # theta | phi | g concatenated along the output dim -> ONE projection GEMM
+        w = torch.zeros((3 * d, a.ld), dtype=torch.float16, device=dev)
+        w[:d, :C] = _conv1x1_matrix(nl.theta).to(torch.float16)
+        w[d:2 * d, :C] = _conv1x1_matrix(nl.phi).to(torch.float16)
+        w[2 * d:, :C] = _conv1x1_matrix(nl.g).to(torch.float16)
+        b = torch.cat([nl.theta.bias.detach(), nl.phi.bias.detach(), nl.g.bias.detach()]).float().contiguous()
+        ones = torch.ones(3 * d, dtype=torch.float32, device=dev)
+        return w, b, ones
 
     sig = _sig(nl.theta.weight, nl.theta.bias, nl.phi.weight, nl.phi.bias, nl.g.weight, nl.g.bias) + (a.ld,)
-    wqk, bqk, ones_qk, wg, bg, ones_g = _cached(nl, "proj", sig, build)
+    wqkv, bqkv, ones = _cached(nl, "proj", sig, build)
 
-    M = a.M
-    Npos = a.positions
-    # theta|phi: [M][2d]
-    qk = ops.gemm(a.data, wqk, ones_qk, bqk, M, 2 * d, a.ld)
-    # g transposed (swap-AB): Vt[dv][M] = Wg . x^T, bias per row -> keys become the contiguous (K) dim
-    Mp = ops._round_up(M, 8)
-    vt = torch.empty((d, Mp), dtype=torch.float16, device=dev)
-    if Mp != M:
-        vt.zero_()
-    ops.gemm(wg, a.data, ones_g, bg, d, M, a.ld, per_row=True, out=vt)
-    y = ops.nonlocal_attention(qk, d, vt, d, a.N, Npos)
+    qkv = ops.gemm(a.data, wqkv, ones, bqkv, a.M, 3 * d, a.ld)          # [M][3d]: theta | phi | g
+    y = ops.nonlocal_attention(qkv, d, d, a.N, a.positions)
     ya = Act(y, a.N, a.T, a.H, a.W, d)
     # W (1x1x1 conv with bias) + BN + residual x, no ReLU
     return conv_bn_act(w_conv, w_bn, ya, residual=a, relu=False, simt=simt)

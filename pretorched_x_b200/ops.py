@@ -320,18 +320,19 @@ def gather_frames(x3d, idx_dev):
 # ---------------------------------------------------------------------------------------------
 # non-local attention
 # ---------------------------------------------------------------------------------------------
-def nonlocal_attention(qk, d, vt, dv, B, Npos):
+def nonlocal_attention(qkv, d, dv, B, Npos):
     """softmax(theta^T phi) . g  (nonlocalnet.py:150-160).
 
-    qk: fp16 [B*Npos][>=2d] with theta in columns [0,d) and phi in [d,2d); vt: fp16 [dv][B*Npos pitch].
-    Returns fp16 [B*Npos][dv].
+    qkv: fp16 [B*Npos][>= 2d + dv] with theta in columns [0,d), phi in [d,2d) and g in [2d,2d+dv) -- the output of
+    one fused projection GEMM.  Returns fp16 [B*Npos][dv].
     """
-    o = torch.empty((B * Npos, _round_up(dv, 8)), dtype=torch.float16, device=qk.device)
-    q = qk
-    k = qk[:, d:]
+    o = torch.empty((B * Npos, _round_up(dv, 8)), dtype=torch.float16, device=qkv.device)
+    esz = qkv.element_size()
+    base, ld = qkv.data_ptr(), qkv.stride(0)
     with _timed("attention", "attention B=%d N=%d d=%d dv=%d" % (B, Npos, d, dv), 2.0 * B * Npos * Npos * (d + dv),
                 2.0 * B * Npos * (2 * d + 2 * dv)):
-        _lib.check(_lib.load().b2_nonlocal_attention(_ptr(q), q.stride(0), ctypes.c_void_p(k.data_ptr()), k.stride(0),
-                                                    _ptr(vt), vt.stride(0), _ptr(o), o.stride(0), B, Npos, d, dv, _stream()),
+        _lib.check(_lib.load().b2_nonlocal_attention(ctypes.c_void_p(base), ld, ctypes.c_void_p(base + d * esz), ld,
+                                                    ctypes.c_void_p(base + 2 * d * esz), ld, _ptr(o), o.stride(0),
+                                                    B, Npos, d, dv, _stream()),
                    "b2_nonlocal_attention")
     return o

@@ -128,7 +128,7 @@ def test_gemm_matches_oracle(dev, case):
         assert float(got[:, N:].abs().max()) == 0.0
 
 
-ATT_CASES = [("one_block", 1, 128, 64, 64), ("ragged_keys_and_queries", 2, 200, 128, 128),
+ATT_CASES = [("one_block", 1, 128, 64, 64), ("ragged_keys_and_queries", 2, 200, 128, 128), ("odd_positions", 3, 99, 64, 128),
              ("layer2_like", 1, 576, 256, 256), ("layer3_like_dv_split", 2, 72, 512, 512), ("n_lt_64", 1, 16, 64, 64)]
 
 
@@ -140,10 +140,8 @@ def test_nonlocal_attention_matches_oracle(dev, case):
     q, k = h(torch.randn(B, Npos, d, generator=g) * 0.3), h(torch.randn(B, Npos, d, generator=g) * 0.3)
     v = h(torch.randn(B, Npos, dv, generator=g))
     ref = torch.softmax(q @ k.transpose(1, 2), dim=-1) @ v            # nonlocalnet.py:156-160, unscaled
-    qk = torch.cat([q, k], dim=2).reshape(B * Npos, 2 * d).half().to(dev).contiguous()
-    vt = torch.zeros(dv, ops._round_up(B * Npos, 8), dtype=torch.float16, device=dev)
-    vt[:, :B * Npos] = v.reshape(B * Npos, dv).t().half().to(dev)
-    o = ops.nonlocal_attention(qk, d, vt, dv, B, Npos)
+    qkv = torch.cat([q, k, v], dim=2).reshape(B * Npos, 2 * d + dv).half().to(dev).contiguous()
+    o = ops.nonlocal_attention(qkv, d, dv, B, Npos)
     assert rel(o[:, :dv].float().view(B, Npos, dv), ref) <= 4e-3
 
 
@@ -152,9 +150,9 @@ def test_attention_rows_are_convex_combinations(dev):
     from pretorched_x_b200 import ops
     B, Npos, d, dv = 2, 1000, 64, 64
     g = torch.Generator().manual_seed(5)
-    qk = (torch.randn(B * Npos, 2 * d, generator=g) * 0.5).half().to(dev)
-    vt = torch.ones(dv, B * Npos, dtype=torch.float16, device=dev)
-    o = ops.nonlocal_attention(qk, d, vt, dv, B, Npos)
+    qkv = (torch.randn(B * Npos, 2 * d + dv, generator=g) * 0.5).half()
+    qkv[:, 2 * d:] = 1.0
+    o = ops.nonlocal_attention(qkv.to(dev), d, dv, B, Npos)
     assert (o[:, :dv].float() - 1.0).abs().max().item() <= 2e-3
 
 

@@ -197,11 +197,8 @@ def run_group(group):
             k = h(torch.randn(B, Npos, d, generator=g) * scale)
             v = h(torch.randn(B, Npos, dv, generator=g))
             ref = torch.softmax(q @ k.transpose(1, 2), dim=-1) @ v
-            qk = torch.cat([q, k], dim=2).reshape(B * Npos, 2 * d).half().to(dev).contiguous()
-            Mp = ops._round_up(B * Npos, 8)
-            vt = torch.zeros(dv, Mp, dtype=torch.float16, device=dev)
-            vt[:, :B * Npos] = v.reshape(B * Npos, dv).t().half().to(dev)
-            o = ops.nonlocal_attention(qk, d, vt, dv, B, Npos)
+            qkv = torch.cat([q, k, v], dim=2).reshape(B * Npos, 2 * d + dv).half().to(dev).contiguous()
+            o = ops.nonlocal_attention(qkv, d, dv, B, Npos)
             torch.cuda.synchronize()
             record(name, rel_err(o[:, :dv].float().view(B, Npos, dv), ref), tol)
 
