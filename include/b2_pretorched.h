@@ -33,7 +33,7 @@ extern "C" {
 #define B2_ERR_UNSUPPORTED (-3) /* valid request the engine does not implement */
 
 #define B2_CONV_AUTO 0  /* generic implicit GEMM: x has channel pitch C (multiple of 8)            */
-#define B2_CONV_STEM7 1 /* kw == 7, sw == 2, pw == 3, Cin <= 4 stored as NDHWC4 (stem convolutions) */
+#define B2_CONV_STEM7 1 /* kw == 7, strides (1,2,2), pw == 3, Cin <= 4 stored as NDHWC4 (stem convs)  */
 
 int b2_version(void);
 const char* b2_last_error(void);
@@ -74,16 +74,16 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream);
 int b2_conv_ndhwc_fprop_simt(const b2_conv_args* a, void* stream);
 
 /* fp32 [K][Cin][kt][kh][kw] (nn.Conv3d.weight layout, resnet3D.py:60,115-119) -> fp16 packed
- * [K][taps][C] with zero padding of channels [Cin, C).  mode B2_CONV_STEM7: [K][kt*kh (padded to even)]
- * [8 px][4 ch] with px 0 and ch >= Cin zero (see DESIGN.md "stem"). */
+ * [K][taps][C] with zero padding of channels [Cin, C).  mode B2_CONV_STEM7: a pre-laid-out shared-memory image
+ * [ntile][kt][kh taps, even dh descending then odd dh descending][BN x 32] (see csrc/b2_stemconv.cuh). */
 size_t b2_pack_conv_weight_elems(int K, int Cin, int kt, int kh, int kw, int C, int mode);
 int b2_pack_conv_weight(const float* w_oidhw, void* w_packed, int K, int Cin, int kt, int kh, int kw, int C,
                         int mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense layer / 1x1x1 convolution as a plain GEMM:  D[M][N] = act(scale * (A[M][Kd] . B[N][Kd]^T) + shift
- * + residual).  scale/shift index the N dimension, or the M dimension when per_row != 0 (used to
- * produce the transposed g projection for the non-local block).  Replaces nn.Linear at
+ * + residual).  scale/shift index the N dimension, or the M dimension when per_row != 0 (swap-AB use:
+ * D^T = B . A^T with the affine following the rows).  Replaces nn.Linear at
  * resnet3D.py:162 / torchvision_models.py:460-464 (head), trn.py:39-49 (Relation MLP).
  * ------------------------------------------------------------------------------------------- */
 typedef struct b2_gemm_args {
