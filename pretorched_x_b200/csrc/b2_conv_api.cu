@@ -40,6 +40,16 @@ int require_sm100() {
   return B2_OK;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 // ------------------------------------------------------------------------------------------
 // tensor maps
 // ------------------------------------------------------------------------------------------
@@ -126,6 +136,7 @@ static int launch_slab(const b2_conv_args* a, int MT, int R, cudaStream_t stream
   p.R = R;
   p.slab_bytes = ((R * p.PW * 128) + 1023) / 1024 * 1024;
   p.MT = MT;
+  p.nacc = (MT * BN <= 256) ? 2 : 1;
   p.P = a->H * p.PW;
   p.Ncols = a->K;
   p.scale = a->scale; p.shift = a->shift;
@@ -134,7 +145,12 @@ static int launch_slab(const b2_conv_args* a, int MT, int R, cudaStream_t stream
   p.y = reinterpret_cast<__half*>(a->y);
   p.ldy = a->ldy;
   p.relu = a->relu;
-  const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * BN * 128 + 128 + 2 * BN * 4 + 1024;
+  p.tiles_n = (a->ldy + BN - 1) / BN;
+  p.tiles_q = (p.P + MT * 128 - 1) / (MT * 128);
+  const long long items = (long long)p.tiles_n * p.tiles_q * a->N * a->T;
+  if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "slab problem too large");
+  p.items_total = (int)items;
+  const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * BN * 128 + 128 + 2 * kSlabAffMax * 4 + 1024;
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(slabconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -148,7 +164,7 @@ static int launch_slab(const b2_conv_args* a, int MT, int R, cudaStream_t stream
     return rc;
   if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)taps * a->C, (uint64_t)a->K, (uint64_t)taps * a->C, 64, BN, true)) != B2_OK)
     return rc;
-  dim3 grid((a->ldy + BN - 1) / BN, (p.P + MT * 128 - 1) / (MT * 128), a->N * a->T);
+  const int grid = p.items_total < sm_count() ? p.items_total : sm_count();
   slabconv_kernel<BN><<<grid, kSlabThreads, smem_bytes, stream>>>(tmX, tmB, p);
   B2_CHECK_LAUNCH("slabconv_kernel");
   return B2_OK;
@@ -172,7 +188,7 @@ static int try_slab(const b2_conv_args* a, cudaStream_t stream) {
   for (int MT = 512 / BN > 4 ? 4 : 512 / BN; MT >= 1; MT >>= 1) {
     const int R = slab_rows(MT, PW, reach, P);
     if (R > 256) continue;
-    const long long smem = 2ll * (((long long)R * PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * BN * 128 + 128 + 2 * BN * 4 + 1024;
+    const long long smem = 2ll * (((long long)R * PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * BN * 128 + 128 + 2 * kSlabAffMax * 4 + 1024;
     if (smem > 227 * 1024) continue;
     if (best_mt == 0) { best_mt = MT; best_R = R; }
     const long long ctas = (long long)ntn * ((P + MT * 128 - 1) / (MT * 128)) * planes;
@@ -184,15 +200,6 @@ static int try_slab(const b2_conv_args* a, cudaStream_t stream) {
   return rc == B2_OK ? 1 : rc;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
 
 // ------------------------------------------------------------------------------------------
 // stem convolution launcher (Toeplitz-descriptor kernel)

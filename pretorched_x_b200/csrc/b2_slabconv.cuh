@@ -10,9 +10,11 @@
 // swizzle is a function of absolute smem address bits, verified by tools/probe_umma.py).  All kh*kw in-plane
 // taps therefore run out of one slab: L2 traffic for activations drops by ~kh*kw.
 //
-// Output positions are enumerated in *padded-row* coordinates q = h*(W+2pw) + w' of one (n,t) plane; a CTA owns
-// MT consecutive 128-position M tiles (MT accumulators in TMEM share every weight tile) and discards the
-// positions that fall on halo columns.
+// Output positions are enumerated in *padded-row* coordinates q = h*(W+2pw) + w' of one (n,t) plane; a work item
+// is MT consecutive 128-position M tiles (MT accumulators in TMEM share every weight tile) x one N tile, and the
+// positions that fall on halo columns are discarded.  CTAs are persistent (one per SM): the producer runs ahead
+// into the next item's slabs, and when MT*BN <= 256 two accumulator sets let the epilogue of item i overlap the
+// MMAs of item i+1.
 #pragma once
 
 #include "b2_ptx.cuh"
@@ -30,9 +32,11 @@ struct SlabParams {
   int PW;                  // W + 2*pw: padded row length
   int R;                   // slab rows (TMA box height)
   int slab_bytes;          // R * PW * 128, rounded up to 1024
-  int MT;                  // M tiles per CTA (MT * BN <= 512)
+  int MT;                  // M tiles per work item (MT * BN <= 512)
+  int nacc;                // accumulator sets in TMEM: 2 when MT * BN <= 256 (epilogue overlaps the next item)
   int P;                   // H * PW: padded positions per plane
   int Ncols;               // logical output channels
+  int tiles_n, tiles_q, items_total;
   const float* scale;
   const float* shift;
   const __half* residual;  // nullable, dense [M][ldr]
@@ -41,6 +45,32 @@ struct SlabParams {
   int ldy;
   int relu;
 };
+
+constexpr int kSlabAffMax = 512;   // scale/shift entries kept in smem (all slab layers have Cout <= 512)
+
+struct SlabItem {
+  int n0, q0, plane, r_lo, dt_lo, n_dt, n_slabs, mt_valid;
+};
+__device__ __forceinline__ SlabItem slab_item(const SlabParams& p, int item, int BN) {
+  SlabItem w;
+  const int tn = item % p.tiles_n; item /= p.tiles_n;
+  const int tq = item % p.tiles_q;
+  w.plane = item / p.tiles_q;
+  w.n0 = tn * BN;
+  w.q0 = tq * (p.MT * 128);
+  const int t = w.plane % p.T;
+  const int pt = (p.kt - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
+  const int reach = ph * p.PW + pw;
+  const int lo = w.q0 - reach;                      // lowest padded position any tap of this item touches
+  w.r_lo = (lo >= 0) ? lo / p.PW : -((-lo + p.PW - 1) / p.PW);
+  w.dt_lo = max(0, pt - t);                         // temporal taps that stay inside the clip
+  const int dt_hi = min(p.kt - 1, p.T - 1 - t + pt);
+  w.n_dt = dt_hi - w.dt_lo + 1;
+  w.n_slabs = p.cchunks * w.n_dt;
+  const int mv = (p.P - w.q0 + 127) / 128;          // M tiles that contain at least one position of the plane
+  w.mt_valid = mv > p.MT ? p.MT : mv;
+  return w;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kSlabThreads, 1)
@@ -57,43 +87,29 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
   uint64_t* slab_empty = slab_full + kSlabSStages;
   uint64_t* w_full = slab_empty + kSlabSStages;
   uint64_t* w_empty = w_full + kSlabWStages;
-  uint64_t* tmem_full = w_empty + kSlabWStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* acc_full = w_empty + kSlabWStages;      // [2]
+  uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_scale = reinterpret_cast<float*>(tail + 128);
-  float* s_shift = s_scale + BN;
+  float* s_shift = s_scale + kSlabAffMax;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * BN;
-  const int q0 = blockIdx.y * (p.MT * 128);          // first padded position of this CTA within the plane
-  const int plane = blockIdx.z;                      // n*T + t
-  const int t = plane % p.T;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int pt = (p.kt - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
-  // slab row origin: the lowest input row any tap of any tile of this CTA touches
-  const int reach = ph * p.PW + pw;
-  int r_lo = (q0 - reach);
-  r_lo = (r_lo >= 0) ? r_lo / p.PW : -((-r_lo + p.PW - 1) / p.PW);
-  // temporal taps that stay inside the clip
-  const int dt_lo = max(0, pt - t), dt_hi = min(p.kt - 1, p.T - 1 - t + pt);
-  const int n_dt = dt_hi - dt_lo + 1;
   const int taps_hw = p.kh * p.kw;
-  const int n_slabs = p.cchunks * n_dt;
-  // M tiles of this CTA that contain at least one position of the plane
-  int mt_valid = (p.P - q0 + 127) / 128;
-  mt_valid = mt_valid > p.MT ? p.MT : mt_valid;
+  const int acc_cols = p.MT * BN;
 
   if (tid == 128) {
     for (int s = 0; s < kSlabSStages; ++s) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
     for (int s = 0; s < kSlabWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  for (int i = tid; i < BN; i += kSlabThreads) {
-    const int c = n0 + i;
-    s_scale[i] = (c < p.Ncols) ? __ldg(&p.scale[c]) : 0.f;
-    s_shift[i] = (c < p.Ncols) ? __ldg(&p.shift[c]) : 0.f;
+  for (int i = tid; i < kSlabAffMax; i += kSlabThreads) {
+    s_scale[i] = (i < p.Ncols) ? __ldg(&p.scale[i]) : 0.f;
+    s_shift[i] = (i < p.Ncols) ? __ldg(&p.shift[i]) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -102,33 +118,49 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
 
   if (warp == 4) {
     // ================================ TMA producer ======================================
-    int wit = 0;
-    auto load_slab = [&](int si) {
-      const int cc = si / n_dt, dt = dt_lo + (si - cc * n_dt);
-      const int s = si % kSlabSStages;
-      mbar_wait(&slab_empty[s], ((si / kSlabSStages) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&slab_full[s], static_cast<uint32_t>(p.R * p.PW * 128));
-        tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64, -pw, r_lo, plane + dt - pt);
-      }
-      __syncwarp();
-    };
-    load_slab(0);
-    // The next slab is requested once the weight ring (kSlabWStages deep) guarantees the MMA thread has
-    // already retired the slab that occupied the target slot, so this wait never stalls weight issue.
-    const int pf = min(kSlabWStages, taps_hw - 1);
-    for (int si = 0; si < n_slabs; ++si) {
-      const int cc = si / n_dt, dt = dt_lo + (si - cc * n_dt);
-      for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
-        if (thw == pf && si + 1 < n_slabs) load_slab(si + 1);
-        const int ws = wit % kSlabWStages;
-        mbar_wait(&w_empty[ws], ((wit / kSlabWStages) & 1) ^ 1);
-        const int tap = dt * taps_hw + thw;
+    // Walks (item, slab) pairs; the slab after the current one -- possibly the first slab of the NEXT item -- is
+    // requested once the weight ring (kSlabWStages deep) guarantees the MMA warp has retired the slab that
+    // occupied the target slot, so that wait never stalls weight issue.
+    int wit = 0, sg = 0;                     // global weight-tile / slab counters (ring phases persist across items)
+    int item = blockIdx.x;
+    if (item < p.items_total) {
+      SlabItem cur = slab_item(p, item, BN);
+      int nxt_item = item, nxt_si = 0;       // (item, slab) of the next slab to load
+      SlabItem nxt = cur;
+      auto load_next = [&]() {
+        const int cc = nxt_si / nxt.n_dt, dt = nxt.dt_lo + (nxt_si - cc * nxt.n_dt);
+        const int s = sg % kSlabSStages;
+        mbar_wait(&slab_empty[s], ((sg / kSlabSStages) & 1) ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&w_full[ws], kWBytes);
-          tma_load_2d(w_base + ws * kWBytes, &tmB, &w_full[ws], tap * p.C + cc * 64, n0);
+          mbar_expect_tx(&slab_full[s], static_cast<uint32_t>(p.R * p.PW * 128));
+          tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64, -pw, nxt.r_lo, nxt.plane + dt - pt);
         }
         __syncwarp();
+        ++sg;
+        if (++nxt_si == nxt.n_slabs) {       // advance to the first slab of the following item
+          nxt_si = 0;
+          nxt_item += gridDim.x;
+          if (nxt_item < p.items_total) nxt = slab_item(p, nxt_item, BN);
+        }
+      };
+      load_next();
+      const int pf = min(kSlabWStages, taps_hw - 1);
+      for (; item < p.items_total; item += gridDim.x) {
+        cur = slab_item(p, item, BN);
+        for (int si = 0; si < cur.n_slabs; ++si) {
+          const int cc = si / cur.n_dt, dt = cur.dt_lo + (si - cc * cur.n_dt);
+          for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
+            if (thw == pf && nxt_item < p.items_total) load_next();
+            const int ws = wit % kSlabWStages;
+            mbar_wait(&w_empty[ws], ((wit / kSlabWStages) & 1) ^ 1);
+            const int tap = dt * taps_hw + thw;
+            if (elect_one()) {
+              mbar_expect_tx(&w_full[ws], kWBytes);
+              tma_load_2d(w_base + ws * kWBytes, &tmB, &w_full[ws], tap * p.C + cc * 64, cur.n0);
+            }
+            __syncwarp();
+          }
+        }
       }
     }
   } else if (warp == 5) {
@@ -137,78 +169,101 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
     constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
     const uint32_t tm = warp_uniform(tmem_base);
     const uint32_t slab0 = smem_u32(slab_base), w0s = smem_u32(w_base);
-    int wit = 0;
-    for (int si = 0; si < n_slabs; ++si) {
-      const int s = si % kSlabSStages;
-      mbar_wait(&slab_full[s], (si / kSlabSStages) & 1);
-      const uint32_t slab_addr = slab0 + s * p.slab_bytes;
-      for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
-        const int dh = thw / p.kw, dw = thw - dh * p.kw;
-        const int ws = wit % kSlabWStages;
-        mbar_wait(&w_full[ws], (wit / kSlabWStages) & 1);
-        tc_fence_after();
-        // slab-local pixel index of padded position q0 under tap (dh, dw)
-        const int pix0 = q0 + (dh - ph) * p.PW + (dw - pw) - r_lo * p.PW;
-        const uint32_t b_lo = sw128_desc_lo(w0s + ws * kWBytes);
-        const uint32_t a_lo0 = sw128_desc_lo(slab_addr + static_cast<uint32_t>(pix0) * 128u);
-        if (elect_one()) {
-          for (int j = 0; j < mt_valid; ++j) {
-            const uint32_t a_lo = a_lo0 + j * (128u * 128u >> 4);
-            const uint32_t d = tm + j * BN;
-            umma_f16(d, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc, wit != 0 ? 1u : 0u);
-            umma_f16(d, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc, 1u);
-            umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
-            umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
+    int wit = 0, sg = 0, lt = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
+      const SlabItem w = slab_item(p, item, BN);
+      const int ab = lt % p.nacc;
+      mbar_wait(&acc_empty[ab], (((lt / p.nacc) & 1) ^ 1));      // epilogue drained this accumulator set
+      tc_fence_after();
+      const uint32_t acc = tm + ab * acc_cols;
+      int wl = 0;                                                // weight step within the item
+      for (int si = 0; si < w.n_slabs; ++si, ++sg) {
+        const int s = sg % kSlabSStages;
+        mbar_wait(&slab_full[s], (sg / kSlabSStages) & 1);
+        const uint32_t slab_addr = slab0 + s * p.slab_bytes;
+        for (int thw = 0; thw < taps_hw; ++thw, ++wit, ++wl) {
+          const int dh = thw / p.kw, dw = thw - dh * p.kw;
+          const int ws = wit % kSlabWStages;
+          mbar_wait(&w_full[ws], (wit / kSlabWStages) & 1);
+          tc_fence_after();
+          // slab-local pixel index of padded position q0 under tap (dh, dw)
+          const int pix0 = w.q0 + (dh - ph) * p.PW + (dw - pw) - w.r_lo * p.PW;
+          const uint32_t b_lo = sw128_desc_lo(w0s + ws * kWBytes);
+          const uint32_t a_lo0 = sw128_desc_lo(slab_addr + static_cast<uint32_t>(pix0) * 128u);
+          if (elect_one()) {
+            for (int j = 0; j < w.mt_valid; ++j) {
+              const uint32_t a_lo = a_lo0 + j * (128u * 128u >> 4);
+              const uint32_t d = acc + j * BN;
+              umma_f16(d, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc, wl != 0 ? 1u : 0u);
+              umma_f16(d, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc, 1u);
+              umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
+              umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
+            }
+            umma_commit(&w_empty[ws]);
+            if (thw == taps_hw - 1) umma_commit(&slab_empty[s]);
+            if (thw == taps_hw - 1 && si == w.n_slabs - 1) umma_commit(&acc_full[ab]);
           }
-          umma_commit(&w_empty[ws]);
-          if (thw == taps_hw - 1) umma_commit(&slab_empty[s]);
-          if (thw == taps_hw - 1 && si == n_slabs - 1) umma_commit(tmem_full);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
     // ================================ epilogue ==========================================
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const int ncols_here = min(BN, p.ldy - n0);     // columns of this tile that exist in y (incl. zero padding)
-    for (int j = 0; j < mt_valid; ++j) {
-      const int q = q0 + j * 128 + tid;
-      const int h = q / p.PW, wp = q - h * p.PW;
-      const bool ok = (q < p.P) && (wp >= pw) && (wp < pw + p.W);
-      const size_t row = (static_cast<size_t>(plane) * p.H + h) * p.W + (wp - pw);
-      __half* yrow = p.y + row * p.ldy + n0;
-      const __half* rrow = p.residual ? p.residual + row * p.ldr + n0 : nullptr;
+    int lt = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
+      const SlabItem w = slab_item(p, item, BN);
+      const int ab = lt % p.nacc;
+      mbar_wait(&acc_full[ab], (lt / p.nacc) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + lane_off + ab * acc_cols;
+      const int ncols_here = min(BN, p.ldy - w.n0);     // columns of this tile that exist in y (incl. zero padding)
+      const bool aff_smem = (w.n0 + BN) <= kSlabAffMax;
+      for (int j = 0; j < w.mt_valid; ++j) {
+        const int q = w.q0 + j * 128 + tid;
+        const int h = q / p.PW, wp = q - h * p.PW;
+        const bool ok = (q < p.P) && (wp >= pw) && (wp < pw + p.W);
+        const size_t row = (static_cast<size_t>(w.plane) * p.H + h) * p.W + (wp - pw);
+        __half* yrow = p.y + row * p.ldy + w.n0;
+        const __half* rrow = p.residual ? p.residual + row * p.ldr + w.n0 : nullptr;
 #pragma unroll 1
-      for (int jc = 0; jc < BN / 32; ++jc) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + j * BN + jc * 32, v);     // warp-collective: outside the `ok` branch
-        tmem_ld_wait();
-        if (ok) {
+        for (int jc = 0; jc < BN / 32; ++jc) {
+          uint32_t v[32];
+          tmem_ld32(acc + j * BN + jc * 32, v);          // warp-collective: outside the `ok` branch
+          tmem_ld_wait();
+          if (ok) {
 #pragma unroll
-          for (int c8 = 0; c8 < 4; ++c8) {
-            const int col = jc * 32 + c8 * 8;
-            if (col < ncols_here) {
-              uint4 rv = make_uint4(0, 0, 0, 0);
-              if (rrow) rv = __ldg(reinterpret_cast<const uint4*>(rrow + col));
-              const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-              uint32_t o[4];
+            for (int c8 = 0; c8 < 4; ++c8) {
+              const int col = jc * 32 + c8 * 8;
+              if (col < ncols_here) {
+                uint4 rv = make_uint4(0, 0, 0, 0);
+                if (rrow) rv = __ldg(reinterpret_cast<const uint4*>(rrow + col));
+                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+                uint32_t o[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int ci = col + e * 2;
-                float a0 = __uint_as_float(v[c8 * 8 + e * 2]) * s_scale[ci] + s_shift[ci];
-                float a1 = __uint_as_float(v[c8 * 8 + e * 2 + 1]) * s_scale[ci + 1] + s_shift[ci + 1];
-                const float2 rf = unpack_half2(rr[e]);
-                a0 += rf.x; a1 += rf.y;
-                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                o[e] = pack_half2(a0, a1);
+                for (int e = 0; e < 4; ++e) {
+                  const int ci = w.n0 + col + e * 2;
+                  float sc0, sc1, sh0, sh1;
+                  if (aff_smem) { sc0 = s_scale[ci]; sc1 = s_scale[ci + 1]; sh0 = s_shift[ci]; sh1 = s_shift[ci + 1]; }
+                  else {
+                    sc0 = ci < p.Ncols ? __ldg(&p.scale[ci]) : 0.f; sc1 = ci + 1 < p.Ncols ? __ldg(&p.scale[ci + 1]) : 0.f;
+                    sh0 = ci < p.Ncols ? __ldg(&p.shift[ci]) : 0.f; sh1 = ci + 1 < p.Ncols ? __ldg(&p.shift[ci + 1]) : 0.f;
+                  }
+                  float a0 = __uint_as_float(v[c8 * 8 + e * 2]) * sc0 + sh0;
+                  float a1 = __uint_as_float(v[c8 * 8 + e * 2 + 1]) * sc1 + sh1;
+                  const float2 rf = unpack_half2(rr[e]);
+                  a0 += rf.x; a1 += rf.y;
+                  if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                  o[e] = pack_half2(a0, a1);
+                }
+                *reinterpret_cast<uint4*>(yrow + col) = make_uint4(o[0], o[1], o[2], o[3]);
               }
-              *reinterpret_cast<uint4*>(yrow + col) = make_uint4(o[0], o[1], o[2], o[3]);
             }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
     }
   }
 
