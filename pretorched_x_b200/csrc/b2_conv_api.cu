@@ -150,7 +150,7 @@ static int launch_slab(const b2_conv_args* a, int MT, int R, cudaStream_t stream
   const long long items = (long long)p.tiles_n * p.tiles_q * a->N * a->T;
   if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "slab problem too large");
   p.items_total = (int)items;
-  const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * BN * 128 + 128 + 2 * kSlabAffMax * 4 + 1024;
+  const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * BN * 128 + 256 + 2 * kSlabAffMax * 4 + 1024;
   static int attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(slabconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -188,7 +188,7 @@ static int try_slab(const b2_conv_args* a, cudaStream_t stream) {
   for (int MT = 512 / BN > 4 ? 4 : 512 / BN; MT >= 1; MT >>= 1) {
     const int R = slab_rows(MT, PW, reach, P);
     if (R > 256) continue;
-    const long long smem = 2ll * (((long long)R * PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * BN * 128 + 128 + 2 * kSlabAffMax * 4 + 1024;
+    const long long smem = 2ll * (((long long)R * PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * BN * 128 + 256 + 2 * kSlabAffMax * 4 + 1024;
     if (smem > 227 * 1024) continue;
     if (best_mt == 0) { best_mt = MT; best_R = R; }
     const long long ctas = (long long)ntn * ((P + MT * 128 - 1) / (MT * 128)) * planes;

@@ -90,7 +90,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
   uint64_t* acc_full = w_empty + kSlabWStages;      // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_scale = reinterpret_cast<float*>(tail + 128);
+  float* s_scale = reinterpret_cast<float*>(tail + 256);     // barriers + TMEM slot occupy the first 132 bytes
   float* s_shift = s_scale + kSlabAffMax;
 
   const int tid = threadIdx.x, warp = tid >> 5;
