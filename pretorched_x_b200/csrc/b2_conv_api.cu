@@ -92,14 +92,17 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 }
 
 int make_tmap_ndhwc_slab(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t planes,
-                         uint32_t box_w, uint32_t box_h) {
+                         uint32_t box_w, uint32_t box_h, uint32_t stride_hw) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(B2_ERR_INVALID, "tensor base not 16-byte aligned");
   cuuint64_t dims[4] = {C, W, H, planes};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {64, box_w, box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // with element strides the box is given in traversed (full-resolution) elements; smem receives every
+  // stride_hw-th pixel / row, i.e. box_w x box_h dense pixels
+  cuuint32_t box[4] = {64, stride_hw * (box_w - 1) + 1, stride_hw * (box_h - 1) + 1, 1};
+  cuuint32_t estr[4] = {1, stride_hw, stride_hw, 1};
+  if (box[1] > 256 || box[2] > 256) return set_error(B2_ERR_UNSUPPORTED, "slab box %ux%u exceeds the TMA box limit", box[1], box[2]);
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -125,19 +128,66 @@ static int slab_rows(int MT, int PW, int reach, int P) {
   return R;
 }
 
+// Fills the geometry part of SlabParams (sub-image / tap tables).  Returns false when the convolution is not of a
+// shape the slab kernel handles.
+static bool slab_geometry(const b2_conv_args* a, SlabParams* p) {
+  if (a->mode != B2_CONV_AUTO || a->out_f32) return false;
+  if ((a->kt & 1) == 0 || (a->kh & 1) == 0 || (a->kw & 1) == 0) return false;
+  if (a->pt != (a->kt - 1) / 2 || a->ph != (a->kh - 1) / 2 || a->pw != (a->kw - 1) / 2) return false;
+  if (a->sh != a->sw || (a->sh != 1 && a->sh != 2) || (a->st != 1 && a->st != 2)) return false;
+  if (a->kh * a->kw > kSlabMaxTaps) return false;
+  const int ss = a->sh;
+  if (ss == 1 && a->st == 1 && a->kt * a->kh * a->kw == 1) return false;      // plain GEMM: persistent GEMM kernel
+  memset(p, 0, sizeof(*p));
+  p->T = a->T; p->C = a->C;
+  p->To = (a->T + 2 * a->pt - a->kt) / a->st + 1;
+  p->Ho = (a->H + 2 * a->ph - a->kh) / ss + 1;
+  p->Wo = (a->W + 2 * a->pw - a->kw) / ss + 1;
+  p->kt = a->kt; p->khw = a->kh * a->kw; p->st = a->st; p->ss = ss; p->pt = a->pt;
+  p->cchunks = (a->C + 63) / 64;
+  // tap (dh, dw) reads input (ss*ho + dh - ph, ss*wo + dw - pw) = phase (rh, rw), sub-image pixel (ho + oi, wo + oj)
+  int oi[8], rh[8], oj[8], rw[8];
+  int min_oj = 0, max_oj = 0;
+  for (int d = 0; d < a->kh; ++d) { int v = d - a->ph; rh[d] = ((v % ss) + ss) % ss; oi[d] = (v - rh[d]) / ss; }
+  for (int d = 0; d < a->kw; ++d) {
+    int v = d - a->pw; rw[d] = ((v % ss) + ss) % ss; oj[d] = (v - rw[d]) / ss;
+    if (oj[d] < min_oj) min_oj = oj[d];
+    if (oj[d] > max_oj) max_oj = oj[d];
+  }
+  p->halo_l = -min_oj;
+  p->PW = p->Wo + p->halo_l + max_oj;
+  p->P = p->Ho * p->PW;
+  p->n_sub = 0;
+  p->reach = 0;
+  for (int ph_ = 0; ph_ < ss; ++ph_)
+    for (int pw_ = 0; pw_ < ss; ++pw_) {
+      int n = 0;
+      const int sidx = p->n_sub;
+      for (int dh = 0; dh < a->kh; ++dh)
+        for (int dw = 0; dw < a->kw; ++dw)
+          if (rh[dh] == ph_ && rw[dw] == pw_) {
+            const int off = oi[dh] * p->PW + oj[dw];
+            p->sub_off[sidx][n] = (short)off;
+            p->sub_tap[sidx][n] = (unsigned char)(dh * a->kw + dw);
+            if (off > p->reach) p->reach = off;
+            if (-off > p->reach) p->reach = -off;
+            ++n;
+          }
+      if (n == 0) continue;
+      p->sub_ntaps[sidx] = n;
+      p->sub_h0[sidx] = ph_;                               // + ss * r_lo at run time
+      p->sub_w0[sidx] = pw_ - ss * p->halo_l;              // slab column 0 = sub-image column -halo_l
+      ++p->n_sub;
+    }
+  return p->n_sub > 0 && p->PW <= 256;
+}
+
 template <int BN>
-static int launch_slab(const b2_conv_args* a, int MT, int R, cudaStream_t stream) {
-  SlabParams p;
-  memset(&p, 0, sizeof(p));
-  p.T = a->T; p.H = a->H; p.W = a->W; p.C = a->C;
-  p.kt = a->kt; p.kh = a->kh; p.kw = a->kw;
-  p.cchunks = (a->C + 63) / 64;
-  p.PW = a->W + (a->kw - 1);
+static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cudaStream_t stream) {
   p.R = R;
   p.slab_bytes = ((R * p.PW * 128) + 1023) / 1024 * 1024;
   p.MT = MT;
   p.nacc = (MT * BN <= 256) ? 2 : 1;
-  p.P = a->H * p.PW;
   p.Ncols = a->K;
   p.scale = a->scale; p.shift = a->shift;
   p.residual = reinterpret_cast<const __half*>(a->residual);
@@ -147,20 +197,20 @@ static int launch_slab(const b2_conv_args* a, int MT, int R, cudaStream_t stream
   p.relu = a->relu;
   p.tiles_n = (a->ldy + BN - 1) / BN;
   p.tiles_q = (p.P + MT * 128 - 1) / (MT * 128);
-  const long long items = (long long)p.tiles_n * p.tiles_q * a->N * a->T;
+  const long long items = (long long)p.tiles_n * p.tiles_q * a->N * p.To;
   if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "slab problem too large");
   p.items_total = (int)items;
   const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * BN * 128 + 256 + 2 * kSlabAffMax * 4 + 1024;
-  static int attr_bytes = 0;
-  if (smem_bytes > attr_bytes) {
+  static bool attr_set = false;
+  if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(slabconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_bytes = 227 * 1024;
+    attr_set = true;
   }
   CUtensorMap tmX, tmB;
   int rc;
   const int taps = a->kt * a->kh * a->kw;
   if ((rc = make_tmap_ndhwc_slab(&tmX, a->x, (uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N * a->T,
-                                 (uint32_t)p.PW, (uint32_t)R)) != B2_OK)
+                                 (uint32_t)p.PW, (uint32_t)R, (uint32_t)p.ss)) != B2_OK)
     return rc;
   if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)taps * a->C, (uint64_t)a->K, (uint64_t)taps * a->C, 64, BN, true)) != B2_OK)
     return rc;
@@ -172,34 +222,27 @@ static int launch_slab(const b2_conv_args* a, int MT, int R, cudaStream_t stream
 
 // returns 1 when the slab kernel took the convolution, 0 when it does not apply, <0 on error
 static int try_slab(const b2_conv_args* a, cudaStream_t stream) {
-  if (g_conv_algo == 1 || a->mode != B2_CONV_AUTO || a->out_f32) return 0;
-  if (a->st != 1 || a->sh != 1 || a->sw != 1) return 0;
-  if ((a->kt & 1) == 0 || (a->kh & 1) == 0 || (a->kw & 1) == 0) return 0;
-  if (a->pt != (a->kt - 1) / 2 || a->ph != (a->kh - 1) / 2 || a->pw != (a->kw - 1) / 2) return 0;
-  if (a->kt * a->kh * a->kw == 1) return 0;                 // 1x1x1: plain GEMM path
-  const int PW = a->W + a->kw - 1;
-  if (PW > 256) return 0;
+  if (g_conv_algo == 1) return 0;
+  SlabParams p;
+  if (!slab_geometry(a, &p)) return 0;
+  if (g_conv_algo == 2 && p.ss != 1) return 0;              // debug: strided convs through the gather kernel
   const int BN = (a->ldy <= 64) ? 64 : 128;
-  const int P = a->H * PW;
-  const int reach = ((a->kh - 1) / 2) * PW + (a->kw - 1) / 2;
-  const int planes = a->N * a->T;
+  const int planes = a->N * p.To;
   const int ntn = (a->ldy + BN - 1) / BN;
   int best_mt = 0, best_R = 0;
   for (int MT = 512 / BN > 4 ? 4 : 512 / BN; MT >= 1; MT >>= 1) {
-    const int R = slab_rows(MT, PW, reach, P);
-    if (R > 256) continue;
-    const long long smem = 2ll * (((long long)R * PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * BN * 128 + 256 + 2 * kSlabAffMax * 4 + 1024;
+    const int R = slab_rows(MT, p.PW, p.reach, p.P);
+    if (p.ss * (R - 1) + 1 > 256) continue;
+    const long long smem = 2ll * (((long long)R * p.PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * BN * 128 + 256 + 2 * kSlabAffMax * 4 + 1024;
     if (smem > 227 * 1024) continue;
-    if (best_mt == 0) { best_mt = MT; best_R = R; }
-    const long long ctas = (long long)ntn * ((P + MT * 128 - 1) / (MT * 128)) * planes;
+    const long long items = (long long)ntn * ((p.P + MT * 128 - 1) / (MT * 128)) * planes;
     best_mt = MT; best_R = R;
-    if (ctas >= 2 * 148) break;      // enough CTAs for two waves: keep the largest MT that achieves it
+    if (items >= 2 * 148) break;      // enough work items for two rounds per SM: keep the largest MT that achieves it
   }
   if (best_mt == 0) return 0;
-  int rc = (BN == 64) ? launch_slab<64>(a, best_mt, best_R, stream) : launch_slab<128>(a, best_mt, best_R, stream);
+  int rc = (BN == 64) ? launch_slab<64>(a, p, best_mt, best_R, stream) : launch_slab<128>(a, p, best_mt, best_R, stream);
   return rc == B2_OK ? 1 : rc;
 }
-
 
 // ------------------------------------------------------------------------------------------
 // stem convolution launcher (Toeplitz-descriptor kernel)

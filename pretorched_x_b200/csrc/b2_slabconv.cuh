@@ -1,5 +1,5 @@
-// b2_slabconv.cuh -- stride-1 "same"-padded convolution (3x3x3, 1x3x3, 3x1x1, 7x1x1 ...) as an implicit GEMM
-// whose A operand is never re-fetched per filter tap.
+// b2_slabconv.cuh -- "same"-padded convolution (3x3x3, 1x3x3, 3x1x1, 7x1x1 ...; spatial stride 1 or 2) as an
+// implicit GEMM whose A operand is never re-fetched per filter tap.
 //
 // The generic gather kernel (b2_igemm.cuh) moves 16 KB of activations from L2 for every (tap, 64-channel)
 // K block: 27 x for a 3x3x3 filter, which makes those layers L2-bandwidth bound at ~20% of tensor peak.
@@ -9,6 +9,11 @@
 // simply the same tile with its descriptor start address advanced by (dh*(W+2pw) + dw) * 128 bytes (the
 // swizzle is a function of absolute smem address bits, verified by tools/probe_umma.py).  All kh*kw in-plane
 // taps therefore run out of one slab: L2 traffic for activations drops by ~kh*kw.
+//
+// Stride 2: the taps of a 3x3 window fall into four input phases (row parity x column parity).  Each phase is a
+// dense sub-image that TMA delivers directly (elementStrides = 2 along W and H), so a strided convolution is four
+// small slabs per temporal tap, each serving the taps of its phase with the same shifted-descriptor trick
+// (1 + 2 + 2 + 4 taps for 3x3); the 1x1x1 stride-2 shortcut projection is the one-phase, one-tap special case.
 //
 // Output positions are enumerated in *padded-row* coordinates q = h*(W+2pw) + w' of one (n,t) plane; a work item
 // is MT consecutive 128-position M tiles (MT accumulators in TMEM share every weight tile) x one N tile, and the
@@ -25,16 +30,30 @@ constexpr int kSlabThreads = 192;
 constexpr int kSlabWStages = 4;     // weight-tile ring depth
 constexpr int kSlabSStages = 2;     // slab ring depth
 
+constexpr int kSlabMaxSub = 4;      // sub-images (input phases) per temporal tap: 1 for stride 1, up to 4 for stride 2
+constexpr int kSlabMaxTaps = 49;    // in-plane taps per sub-image (7x7 for stride 1)
+
 struct SlabParams {
-  int T, H, W, C;          // input dims per clip, C = channel pitch
-  int kt, kh, kw;          // filter (odd), stride 1, padding (k-1)/2
+  int T, C;                // input frames per clip, channel pitch
+  int To, Ho, Wo;          // output dims per clip
+  int kt, khw;             // temporal taps, in-plane taps (kh*kw)
+  int st, ss;              // temporal / spatial stride
+  int pt;                  // temporal padding
   int cchunks;             // ceil(C / 64)
-  int PW;                  // W + 2*pw: padded row length
-  int R;                   // slab rows (TMA box height)
+  int PW;                  // padded output-row length: Wo + halo_l + halo_r
+  int halo_l;              // halo columns left of output column 0
+  int R;                   // slab rows (sub-image rows per TMA box)
+  // sub-image table: slab row 0 / col 0 of sub-image s is input pixel (ss*r_lo + sub_h0[s], sub_w0[s]); its taps read
+  // slab pixel q + sub_off[s][i] and use in-plane weight tap sub_tap[s][i]
+  int n_sub;
+  int sub_h0[kSlabMaxSub], sub_w0[kSlabMaxSub], sub_ntaps[kSlabMaxSub];
+  short sub_off[kSlabMaxSub][kSlabMaxTaps];
+  unsigned char sub_tap[kSlabMaxSub][kSlabMaxTaps];
+  int reach;               // max |sub_off|
   int slab_bytes;          // R * PW * 128, rounded up to 1024
   int MT;                  // M tiles per work item (MT * BN <= 512)
   int nacc;                // accumulator sets in TMEM: 2 when MT * BN <= 256 (epilogue overlaps the next item)
-  int P;                   // H * PW: padded positions per plane
+  int P;                   // Ho * PW: padded positions per output plane
   int Ncols;               // logical output channels
   int tiles_n, tiles_q, items_total;
   const float* scale;
@@ -49,24 +68,24 @@ struct SlabParams {
 constexpr int kSlabAffMax = 512;   // scale/shift entries kept in smem (all slab layers have Cout <= 512)
 
 struct SlabItem {
-  int n0, q0, plane, r_lo, dt_lo, n_dt, n_slabs, mt_valid;
+  int n0, q0, plane_o, plane_i0, r_lo, dt_lo, n_dt, n_slabs, mt_valid;   // plane_i0: input plane of temporal tap 0
 };
 __device__ __forceinline__ SlabItem slab_item(const SlabParams& p, int item, int BN) {
   SlabItem w;
   const int tn = item % p.tiles_n; item /= p.tiles_n;
   const int tq = item % p.tiles_q;
-  w.plane = item / p.tiles_q;
+  w.plane_o = item / p.tiles_q;
   w.n0 = tn * BN;
   w.q0 = tq * (p.MT * 128);
-  const int t = w.plane % p.T;
-  const int pt = (p.kt - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
-  const int reach = ph * p.PW + pw;
-  const int lo = w.q0 - reach;                      // lowest padded position any tap of this item touches
+  const int to = w.plane_o % p.To, n = w.plane_o / p.To;
+  const int t0 = to * p.st - p.pt;                  // input frame of temporal tap 0
+  w.plane_i0 = n * p.T + t0;
+  const int lo = w.q0 - p.reach;                    // lowest padded position any tap of this item touches
   w.r_lo = (lo >= 0) ? lo / p.PW : -((-lo + p.PW - 1) / p.PW);
-  w.dt_lo = max(0, pt - t);                         // temporal taps that stay inside the clip
-  const int dt_hi = min(p.kt - 1, p.T - 1 - t + pt);
+  w.dt_lo = max(0, -t0);                            // temporal taps that stay inside the clip
+  const int dt_hi = min(p.kt - 1, p.T - 1 - t0);
   w.n_dt = dt_hi - w.dt_lo + 1;
-  w.n_slabs = p.cchunks * w.n_dt;
+  w.n_slabs = p.cchunks * w.n_dt * p.n_sub;
   const int mv = (p.P - w.q0 + 127) / 128;          // M tiles that contain at least one position of the plane
   w.mt_valid = mv > p.MT ? p.MT : mv;
   return w;
@@ -94,8 +113,6 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
   float* s_shift = s_scale + kSlabAffMax;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int pt = (p.kt - 1) / 2, ph = (p.kh - 1) / 2, pw = (p.kw - 1) / 2;
-  const int taps_hw = p.kh * p.kw;
   const int acc_cols = p.MT * BN;
 
   if (tid == 128) {
@@ -127,13 +144,17 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
       SlabItem cur = slab_item(p, item, BN);
       int nxt_item = item, nxt_si = 0;       // (item, slab) of the next slab to load
       SlabItem nxt = cur;
+      // slab index si of an item enumerates (cc, dt, sub) with sub fastest
       auto load_next = [&]() {
-        const int cc = nxt_si / nxt.n_dt, dt = nxt.dt_lo + (nxt_si - cc * nxt.n_dt);
+        const int sub = nxt_si % p.n_sub;
+        const int r2 = nxt_si / p.n_sub;
+        const int cc = r2 / nxt.n_dt, dt = nxt.dt_lo + (r2 - cc * nxt.n_dt);
         const int s = sg % kSlabSStages;
         mbar_wait(&slab_empty[s], ((sg / kSlabSStages) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&slab_full[s], static_cast<uint32_t>(p.R * p.PW * 128));
-          tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64, -pw, nxt.r_lo, nxt.plane + dt - pt);
+          tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64, p.sub_w0[sub],
+                      p.ss * nxt.r_lo + p.sub_h0[sub], nxt.plane_i0 + dt);
         }
         __syncwarp();
         ++sg;
@@ -144,16 +165,19 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
         }
       };
       load_next();
-      const int pf = min(kSlabWStages, taps_hw - 1);
       for (; item < p.items_total; item += gridDim.x) {
         cur = slab_item(p, item, BN);
         for (int si = 0; si < cur.n_slabs; ++si) {
-          const int cc = si / cur.n_dt, dt = cur.dt_lo + (si - cc * cur.n_dt);
-          for (int thw = 0; thw < taps_hw; ++thw, ++wit) {
-            if (thw == pf && nxt_item < p.items_total) load_next();
+          const int sub = si % p.n_sub;
+          const int r2 = si / p.n_sub;
+          const int cc = r2 / cur.n_dt, dt = cur.dt_lo + (r2 - cc * cur.n_dt);
+          const int ntaps = p.sub_ntaps[sub];
+          const int pf = min(kSlabWStages, ntaps - 1);
+          for (int ti = 0; ti < ntaps; ++ti, ++wit) {
+            if (ti == pf && nxt_item < p.items_total) load_next();
             const int ws = wit % kSlabWStages;
             mbar_wait(&w_empty[ws], ((wit / kSlabWStages) & 1) ^ 1);
-            const int tap = dt * taps_hw + thw;
+            const int tap = dt * p.khw + p.sub_tap[sub][ti];
             if (elect_one()) {
               mbar_expect_tx(&w_full[ws], kWBytes);
               tma_load_2d(w_base + ws * kWBytes, &tmB, &w_full[ws], tap * p.C + cc * 64, cur.n0);
@@ -178,16 +202,17 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
       const uint32_t acc = tm + ab * acc_cols;
       int wl = 0;                                                // weight step within the item
       for (int si = 0; si < w.n_slabs; ++si, ++sg) {
+        const int sub = si % p.n_sub;
+        const int ntaps = p.sub_ntaps[sub];
         const int s = sg % kSlabSStages;
         mbar_wait(&slab_full[s], (sg / kSlabSStages) & 1);
         const uint32_t slab_addr = slab0 + s * p.slab_bytes;
-        for (int thw = 0; thw < taps_hw; ++thw, ++wit, ++wl) {
-          const int dh = thw / p.kw, dw = thw - dh * p.kw;
+        for (int ti = 0; ti < ntaps; ++ti, ++wit, ++wl) {
           const int ws = wit % kSlabWStages;
           mbar_wait(&w_full[ws], (wit / kSlabWStages) & 1);
           tc_fence_after();
-          // slab-local pixel index of padded position q0 under tap (dh, dw)
-          const int pix0 = w.q0 + (dh - ph) * p.PW + (dw - pw) - w.r_lo * p.PW;
+          // slab-local pixel index of padded output position q0 under this tap
+          const int pix0 = w.q0 + p.sub_off[sub][ti] - w.r_lo * p.PW;
           const uint32_t b_lo = sw128_desc_lo(w0s + ws * kWBytes);
           const uint32_t a_lo0 = sw128_desc_lo(slab_addr + static_cast<uint32_t>(pix0) * 128u);
           if (elect_one()) {
@@ -200,8 +225,8 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
               umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
             }
             umma_commit(&w_empty[ws]);
-            if (thw == taps_hw - 1) umma_commit(&slab_empty[s]);
-            if (thw == taps_hw - 1 && si == w.n_slabs - 1) umma_commit(&acc_full[ab]);
+            if (ti == ntaps - 1) umma_commit(&slab_empty[s]);
+            if (ti == ntaps - 1 && si == w.n_slabs - 1) umma_commit(&acc_full[ab]);
           }
           __syncwarp();
         }
@@ -222,8 +247,8 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
       for (int j = 0; j < w.mt_valid; ++j) {
         const int q = w.q0 + j * 128 + tid;
         const int h = q / p.PW, wp = q - h * p.PW;
-        const bool ok = (q < p.P) && (wp >= pw) && (wp < pw + p.W);
-        const size_t row = (static_cast<size_t>(w.plane) * p.H + h) * p.W + (wp - pw);
+        const bool ok = (q < p.P) && (wp >= p.halo_l) && (wp < p.halo_l + p.Wo);
+        const size_t row = (static_cast<size_t>(w.plane_o) * p.Ho + h) * p.Wo + (wp - p.halo_l);
         __half* yrow = p.y + row * p.ldy + w.n0;
         const __half* rrow = p.residual ? p.residual + row * p.ldr + w.n0 : nullptr;
 #pragma unroll 1

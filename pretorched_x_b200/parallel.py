@@ -60,7 +60,11 @@ def gather_logits(local_logits, total):
         return local_logits
     world = dist.get_world_size()
     base, extra = divmod(total, world)
-    pad_rows = base + (1 if extra else 0)
+    if extra == 0:                            # equal shards: one flat all-gather straight into batch order
+        out = torch.empty((total, local_logits.shape[1]), dtype=local_logits.dtype, device=local_logits.device)
+        dist.all_gather_into_tensor(out, local_logits.contiguous())
+        return out
+    pad_rows = base + 1
     padded = local_logits
     if local_logits.shape[0] < pad_rows:      # equal-size buffers for all_gather
         padded = torch.cat([local_logits, local_logits.new_zeros(pad_rows - local_logits.shape[0],
