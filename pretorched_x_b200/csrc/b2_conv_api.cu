@@ -137,7 +137,7 @@ static bool slab_geometry(const b2_conv_args* a, SlabParams* p) {
   if (a->sh != a->sw || (a->sh != 1 && a->sh != 2) || (a->st != 1 && a->st != 2)) return false;
   if (a->kh * a->kw > kSlabMaxTaps) return false;
   const int ss = a->sh;
-  if (ss == 1 && a->st == 1 && a->kt * a->kh * a->kw == 1) return false;      // plain GEMM: persistent GEMM kernel
+  if (a->kt * a->kh * a->kw == 1) return false;   // 1x1x1: persistent GEMM (stride 1) / gather kernel (strided): no tap reuse to exploit
   memset(p, 0, sizeof(*p));
   p->T = a->T; p->C = a->C;
   p->To = (a->T + 2 * a->pt - a->kt) / a->st + 1;

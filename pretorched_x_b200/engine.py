@@ -58,12 +58,14 @@ def _conv_geometry(conv):
     return _triple(conv.stride), _triple(conv.padding)
 
 
-def packed_conv(conv, bn, in_pitch, stem=False):
+def packed_conv(conv, bn, in_pitch, stem=False, stride=None):
     """PackedConv for a plain nn.Conv3d / nn.Conv2d followed (optionally) by BatchNorm ``bn``."""
     if conv.groups != 1 or any(d != 1 for d in conv.dilation):
         raise NotImplementedError("grouped / dilated convolutions are outside the engine's scope")
-    sig = _sig(conv.weight, conv.bias, *_bn_tensors(bn)) + (in_pitch, stem, id(bn))
-    stride, padding = _conv_geometry(conv)
+    sig = _sig(conv.weight, conv.bias, *_bn_tensors(bn)) + (in_pitch, stem, id(bn), stride)
+    cstride, padding = _conv_geometry(conv)
+    if stride is None:
+        stride = cstride
     return _cached(conv, "pc", sig,
                    lambda: ops.PackedConv(conv.weight, conv.bias, bn, stride, padding, in_pitch=in_pitch, stem=stem))
 
@@ -85,9 +87,17 @@ def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False):
     stem = a.ld == 4
     if stem and not _is_stem_shape(conv):
         raise NotImplementedError("NDHWC4 inputs are only supported by 7-wide stride-2 stem convolutions")
-    pc = packed_conv(conv, bn, a.ld, stem=stem)
     if a.W % 2 != 0 and stem:
         raise ValueError("stem convolution needs an even input width (got %d)" % a.W)
+    stride, padding = _conv_geometry(conv)
+    if (not simt and tuple(conv.weight.shape[2:]) in ((1, 1, 1), (1, 1)) and padding == (0, 0, 0)
+            and stride[0] == stride[1] == stride[2] and stride[0] > 1 and a.T > 1):
+        # strided 1x1x1 projection (type-B shortcut, resnet3D.py:176-185): the strided pixel subset is gathered
+        # once (1/s^3 of the input) and the projection becomes a plain HBM-bound GEMM on the persistent kernel
+        sub = ops.shortcut_a(a, stride[0], a.C)
+        pc = packed_conv(conv, bn, sub.ld, stride=(1, 1, 1))
+        return ops.conv(sub, pc, residual=residual, relu=relu)
+    pc = packed_conv(conv, bn, a.ld, stem=stem)
     return ops.conv(a, pc, residual=residual, relu=relu, simt=simt)
 
 
