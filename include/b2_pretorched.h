@@ -121,6 +121,8 @@ int b2_maxpool3d_ndhwc(const void* x, void* y, int N, int T, int H, int W, int C
 int b2_avgpool_global_ndhwc(const void* x, void* y, int N, int S, int C, void* stream);
 /* fp32 NCDHW (the reference's input layout) -> fp16 NDHWC with channel pitch Cp (zero padded). */
 int b2_ncdhw_f32_to_ndhwc_f16(const float* x, void* y, int N, int C, int T, int H, int W, int Cp, void* stream);
+/* Same for callers that already hold fp16 clips (halves the host->device traffic of the input). */
+int b2_ncdhw_f16_to_ndhwc_f16(const void* x, void* y, int N, int C, int T, int H, int W, int Cp, void* stream);
 /* fp16 NDHWC (pitch Cp) -> fp32 NCDHW, for `features()` callers that want the reference layout. */
 int b2_ndhwc_f16_to_ncdhw_f32(const void* x, float* y, int N, int C, int T, int H, int W, int Cp, void* stream);
 /* y[r][c] = (relu ? max(x,0) : x) as fp16, rows x cols with pitches ldx / ldy; columns [cols, ldy) zeroed.

@@ -233,21 +233,25 @@ __global__ void avgpool_kernel(const __half* __restrict__ x, __half* __restrict_
 // ------------------------------------------------------------------------------------------
 // fp32 NCDHW -> fp16 NDHWC(pitch Cp).  One thread per pixel: reads are coalesced along W within each
 // channel plane, the write is Cp*2 contiguous bytes per thread (8 B for the NDHWC4 stem input).
-__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ x, __half* __restrict__ y, int C, long long S,
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+
+template <typename TIn>
+__global__ void ncdhw_to_ndhwc_kernel(const TIn* __restrict__ x, __half* __restrict__ y, int C, long long S,
                                       int Cp, long long total_px) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total_px) return;
   const long long n = i / S, s = i - n * S;
-  const float* xp = x + n * C * S + s;
+  const TIn* xp = x + n * C * S + s;
   __half* yp = y + i * Cp;
   if (Cp == 4) {
     float v[4] = {0, 0, 0, 0};
-    for (int c = 0; c < C && c < 4; ++c) v[c] = __ldg(xp + (long long)c * S);
+    for (int c = 0; c < C && c < 4; ++c) v[c] = to_f32(__ldg(xp + (long long)c * S));
     __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
     uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
     *reinterpret_cast<uint2*>(yp) = o;
   } else {
-    for (int c = 0; c < Cp; ++c) yp[c] = __float2half_rn(c < C ? __ldg(xp + (long long)c * S) : 0.f);
+    for (int c = 0; c < Cp; ++c) yp[c] = __float2half_rn(c < C ? to_f32(__ldg(xp + (long long)c * S)) : 0.f);
   }
 }
 
@@ -396,8 +400,17 @@ int b2_avgpool_global_ndhwc(const void* x, void* y, int N, int S, int C, void* s
 int b2_ncdhw_f32_to_ndhwc_f16(const float* x, void* y, int N, int C, int T, int H, int W, int Cp, void* stream) {
   B2_CHECK_ARG(x && y && Cp >= C && (Cp == 4 || Cp % 8 == 0), "bad argument (Cp must be 4 or a multiple of 8, >= C)");
   const long long S = (long long)T * H * W, total = (long long)N * S;
-  ncdhw_to_ndhwc_kernel<<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, (__half*)y, C, S, Cp, total);
+  ncdhw_to_ndhwc_kernel<float><<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, (__half*)y, C, S, Cp, total);
   B2_CHECK_LAUNCH("ncdhw_to_ndhwc");
+  return B2_OK;
+}
+
+int b2_ncdhw_f16_to_ndhwc_f16(const void* x, void* y, int N, int C, int T, int H, int W, int Cp, void* stream) {
+  B2_CHECK_ARG(x && y && Cp >= C && (Cp == 4 || Cp % 8 == 0), "bad argument (Cp must be 4 or a multiple of 8, >= C)");
+  const long long S = (long long)T * H * W, total = (long long)N * S;
+  ncdhw_to_ndhwc_kernel<__half><<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __half*)x, (__half*)y, C, S, Cp, total);
+  B2_CHECK_LAUNCH("ncdhw_to_ndhwc_f16");
   return B2_OK;
 }
 

@@ -107,14 +107,17 @@ def from_ncdhw(x, pitch=None):
         x = x.unsqueeze(2)
     if x.dim() != 5:
         raise ValueError("expected a [N,C,T,H,W] or [N,C,H,W] tensor, got %s" % (tuple(x.shape),))
-    x = x.contiguous().float()
+    half_in = x.dtype == torch.float16
+    x = x.contiguous() if half_in else x.contiguous().float()
     N, C, T, H, W = x.shape
     if pitch is None:
         pitch = 4 if C <= 4 else _round_up(C, 8)
     y = torch.empty((N * T * H * W, pitch), dtype=torch.float16, device=x.device)
     lib = _lib.load()
-    with _timed("layout", "ncdhw_f32->ndhwc_f16 C%d px=%d" % (C, N * T * H * W), 0.0, N * T * H * W * (4.0 * C + 2.0 * pitch)):
-        _lib.check(lib.b2_ncdhw_f32_to_ndhwc_f16(_ptr(x), _ptr(y), N, C, T, H, W, pitch, _stream()), "b2_ncdhw_f32_to_ndhwc_f16")
+    fn = lib.b2_ncdhw_f16_to_ndhwc_f16 if half_in else lib.b2_ncdhw_f32_to_ndhwc_f16
+    with _timed("layout", "ncdhw_%s->ndhwc_f16 C%d px=%d" % ("f16" if half_in else "f32", C, N * T * H * W), 0.0,
+                N * T * H * W * (x.element_size() * C + 2.0 * pitch)):
+        _lib.check(fn(_ptr(x), _ptr(y), N, C, T, H, W, pitch, _stream()), "b2_ncdhw_to_ndhwc_f16")
     return Act(y, N, T, H, W, C)
 
 
