@@ -101,6 +101,11 @@ typedef struct b2_gemm_args {
   int32_t accumulate;
 } b2_gemm_args;
 int b2_gemm_f16(const b2_gemm_args* a, void* stream);
+/* D = act(scale * (A.B^T + A2.B2^T) + shift + residual): both products accumulate in the same TMEM tile.  Used to
+ * fuse the type-B shortcut projection (resnet3D.py:176-185) into the block-closing 1x1x1 convolution
+ * (resnet3D.py:136-143) with the two BatchNorm scales folded into B and B2: the shortcut never touches HBM.
+ * fp16 output, per-column affine only. */
+int b2_gemm2_f16(const b2_gemm_args* a, const void* a2, int lda2, const void* b2, int ldb2, int k2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Non-local block core (nonlocalnet.py:143-166, `_embedded_gaussian`):

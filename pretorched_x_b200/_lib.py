@@ -57,6 +57,7 @@ SYMBOLS = {
     "b2_pack_conv_weight_elems": (ctypes.c_size_t, [c_int] * 7),
     "b2_pack_conv_weight": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "b2_gemm_f16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "b2_gemm2_f16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b2_nonlocal_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                       c_int, c_int, c_int, c_int, c_void_p]),
     "b2_maxpool3d_ndhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 14 + [c_void_p]),

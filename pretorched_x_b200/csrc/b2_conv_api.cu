@@ -316,6 +316,8 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 struct IgemmLaunch {
   IgemmParams p;
+  // optional second operand pair (persistent GEMM only): D += A2[M][k2] . B2[N][k2]^T
+  const void* a2 = nullptr; int lda2 = 0; const void* w2 = nullptr; int ldb2 = 0; int k2 = 0;
   const void* a_mat;      // AMODE_TMA: A as [M][lda]
   int lda;
   int a_cols;             // logical K extent of A (columns readable)
@@ -383,15 +385,21 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   } else {
     tmR = tmC;
   }
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  if (L.k2 > 0) {
+    if ((rc = make_tmap_2d_f16(&tmA2, L.a2, (uint64_t)L.k2, (uint64_t)ip.M_total, (uint64_t)L.lda2, 64, 128, true)) != B2_OK) return rc;
+    if ((rc = make_tmap_2d_f16(&tmB2, L.w2, (uint64_t)L.k2, (uint64_t)ip.Ncols, (uint64_t)L.ldb2, 64, BN, true)) != B2_OK) return rc;
+  }
   PgemmParams p;
   p.M = ip.M_total; p.Ncols = ip.Ncols; p.ldy = ip.ldy; p.nkb = ip.nkb;
+  p.nkb2 = (L.k2 + 63) / 64;
   p.tiles_n = (ip.ldy + BN - 1) / BN;
   p.tiles_total = p.tiles_n * ((ip.M_total + 127) / 128);
   p.scale = ip.scale; p.shift = ip.shift;
   p.has_residual = ip.residual != nullptr;
   p.relu = ip.relu;
   const int grid = p.tiles_total < sm_count() ? p.tiles_total : sm_count();
-  pgemm_kernel<BN><<<grid, kPgThreads, S::kTotal, stream>>>(tmA, tmB, tmC, tmR, p);
+  pgemm_kernel<BN><<<grid, kPgThreads, S::kTotal, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmR, p);
   B2_CHECK_LAUNCH("pgemm_kernel");
   return B2_OK;
 }
@@ -502,7 +510,18 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   return dispatch_igemm(L, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int b2_gemm_f16(const b2_gemm_args* g, void* stream) {
+static int gemm_common(const b2_gemm_args* g, const void* a2, int lda2, const void* b2, int ldb2, int k2, void* stream);
+
+int b2_gemm_f16(const b2_gemm_args* g, void* stream) { return gemm_common(g, nullptr, 0, nullptr, 0, 0, stream); }
+
+int b2_gemm2_f16(const b2_gemm_args* g, const void* a2, int lda2, const void* b2, int ldb2, int k2, void* stream) {
+  B2_CHECK_ARG(g != nullptr && a2 && b2 && k2 > 0, "null / empty second operand pair");
+  B2_CHECK_ARG(lda2 % 8 == 0 && ldb2 % 8 == 0 && lda2 >= k2 && ldb2 >= k2, "bad second operand pitch");
+  B2_CHECK_ARG(!g->out_f32 && !g->per_row, "the fused two-operand GEMM produces fp16 output with per-column affine");
+  return gemm_common(g, a2, lda2, b2, ldb2, k2, stream);
+}
+
+static int gemm_common(const b2_gemm_args* g, const void* a2, int lda2, const void* b2, int ldb2, int k2, void* stream) {
   B2_CHECK_ARG(g != nullptr, "null args");
   B2_CHECK_ARG(g->a && g->b && g->scale && g->shift && g->d, "null tensor pointer");
   B2_CHECK_ARG(g->M > 0 && g->N > 0 && g->Kd > 0, "non-positive dimension");
@@ -532,6 +551,8 @@ int b2_gemm_f16(const b2_gemm_args* g, void* stream) {
   p.x = reinterpret_cast<const __half*>(g->a);
   L.a_mat = g->a; L.lda = g->lda; L.a_cols = g->Kd;
   L.w = g->b; L.ldb = g->ldb; L.b_cols = g->Kd;
+  L.a2 = a2; L.lda2 = lda2; L.w2 = b2; L.ldb2 = ldb2; L.k2 = k2;
+  if (k2 > 0 && g_gemm_algo != 0) return set_error(B2_ERR_UNSUPPORTED, "two-operand GEMM needs the persistent kernel");
   return dispatch_igemm(L, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -1,6 +1,10 @@
 // b2_pgemm.cuh -- persistent, warp-specialised GEMM for the 1x1x1 convolutions and dense layers:
 //
-//     D[M][N] = act( scale[n] * (A[M][K] . B[N][K]^T) + shift[n] + residual[M][N] )      (fp16 in/out, fp32 accumulate)
+//     D[M][N] = act( scale[n] * (A[M][K] . B[N][K]^T  [+ A2[M][K2] . B2[N][K2]^T]) + shift[n] + residual[M][N] )
+//                                                                                   (fp16 in/out, fp32 accumulate)
+// The optional second operand pair accumulates into the same TMEM tile: it fuses the type-B shortcut projection of a
+// bottleneck into its closing 1x1x1 convolution (BN scales folded into the two weight matrices), so the projected
+// shortcut never goes through HBM.
 //
 // These layers are HBM-bound (K is 64..2048 while every output element is written once and, for the block-closing
 // conv3, a residual element is read once), so the kernel is organised around keeping the memory system busy rather
@@ -25,7 +29,8 @@ constexpr int kPgStages = 3;
 
 struct PgemmParams {
   int M, Ncols, ldy;        // rows, logical columns, output pitch (columns [Ncols, ldy) are written as zero)
-  int nkb;                  // K blocks of 64
+  int nkb;                  // K blocks of 64 of the first operand pair
+  int nkb2;                 // K blocks of the second operand pair (0 = none)
   int tiles_n, tiles_total;
   const float* scale;
   const float* shift;
@@ -50,6 +55,7 @@ struct PgemmSmem {
 template <int BN>
 __global__ void __launch_bounds__(kPgThreads, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const PgemmParams p) {
   using S = PgemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -95,14 +101,19 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __syncwarp();
       }
-      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+      for (int kb = 0; kb < p.nkb + p.nkb2; ++kb, ++it) {
         const int s = it % kPgStages;
         mbar_wait(&empty[s], ((it / kPgStages) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&full[s], S::kStage);
           uint8_t* dst = smem + s * S::kStage;
-          tma_load_2d(dst, &tmA, &full[s], kb * 64, m0);
-          tma_load_2d(dst + S::kABytes, &tmB, &full[s], kb * 64, n0);
+          if (kb < p.nkb) {
+            tma_load_2d(dst, &tmA, &full[s], kb * 64, m0);
+            tma_load_2d(dst + S::kABytes, &tmB, &full[s], kb * 64, n0);
+          } else {
+            tma_load_2d(dst, &tmA2, &full[s], (kb - p.nkb) * 64, m0);
+            tma_load_2d(dst + S::kABytes, &tmB2, &full[s], (kb - p.nkb) * 64, n0);
+          }
         }
         __syncwarp();
       }
@@ -118,7 +129,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&acc_empty[ab], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d = tm + ab * BN;
-      for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+      const int nkb_all = p.nkb + p.nkb2;
+      for (int kb = 0; kb < nkb_all; ++kb, ++it) {
         const int s = it % kPgStages;
         mbar_wait(&full[s], (it / kPgStages) & 1);
         tc_fence_after();
@@ -130,7 +142,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
           umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
           umma_commit(&empty[s]);
-          if (kb == p.nkb - 1) umma_commit(&acc_full[ab]);
+          if (kb == nkb_all - 1) umma_commit(&acc_full[ab]);
         }
         __syncwarp();
       }

@@ -123,8 +123,49 @@ def run_basic(block, a, simt=False):
     return out
 
 
+def _plain_1x1(conv):
+    return (isinstance(conv, (nn.Conv3d, nn.Conv2d)) and all(k == 1 for k in conv.weight.shape[2:]) and conv.groups == 1
+            and all(p == 0 for p in _conv_geometry(conv)[1]))
+
+
+def _fused_close_with_projection(block, a, h):
+    """conv3 + bn3 + (downsample conv + bn)(x) + ReLU as ONE two-operand GEMM (resnet3D.py:136-143 with the type-B
+    shortcut of resnet3D.py:176-185): both BatchNorm scales are folded into the fp16 weight matrices, both products
+    accumulate in the same TMEM tile, and the projected shortcut never goes through HBM."""
+    ds_conv, ds_bn = block.downsample[0], block.downsample[1]
+    stride = _conv_geometry(ds_conv)[0]
+    xs = a if stride == (1, 1, 1) else ops.shortcut_a(a, stride[0], a.C)
+    if xs.M != h.M:
+        raise RuntimeError("shortcut / main path shape mismatch")
+    dev = a.data.device
+
+    def build():
+        s3, b3 = ops.fold_affine(block.conv3.weight.shape[0], block.conv3.bias, block.bn3, dev)
+        sd, bd = ops.fold_affine(ds_conv.weight.shape[0], ds_conv.bias, ds_bn, dev)
+        K = block.conv3.weight.shape[0]
+        w3 = torch.zeros((K, h.ld), dtype=torch.float16, device=dev)
+        w3[:, :h.C] = (_conv1x1_matrix(block.conv3).float() * s3[:, None]).to(torch.float16)
+        wd = torch.zeros((K, xs.ld), dtype=torch.float16, device=dev)
+        wd[:, :xs.C] = (_conv1x1_matrix(ds_conv).float() * sd[:, None]).to(torch.float16)
+        return w3, wd, torch.ones(K, dtype=torch.float32, device=dev), (b3 + bd).contiguous()
+
+    sig = _sig(block.conv3.weight, block.conv3.bias, *_bn_tensors(block.bn3), ds_conv.weight, ds_conv.bias,
+               *_bn_tensors(ds_bn)) + (h.ld, xs.ld)
+    w3, wd, ones, shift = _cached(block, "close2", sig, build)
+    K = w3.shape[0]
+    y = ops.gemm(h.data, w3, ones, shift, h.M, K, h.ld, relu=True, second=(xs.data, wd, xs.ld))
+    return Act(y, h.N, h.T, h.H, h.W, K)
+
+
 def run_bottleneck(block, a, simt=False):
     """1x1x1-BN-ReLU, 3x3x3(stride)-BN-ReLU, 1x1x1-BN-(+shortcut)-ReLU (resnet3D.py:125-143)."""
+    ds = block.downsample
+    if (not simt and isinstance(ds, nn.Sequential) and len(ds) == 2 and _plain_1x1(ds[0]) and _plain_1x1(block.conv3)
+            and not ds[1].training and len(set(_conv_geometry(ds[0])[0])) == 1 and (a.T > 1 or _conv_geometry(ds[0])[0][0] == 1)
+            and isinstance(ds[0], nn.Conv3d)):
+        out = conv_bn_act(block.conv1, block.bn1, a, relu=True)
+        out = conv_bn_act(block.conv2, block.bn2, out, relu=True)
+        return _fused_close_with_projection(block, a, out)
     res = _shortcut(block, a, simt)
     out = conv_bn_act(block.conv1, block.bn1, a, relu=True, simt=simt)
     out = conv_bn_act(block.conv2, block.bn2, out, relu=True, simt=simt)

@@ -222,8 +222,9 @@ def conv(a, pc, residual=None, relu=False, simt=False):
 
 
 def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=False, out=None, out_f32=False,
-         accumulate=False):
-    """D[M][N] = act(scale * A[M][Kd] . B[N][Kd]^T + shift + residual) on tcgen05 (b2_gemm_f16)."""
+         accumulate=False, second=None):
+    """D[M][N] = act(scale * A[M][Kd] . B[N][Kd]^T + shift + residual) on tcgen05 (b2_gemm_f16).
+    ``second=(A2, B2, K2)`` adds A2[M][K2] . B2[N][K2]^T into the same accumulator (b2_gemm2_f16)."""
     dev = a2d.device
     if out is None:
         ldd = N if out_f32 else _round_up(N, 8)
@@ -236,6 +237,13 @@ def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=Fa
     g.lda, g.ldb, g.ldd = a2d.stride(0), b2d.stride(0), out.stride(0)
     g.ldr = residual.stride(0) if residual is not None else 0
     g.per_row, g.relu, g.out_f32, g.accumulate = int(per_row), int(relu), int(out_f32), int(accumulate)
+    if second is not None:
+        a2, b2, k2 = second
+        with _timed("gemm", "gemm2 M=%d N=%d K=%d+%d" % (M, N, Kd, k2), 2.0 * M * N * (Kd + k2),
+                    2.0 * (M * (Kd + k2) + N * (Kd + k2)) + out.element_size() * M * N):
+            _lib.check(_lib.load().b2_gemm2_f16(ctypes.byref(g), _ptr(a2), a2.stride(0), _ptr(b2), b2.stride(0), k2,
+                                               _stream()), "b2_gemm2_f16")
+        return out
     with _timed("gemm", "gemm M=%d N=%d K=%d" % (M, N, Kd), 2.0 * M * N * Kd,
                 2.0 * (M * Kd + N * Kd) + out.element_size() * M * N):
         _lib.check(_lib.load().b2_gemm_f16(ctypes.byref(g), _stream()), "b2_gemm_f16")
