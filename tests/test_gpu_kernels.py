@@ -54,6 +54,16 @@ CONV_CASES = [
     ("stem_7x7x7", 1, 3, 4, 32, 32, 64, (7, 7, 7), (1, 2, 2), (3, 3, 3), False, True, False, True),
     ("stem_r2p1d_1x7x7_to_110", 1, 3, 4, 32, 32, 110, (1, 7, 7), (1, 2, 2), (0, 3, 3), False, True, False, True),
     ("single_output_pixel", 1, 64, 1, 1, 1, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    # slab kernel: full layer shapes, several planes / tiles / N tiles, strided phases
+    ("slab_layer1_56x56", 2, 64, 4, 56, 56, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    ("slab_layer2_28x28_res", 2, 128, 3, 28, 28, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), True, True, False, True),
+    ("slab_layer3_14x14", 3, 256, 2, 14, 14, 256, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    ("slab_odd_sizes_200ch", 1, 64, 5, 13, 11, 200, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    ("slab_s2_56_to_28", 2, 128, 4, 56, 56, 128, (3, 3, 3), (2, 2, 2), (1, 1, 1), False, True, False, True),
+    ("slab_s2_odd_input_7x7", 2, 256, 3, 7, 7, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1), False, True, False, True),
+    ("slab_2d_3x3_s2_resnet18", 2, 64, 1, 56, 56, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), False, True, False, True),
+    ("slab_temporal7_wide", 1, 110, 8, 56, 56, 64, (7, 1, 1), (1, 1, 1), (3, 0, 0), False, False, False, True),
+    ("projection_1x1x1_s2_subsample", 2, 256, 4, 8, 8, 512, (1, 1, 1), (2, 2, 2), (0, 0, 0), False, False, False, True),
 ]
 
 
@@ -143,6 +153,45 @@ def test_nonlocal_attention_matches_oracle(dev, case):
     qkv = torch.cat([q, k, v], dim=2).reshape(B * Npos, 2 * d + dv).half().to(dev).contiguous()
     o = ops.nonlocal_attention(qkv, d, dv, B, Npos)
     assert rel(o[:, :dv].float().view(B, Npos, dv), ref) <= 4e-3
+
+
+def test_two_operand_gemm_matches_oracle(dev):
+    """b2_gemm2_f16: D = relu(A.B^T + A2.B2^T + shift) -- the fused conv3 + shortcut-projection GEMM."""
+    from pretorched_x_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    M, N, K1, K2 = 1000, 256, 64, 192
+    A1, B1 = h(torch.randn(M, K1, generator=g)), h(torch.randn(N, K1, generator=g) / K1 ** 0.5)
+    A2, B2 = h(torch.randn(M, K2, generator=g)), h(torch.randn(N, K2, generator=g) / K2 ** 0.5)
+    sh = torch.randn(N, generator=g)
+    want = F.relu(A1 @ B1.t() + A2 @ B2.t() + sh)
+    got = ops.gemm(A1.half().to(dev), B1.half().to(dev), torch.ones(N, device=dev), sh.to(dev), M, N, K1, relu=True,
+                   second=(A2.half().to(dev), B2.half().to(dev), K2))
+    assert rel(got.float(), want) <= TOL_F16
+
+
+def test_bottleneck_with_fused_projection_matches_unfused_blocks(dev):
+    """A type-B bottleneck (resnet3D.py:125-143 + 176-185) through the fused two-operand close vs the CPU oracle."""
+    from pretorched_x_b200.models import resnet3d
+    torch.manual_seed(0)
+    ds = nn.Sequential(nn.Conv3d(64, 256, kernel_size=1, stride=2, bias=False), nn.BatchNorm3d(256))
+    blk = resnet3d.Bottleneck(64, 64, stride=2, downsample=ds)
+    OF.randomize_bn_(blk, 5)
+    blk.eval()
+    x = OF.seeded_input((2, 64, 4, 16, 16), 6).half().float()
+    sd = {"b." + k: v for k, v in blk.state_dict().items()}
+    with torch.no_grad():
+        want = OF.bottleneck(x, sd, "b", "resnet3d", "B", 64, 2, True)
+        got = blk.to(dev)(x.to(dev))
+    assert tuple(got.shape) == tuple(want.shape)
+    assert rel(got, want) <= 3e-3
+
+
+def test_fp16_input_is_equivalent_to_fp32_input(dev):
+    from pretorched_x_b200 import ops
+    x = OF.seeded_input((2, 3, 4, 16, 16), 3)
+    a32 = ops.from_ncdhw(x.to(dev))
+    a16 = ops.from_ncdhw(x.half().to(dev))
+    assert torch.equal(a32.data, a16.data)
 
 
 def test_attention_rows_are_convex_combinations(dev):

@@ -37,8 +37,13 @@ for arch, kw, shape, gflop in CASES:
     ms = e0.elapsed_time(e1) / steps
     rate = shape[0] / (ms / 1e3)
     agg = {}
+    lay = {}
     for r in prof.rows:
         a = agg.setdefault(r["kind"], [0.0, 0]); a[0] += r["ms"]; a[1] += 1
+        b = lay.setdefault(r["desc"], [0.0, 0, 0.0]); b[0] += r["ms"]; b[1] += 1; b[2] += r["flops"]
+    if "--layers" in sys.argv:
+        for d, v in sorted(lay.items(), key=lambda kv: -kv[1][0])[:14]:
+            print("   %-52s n=%2d %7.3f ms %7.1f TF/s" % (d, v[1], v[0], v[2] / v[0] / 1e9 if v[0] else 0), file=sys.stderr)
     print(json.dumps({"arch": arch, "input": shape, "ms_per_step": ms, "samples_per_s": rate,
                       "tflops_algorithmic": gflop * rate / 1e3,
                       "eager_ms_by_kind": {k: round(v[0], 3) for k, v in agg.items()}, "launches": len(prof.rows)}), flush=True)
