@@ -196,6 +196,79 @@ def forward(x, sd, arch, stages=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# SlowFast (slowfast.py) -- SURVEY.md section 8f row n2
+# ---------------------------------------------------------------------------------------------
+def _sf_block(x, sd, p, bottleneck, stride, head_conv, has_ds):
+    """slowfast.py BasicBlock.forward (:38-54) / Bottleneck.forward (:83-101)."""
+    if bottleneck:
+        c1 = _conv(x, sd, p + '.conv1', 1, (1, 0, 0) if head_conv == 3 else 0)
+        out = F.relu(_bn(c1, sd, p + '.bn1'))
+        out = F.relu(_bn(_conv(out, sd, p + '.conv2', (1, stride, stride), (0, 1, 1)), sd, p + '.bn2'))
+        out = _bn(_conv(out, sd, p + '.conv3'), sd, p + '.bn3')
+    else:
+        if head_conv == 1:
+            c1 = _conv(x, sd, p + '.conv1', (1, stride, stride), (0, 1, 1))
+        else:
+            c1 = _conv(x, sd, p + '.conv1', 1, (1, 0, 0))
+        out = F.relu(_bn(c1, sd, p + '.bn1'))
+        out = _bn(_conv(out, sd, p + '.conv2', (1, stride, stride), (0, 1, 1)), sd, p + '.bn2')
+    res = x
+    if has_ds:
+        res = _bn(_conv(x, sd, p + '.downsample.0', (1, stride, stride), 0), sd, p + '.downsample.1')
+    return F.relu(out + res)
+
+
+def _sf_stage(x, sd, p, bottleneck, nblocks, stride, head_conv, inplanes, planes):
+    exp = 4 if bottleneck else 1
+    for i in range(nblocks):
+        s = stride if i == 0 else 1
+        has_ds = i == 0 and (stride != 1 or inplanes != planes * exp)
+        x = _sf_block(x, sd, '%s.%d' % (p, i), bottleneck, s, head_conv, has_ds)
+    return x
+
+
+def slowfast_forward(x, sd, layers, bottleneck=True, mode='sf', slow_stride=16, fast_stride=2):
+    """SlowFast.forward (slowfast.py:390-396), SlowOnly.forward (:217-231), FastOnly.forward (:362-374)."""
+    exp = 4 if bottleneck else 1
+    res3_stride = 2 if bottleneck else 1
+    pool = lambda t: F.max_pool3d(t, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    gap = lambda t: t.mean(dim=(2, 3, 4))
+    fp = 'fast.' if mode == 'sf' else ''
+    sp = 'slow.' if mode == 'sf' else ''
+    lateral = None
+    fast = None
+    if mode in ('sf', 'f'):
+        xf = x[:, :, ::fast_stride]
+        a = pool(F.relu(_bn(_conv(xf, sd, fp + 'conv1', (1, 2, 2), (2, 3, 3)), sd, fp + 'bn1')))
+        lateral = [] if mode == 'sf' else None
+        if lateral is not None:
+            lateral.append(_conv(a, sd, fp + 'lateral_p1', (8, 1, 1), (2, 0, 0)))
+        inpl = 8
+        for name, planes, n, stride in (('res2', 8, layers[0], 1), ('res3', 16, layers[1], res3_stride),
+                                        ('res4', 32, layers[2], 2), ('res5', 64, layers[3], 2)):
+            a = _sf_stage(a, sd, fp + name, bottleneck, n, stride, 3, inpl, planes)
+            inpl = planes * exp
+            if lateral is not None and name != 'res5':
+                lateral.append(_conv(a, sd, fp + 'lateral_' + name, (8, 1, 1), (2, 0, 0)))
+        fast = gap(a)
+        if mode == 'f':
+            return F.linear(fast, sd['last_linear.weight'], sd['last_linear.bias'])
+    xs = x[:, :, ::slow_stride]
+    a = pool(F.relu(_bn(_conv(xs, sd, sp + 'conv1', (1, 2, 2), (0, 3, 3)), sd, sp + 'bn1')))
+    inpl = 64 + (16 if mode == 'sf' else 0)
+    for i, (name, planes, n, stride, head) in enumerate((('res2', 64, layers[0], 1, 1), ('res3', 128, layers[1], res3_stride, 1),
+                                                         ('res4', 256, layers[2], 2, 3), ('res5', 512, layers[3], 2, 3))):
+        if mode == 'sf':
+            a = torch.cat([a, lateral[i]], dim=1)
+        a = _sf_stage(a, sd, sp + name, bottleneck, n, stride, head, inpl, planes)
+        inpl = planes * exp + (planes * exp // 8 * 2 if mode == 'sf' else 0)
+    slow = gap(a)
+    if mode == 's':
+        return F.linear(slow, sd['last_linear.weight'], sd['last_linear.bias'])
+    return F.linear(torch.cat([slow, fast], dim=1), sd['last_linear.weight'], sd.get('last_linear.bias'))
+
+
+# ---------------------------------------------------------------------------------------------
 # TRN relation heads
 # ---------------------------------------------------------------------------------------------
 def relation(x, sd, p, num_inputs, in_features):

@@ -133,6 +133,35 @@ def run_relation_cases():
     print("%-32s out %s" % ("msrelation_small", tuple(y.shape)))
 
 
+SLOWFAST_CASES = {
+    # name -> (factory, mode, layers, bottleneck, kwargs, input shape)
+    "slowfast50_sf_b1_t32_64": ("resnet50", "sf", [3, 4, 6, 3], True, dict(num_classes=12), (1, 3, 32, 64, 64)),
+    "slowfast18_sf_b2_t32_64": ("resnet18", "sf", [2, 2, 2, 2], False, dict(num_classes=12), (2, 3, 32, 64, 64)),
+    "slowonly50_b1_t32_64": ("resnet50", "s", [3, 4, 6, 3], True, dict(num_classes=12), (1, 3, 32, 64, 64)),
+    "fastonly50_b1_t16_64": ("resnet50", "f", [3, 4, 6, 3], True, dict(num_classes=12), (1, 3, 16, 64, 64)),
+}
+
+
+def run_slowfast_cases():
+    ref_pkg = RL.load()
+    for name, (factory, mode, layers, bott, kwargs, shape) in SLOWFAST_CASES.items():
+        torch.manual_seed(SEED_INIT)
+        ref = getattr(ref_pkg.slowfast, factory)(mode=mode, **kwargs)
+        OF.randomize_bn_(ref, SEED_BN)
+        ref.eval()
+        x = OF.seeded_input(shape, SEED_INPUT)
+        with torch.no_grad():
+            y = ref(x)
+            sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+            y_or = OF.slowfast_forward(x, sd, layers, bott, mode)
+        assert torch.equal(y, y_or), "oracle restatement differs from the reference for %s" % name
+        torch.save(dict(kind="slowfast", factory=factory, mode=mode, layers=layers, bottleneck=bott, kwargs=kwargs,
+                        input_shape=tuple(shape), seeds=dict(init=SEED_INIT, bn=SEED_BN, input=SEED_INPUT),
+                        logits=y.clone(), weight_digest=OF.state_digest(sd), n_state=len(sd)),
+                   os.path.join(GOLDEN_DIR, name + ".pt"))
+        print("%-32s logits %s absmax %.4f" % (name, tuple(y.shape), y.abs().max()))
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -141,6 +170,7 @@ def main():
     for name in order:
         run_model_case(name, *MODEL_CASES[name])
     run_relation_cases()
+    run_slowfast_cases()
 
 
 if __name__ == "__main__":

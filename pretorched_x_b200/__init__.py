@@ -20,3 +20,4 @@ from .models.r2plus1d import (r2plus1d10, r2plus1d18, r2plus1d34, r2plus1d50, r2
                               r2plus1d152, r2plus1d200)
 from .models.trn import Relation, MultiScaleRelation, HierarchicalRelation  # noqa: F401
 from .models.utils import Identity  # noqa: F401
+from .models import slowfast  # noqa: F401  (module, as in pretorched/__init__.py:83)

@@ -304,6 +304,19 @@ __global__ void shortcut_a_kernel(const __half* __restrict__ x, __half* __restri
   reinterpret_cast<uint4*>(y)[i] = v;
 }
 
+// y[r] = [ a[r][0:Ca8*8] | b[r][0:Cb8*8] | 0 ... ]   (torch.cat along channels, slowfast.py:143-150)
+__global__ void concat_channels_kernel(const __half* __restrict__ a, int lda8, int Ca8, const __half* __restrict__ b,
+                                       int ldb8, int Cb8, __half* __restrict__ y, int ldy8, long long total) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % ldy8);
+  const long long r = i / ldy8;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (c8 < Ca8) v = __ldg(reinterpret_cast<const uint4*>(a) + r * lda8 + c8);
+  else if (c8 < Ca8 + Cb8) v = __ldg(reinterpret_cast<const uint4*>(b) + r * ldb8 + (c8 - Ca8));
+  reinterpret_cast<uint4*>(y)[i] = v;
+}
+
 __global__ void gather_frames_kernel(const __half* __restrict__ x, __half* __restrict__ y, const int* __restrict__ idx,
                                      int T, int F8, int n_idx, long long total) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -440,6 +453,19 @@ int b2_shortcut_a_ndhwc(const void* x, void* y, int N, int T, int H, int W, int 
   shortcut_a_kernel<<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       (const __half*)x, (__half*)y, T, H, W, C / 8, stride, To, Ho, Wo, Cout / 8, total);
   B2_CHECK_LAUNCH("shortcut_a");
+  return B2_OK;
+}
+
+int b2_concat_channels(const void* a, int lda, int Ca, const void* b, int ldb, int Cb, void* y, int ldy, long long rows,
+                       void* stream) {
+  B2_CHECK_ARG(a && b && y && rows > 0, "bad argument");
+  B2_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldy % 8 == 0 && Ca % 8 == 0 && Cb % 8 == 0,
+               "channel counts and pitches must be multiples of 8");
+  B2_CHECK_ARG(lda >= Ca && ldb >= Cb && ldy >= Ca + Cb, "pitch smaller than extent");
+  const long long total = rows * (ldy / 8);
+  concat_channels_kernel<<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __half*)a, lda / 8, Ca / 8, (const __half*)b, ldb / 8, Cb / 8, (__half*)y, ldy / 8, total);
+  B2_CHECK_LAUNCH("concat_channels");
   return B2_OK;
 }
 

@@ -308,6 +308,25 @@ def shortcut_a(a, stride, out_channels):
     return Act(y, a.N, To, Ho, Wo, out_channels)
 
 
+def concat_rows(a2d, Ca, b2d, Cb):
+    """fp16 [rows][>=Ca] ++ [rows][>=Cb] -> [rows][round_up(Ca+Cb, 8)] (torch.cat(dim=1), slowfast.py:143-150, 392)."""
+    rows = a2d.shape[0]
+    if Ca % 8 or Cb % 8:
+        raise ValueError("channel concatenation needs channel counts that are multiples of 8 (got %d, %d)" % (Ca, Cb))
+    y = torch.empty((rows, _round_up(Ca + Cb, 8)), dtype=torch.float16, device=a2d.device)
+    with _timed("concat", "concat C%d+%d rows=%d" % (Ca, Cb, rows), 0.0, 4.0 * rows * (Ca + Cb)):
+        _lib.check(_lib.load().b2_concat_channels(_ptr(a2d), a2d.stride(0), Ca, _ptr(b2d), b2d.stride(0), Cb, _ptr(y),
+                                                 y.stride(0), rows, _stream()), "b2_concat_channels")
+    return y
+
+
+def concat_channels(a, b):
+    """Act ++ Act along channels (same N, T, H, W)."""
+    if (a.N, a.T, a.H, a.W) != (b.N, b.T, b.H, b.W):
+        raise ValueError("cannot concatenate %r and %r" % (a, b))
+    return Act(concat_rows(a.data, a.C, b.data, b.C), a.N, a.T, a.H, a.W, a.C + b.C)
+
+
 def cast_rows(x2d, relu=False):
     """fp32 [rows][cols] -> fp16 [rows][round_up(cols, 8)], optional ReLU (trn.py:40-41)."""
     _require_cuda(x2d, "input")

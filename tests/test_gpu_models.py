@@ -187,3 +187,23 @@ def test_full_size_clips_are_independent_and_graph_replay_is_exact(dev):
     g = GraphedForward(m, x)
     assert torch.equal(g(x), full)
     assert torch.equal(g(), full)
+
+
+SF_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "slowfast"]
+
+
+@pytest.mark.parametrize("path", SF_FIX, ids=[os.path.basename(p)[:-3] for p in SF_FIX])
+def test_slowfast_matches_reference_golden(dev, path):
+    """SlowFast / SlowOnly / FastOnly (slowfast.py) end to end against the reference's own logits."""
+    fx = torch.load(path, weights_only=False)
+    torch.manual_seed(fx["seeds"]["init"])
+    m = getattr(P.slowfast, fx["factory"])(mode=fx["mode"], **fx["kwargs"])
+    OF.randomize_bn_(m, fx["seeds"]["bn"])
+    m = m.eval().to(dev)
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"]).to(dev)
+    with torch.no_grad():
+        y = m(x)
+    assert tuple(y.shape) == tuple(fx["logits"].shape)
+    err = (y.cpu().double() - fx["logits"].double()).abs().max().item() / fx["logits"].abs().max().item()
+    assert err <= 5e-3, err
+    assert torch.equal(y.argmax(1).cpu(), fx["logits"].argmax(1))

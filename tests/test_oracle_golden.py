@@ -101,3 +101,24 @@ def test_state_dict_identical_to_live_reference():
         assert list(a) == list(b)
         for k in a:
             assert torch.equal(a[k], b[k]), (arch, k)
+
+
+SF_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "slowfast"]
+
+
+def build_slowfast(fx):
+    torch.manual_seed(fx["seeds"]["init"])
+    m = getattr(P.slowfast, fx["factory"])(mode=fx["mode"], **fx["kwargs"])
+    OF.randomize_bn_(m, fx["seeds"]["bn"])
+    return m.eval()
+
+
+@pytest.mark.parametrize("path", SF_FIX, ids=[os.path.basename(p)[:-3] for p in SF_FIX])
+def test_slowfast_init_and_oracle_match_reference(path):
+    fx = torch.load(path, weights_only=False)
+    sd = build_slowfast(fx).state_dict()
+    assert list(sd) == list(fx["weight_digest"]) and OF.digests_match(OF.state_digest(sd), fx["weight_digest"])
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"])
+    with torch.no_grad():
+        y = OF.slowfast_forward(x, sd, fx["layers"], fx["bottleneck"], fx["mode"])
+    assert (y - fx["logits"]).abs().max().item() <= 1e-5 * fx["logits"].abs().max().item()
