@@ -108,13 +108,16 @@ int b2_gemm_f16(const b2_gemm_args* a, void* stream);
 int b2_gemm2_f16(const b2_gemm_args* a, const void* a2, int lda2, const void* b2, int ldb2, int k2, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Non-local block core (nonlocalnet.py:143-166, `_embedded_gaussian`):
- *     O[b] = softmax_rows(Q[b] . K[b]^T) . V[b]        (unscaled logits, softmax over keys)
- * Q, K, V: fp16 [B*Npos][ld] (d resp. dv columns used; typically three column ranges of one projection
- * output); O: fp16 [B*Npos][ldo].  One fused kernel, the Npos x Npos matrix is never materialised.
+ * Non-local block core (nonlocalnet.py:143-211):
+ *     mode 0:  O[b] = softmax_rows(Q[b] . K[b]^T) . V[b]   (`_embedded_gaussian` :143-166, `_gaussian` :168-190;
+ *                                                          unscaled logits, softmax over keys)
+ *     mode 1:  O[b] = (Q[b] . K[b]^T / Nk) . V[b]          (`_dot_product` :192-211)
+ * Q: fp16 [B*Nq][ldq] (d columns used); K, V: fp16 [B*Nk][ld] (d resp. dv columns; Nk < Nq when phi and g were
+ * max-pooled, `sub_sample=True` :126-131); O: fp16 [B*Nq][ldo].  One fused kernel, the Nq x Nk matrix is never
+ * materialised.
  * ------------------------------------------------------------------------------------------- */
 int b2_nonlocal_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o,
-                          int ldo, int B, int Npos, int d, int dv, void* stream);
+                          int ldo, int B, int Nq, int Nk, int d, int dv, int mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Pooling / layout / elementwise helpers (all HBM-bound, 128-bit accesses)

@@ -136,6 +136,41 @@ def nonlocal_block(x, sd, p):
     return w_y + x
 
 
+def nonlocal_block_nd(x, sd, p, dimension, mode, sub_sample, bn_layer=True):
+    """_NonLocalBlockND.forward for the three softmax / dot-product modes (nonlocalnet.py:143-211), any of 1/2/3
+    position axes, with optional max-pooled phi / g (:126-131).  ``p`` is the key prefix ('' for a bare block)."""
+    key = (lambda k: p + '.' + k) if p else (lambda k: k)
+    conv = (None, F.conv1d, F.conv2d, F.conv3d)[dimension]
+    pool = (None, F.max_pool1d, F.max_pool2d, F.max_pool3d)[dimension]
+    cw = lambda name: conv(x, sd[key(name + '.weight')], sd[key(name + '.bias')])
+    b = x.size(0)
+    gk, pk = ('g.0', 'phi.0') if sub_sample else ('g', 'phi')
+    g_x = cw(gk)
+    if sub_sample:
+        g_x = pool(g_x, 2)
+    d = g_x.shape[1]
+    g_x = g_x.reshape(b, d, -1).permute(0, 2, 1)
+    if mode == 'gaussian':
+        theta_x = x.reshape(b, x.shape[1], -1).permute(0, 2, 1)
+        phi_x = (pool(x, 2) if sub_sample else x).reshape(b, x.shape[1], -1)
+    else:
+        theta_x = cw('theta').reshape(b, d, -1).permute(0, 2, 1)
+        phi_x = cw(pk)
+        if sub_sample:
+            phi_x = pool(phi_x, 2)
+        phi_x = phi_x.reshape(b, d, -1)
+    f = torch.matmul(theta_x, phi_x)
+    f_div_c = f / f.size(-1) if mode == 'dot_product' else F.softmax(f, dim=-1)
+    y = torch.matmul(f_div_c, g_x).permute(0, 2, 1).contiguous().view(b, d, *x.shape[2:])
+    if bn_layer:
+        w_y = conv(y, sd[key('W.0.weight')], sd[key('W.0.bias')])
+        w_y = F.batch_norm(w_y, sd[key('W.1.running_mean')], sd[key('W.1.running_var')], sd[key('W.1.weight')],
+                           sd[key('W.1.bias')], False, 0.0, BN_EPS)
+    else:
+        w_y = conv(y, sd[key('W.weight')], sd[key('W.bias')])
+    return w_y + x
+
+
 # ---------------------------------------------------------------------------------------------
 # whole networks
 # ---------------------------------------------------------------------------------------------

@@ -133,6 +133,49 @@ def run_relation_cases():
     print("%-32s out %s" % ("msrelation_small", tuple(y.shape)))
 
 
+NLBLOCK_CASES = {
+    # name -> (dimension, mode, sub_sample, bn_layer, channels, input shape)
+    "nlblock3d_gaussian_sub": (3, "gaussian", True, True, 64, (2, 64, 4, 8, 8)),
+    "nlblock3d_dot_product": (3, "dot_product", False, True, 128, (2, 128, 2, 7, 7)),
+    "nlblock3d_embedded_sub": (3, "embedded_gaussian", True, True, 128, (1, 128, 4, 8, 8)),
+    "nlblock2d_embedded": (2, "embedded_gaussian", False, True, 128, (2, 128, 12, 12)),
+    "nlblock2d_dot_sub_nobn": (2, "dot_product", True, False, 128, (2, 128, 12, 12)),
+    "nlblock1d_gaussian": (1, "gaussian", False, True, 64, (3, 64, 50)),
+}
+
+
+def condition_nlblock_(blk, seed):
+    """Deterministic, benign parameters for a bare non-local block: BN statistics randomised, projections scaled so
+    the logits stay O(1), the zero-initialised output projection (nonlocalnet.py:95-102) replaced by seeded noise."""
+    OF.randomize_bn_(blk, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for name, prm in blk.named_parameters():
+            if name.startswith(("theta", "phi")) and name.endswith("weight"):
+                prm.mul_(0.3)
+            if name in ("W.weight", "W.bias"):
+                prm.copy_(torch.randn(prm.shape, generator=g) * 0.05)
+    return blk
+
+
+def run_nlblock_cases():
+    ref_nl = RL.load().models.nonlocalnet
+    for name, (dim, mode, sub, bn, C, shape) in NLBLOCK_CASES.items():
+        cls = getattr(ref_nl, "NonLocalBlock%dD" % dim)
+        torch.manual_seed(SEED_INIT)
+        ref = condition_nlblock_(cls(C, mode=mode, sub_sample=sub, bn_layer=bn), SEED_BN).eval()
+        x = OF.seeded_input(shape, SEED_INPUT) * (0.3 if mode == "gaussian" else 1.0)
+        with torch.no_grad():
+            y = ref(x)
+            y_or = OF.nonlocal_block_nd(x, ref.state_dict(), "", dim, mode, sub, bn)
+        assert torch.equal(y, y_or), "oracle restatement differs from the reference for %s" % name
+        torch.save(dict(kind="nlblock", dimension=dim, mode=mode, sub_sample=sub, bn_layer=bn, channels=C,
+                        input_shape=tuple(shape), input_scale=(0.3 if mode == "gaussian" else 1.0),
+                        seeds=dict(init=SEED_INIT, bn=SEED_BN, input=SEED_INPUT), output=y.clone(),
+                        weight_digest=OF.state_digest(ref.state_dict())), os.path.join(GOLDEN_DIR, name + ".pt"))
+        print("%-32s out %s absmax %.4f" % (name, tuple(y.shape), y.abs().max()))
+
+
 SLOWFAST_CASES = {
     # name -> (factory, mode, layers, bottleneck, kwargs, input shape)
     "slowfast50_sf_b1_t32_64": ("resnet50", "sf", [3, 4, 6, 3], True, dict(num_classes=12), (1, 3, 32, 64, 64)),
@@ -171,6 +214,7 @@ def main():
         run_model_case(name, *MODEL_CASES[name])
     run_relation_cases()
     run_slowfast_cases()
+    run_nlblock_cases()
 
 
 if __name__ == "__main__":

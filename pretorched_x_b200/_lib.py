@@ -59,7 +59,7 @@ SYMBOLS = {
     "b2_gemm_f16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "b2_gemm2_f16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b2_nonlocal_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
-                                      c_int, c_int, c_int, c_int, c_void_p]),
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b2_maxpool3d_ndhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 14 + [c_void_p]),
     "b2_avgpool_global_ndhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2_ncdhw_f32_to_ndhwc_f16": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),

@@ -28,9 +28,12 @@ constexpr int kAttSlots = 4;       // smem ring slots
 constexpr int kAttSlotBytes = 32768;
 
 struct AttParams {
-  int Npos;       // positions per sample (queries == keys)
+  int Nq;         // query positions per sample
+  int Nk;         // key / value positions per sample (== Nq unless phi and g were sub-sampled)
   int nkb;        // d / 64
-  int nkv;        // ceil(Npos / 64)
+  int nkv;        // ceil(Nk / 64)
+  int mode;       // 0: softmax over keys (embedded gaussian / gaussian); 1: f / Nk without softmax (dot product)
+  float scale;    // mode 1: 1 / Nk
   __half* o;
   int ldo;
 };
@@ -65,7 +68,9 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   const int q0 = blockIdx.x * kAttBM;            // first query row of this CTA within the sample
   const int b = blockIdx.y;
   const int dv0 = blockIdx.z * DVT;
-  const int row_base = b * p.Npos;               // first global row of the sample
+  const int q_base = b * p.Nq;                   // first global query row of the sample
+  const int k_base = b * p.Nk;                   // first global key / value row of the sample
+  const bool two_pass = (p.mode == 0);
 
   if (tid == 128) {
     for (int s = 0; s < kAttSlots; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -92,12 +97,12 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     float m_run = -INFINITY, l_run = 0.f;
     uint32_t v[32];
     int g = 0;
-    // ---- pass 1: row max and row sum ----
-    for (int kvb = 0; kvb < p.nkv; ++kvb, ++g) {
+    // ---- pass 1: row max and row sum (softmax modes only) ----
+    for (int kvb = 0; two_pass && kvb < p.nkv; ++kvb, ++g) {
       const int buf = g & 1;
       mbar_wait(&s_full[buf], (g >> 1) & 1);
       tc_fence_after();
-      const int nvalid = p.Npos - kvb * kAttBKV;    // keys >= nvalid belong to the next sample / OOB
+      const int nvalid = p.Nk - kvb * kAttBKV;      // keys >= nvalid belong to the next sample / OOB
       float sv[64];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -118,7 +123,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       l_run = l_run * exp2f((m_run - mx) * L2E) + sum;
       m_run = mx;
     }
-    const float inv_l = 1.f / l_run;
+    const float inv_l = two_pass ? 1.f / l_run : 0.f;
     const float mb = m_run * L2E;
     // ---- pass 2: probabilities -> smem (A operand of P.V) ----
     const uint32_t swz = static_cast<uint32_t>(r & 7);
@@ -127,7 +132,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       const int pb = j & 1;
       mbar_wait(&s_full[buf], (g >> 1) & 1);
       tc_fence_after();
-      const int nvalid = p.Npos - j * kAttBKV;
+      const int nvalid = p.Nk - j * kAttBKV;
       mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
       uint8_t* prow = smem + S::kPOff + pb * S::kPBytes + r * 128;
 #pragma unroll
@@ -141,8 +146,14 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           for (int e = 0; e < 4; ++e) {
             const int i = c * 8 + e * 2;
             const int key = h * 32 + i;
-            const float p0 = (key < nvalid) ? exp2f(__uint_as_float(v[i]) * L2E - mb) * inv_l : 0.f;
-            const float p1 = (key + 1 < nvalid) ? exp2f(__uint_as_float(v[i + 1]) * L2E - mb) * inv_l : 0.f;
+            float p0, p1;
+            if (two_pass) {
+              p0 = (key < nvalid) ? exp2f(__uint_as_float(v[i]) * L2E - mb) * inv_l : 0.f;
+              p1 = (key + 1 < nvalid) ? exp2f(__uint_as_float(v[i + 1]) * L2E - mb) * inv_l : 0.f;
+            } else {                                   // dot-product mode: f / N (nonlocalnet.py:203-204)
+              p0 = (key < nvalid) ? __uint_as_float(v[i]) * p.scale : 0.f;
+              p1 = (key + 1 < nvalid) ? __uint_as_float(v[i + 1]) * p.scale : 0.f;
+            }
             o4[e] = pack_half2(p0, p1);
           }
           const uint32_t chunk = static_cast<uint32_t>(h * 4 + c);
@@ -157,8 +168,8 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     // ---- epilogue: O (TMEM) -> fp16 global ----
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const bool row_ok = (q0 + r) < p.Npos;
-    __half* orow = p.o + (size_t)(row_base + q0 + r) * p.ldo + dv0;
+    const bool row_ok = (q0 + r) < p.Nq;
+    __half* orow = p.o + (size_t)(q_base + q0 + r) * p.ldo + dv0;
 #pragma unroll 1
     for (int jc = 0; jc < DVT / 32; ++jc) {
       tmem_ld32(tmem_O + lane_off + jc * 32, v);
@@ -185,13 +196,13 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         if (elect_one()) {
           mbar_expect_tx(&full_bar[s], kAttBM * 128 + kAttBKV * 128);
           uint8_t* dst = smem + s * kAttSlotBytes;
-          tma_load_2d(dst, &tmQ, &full_bar[s], kb * 64, row_base + q0);
-          tma_load_2d(dst + kAttBM * 128, &tmK, &full_bar[s], kb * 64, row_base + kvb * kAttBKV);
+          tma_load_2d(dst, &tmQ, &full_bar[s], kb * 64, q_base + q0);
+          tma_load_2d(dst + kAttBM * 128, &tmK, &full_bar[s], kb * 64, k_base + kvb * kAttBKV);
         }
         __syncwarp();
       }
     };
-    for (int kvb = 0; kvb < p.nkv; ++kvb) load_qk(kvb);           // pass 1
+    for (int kvb = 0; two_pass && kvb < p.nkv; ++kvb) load_qk(kvb);   // pass 1
     load_qk(0);                                                   // pass 2 prologue
     for (int j = 0; j < p.nkv; ++j) {
       if (j + 1 < p.nkv) load_qk(j + 1);
@@ -201,7 +212,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         mbar_expect_tx(&full_bar[s], DVT * 128);
 #pragma unroll
         for (int blk = 0; blk < DVT / 64; ++blk)      // [64 dv x 64 keys] boxes, 8 KB apart
-          tma_load_2d(smem + s * kAttSlotBytes + blk * 8192, &tmV, &full_bar[s], dv0 + blk * 64, row_base + j * kAttBKV);
+          tma_load_2d(smem + s * kAttSlotBytes + blk * 8192, &tmV, &full_bar[s], dv0 + blk * 64, k_base + j * kAttBKV);
       }
       __syncwarp();
       ++it;
@@ -238,7 +249,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
       ++g;
     };
-    for (int kvb = 0; kvb < p.nkv; ++kvb) issue_qk();             // pass 1
+    for (int kvb = 0; two_pass && kvb < p.nkv; ++kvb) issue_qk();     // pass 1
     issue_qk();                                                   // pass 2 prologue: S for block 0
     for (int j = 0; j < p.nkv; ++j) {
       if (j + 1 < p.nkv) issue_qk();                              // overlap softmax(j) with QK(j+1)
@@ -271,7 +282,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 
 template <int DVT>
 static int launch_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                            int B, int Npos, int d, int dv, cudaStream_t stream) {
+                            int B, int Nq, int Nk, int d, int dv, int mode, cudaStream_t stream) {
   using S = AttSmem<DVT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -280,14 +291,15 @@ static int launch_attention(const void* q, int ldq, const void* k, int ldk, cons
   }
   CUtensorMap tmQ, tmK, tmV;
   int rc;
-  const uint64_t rows = (uint64_t)B * Npos;
-  if ((rc = make_tmap_2d_f16(&tmQ, q, (uint64_t)d, rows, (uint64_t)ldq, 64, kAttBM, true)) != B2_OK) return rc;
-  if ((rc = make_tmap_2d_f16(&tmK, k, (uint64_t)d, rows, (uint64_t)ldk, 64, kAttBKV, true)) != B2_OK) return rc;
-  if ((rc = make_tmap_2d_f16(&tmV, v, (uint64_t)dv, rows, (uint64_t)ldv, 64, kAttBKV, true)) != B2_OK) return rc;
+  const uint64_t qrows = (uint64_t)B * Nq, krows = (uint64_t)B * Nk;
+  if ((rc = make_tmap_2d_f16(&tmQ, q, (uint64_t)d, qrows, (uint64_t)ldq, 64, kAttBM, true)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmK, k, (uint64_t)d, krows, (uint64_t)ldk, 64, kAttBKV, true)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmV, v, (uint64_t)dv, krows, (uint64_t)ldv, 64, kAttBKV, true)) != B2_OK) return rc;
   AttParams p;
-  p.Npos = Npos; p.nkb = d / 64; p.nkv = (Npos + kAttBKV - 1) / kAttBKV;
+  p.Nq = Nq; p.Nk = Nk; p.nkb = d / 64; p.nkv = (Nk + kAttBKV - 1) / kAttBKV;
+  p.mode = mode; p.scale = 1.0f / (float)Nk;
   p.o = reinterpret_cast<__half*>(o); p.ldo = ldo;
-  dim3 grid((Npos + kAttBM - 1) / kAttBM, B, dv / DVT);
+  dim3 grid((Nq + kAttBM - 1) / kAttBM, B, dv / DVT);
   nonlocal_attention_kernel<DVT><<<grid, kAttThreads, S::kTotal, stream>>>(tmQ, tmK, tmV, p);
   B2_CHECK_LAUNCH("nonlocal_attention_kernel");
   return B2_OK;
@@ -298,9 +310,10 @@ static int launch_attention(const void* q, int ldq, const void* k, int ldk, cons
 using namespace b2;
 
 extern "C" int b2_nonlocal_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o,
-                                     int ldo, int B, int Npos, int d, int dv, void* stream) {
+                                     int ldo, int B, int Nq, int Nk, int d, int dv, int mode, void* stream) {
   B2_CHECK_ARG(q && k && v && o, "null pointer");
-  B2_CHECK_ARG(B > 0 && Npos > 0 && d > 0 && dv > 0, "non-positive dimension");
+  B2_CHECK_ARG(B > 0 && Nq > 0 && Nk > 0 && d > 0 && dv > 0, "non-positive dimension");
+  B2_CHECK_ARG(mode == 0 || mode == 1, "unknown attention mode %d", mode);
   B2_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "pitches must be multiples of 8");
   B2_CHECK_ARG(ldq >= d && ldk >= d && ldo >= dv && ldv >= dv, "pitch smaller than extent");
   if (d % 64 != 0 || dv % 64 != 0)
@@ -308,7 +321,7 @@ extern "C" int b2_nonlocal_attention(const void* q, int ldq, const void* k, int 
   int rc;
   if ((rc = require_sm100()) != B2_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dv % 256 == 0) return launch_attention<256>(q, ldq, k, ldk, v, ldv, o, ldo, B, Npos, d, dv, st);
-  if (dv % 128 == 0) return launch_attention<128>(q, ldq, k, ldk, v, ldv, o, ldo, B, Npos, d, dv, st);
-  return launch_attention<64>(q, ldq, k, ldk, v, ldv, o, ldo, B, Npos, d, dv, st);
+  if (dv % 256 == 0) return launch_attention<256>(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, d, dv, mode, st);
+  if (dv % 128 == 0) return launch_attention<128>(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, d, dv, mode, st);
+  return launch_attention<64>(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, d, dv, mode, st);
 }

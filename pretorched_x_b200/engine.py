@@ -188,34 +188,60 @@ def _conv1x1_matrix(conv):
     return conv.weight.detach().reshape(conv.weight.shape[0], -1)
 
 
+def _first(m):
+    return m[0] if isinstance(m, nn.Sequential) else m
+
+
 def run_nonlocal(nl, a, simt=False):
-    """z = BN(W(softmax(theta(x)^T phi(x)) g(x))) + x   (nonlocalnet.py:143-166)."""
-    if nl.mode != "embedded_gaussian" or nl.sub_sample or nl.dimension != 3:
-        raise NotImplementedError("engine implements the 3-D embedded-gaussian non-local block without sub-sampling")
-    d = nl.inter_channels
-    C = nl.in_channels
+    """z = W(y) + x with y = softmax(theta^T phi) g  (embedded gaussian, nonlocalnet.py:143-166),
+    y = softmax(x^T phi(x)) g (gaussian, :168-190) or y = (theta^T phi / N) g (dot product, :192-211); phi and g are
+    max-pooled when ``sub_sample`` (:126-131)."""
+    if nl.mode not in ("embedded_gaussian", "gaussian", "dot_product"):
+        raise NotImplementedError("non-local mode %r is outside the engine's scope" % (nl.mode,))
+    d, C = nl.inter_channels, nl.in_channels
     dev = a.data.device
-    Wseq = nl.W
-    w_conv, w_bn = (Wseq[0], Wseq[1]) if isinstance(Wseq, nn.Sequential) else (Wseq, None)
+    w_conv, w_bn = (nl.W[0], nl.W[1]) if isinstance(nl.W, nn.Sequential) else (nl.W, None)
+    g_conv = _first(nl.g)
+    projected = [g_conv] if nl.mode == "gaussian" else [nl.theta, _first(nl.phi), g_conv]   # column order of the GEMM
 
     def build():
-        # theta | phi | g concatenated along the output dim -> ONE projection GEMM
-        w = torch.zeros((3 * d, a.ld), dtype=torch.float16, device=dev)
-        w[:d, :C] = _conv1x1_matrix(nl.theta).to(torch.float16)
-        w[d:2 * d, :C] = _conv1x1_matrix(nl.phi).to(torch.float16)
-        w[2 * d:, :C] = _conv1x1_matrix(nl.g).to(torch.float16)
-        b = torch.cat([nl.theta.bias.detach(), nl.phi.bias.detach(), nl.g.bias.detach()]).float().contiguous()
-        ones = torch.ones(3 * d, dtype=torch.float32, device=dev)
-        return w, b, ones
+        n = len(projected) * d
+        w = torch.zeros((n, a.ld), dtype=torch.float16, device=dev)
+        for i, conv in enumerate(projected):
+            w[i * d:(i + 1) * d, :C] = _conv1x1_matrix(conv).to(torch.float16)
+        b = torch.cat([conv.bias.detach() for conv in projected]).float().contiguous()
+        wo = torch.zeros((C, ops._round_up(d, 8)), dtype=torch.float16, device=dev)
+        wo[:, :d] = _conv1x1_matrix(w_conv).to(torch.float16)
+        so, bo = ops.fold_affine(C, w_conv.bias, w_bn, dev)
+        return w, b, torch.ones(n, dtype=torch.float32, device=dev), wo, so, bo
 
-    sig = _sig(nl.theta.weight, nl.theta.bias, nl.phi.weight, nl.phi.bias, nl.g.weight, nl.g.bias) + (a.ld,)
-    wqkv, bqkv, ones = _cached(nl, "proj", sig, build)
+    sig = _sig(*[t for conv in projected for t in (conv.weight, conv.bias)], w_conv.weight, w_conv.bias,
+               *_bn_tensors(w_bn)) + (a.ld, nl.mode)
+    wp, bp, ones, wo, so, bo = _cached(nl, "proj", sig, build)
 
-    qkv = ops.gemm(a.data, wqkv, ones, bqkv, a.M, 3 * d, a.ld)          # [M][3d]: theta | phi | g
-    y = ops.nonlocal_attention(qkv, d, d, a.N, a.positions)
-    ya = Act(y, a.N, a.T, a.H, a.W, d)
-    # W (1x1x1 conv with bias) + BN + residual x, no ReLU
-    return conv_bn_act(w_conv, w_bn, ya, residual=a, relu=False, simt=simt)
+    pool = {3: (2, 2, 2), 2: (1, 2, 2), 1: (1, 1, 2)}[nl.dimension]
+    B, Nq = a.N, a.positions
+    dot = nl.mode == "dot_product"
+    if nl.mode == "gaussian":
+        gv = ops.gemm(a.data, wp, ones, bp, a.M, d, a.ld)                       # g(x): [M][d]
+        if nl.sub_sample:
+            xk = ops.maxpool3d(a, pool, pool, (0, 0, 0))                           # phi = max_pool(x)
+            gk = ops.maxpool3d(Act(gv, a.N, a.T, a.H, a.W, d), pool, pool, (0, 0, 0))
+            k2d, v2d, Nk = xk.data, gk.data, xk.positions
+        else:
+            k2d, v2d, Nk = a.data, gv, Nq
+        y = ops.attention(a.data, k2d, v2d, C, d, B, Nq, Nk)                      # theta = x itself
+    elif not nl.sub_sample:
+        qkv = ops.gemm(a.data, wp, ones, bp, a.M, 3 * d, a.ld)                   # [M][3d]: theta | phi | g
+        y = ops.attention(qkv, qkv[:, d:], qkv[:, 2 * d:], d, d, B, Nq, Nq, dot_product=dot)
+    else:
+        q = ops.gemm(a.data, wp[:d], ones[:d], bp[:d], a.M, d, a.ld)             # theta at full resolution
+        kv = ops.gemm(a.data, wp[d:], ones[d:], bp[d:], a.M, 2 * d, a.ld)        # phi | g ...
+        kvp = ops.maxpool3d(Act(kv, a.N, a.T, a.H, a.W, 2 * d), pool, pool, (0, 0, 0))   # ... max-pooled together
+        y = ops.attention(q, kvp.data, kvp.data[:, d:], d, d, B, Nq, kvp.positions, dot_product=dot)
+    # W (1x1 conv with bias) + BN + residual x, no ReLU
+    z = ops.gemm(y, wo, so, bo, a.M, C, d, residual=a.data)
+    return Act(z, a.N, a.T, a.H, a.W, C)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,9 +1,9 @@
 """Non-local 3-D ResNets (reference: pretorched/models/nonlocalnet.py).
 
-``NonLocalBlock3D`` holds the theta / phi / g / W(+BN) parameters of the embedded-gaussian block
-(nonlocalnet.py:51-131); its body (nonlocalnet.py:143-166) runs in ``engine.run_nonlocal``: one GEMM for
-theta|phi, one swap-AB GEMM for g^T, the fused QK^T-softmax-V kernel, and the W conv with BN and the
-``+x`` residual in its epilogue.  The THW x THW matrix is never written to memory.
+``NonLocalBlock{1,2,3}D`` hold the theta / phi / g / W(+BN) parameters of the non-local block
+(nonlocalnet.py:51-131); the body (nonlocalnet.py:143-211) runs in ``engine.run_nonlocal``: one GEMM for
+theta|phi|g, the fused QK^T-softmax-V kernel (V consumed in place as an MN-major operand), and the W projection
+with BN and the ``+x`` residual in its epilogue.  The positions x positions matrix is never written to memory.
 
 Reference behaviours reproduced on purpose:
   * ``nonlocalresnet3d50(num_classes=...)`` does not forward ``num_classes`` (nonlocalnet.py:553-561):
@@ -19,7 +19,7 @@ import torch.nn as nn
 from .. import engine
 from .resnet3d import EngineModule, ShortcutA, _attach_settings, conv3x3x3
 
-__all__ = ['NonLocalBlock3D', 'NonLocalResNet3D', 'nonlocalresnet3d', 'nonlocalresnet3d18', 'nonlocalresnet3d34',
+__all__ = ['NonLocalBlock1D', 'NonLocalBlock2D', 'NonLocalBlock3D', 'NonLocalResNet3D', 'nonlocalresnet3d', 'nonlocalresnet3d18', 'nonlocalresnet3d34',
            'nonlocalresnet3d50', 'nonlocalresnet3d101', 'nonlocalresnet3d152', 'nonlocalresnet3d200']
 
 _URL = 'http://pretorched-x.csail.mit.edu/models/resnet3d50_kinetics-aad059c9.pth'
@@ -33,33 +33,75 @@ for _dataset, _n in (('kinetics-400', 400), ('moments', 339)):
     }
 
 
-class NonLocalBlock3D(EngineModule):
-    """Embedded-gaussian non-local block over (T,H,W); parameters only."""
+class _NonLocalBlockND(EngineModule):
+    """Non-local block over 1, 2 or 3 position axes (nonlocalnet.py:51-131); parameters only.
 
-    def __init__(self, in_channels, inter_channels=None, mode='embedded_gaussian', sub_sample=False, bn_layer=True):
+    Modes on the engine: ``embedded_gaussian`` (:143-166), ``gaussian`` (:168-190), ``dot_product`` (:192-211), each
+    with or without ``sub_sample`` (max-pooled phi / g, :126-131) and with or without the output BatchNorm.
+    ``concatenation`` (:213-243) is not implemented."""
+
+    def __init__(self, in_channels, inter_channels=None, dimension=3, mode='embedded_gaussian', sub_sample=False,
+                 bn_layer=True):
         super().__init__()
-        if mode != 'embedded_gaussian' or sub_sample:
-            raise NotImplementedError("engine scope: embedded_gaussian mode without sub-sampling "
-                                      "(the configuration every reference 3-D net uses, nonlocalnet.py:395)")
-        self.mode, self.dimension, self.sub_sample = mode, 3, sub_sample
+        assert dimension in [1, 2, 3]
+        assert mode in ['embedded_gaussian', 'gaussian', 'dot_product', 'concatenation']
+        if mode == 'concatenation':
+            raise NotImplementedError("the 'concatenation' non-local mode is outside the engine's scope")
+        self.mode, self.dimension, self.sub_sample = mode, dimension, sub_sample
         self.in_channels = in_channels
         self.inter_channels = inter_channels if inter_channels is not None else max(in_channels // 2, 1)
+        conv_nd = (None, nn.Conv1d, nn.Conv2d, nn.Conv3d)[dimension]
+        max_pool = (None, nn.MaxPool1d, nn.MaxPool2d, nn.MaxPool3d)[dimension]
+        bn = (None, nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)[dimension]
         d = self.inter_channels
-        self.g = nn.Conv3d(in_channels, d, kernel_size=1, stride=1, padding=0)
+        self.g = conv_nd(in_channels, d, kernel_size=1, stride=1, padding=0)
         if bn_layer:
-            self.W = nn.Sequential(nn.Conv3d(d, in_channels, kernel_size=1, stride=1, padding=0),
-                                   nn.BatchNorm3d(in_channels))
+            self.W = nn.Sequential(conv_nd(d, in_channels, kernel_size=1, stride=1, padding=0), bn(in_channels))
             nn.init.constant_(self.W[1].weight, 0)
             nn.init.constant_(self.W[1].bias, 0)
         else:
-            self.W = nn.Conv3d(d, in_channels, kernel_size=1, stride=1, padding=0)
+            self.W = conv_nd(d, in_channels, kernel_size=1, stride=1, padding=0)
             nn.init.constant_(self.W.weight, 0)
             nn.init.constant_(self.W.bias, 0)
-        self.theta = nn.Conv3d(in_channels, d, kernel_size=1, stride=1, padding=0)
-        self.phi = nn.Conv3d(in_channels, d, kernel_size=1, stride=1, padding=0)
+        self.theta = None
+        self.phi = None
+        self.concat_project = None
+        if mode in ('embedded_gaussian', 'dot_product'):
+            self.theta = conv_nd(in_channels, d, kernel_size=1, stride=1, padding=0)
+            self.phi = conv_nd(in_channels, d, kernel_size=1, stride=1, padding=0)
+        if sub_sample:
+            self.g = nn.Sequential(self.g, max_pool(kernel_size=2))
+            self.phi = max_pool(kernel_size=2) if self.phi is None else nn.Sequential(self.phi, max_pool(kernel_size=2))
 
     def _run(self, a):
         return engine.run_nonlocal(self, a)
+
+    def forward(self, x):
+        from .. import ops
+        if isinstance(x, ops.Act):
+            return self._run(x)
+        shape = x.shape
+        x5 = x.reshape(shape[0], shape[1], *([1] * (3 - self.dimension)), *shape[2:])      # -> [N, C, T, H, W]
+        out = ops.to_ncdhw(self._run(ops.from_ncdhw(x5, pitch=ops._round_up(shape[1], 8))))
+        return out.reshape(shape)
+
+
+class NonLocalBlock1D(_NonLocalBlockND):
+    def __init__(self, in_channels, inter_channels=None, mode='embedded_gaussian', sub_sample=False, bn_layer=True):
+        super().__init__(in_channels, inter_channels=inter_channels, dimension=1, mode=mode, sub_sample=sub_sample,
+                         bn_layer=bn_layer)
+
+
+class NonLocalBlock2D(_NonLocalBlockND):
+    def __init__(self, in_channels, inter_channels=None, mode='embedded_gaussian', sub_sample=False, bn_layer=True):
+        super().__init__(in_channels, inter_channels=inter_channels, dimension=2, mode=mode, sub_sample=sub_sample,
+                         bn_layer=bn_layer)
+
+
+class NonLocalBlock3D(_NonLocalBlockND):
+    def __init__(self, in_channels, inter_channels=None, mode='embedded_gaussian', sub_sample=False, bn_layer=True):
+        super().__init__(in_channels, inter_channels=inter_channels, dimension=3, mode=mode, sub_sample=sub_sample,
+                         bn_layer=bn_layer)
 
 
 class _NLBlockBase(EngineModule):

@@ -350,19 +350,20 @@ def gather_frames(x3d, idx_dev):
 # ---------------------------------------------------------------------------------------------
 # non-local attention
 # ---------------------------------------------------------------------------------------------
-def nonlocal_attention(qkv, d, dv, B, Npos):
-    """softmax(theta^T phi) . g  (nonlocalnet.py:150-160).
+def attention(q2d, k2d, v2d, d, dv, B, Nq, Nk, dot_product=False):
+    """softmax(Q K^T) V, or (Q K^T / Nk) V when ``dot_product`` (nonlocalnet.py:143-211).
 
-    qkv: fp16 [B*Npos][>= 2d + dv] with theta in columns [0,d), phi in [d,2d) and g in [2d,2d+dv) -- the output of
-    one fused projection GEMM.  Returns fp16 [B*Npos][dv].
-    """
-    o = torch.empty((B * Npos, _round_up(dv, 8)), dtype=torch.float16, device=qkv.device)
-    esz = qkv.element_size()
-    base, ld = qkv.data_ptr(), qkv.stride(0)
-    with _timed("attention", "attention B=%d N=%d d=%d dv=%d" % (B, Npos, d, dv), 2.0 * B * Npos * Npos * (d + dv),
-                2.0 * B * Npos * (2 * d + 2 * dv)):
-        _lib.check(_lib.load().b2_nonlocal_attention(ctypes.c_void_p(base), ld, ctypes.c_void_p(base + d * esz), ld,
-                                                    ctypes.c_void_p(base + 2 * d * esz), ld, _ptr(o), o.stride(0),
-                                                    B, Npos, d, dv, _stream()),
-                   "b2_nonlocal_attention")
+    q2d: fp16 [B*Nq][>= d]; k2d: fp16 [B*Nk][>= d]; v2d: fp16 [B*Nk][>= dv] (row views of projection outputs, 16-byte
+    aligned).  Returns fp16 [B*Nq][dv]."""
+    o = torch.empty((B * Nq, _round_up(dv, 8)), dtype=torch.float16, device=q2d.device)
+    with _timed("attention", "attention B=%d Nq=%d Nk=%d d=%d dv=%d" % (B, Nq, Nk, d, dv), 2.0 * B * Nq * Nk * (d + dv),
+                2.0 * B * (Nq * (d + dv) + Nk * (d + dv))):
+        _lib.check(_lib.load().b2_nonlocal_attention(_ptr(q2d), q2d.stride(0), _ptr(k2d), k2d.stride(0), _ptr(v2d),
+                                                    v2d.stride(0), _ptr(o), o.stride(0), B, Nq, Nk, d, dv,
+                                                    int(dot_product), _stream()), "b2_nonlocal_attention")
     return o
+
+
+def nonlocal_attention(qkv, d, dv, B, Npos):
+    """Embedded-gaussian core on one fused projection: qkv fp16 [B*Npos][>= 2d + dv] = theta | phi | g."""
+    return attention(qkv, qkv[:, d:], qkv[:, 2 * d:], d, dv, B, Npos, Npos)

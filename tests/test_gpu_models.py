@@ -207,3 +207,21 @@ def test_slowfast_matches_reference_golden(dev, path):
     err = (y.cpu().double() - fx["logits"].double()).abs().max().item() / fx["logits"].abs().max().item()
     assert err <= 5e-3, err
     assert torch.equal(y.argmax(1).cpu(), fx["logits"].argmax(1))
+
+
+NL_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "nlblock"]
+
+
+@pytest.mark.parametrize("path", NL_FIX, ids=[os.path.basename(p)[:-3] for p in NL_FIX])
+def test_nonlocal_block_modes_match_reference_golden(dev, path):
+    """NonLocalBlock{1,2,3}D in gaussian / dot_product / embedded_gaussian mode, with and without sub-sampling and
+    the output BatchNorm (nonlocalnet.py:143-211), against outputs of the reference's own modules."""
+    from tests.test_oracle_golden import build_nlblock
+    fx = torch.load(path, weights_only=False)
+    blk = build_nlblock(fx).to(dev)
+    x = (OF.seeded_input(fx["input_shape"], fx["seeds"]["input"]) * fx["input_scale"]).to(dev)
+    with torch.no_grad():
+        y = blk(x)
+    assert tuple(y.shape) == tuple(fx["output"].shape)
+    err = (y.cpu().double() - fx["output"].double()).abs().max().item() / fx["output"].abs().max().item()
+    assert err <= 5e-3, err

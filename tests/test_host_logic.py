@@ -73,7 +73,10 @@ def test_nonlocal_quirks():
     assert float(m.layer2[0].nonlocalblock.W[1].weight.abs().mean()) == 1.0   # init_weights overrides the zero init
     assert OF.nonlocal_positions([3, 4, 6, 3], [0, 2, 3, 0]) == [[], [0, 2], [0, 2, 4], []]
     with pytest.raises(NotImplementedError):
-        nonlocalnet.NonLocalBlock3D(64, mode="gaussian")
+        nonlocalnet.NonLocalBlock3D(64, mode="concatenation")
+    sub = nonlocalnet.NonLocalBlock2D(64, mode="gaussian", sub_sample=True)     # reference layout with sub_sample
+    assert set(sub.state_dict()) >= {"g.0.weight", "g.0.bias", "W.0.weight", "W.1.running_mean"}
+    assert "theta.weight" not in sub.state_dict()
 
 
 def test_trn_upstream_defects_are_explicit():

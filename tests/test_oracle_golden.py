@@ -122,3 +122,26 @@ def test_slowfast_init_and_oracle_match_reference(path):
     with torch.no_grad():
         y = OF.slowfast_forward(x, sd, fx["layers"], fx["bottleneck"], fx["mode"])
     assert (y - fx["logits"]).abs().max().item() <= 1e-5 * fx["logits"].abs().max().item()
+
+
+NL_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "nlblock"]
+
+
+def build_nlblock(fx):
+    from oracle.make_golden import condition_nlblock_
+    from pretorched_x_b200.models import nonlocalnet
+    torch.manual_seed(fx["seeds"]["init"])
+    cls = getattr(nonlocalnet, "NonLocalBlock%dD" % fx["dimension"])
+    blk = cls(fx["channels"], mode=fx["mode"], sub_sample=fx["sub_sample"], bn_layer=fx["bn_layer"])
+    return condition_nlblock_(blk, fx["seeds"]["bn"]).eval()
+
+
+@pytest.mark.parametrize("path", NL_FIX, ids=[os.path.basename(p)[:-3] for p in NL_FIX])
+def test_nonlocal_block_modes_init_and_oracle_match_reference(path):
+    fx = torch.load(path, weights_only=False)
+    blk = build_nlblock(fx)
+    assert OF.digests_match(OF.state_digest(blk.state_dict()), fx["weight_digest"])
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"]) * fx["input_scale"]
+    with torch.no_grad():
+        y = OF.nonlocal_block_nd(x, blk.state_dict(), "", fx["dimension"], fx["mode"], fx["sub_sample"], fx["bn_layer"])
+    assert (y - fx["output"]).abs().max().item() <= 1e-5 * fx["output"].abs().max().item()
