@@ -135,12 +135,12 @@ def run_relation_cases():
 
 NLBLOCK_CASES = {
     # name -> (dimension, mode, sub_sample, bn_layer, channels, input shape)
-    "nlblock3d_gaussian_sub": (3, "gaussian", True, True, 64, (2, 64, 4, 8, 8)),
+    "nlblock3d_gaussian_sub": (3, "gaussian", True, True, 128, (2, 128, 4, 8, 8)),
     "nlblock3d_dot_product": (3, "dot_product", False, True, 128, (2, 128, 2, 7, 7)),
     "nlblock3d_embedded_sub": (3, "embedded_gaussian", True, True, 128, (1, 128, 4, 8, 8)),
     "nlblock2d_embedded": (2, "embedded_gaussian", False, True, 128, (2, 128, 12, 12)),
     "nlblock2d_dot_sub_nobn": (2, "dot_product", True, False, 128, (2, 128, 12, 12)),
-    "nlblock1d_gaussian": (1, "gaussian", False, True, 64, (3, 64, 50)),
+    "nlblock1d_gaussian": (1, "gaussian", False, True, 128, (3, 128, 50)),
 }
 
 
