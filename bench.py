@@ -272,7 +272,7 @@ def run_ours(args, rank, world, local):
     all_ms = sum(r["ms"] for r in rows) / nrep
     achieved_tflops = conv_flops / (conv_ms * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "kernel": "b2::igemm_kernel (all %d conv/linear launches of one forward)" % (len(conv_rows) // nrep),
+        "bound": "tensor", "kernel": "tcgen05 conv/GEMM family (stemconv, slabconv, pgemm, igemm): all %d conv/linear launches of one forward" % (len(conv_rows) // nrep),
         "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"],
         "traffic": None, "peak_source": peaks["source"] + ", sustained bf16/fp16 GEMM",
         "share_of_step": conv_ms / all_ms,

@@ -64,7 +64,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* o_full = p_empty + 2;                                        // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * kAttBM;            // first query row of this CTA within the sample
   const int b = blockIdx.y;
   const int dv0 = blockIdx.z * DVT;

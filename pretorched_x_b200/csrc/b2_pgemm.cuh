@@ -68,7 +68,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* res_empty = res_full + 2;                                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
 
   if (tid == kPgEpiWarps * 32) {
     for (int s = 0; s < kPgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
