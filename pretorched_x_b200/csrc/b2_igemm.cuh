@@ -87,7 +87,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA,   // activations as [M][C]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int lane = tid & 31;
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * kBM;
   const bool gather = (p.amode != AMODE_TMA);
