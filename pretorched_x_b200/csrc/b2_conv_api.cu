@@ -117,6 +117,8 @@ int make_tmap_ndhwc_slab(CUtensorMap* out, const void* base, uint64_t C, uint64_
 // ------------------------------------------------------------------------------------------
 static int g_conv_algo = 0;   // 0 auto, 1 force gather (debug / A-B comparisons)
 
+static int slab_naff(int ldy) { return (ldy + 31) / 32 * 32 + 256; }   // chunk reads may run past ldy inside the last N tile
+
 static int slab_rows(int MT, int PW, int reach, int P) {
   int R = 0;
   for (int q0 = 0; q0 < P; q0 += MT * 128) {
@@ -130,7 +132,7 @@ static int slab_rows(int MT, int PW, int reach, int P) {
 
 // Fills the geometry part of SlabParams (sub-image / tap tables).  Returns false when the convolution is not of a
 // shape the slab kernel handles.
-static bool slab_geometry(const b2_conv_args* a, SlabParams* p) {
+static bool slab_geometry(const b2_conv_args* a, SlabParams* p, int wc_hint) {
   if (a->mode != B2_CONV_AUTO || a->out_f32) return false;
   if ((a->kt & 1) == 0 || (a->kh & 1) == 0 || (a->kw & 1) == 0) return false;
   if (a->pt != (a->kt - 1) / 2 || a->ph != (a->kh - 1) / 2 || a->pw != (a->kw - 1) / 2) return false;
@@ -155,7 +157,17 @@ static bool slab_geometry(const b2_conv_args* a, SlabParams* p) {
     if (oj[d] > max_oj) max_oj = oj[d];
   }
   p->halo_l = -min_oj;
-  p->PW = p->Wo + p->halo_l + max_oj;
+  // W chunking: rows longer than a TMA box (256 pixels incl. halo) are cut into chunks of WC output columns.  For the
+  // temporal remap (kw = 1, "rows" are H*W positions of one frame) a short chunk keeps MT+kt-1 frames in one slab.
+  p->WC = p->Wo; p->wchunks = 1;
+  const int wc_max = wc_hint > 0 ? wc_hint : (ss == 1 ? 256 : 128) - p->halo_l - max_oj;   // TMA box <= 256 traversed pixels
+  if (p->Wo > wc_max) {
+    int best = 0;
+    for (int c = wc_max; c >= (wc_max * 3) / 4; --c) if (p->Wo % c == 0) { best = c; break; }   // prefer an exact divisor
+    p->WC = best ? best : wc_max;
+    p->wchunks = (p->Wo + p->WC - 1) / p->WC;
+  }
+  p->PW = p->WC + p->halo_l + max_oj;
   p->P = p->Ho * p->PW;
   p->n_sub = 0;
   p->reach = 0;
@@ -182,12 +194,14 @@ static bool slab_geometry(const b2_conv_args* a, SlabParams* p) {
   return p->n_sub > 0 && p->PW <= 256;
 }
 
-template <int BN>
+template <int BNT>   // BNT = 0: runtime N tile p.bn (set by the caller)
 static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cudaStream_t stream) {
+  if (BNT) { p.bn = BNT; p.wbytes = BNT * 128; p.accs = BNT; }
+  const int BN = p.bn;
   p.R = R;
   p.slab_bytes = ((R * p.PW * 128) + 1023) / 1024 * 1024;
   p.MT = MT;
-  p.nacc = (MT * BN <= 256) ? 2 : 1;
+  p.nacc = (MT * p.accs <= 256) ? 2 : 1;
   p.Ncols = a->K;
   p.scale = a->scale; p.shift = a->shift;
   p.residual = reinterpret_cast<const __half*>(a->residual);
@@ -195,15 +209,16 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   p.y = reinterpret_cast<__half*>(a->y);
   p.ldy = a->ldy;
   p.relu = a->relu;
+  p.naff = slab_naff(a->ldy);
   p.tiles_n = (a->ldy + BN - 1) / BN;
   p.tiles_q = (p.P + MT * 128 - 1) / (MT * 128);
-  const long long items = (long long)p.tiles_n * p.tiles_q * a->N * p.To;
+  const long long items = (long long)p.tiles_n * p.tiles_q * p.wchunks * a->N * p.To;
   if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "slab problem too large");
   p.items_total = (int)items;
-  const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * BN * 128 + 256 + 2 * kSlabAffMax * 4 + 1024;
+  const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * p.wbytes + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(slabconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(slabconv_kernel<BNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   CUtensorMap tmX, tmB;
@@ -215,32 +230,58 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)taps * a->C, (uint64_t)a->K, (uint64_t)taps * a->C, 64, BN, true)) != B2_OK)
     return rc;
   const int grid = p.items_total < sm_count() ? p.items_total : sm_count();
-  slabconv_kernel<BN><<<grid, kSlabThreads, smem_bytes, stream>>>(tmX, tmB, p);
+  slabconv_kernel<BNT><<<grid, kSlabThreads, smem_bytes, stream>>>(tmX, tmB, p);
   B2_CHECK_LAUNCH("slabconv_kernel");
   return B2_OK;
 }
 
 // returns 1 when the slab kernel took the convolution, 0 when it does not apply, <0 on error
-static int try_slab(const b2_conv_args* a, cudaStream_t stream) {
+static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
   if (g_conv_algo == 1) return 0;
   SlabParams p;
-  if (!slab_geometry(a, &p)) return 0;
+  b2_conv_args remap = *a_in;
+  const b2_conv_args* a = a_in;
+  int wc_hint = 0;
+  if (a_in->kt > 1 && a_in->kh == 1 && a_in->kw == 1 && a_in->st == 1 && a_in->sh == 1 && a_in->sw == 1 &&
+      a_in->ph == 0 && a_in->pw == 0 && g_conv_algo != 3) {
+    // (kt,1,1) over [N][T][H][W] == (1,kt,1) over N images of T rows x (H*W) columns
+    remap.T = 1; remap.H = a_in->T; remap.W = a_in->H * a_in->W;
+    remap.kt = 1; remap.kh = a_in->kt; remap.kw = 1;
+    remap.pt = 0; remap.ph = a_in->pt; remap.pw = 0;
+    a = &remap;
+    wc_hint = 64;
+  }
+  if (!slab_geometry(a, &p, wc_hint)) return 0;
   if (g_conv_algo == 2 && p.ss != 1) return 0;              // debug: strided convs through the gather kernel
-  const int BN = (a->ldy <= 64) ? 64 : 128;
+  int BN = (a->ldy <= 64) ? 64 : 128;
   const int planes = a->N * p.To;
-  const int ntn = (a->ldy + BN - 1) / BN;
+  int ntn = (a->ldy + BN - 1) / BN;
+  // Channel counts that tile badly by 128 (144, 288, 576 ... of R(2+1)D) take the runtime-N instance: the fewest
+  // tiles of <= 256 columns, each a multiple of 16 wide.
+  bool flex = false;
+  if (a->ldy > 128) {
+    const int tn = (a->ldy + 255) / 256;
+    const int bn = (((a->ldy + tn - 1) / tn) + 15) / 16 * 16;
+    if ((long long)bn * tn * 21 <= (long long)ntn * 128 * 20) {
+      flex = true; BN = bn; ntn = tn;
+      p.bn = bn; p.wbytes = (bn * 128 + 1023) / 1024 * 1024; p.accs = (bn + 31) / 32 * 32;
+    }
+  }
+  const int acc_stride = flex ? p.accs : BN;
+  const int w_stage = flex ? p.wbytes : BN * 128;
   int best_mt = 0, best_R = 0;
-  for (int MT = 512 / BN > 4 ? 4 : 512 / BN; MT >= 1; MT >>= 1) {
+  for (int MT = 512 / acc_stride > 4 ? 4 : 512 / acc_stride; MT >= 1; MT = flex ? MT - 1 : MT >> 1) {
     const int R = slab_rows(MT, p.PW, p.reach, p.P);
     if (p.ss * (R - 1) + 1 > 256) continue;
-    const long long smem = 2ll * (((long long)R * p.PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * BN * 128 + 256 + 2 * kSlabAffMax * 4 + 1024;
+    const long long smem = 2ll * (((long long)R * p.PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * w_stage + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
     if (smem > 227 * 1024) continue;
-    const long long items = (long long)ntn * ((p.P + MT * 128 - 1) / (MT * 128)) * planes;
+    const long long items = (long long)ntn * ((p.P + MT * 128 - 1) / (MT * 128)) * planes * p.wchunks;
     best_mt = MT; best_R = R;
     if (items >= 2 * 148) break;      // enough work items for two rounds per SM: keep the largest MT that achieves it
   }
   if (best_mt == 0) return 0;
-  int rc = (BN == 64) ? launch_slab<64>(a, p, best_mt, best_R, stream) : launch_slab<128>(a, p, best_mt, best_R, stream);
+  int rc = flex ? launch_slab<0>(a, p, best_mt, best_R, stream)
+                : (BN == 64) ? launch_slab<64>(a, p, best_mt, best_R, stream) : launch_slab<128>(a, p, best_mt, best_R, stream);
   return rc == B2_OK ? 1 : rc;
 }
 

@@ -17,7 +17,10 @@
 //
 // Output positions are enumerated in *padded-row* coordinates q = h*(W+2pw) + w' of one (n,t) plane; a work item
 // is MT consecutive 128-position M tiles (MT accumulators in TMEM share every weight tile) x one N tile, and the
-// positions that fall on halo columns are discarded.  CTAs are persistent (one per SM): the producer runs ahead
+// positions that fall on halo columns are discarded.  Rows longer than a TMA box are cut into W chunks (each with
+// its own halo); a purely temporal (kt,1,1) filter is run as a (1,kt,1) filter over the image "frames x (H*W)",
+// so its slab holds MT+kt-1 frames of one position chunk and every temporal tap is a whole-row shift of it.
+// CTAs are persistent (one per SM): the producer runs ahead
 // into the next item's slabs, and when MT*BN <= 256 two accumulator sets let the epilogue of item i overlap the
 // MMAs of item i+1.
 #pragma once
@@ -26,7 +29,7 @@
 
 namespace b2 {
 
-constexpr int kSlabThreads = 192;
+constexpr int kSlabThreads = 320;   // warps 0-3 and 6-9: epilogue (even / odd 32-column chunks), 4: TMA producer, 5: MMA issuer
 constexpr int kSlabWStages = 4;     // weight-tile ring depth
 constexpr int kSlabSStages = 2;     // slab ring depth
 
@@ -40,7 +43,8 @@ struct SlabParams {
   int st, ss;              // temporal / spatial stride
   int pt;                  // temporal padding
   int cchunks;             // ceil(C / 64)
-  int PW;                  // padded output-row length: Wo + halo_l + halo_r
+  int PW;                  // padded output-row length: WC + halo_l + halo_r
+  int WC, wchunks;         // output columns per W chunk (= Wo when the row fits one TMA box) and chunks per row
   int halo_l;              // halo columns left of output column 0
   int R;                   // slab rows (sub-image rows per TMA box)
   // sub-image table: slab row 0 / col 0 of sub-image s is input pixel (ss*r_lo + sub_h0[s], sub_w0[s]); its taps read
@@ -51,8 +55,13 @@ struct SlabParams {
   unsigned char sub_tap[kSlabMaxSub][kSlabMaxTaps];
   int reach;               // max |sub_off|
   int slab_bytes;          // R * PW * 128, rounded up to 1024
-  int MT;                  // M tiles per work item (MT * BN <= 512)
-  int nacc;                // accumulator sets in TMEM: 2 when MT * BN <= 256 (epilogue overlaps the next item)
+  int MT;                  // M tiles per work item (MT * accs <= 512)
+  int nacc;                // accumulator sets in TMEM: 2 when MT * accs <= 256 (epilogue overlaps the next item)
+  // runtime N tile (slabconv_kernel<0> only; the <64>/<128> instances use their template value): Cout = 144, 288,
+  // 576 ... of the (2+1)D factorisation would waste up to 44% of the MMA columns on 128-wide tiles
+  int bn;                  // N per MMA / per tile, multiple of 16, <= 256
+  int wbytes;              // weight stage stride in smem: bn * 128 rounded up to 1024
+  int accs;                // TMEM column stride between the MT accumulators: bn rounded up to 32
   int P;                   // Ho * PW: padded positions per output plane
   int Ncols;               // logical output channels
   int tiles_n, tiles_q, items_total;
@@ -63,18 +72,20 @@ struct SlabParams {
   __half* y;               // dense [M][ldy]
   int ldy;
   int relu;
+  int naff;                // scale/shift entries staged in smem (>= every column an epilogue chunk can touch)
 };
 
-constexpr int kSlabAffMax = 512;   // scale/shift entries kept in smem (all slab layers have Cout <= 512)
+// scale/shift live in smem for all (padded) output channels: SlabParams::naff = round_up(ldy, 32) + 32 entries each
 
 struct SlabItem {
-  int n0, q0, plane_o, plane_i0, r_lo, dt_lo, n_dt, n_slabs, mt_valid;   // plane_i0: input plane of temporal tap 0
+  int n0, q0, wc, plane_o, plane_i0, r_lo, dt_lo, n_dt, n_slabs, mt_valid;   // plane_i0: input plane of temporal tap 0
 };
 __device__ __forceinline__ SlabItem slab_item(const SlabParams& p, int item, int BN) {
   SlabItem w;
   const int tn = item % p.tiles_n; item /= p.tiles_n;
-  const int tq = item % p.tiles_q;
-  w.plane_o = item / p.tiles_q;
+  const int tq = item % p.tiles_q; item /= p.tiles_q;
+  w.wc = item % p.wchunks;
+  w.plane_o = item / p.wchunks;
   w.n0 = tn * BN;
   w.q0 = tq * (p.MT * 128);
   const int to = w.plane_o % p.To, n = w.plane_o / p.To;
@@ -91,14 +102,16 @@ __device__ __forceinline__ SlabItem slab_item(const SlabParams& p, int item, int
   return w;
 }
 
-template <int BN>
+template <int BN>   // BN = 0: N tile taken from SlabParams::bn at run time
 __global__ void __launch_bounds__(kSlabThreads, 1)
 slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H, N*T), box (64, PW, R, 1)
                 const __grid_constant__ CUtensorMap tmB,   // weights [Ncols][taps*C], box (64, BN)
                 const SlabParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kWBytes = BN * 128;
+  const int bn = BN ? BN : p.bn;
+  const int kWBytes = BN ? BN * 128 : p.wbytes;      // stage stride; a stage receives bn * 128 bytes
+  const int accs = BN ? BN : p.accs;
   uint8_t* slab_base = smem;
   uint8_t* w_base = smem + kSlabSStages * p.slab_bytes;
   uint8_t* tail = w_base + kSlabWStages * kWBytes;
@@ -110,21 +123,21 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
   uint64_t* acc_empty = acc_full + 2;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_scale = reinterpret_cast<float*>(tail + 256);     // barriers + TMEM slot occupy the first 132 bytes
-  float* s_shift = s_scale + kSlabAffMax;
+  float* s_shift = s_scale + p.naff;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int acc_cols = p.MT * BN;
+  const int acc_cols = p.MT * accs;
 
   if (tid == 128) {
     for (int s = 0; s < kSlabSStages; ++s) { mbar_init(&slab_full[s], 1); mbar_init(&slab_empty[s], 1); }
     for (int s = 0; s < kSlabWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  for (int i = tid; i < kSlabAffMax; i += kSlabThreads) {
+  for (int i = tid; i < p.naff; i += kSlabThreads) {
     s_scale[i] = (i < p.Ncols) ? __ldg(&p.scale[i]) : 0.f;
     s_shift[i] = (i < p.Ncols) ? __ldg(&p.shift[i]) : 0.f;
   }
@@ -141,7 +154,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
     int wit = 0, sg = 0;                     // global weight-tile / slab counters (ring phases persist across items)
     int item = blockIdx.x;
     if (item < p.items_total) {
-      SlabItem cur = slab_item(p, item, BN);
+      SlabItem cur = slab_item(p, item, bn);
       int nxt_item = item, nxt_si = 0;       // (item, slab) of the next slab to load
       SlabItem nxt = cur;
       // slab index si of an item enumerates (cc, dt, sub) with sub fastest
@@ -153,20 +166,20 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
         mbar_wait(&slab_empty[s], ((sg / kSlabSStages) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&slab_full[s], static_cast<uint32_t>(p.R * p.PW * 128));
-          tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64, p.sub_w0[sub],
-                      p.ss * nxt.r_lo + p.sub_h0[sub], nxt.plane_i0 + dt);
+          tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64,
+                      p.sub_w0[sub] + p.ss * nxt.wc * p.WC, p.ss * nxt.r_lo + p.sub_h0[sub], nxt.plane_i0 + dt);
         }
         __syncwarp();
         ++sg;
         if (++nxt_si == nxt.n_slabs) {       // advance to the first slab of the following item
           nxt_si = 0;
           nxt_item += gridDim.x;
-          if (nxt_item < p.items_total) nxt = slab_item(p, nxt_item, BN);
+          if (nxt_item < p.items_total) nxt = slab_item(p, nxt_item, bn);
         }
       };
       load_next();
       for (; item < p.items_total; item += gridDim.x) {
-        cur = slab_item(p, item, BN);
+        cur = slab_item(p, item, bn);
         for (int si = 0; si < cur.n_slabs; ++si) {
           const int sub = si % p.n_sub;
           const int r2 = si / p.n_sub;
@@ -179,7 +192,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
             mbar_wait(&w_empty[ws], ((wit / kSlabWStages) & 1) ^ 1);
             const int tap = dt * p.khw + p.sub_tap[sub][ti];
             if (elect_one()) {
-              mbar_expect_tx(&w_full[ws], kWBytes);
+              mbar_expect_tx(&w_full[ws], static_cast<uint32_t>(bn * 128));
               tma_load_2d(w_base + ws * kWBytes, &tmB, &w_full[ws], tap * p.C + cc * 64, cur.n0);
             }
             __syncwarp();
@@ -190,12 +203,12 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
   } else if (warp == 5) {
     // ================================ MMA issuer ========================================
     // whole warp, warp-uniform operands; one elected lane issues (see elect_one())
-    constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
+    const uint32_t idesc = make_idesc_f16(128, bn, 0);
     const uint32_t tm = warp_uniform(tmem_base);
     const uint32_t slab0 = smem_u32(slab_base), w0s = smem_u32(w_base);
     int wit = 0, sg = 0, lt = 0;
     for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
-      const SlabItem w = slab_item(p, item, BN);
+      const SlabItem w = slab_item(p, item, bn);
       const int ab = lt % p.nacc;
       mbar_wait(&acc_empty[ab], (((lt / p.nacc) & 1) ^ 1));      // epilogue drained this accumulator set
       tc_fence_after();
@@ -218,7 +231,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
           if (elect_one()) {
             for (int j = 0; j < w.mt_valid; ++j) {
               const uint32_t a_lo = a_lo0 + j * (128u * 128u >> 4);
-              const uint32_t d = acc + j * BN;
+              const uint32_t d = acc + j * accs;
               umma_f16(d, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc, wl != 0 ? 1u : 0u);
               umma_f16(d, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc, 1u);
               umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
@@ -234,54 +247,66 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
     }
   } else {
     // ================================ epilogue ==========================================
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    // a warp may only touch TMEM lanes 32*(warp%4)..+31; the two warpgroups split the accumulator columns
+    const int erow = (warp & 3) * 32 + (tid & 31);
+    const int egroup = warp >= 6 ? 1 : 0;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     int lt = 0;
     for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
-      const SlabItem w = slab_item(p, item, BN);
+      const SlabItem w = slab_item(p, item, bn);
       const int ab = lt % p.nacc;
       mbar_wait(&acc_full[ab], (lt / p.nacc) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_off + ab * acc_cols;
-      const int ncols_here = min(BN, p.ldy - w.n0);     // columns of this tile that exist in y (incl. zero padding)
-      const bool aff_smem = (w.n0 + BN) <= kSlabAffMax;
-      for (int j = 0; j < w.mt_valid; ++j) {
-        const int q = w.q0 + j * 128 + tid;
+      const int ncols_here = min(bn, p.ldy - w.n0);     // columns of this tile that exist in y (incl. zero padding)
+      // output row of this thread in each of the item's M tiles
+      size_t row[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = w.q0 + j * 128 + erow;
         const int h = q / p.PW, wp = q - h * p.PW;
-        const bool ok = (q < p.P) && (wp >= p.halo_l) && (wp < p.halo_l + p.Wo);
-        const size_t row = (static_cast<size_t>(w.plane_o) * p.Ho + h) * p.Wo + (wp - p.halo_l);
-        __half* yrow = p.y + row * p.ldy + w.n0;
-        const __half* rrow = p.residual ? p.residual + row * p.ldr + w.n0 : nullptr;
+        const int wo = w.wc * p.WC + wp - p.halo_l;       // output column
+        ok[j] = (j < w.mt_valid) && (q < p.P) && (wp >= p.halo_l) && (wp < p.halo_l + p.WC) && (wo < p.Wo);
+        row[j] = (static_cast<size_t>(w.plane_o) * p.Ho + h) * p.Wo + wo;
+      }
 #pragma unroll 1
-        for (int jc = 0; jc < BN / 32; ++jc) {
-          uint32_t v[32];
-          tmem_ld32(acc + j * BN + jc * 32, v);          // warp-collective: outside the `ok` branch
-          tmem_ld_wait();
-          if (ok) {
+      for (int jc = egroup; jc * 32 < ncols_here; jc += 2) {
+        // folded-BN scale/shift of these 32 channels: registers, reused by every M tile of the item
+        float sc[32], sh[32];
+        const int c0 = w.n0 + jc * 32;
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              const int col = jc * 32 + c8 * 8;
-              if (col < ncols_here) {
-                uint4 rv = make_uint4(0, 0, 0, 0);
-                if (rrow) rv = __ldg(reinterpret_cast<const uint4*>(rrow + col));
-                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-                uint32_t o[4];
+        for (int c = 0; c < 32; ++c) {
+          sc[c] = s_scale[c0 + c];
+          sh[c] = s_shift[c0 + c];
+        }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int ci = w.n0 + col + e * 2;
-                  float sc0, sc1, sh0, sh1;
-                  if (aff_smem) { sc0 = s_scale[ci]; sc1 = s_scale[ci + 1]; sh0 = s_shift[ci]; sh1 = s_shift[ci + 1]; }
-                  else {
-                    sc0 = ci < p.Ncols ? __ldg(&p.scale[ci]) : 0.f; sc1 = ci + 1 < p.Ncols ? __ldg(&p.scale[ci + 1]) : 0.f;
-                    sh0 = ci < p.Ncols ? __ldg(&p.shift[ci]) : 0.f; sh1 = ci + 1 < p.Ncols ? __ldg(&p.shift[ci + 1]) : 0.f;
+        for (int j = 0; j < 4; ++j) {
+          if (j < w.mt_valid) {                            // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(acc + j * accs + jc * 32, v);        // warp-collective: outside the `ok` branch
+            tmem_ld_wait();
+            if (ok[j]) {
+              __half* yrow = p.y + row[j] * p.ldy + c0;
+              const __half* rrow = p.residual ? p.residual + row[j] * p.ldr + c0 : nullptr;
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                if (jc * 32 + c8 * 8 < ncols_here) {
+                  uint4 rv = make_uint4(0, 0, 0, 0);
+                  if (rrow) rv = __ldg(reinterpret_cast<const uint4*>(rrow + c8 * 8));
+                  const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+                  uint32_t o[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int c = c8 * 8 + e * 2;
+                    const float2 rf = unpack_half2(rr[e]);
+                    float a0 = fmaf(__uint_as_float(v[c]), sc[c], sh[c]) + rf.x;
+                    float a1 = fmaf(__uint_as_float(v[c + 1]), sc[c + 1], sh[c + 1]) + rf.y;
+                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                    o[e] = pack_half2(a0, a1);
                   }
-                  float a0 = __uint_as_float(v[c8 * 8 + e * 2]) * sc0 + sh0;
-                  float a1 = __uint_as_float(v[c8 * 8 + e * 2 + 1]) * sc1 + sh1;
-                  const float2 rf = unpack_half2(rr[e]);
-                  a0 += rf.x; a1 += rf.y;
-                  if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                  o[e] = pack_half2(a0, a1);
+                  *reinterpret_cast<uint4*>(yrow + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
-                *reinterpret_cast<uint4*>(yrow + col) = make_uint4(o[0], o[1], o[2], o[3]);
               }
             }
           }

@@ -63,6 +63,17 @@ CONV_CASES = [
     ("slab_s2_odd_input_7x7", 2, 256, 3, 7, 7, 256, (3, 3, 3), (2, 2, 2), (1, 1, 1), False, True, False, True),
     ("slab_2d_3x3_s2_resnet18", 2, 64, 1, 56, 56, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), False, True, False, True),
     ("slab_temporal7_wide", 1, 110, 8, 56, 56, 64, (7, 1, 1), (1, 1, 1), (3, 0, 0), False, False, False, True),
+    # runtime-N slab instance (Cout that tiles badly by 128): several N tiles, residual, strided phases
+    ("flexn_144_56x56", 2, 64, 2, 56, 56, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False, True),
+    ("flexn_288_28x28_res", 2, 128, 3, 28, 28, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, False, True),
+    ("flexn_576_14x14_3tiles", 2, 256, 2, 14, 14, 576, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False, True),
+    ("flexn_460_s2", 1, 128, 2, 28, 28, 460, (1, 3, 3), (1, 2, 2), (0, 1, 1), False, True, False, True),
+    # W chunking: rows longer than one TMA box; temporal filters remapped to (1,kt,1) over frames x positions
+    ("wide_row_chunks_3x3", 1, 64, 2, 6, 300, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False, True),
+    ("wide_row_chunks_3x3_s2", 1, 64, 1, 9, 301, 128, (1, 3, 3), (1, 2, 2), (0, 1, 1), False, True, False, True),
+    ("temporal3_chunked_28x28_res", 2, 288, 6, 28, 28, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
+    ("temporal3_14x14_from_576", 2, 576, 4, 14, 14, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0), False, True, False, True),
+    ("temporal5_ragged_positions", 1, 64, 7, 9, 11, 64, (5, 1, 1), (1, 1, 1), (2, 0, 0), False, True, False, True),
     ("projection_1x1x1_s2_subsample", 2, 256, 4, 8, 8, 512, (1, 1, 1), (2, 2, 2), (0, 0, 0), False, False, False, True),
 ]
 
