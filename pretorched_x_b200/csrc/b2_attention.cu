@@ -54,7 +54,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                           const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   using S = AttSmem<DVT>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align<1024>(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);   // [4]
   uint64_t* empty_bar = full_bar + kAttSlots;                            // [4]
   uint64_t* s_full = empty_bar + kAttSlots;                              // [2]

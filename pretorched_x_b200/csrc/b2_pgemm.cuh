@@ -59,7 +59,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const PgemmParams p) {
   using S = PgemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align<1024>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);   // [3]
   uint64_t* empty = full + kPgStages;                                // [3]
   uint64_t* acc_full = empty + kPgStages;                            // [2]

@@ -23,7 +23,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __half* __restrict__ lin_a, const __half* __restrict__ lin_b, float* __restrict__ out,
                   int mode, int shift, int base_off) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align<1024>(smem_raw);
   uint8_t* sA = smem;                 // 256 rows x 128 B = 32 KB
   uint8_t* sB = smem + 32768;         // 64 rows x 128 B  = 8 KB (mode 0) / no-swizzle B (mode 1)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768 + 8192);

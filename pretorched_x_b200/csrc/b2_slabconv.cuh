@@ -108,7 +108,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
                 const __grid_constant__ CUtensorMap tmB,   // weights [Ncols][taps*C], box (64, BN)
                 const SlabParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align<1024>(smem_raw);
   const int bn = BN ? BN : p.bn;
   const int kWBytes = BN ? BN * 128 : p.wbytes;      // stage stride; a stage receives bn * 128 bytes
   const int accs = BN ? BN : p.accs;

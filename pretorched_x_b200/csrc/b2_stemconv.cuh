@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kStemThreads, 1)
 stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pixels (W, H, N*T), box (256, rows, 1), no swizzle
                 const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = smem_align<128>(smem_raw);
   uint8_t* tail = smem + p.nstages * p.stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);          // [kStemMaxStages]
   uint64_t* empty = full + kStemMaxStages;
