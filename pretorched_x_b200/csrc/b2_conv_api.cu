@@ -2,6 +2,7 @@
 // plus library-wide error/launch bookkeeping and the CUtensorMap builder.
 #include <atomic>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 #include "b2_host.h"
@@ -269,15 +270,34 @@ static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
   }
   const int acc_stride = flex ? p.accs : BN;
   const int w_stage = flex ? p.wbytes : BN * 128;
+  // Pick the M tiles per work item from a cycle model of one SM's share: rounds of items x the slower of the MMA
+  // stream and the slab/weight loads, plus the epilogue when a single accumulator set leaves it exposed.  (Constants
+  // from ncu: a 128xNx16 MMA retires in ~40 + N/2 cycles, TMA delivers ~48 B/cycle/SM out of L2.)
   int best_mt = 0, best_R = 0;
-  for (int MT = 512 / acc_stride > 4 ? 4 : 512 / acc_stride; MT >= 1; MT = flex ? MT - 1 : MT >> 1) {
+  double best_cost = 0.0;
+  static int force_mt = -1;
+  if (force_mt < 0) { const char* e = getenv("B2_SLAB_MT"); force_mt = e ? atoi(e) : 0; }   // debug / tuning only
+  int ksteps = 0;
+  for (int cc = 0; cc < p.cchunks; ++cc) { const int k = (a->C - cc * 64 + 15) / 16; ksteps += k > 4 ? 4 : k; }
+  int taps_hw = 0;
+  for (int sidx = 0; sidx < p.n_sub; ++sidx) taps_hw += p.sub_ntaps[sidx];
+  for (int MT = 512 / acc_stride > 4 ? 4 : 512 / acc_stride; MT >= 1; --MT) {
+    if (force_mt > 0 && MT != force_mt && MT != 1) continue;
     const int R = slab_rows(MT, p.PW, p.reach, p.P);
     if (p.ss * (R - 1) + 1 > 256) continue;
-    const long long smem = 2ll * (((long long)R * p.PW * 128 + 1023) / 1024 * 1024) + kSlabWStages * w_stage + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
+    const long long slab_b = ((long long)R * p.PW * 128 + 1023) / 1024 * 1024;
+    const long long smem = 2ll * slab_b + kSlabWStages * w_stage + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
     if (smem > 227 * 1024) continue;
-    const long long items = (long long)ntn * ((p.P + MT * 128 - 1) / (MT * 128)) * planes * p.wchunks;
-    best_mt = MT; best_R = R;
-    if (items >= 2 * 148) break;      // enough work items for two rounds per SM: keep the largest MT that achieves it
+    const long long tq = (p.P + MT * 128 - 1) / (MT * 128);
+    const long long items = (long long)ntn * tq * planes * p.wchunks;
+    const double rounds = (double)((items + sm_count() - 1) / sm_count());
+    const double tiles_per_item = (double)((p.P + 127) / 128) / (double)tq;          // average (the last item of a plane is short)
+    const double mma = tiles_per_item * p.kt * taps_hw * ksteps * (40.0 + 0.5 * BN);
+    const double load = (double)p.kt * p.n_sub * p.cchunks * slab_b / 48.0 + (double)p.kt * taps_hw * p.cchunks * w_stage / 48.0;
+    const double epi = (MT * acc_stride <= 256) ? 0.0 : tiles_per_item * ((BN + 31) / 32) * 250.0;
+    const double cost = rounds * ((mma > load ? mma : load) + epi + 1500.0);
+    if (best_mt == 0 || cost < best_cost || (force_mt > 0 && MT == force_mt)) { best_mt = MT; best_R = R; best_cost = cost; }
+    if (force_mt > 0 && MT == force_mt) break;
   }
   if (best_mt == 0) return 0;
   int rc = flex ? launch_slab<0>(a, p, best_mt, best_R, stream)

@@ -217,6 +217,8 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
       for (int si = 0; si < w.n_slabs; ++si, ++sg) {
         const int sub = si % p.n_sub;
         const int ntaps = p.sub_ntaps[sub];
+        const int cc = (si / p.n_sub) / w.n_dt;
+        const int ksteps = min(4, (p.C - cc * 64 + 15) >> 4);       // 16-channel K steps that hold real channels
         const int s = sg % kSlabSStages;
         mbar_wait(&slab_full[s], (sg / kSlabSStages) & 1);
         const uint32_t slab_addr = slab0 + s * p.slab_bytes;
@@ -233,9 +235,14 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
               const uint32_t a_lo = a_lo0 + j * (128u * 128u >> 4);
               const uint32_t d = acc + j * accs;
               umma_f16(d, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc, wl != 0 ? 1u : 0u);
-              umma_f16(d, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc, 1u);
-              umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
-              umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
+              if (ksteps == 4) {
+                umma_f16(d, desc_from(kSw128DescHi, a_lo + 2), desc_from(kSw128DescHi, b_lo + 2), idesc, 1u);
+                umma_f16(d, desc_from(kSw128DescHi, a_lo + 4), desc_from(kSw128DescHi, b_lo + 4), idesc, 1u);
+                umma_f16(d, desc_from(kSw128DescHi, a_lo + 6), desc_from(kSw128DescHi, b_lo + 6), idesc, 1u);
+              } else {                                     // last channel chunk of C = 144, 288, 232 ...: skip all-zero K steps
+                for (int k = 1; k < ksteps; ++k)
+                  umma_f16(d, desc_from(kSw128DescHi, a_lo + 2 * k), desc_from(kSw128DescHi, b_lo + 2 * k), idesc, 1u);
+              }
             }
             umma_commit(&w_empty[ws]);
             if (ti == ntaps - 1) umma_commit(&slab_empty[s]);
