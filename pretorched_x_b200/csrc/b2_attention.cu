@@ -86,6 +86,8 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                       // everything above touched only weights / on-chip state
   const uint32_t tmem_S = tmem_base;             // 2 x 64 columns
   const uint32_t tmem_O = tmem_base + 128;       // DVT columns
 
@@ -300,7 +302,7 @@ static int launch_attention(const void* q, int ldq, const void* k, int ldk, cons
   p.mode = mode; p.scale = 1.0f / (float)Nk;
   p.o = reinterpret_cast<__half*>(o); p.ldo = ldo;
   dim3 grid((Nq + kAttBM - 1) / kAttBM, B, dv / DVT);
-  nonlocal_attention_kernel<DVT><<<grid, kAttThreads, S::kTotal, stream>>>(tmQ, tmK, tmV, p);
+  B2_CHECK_CUDA(launch_pdl(nonlocal_attention_kernel<DVT>, grid, dim3(kAttThreads), S::kTotal, stream, tmQ, tmK, tmV, p));
   B2_CHECK_LAUNCH("nonlocal_attention_kernel");
   return B2_OK;
 }

@@ -231,7 +231,7 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)taps * a->C, (uint64_t)a->K, (uint64_t)taps * a->C, 64, BN, true)) != B2_OK)
     return rc;
   const int grid = p.items_total < sm_count() ? p.items_total : sm_count();
-  slabconv_kernel<BNT><<<grid, kSlabThreads, smem_bytes, stream>>>(tmX, tmB, p);
+  B2_CHECK_CUDA(launch_pdl(slabconv_kernel<BNT>, dim3(grid), dim3(kSlabThreads), smem_bytes, stream, tmX, tmB, p));
   B2_CHECK_LAUNCH("slabconv_kernel");
   return B2_OK;
 }
@@ -296,6 +296,12 @@ static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
     const double load = (double)p.kt * p.n_sub * p.cchunks * slab_b / 48.0 + (double)p.kt * taps_hw * p.cchunks * w_stage / 48.0;
     const double epi = (MT * acc_stride <= 256) ? 0.0 : tiles_per_item * ((BN + 31) / 32) * 250.0;
     const double cost = rounds * ((mma > load ? mma : load) + epi + 1500.0);
+    if (force_mt == -1) {                                   // previous rule (A/B): largest power-of-two MT with >= 2 rounds of items
+      if ((MT & (MT - 1)) != 0 && !flex) continue;
+      best_mt = MT; best_R = R;
+      if (items >= 2 * 148) break;
+      continue;
+    }
     if (best_mt == 0 || cost < best_cost || (force_mt > 0 && MT == force_mt)) { best_mt = MT; best_R = R; best_cost = cost; }
     if (force_mt > 0 && MT == force_mt) break;
   }
@@ -367,7 +373,7 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled(stem) failed (%d)", (int)r);
   const int grid = p.items_total < sm_count() ? p.items_total : sm_count();
-  stemconv_kernel<BN><<<grid, kStemThreads, smem_bytes, stream>>>(tmX, p);
+  B2_CHECK_CUDA(launch_pdl(stemconv_kernel<BN>, dim3(grid), dim3(kStemThreads), smem_bytes, stream, tmX, p));
   B2_CHECK_LAUNCH("stemconv_kernel");
   return B2_OK;
 }
@@ -420,7 +426,7 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
     tmC = tmB; tmR = tmB;
   }
   dim3 grid((p.epi == EPI_TMA_F16 ? (p.ldy + BN - 1) / BN : (p.Ncols + BN - 1) / BN), (p.M_total + kBM - 1) / kBM, 1);
-  igemm_kernel<BN><<<grid, kThreads, S::kTotalBytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  B2_CHECK_CUDA(launch_pdl(igemm_kernel<BN>, grid, dim3(kThreads), S::kTotalBytes, stream, tmA, tmB, tmC, tmR, p));
   B2_CHECK_LAUNCH("igemm_kernel");
   return B2_OK;
 }
@@ -460,7 +466,7 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.has_residual = ip.residual != nullptr;
   p.relu = ip.relu;
   const int grid = p.tiles_total < sm_count() ? p.tiles_total : sm_count();
-  pgemm_kernel<BN><<<grid, kPgThreads, S::kTotal, stream>>>(tmA, tmB, tmA2, tmB2, tmC, tmR, p);
+  B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN>, dim3(grid), dim3(kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, p));
   B2_CHECK_LAUNCH("pgemm_kernel");
   return B2_OK;
 }
@@ -473,6 +479,12 @@ static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   const int width = (L.p.epi == EPI_TMA_F16) ? L.p.ldy : L.p.Ncols;
   if (width <= 64) return launch_igemm<64>(L, stream);
   return launch_igemm<128>(L, stream);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B2_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
 }
 
 }  // namespace b2

@@ -125,6 +125,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA,   // activations as [M][C]
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                       // everything above touched only weights / on-chip state
 
   // ---- warp roles -----------------------------------------------------------------------
   if (warp < 4) {

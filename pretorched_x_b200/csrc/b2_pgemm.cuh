@@ -84,6 +84,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                       // everything above touched only weights / on-chip state
 
   if (warp == kPgEpiWarps) {
     // ================================ producer ==========================================

@@ -23,6 +23,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // Aligns the dynamic shared-memory base with pointer arithmetic on the __shared__ array itself.  Going through
 // uintptr_t makes the compiler lose the address space: every later access became a generic LD/ST plus an R2UR
 // (measured: 2 generic loads per output element in the conv epilogues).
+// Programmatic dependent launch: the tensor-core kernels are launched with programmatic stream serialization, so a
+// CTA of launch i+1 starts (barrier init, TMEM allocation, tensor-map prefetch, BN-affine staging) on every SM that
+// launch i has vacated and only then waits for launch i to finish; without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int ALIGN>
 __device__ __forceinline__ uint8_t* smem_align(uint8_t* smem_raw) {
   return smem_raw + ((ALIGN - (smem_u32(smem_raw) & (ALIGN - 1))) & (ALIGN - 1));

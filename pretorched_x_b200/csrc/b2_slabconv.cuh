@@ -145,6 +145,8 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                       // everything above touched only weights / on-chip state
 
   if (warp == 4) {
     // ================================ TMA producer ======================================

@@ -133,6 +133,8 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                       // everything above touched only weights / on-chip state
 
   if (warp == 4) {
     // ================================ producer ==========================================
