@@ -150,7 +150,8 @@ def test_gemm_matches_oracle(dev, case):
 
 
 ATT_CASES = [("one_block", 1, 128, 64, 64), ("ragged_keys_and_queries", 2, 200, 128, 128), ("odd_positions", 3, 99, 64, 128),
-             ("layer2_like", 1, 576, 256, 256), ("layer3_like_dv_split", 2, 72, 512, 512), ("n_lt_64", 1, 16, 64, 64)]
+             ("layer2_like", 1, 576, 256, 256), ("layer3_like_dv_split", 2, 72, 512, 512), ("n_lt_64", 1, 16, 64, 64),
+             ("three_d_chunks", 2, 300, 192, 64), ("many_blocks_dv128", 2, 1111, 128, 128)]
 
 
 @pytest.mark.parametrize("case", ATT_CASES, ids=[c[0] for c in ATT_CASES])
@@ -163,6 +164,27 @@ def test_nonlocal_attention_matches_oracle(dev, case):
     ref = torch.softmax(q @ k.transpose(1, 2), dim=-1) @ v            # nonlocalnet.py:156-160, unscaled
     qkv = torch.cat([q, k, v], dim=2).reshape(B * Npos, 2 * d + dv).half().to(dev).contiguous()
     o = ops.nonlocal_attention(qkv, d, dv, B, Npos)
+    assert rel(o[:, :dv].float().view(B, Npos, dv), ref) <= 4e-3
+
+
+@pytest.mark.parametrize("two_pass", [False, True], ids=["single_pass", "two_pass"])
+def test_attention_with_growing_logits(dev, two_pass):
+    """Keys whose norm grows along the sequence: the running row maximum jumps by far more than 2^8 several times, so
+    the single-pass kernel must rescale its TMEM accumulator (lazy rescaling) -- and agree with the exact two-pass one."""
+    from pretorched_x_b200 import ops, _lib
+    B, Npos, d, dv = 2, 700, 128, 256
+    g = torch.Generator().manual_seed(77)
+    q = h(torch.randn(B, Npos, d, generator=g))
+    k = h(torch.randn(B, Npos, d, generator=g) * torch.linspace(0.05, 2.0, Npos).view(1, Npos, 1))
+    v = h(torch.randn(B, Npos, dv, generator=g))
+    ref = (torch.softmax((q.double() @ k.double().transpose(1, 2)), dim=-1) @ v.double()).float()
+    qkv = torch.cat([q, k, v], dim=2).reshape(B * Npos, 2 * d + dv).half().to(dev).contiguous()
+    lib = _lib.load()
+    lib.b2_debug_set_attention_algo(1 if two_pass else 0)
+    try:
+        o = ops.nonlocal_attention(qkv, d, dv, B, Npos)
+    finally:
+        lib.b2_debug_set_attention_algo(0)
     assert rel(o[:, :dv].float().view(B, Npos, dv), ref) <= 4e-3
 
 
