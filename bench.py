@@ -270,12 +270,28 @@ def run_ours(args, rank, world, local):
     conv_ms = sum(r["ms"] for r in conv_rows) / nrep
     conv_flops = sum(r["flops"] for r in conv_rows) / nrep
     all_ms = sum(r["ms"] for r in rows) / nrep
-    achieved_tflops = conv_flops / (conv_ms * 1e-3) / 1e12
+    family_tflops = conv_flops / (conv_ms * 1e-3) / 1e12
+    # dominant kernel = the conv/GEMM layer group with the largest share of the step (the 7x7x7 stem at the BASELINE config)
+    groups = {}
+    for r in conv_rows:
+        g = groups.setdefault(r["desc"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+        g["ms"] += r["ms"]; g["flops"] += r["flops"]; g["bytes"] += r["bytes"]; g["n"] += 1
+    top_desc, top = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    top_tflops = top["flops"] / (top["ms"] * 1e-3) / 1e12
+    traffic = None
+    try:       # DRAM bytes per launch from the committed `ncu --set full` capture of the same shape (profiles/)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+            traffic = json.load(f).get("B=%d" % B, {}).get(top_desc)
+    except OSError:
+        pass
     roofline = {
-        "bound": "tensor", "kernel": "tcgen05 conv/GEMM family (stemconv, slabconv, pgemm, igemm): all %d conv/linear launches of one forward" % (len(conv_rows) // nrep),
-        "achieved": achieved_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops"],
-        "traffic": None, "peak_source": peaks["source"] + ", sustained bf16/fp16 GEMM",
-        "share_of_step": conv_ms / all_ms,
+        "bound": "tensor", "kernel": "%s (%d launch per forward; %s)" % (top_desc, top["n"] // nrep, kernel_of(top_desc)),
+        "achieved": top_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": top_tflops / peaks["tflops"],
+        "traffic": traffic, "algorithmic_bytes": top["bytes"] / top["n"],
+        "ms_per_launch": top["ms"] / top["n"], "share_of_step": top["ms"] / nrep / all_ms,
+        "peak_source": peaks["source"] + ", sustained bf16/fp16 GEMM",
+        "family": {"kernels": "all %d tcgen05 conv/GEMM launches of one forward (stemconv, slabconv, pgemm, igemm)" % (len(conv_rows) // nrep),
+                   "achieved": family_tflops, "frac": family_tflops / peaks["tflops"], "share_of_step": conv_ms / all_ms},
         "whole_step_tflops": GFLOP_PER_CLIP * 1e9 * value / world / 1e12,
         "whole_step_frac": GFLOP_PER_CLIP * 1e9 * value / world / 1e12 / peaks["tflops"],
     }
@@ -313,6 +329,15 @@ def run_ours(args, rank, world, local):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+
+
+def kernel_of(desc):
+    """Kernel that the C ABI dispatches a profiled layer description to (see csrc/b2_conv_api.cu)."""
+    if desc.startswith("conv 7x7x7") or desc.startswith("conv 1x7x7"):
+        return "stemconv_kernel"
+    if desc.startswith("conv 1x1x1 s111") or desc.startswith("gemm"):
+        return "pgemm_kernel"
+    return "slabconv_kernel" if desc.startswith("conv") else "?"
 
 
 def main():

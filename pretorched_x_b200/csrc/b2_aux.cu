@@ -202,30 +202,44 @@ maxpool3d_k3s2p1_kernel(const __half* __restrict__ x, __half* __restrict__ y, in
   reinterpret_cast<uint4*>(y)[i] = o;
 }
 
-// global average: grid (C8 chunks / 32-wide, N); each thread owns 8 channels and walks S positions.
-__global__ void avgpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, int S, int C8) {
-  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+// global average: grid (C8 chunks / 32, N), 1024 threads.  Lane = one 8-channel chunk (a warp reads 512 contiguous
+// bytes of a pixel), warp w walks positions w, w+32, ... ; the 32 partial sums meet in shared memory in a fixed order.
+__global__ void __launch_bounds__(1024) avgpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, int S, int C8) {
+  __shared__ float part[32][32][9];                 // [slice][lane][8 + pad]
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c8 = blockIdx.x * 32 + lane;
   const int n = blockIdx.y;
-  if (c8 >= C8) return;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)n * S * (C8 * 8)) + c8;
-  for (int s = 0; s < S; ++s) {
-    const uint4 v = __ldg(base + (size_t)s * C8);
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  if (c8 < C8) {
+    const uint4* base = reinterpret_cast<const uint4*>(x + (size_t)n * S * (C8 * 8)) + c8;
+#pragma unroll 4
+    for (int s = slice; s < S; s += 32) {
+      const uint4 v = __ldg(base + (size_t)s * C8);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
-      acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[e]));
+        acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+      }
     }
   }
-  const float inv = 1.f / (float)S;
-  uint32_t o[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    __half2 h = __floats2half2_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
-    o[e] = *reinterpret_cast<uint32_t*>(&h);
+  for (int e = 0; e < 8; ++e) part[slice][lane][e] = acc[e];
+  __syncthreads();
+  if (slice == 0 && c8 < C8) {
+    float tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < 32; ++w)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tot[e] += part[w][lane][e];
+    const float inv = 1.f / (float)S;
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __half2 h = __floats2half2_rn(tot[2 * e] * inv, tot[2 * e + 1] * inv);
+      o[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(y + (size_t)n * (C8 * 8))[c8] = make_uint4(o[0], o[1], o[2], o[3]);
   }
-  reinterpret_cast<uint4*>(y + (size_t)n * (C8 * 8))[c8] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -404,8 +418,8 @@ int b2_maxpool3d_ndhwc(const void* x, void* y, int N, int T, int H, int W, int C
 int b2_avgpool_global_ndhwc(const void* x, void* y, int N, int S, int C, void* stream) {
   B2_CHECK_ARG(x && y && N > 0 && S > 0, "bad argument");
   B2_CHECK_ARG(C % 8 == 0, "channel pitch %d is not a multiple of 8", C);
-  dim3 grid(div_up(C / 8, 64), N);
-  avgpool_kernel<<<grid, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __half*)x, (__half*)y, S, C / 8);
+  dim3 grid(div_up(C / 8, 32), N);
+  avgpool_kernel<<<grid, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __half*)x, (__half*)y, S, C / 8);
   B2_CHECK_LAUNCH("avgpool");
   return B2_OK;
 }

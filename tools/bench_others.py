@@ -12,10 +12,16 @@ from oracle import functional as OF
 dev = torch.device("cuda:0")
 CASES = [("r2plus1d34", dict(num_classes=400), (16, 3, 32, 112, 112), 51.48),
          ("nonlocalresnet3d50", dict(pretrained=None), (8, 3, 32, 224, 224), 262.22),
-         ("resnet18", dict(num_classes=1000, pretrained=None), (256, 3, 224, 224), 3.63)]
+         ("resnet18", dict(num_classes=1000, pretrained=None), (256, 3, 224, 224), 3.63),
+         ("slowfast.resnet50", dict(mode="sf", num_classes=400), (8, 3, 64, 224, 224), 0.0)]
+if len(sys.argv) > 1 and not sys.argv[1].startswith("--"):
+    CASES = [c for c in CASES if c[0] in sys.argv[1].split(",")]
 for arch, kw, shape, gflop in CASES:
     torch.manual_seed(0)
-    m = getattr(P, arch)(**kw)
+    f = P
+    for part in arch.split("."):
+        f = getattr(f, part)
+    m = f(**kw)
     OF.randomize_bn_(m, 1)
     m = m.eval().to(dev)
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).to(dev)
