@@ -83,7 +83,7 @@ def main():
     # ---- ncu --set full captures ----
     want = [("duration_us", "gpu__time_duration.sum"), ("grid", "launch__grid_size"), ("regs", "launch__registers_per_thread"),
             ("dram_read_MB", "dram__bytes_read.sum"), ("dram_write_MB", "dram__bytes_write.sum"),
-            ("dram_pct", "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
+            ("dram_pct", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed"),
             ("tensor_pipe_active_pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
             ("sm_throughput_pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
             ("l2_hit_pct", "lts__t_sector_hit_rate.pct"), ("l1tex_pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed")]
