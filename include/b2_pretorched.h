@@ -66,6 +66,9 @@ typedef struct b2_conv_args {
   int32_t out_f32;      /* y is fp32 (direct-store epilogue)                                       */
   int32_t accumulate;   /* out_f32 only: y += result                                               */
   int32_t mode;         /* B2_CONV_AUTO | B2_CONV_STEM7                                            */
+  int32_t aff_ld;       /* 0: scale/shift are [K].  > 0: per-SAMPLE affine, scale/shift are fp32 [N][aff_ld]
+                           (class-conditional BatchNorm of the layer that FOLLOWS this convolution, BigGAN GBlock);
+                           multi-tap "same" convolutions and 1x1x1 convolutions with To*Ho*Wo % 128 == 0 only      */
 } b2_conv_args;
 
 int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream);
@@ -99,6 +102,9 @@ typedef struct b2_gemm_args {
   int32_t relu;
   int32_t out_f32;
   int32_t accumulate;
+  int32_t aff_ld;   /* 0: scale/shift are [N] (or [M] when per_row).  > 0: per-sample affine, fp32 [M / aff_rows][aff_ld]:
+                       row m uses scale[(m / aff_rows) * aff_ld + n]; fp16 output only, aff_rows % 128 == 0 */
+  int32_t aff_rows;
 } b2_gemm_args;
 int b2_gemm_f16(const b2_gemm_args* a, void* stream);
 /* D = act(scale * (A.B^T + A2.B2^T) + shift + residual): both products accumulate in the same TMEM tile.  Used to
@@ -147,6 +153,24 @@ int b2_concat_channels(const void* a, int lda, int Ca, const void* b, int ldb, i
 /* y[n][j*F + f] = x[n][idx[j]][f]: frame-tuple gather of MultiScaleRelation (trn.py:108), fp16. */
 int b2_gather_frames(const void* x, void* y, const int32_t* idx_dev, int N, int T, int F, int n_idx,
                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BigGAN-deep generator helpers (BASELINE.json configs[4]).  The architecture is NOT in the reference tree
+ * (SURVEY.md section 8a row a14): these replace the F.batch_norm * (1 + gain(y)) + bias(y) -> ReLU ->
+ * F.interpolate(scale_factor=2) chain of the published GBlock, its embedding lookup + torch.cat, and the final
+ * torch.tanh; see oracle/biggan.py for the restatement they are checked against.
+ * ------------------------------------------------------------------------------------------- */
+/* y[b] = fp16 [ (embedded ? embedded[b] : table[labels[b]]) (ds) | z[b] (dz) | 0 ] with pitch ldy.  z, table, embedded
+ * fp32; labels int64 (clamped to [0, n_classes)). */
+int b2_embed_concat(const float* z, const long long* labels, const float* table, const float* embedded, void* y, int B,
+                    int dz, int ds, int n_classes, int ldy, void* stream);
+/* y[n, up*h+i, up*w+j, c] = act(x[n,h,w,c] * scale[n*lda + c] + shift[n*lda + c]) for c < C, i,j < up (up = 1 or 2,
+ * nearest-neighbour upsampling); channels [C, ldy) written as zero.  scale/shift fp32 [N][lda] (lda = 0: one row shared
+ * by all samples, i.e. a plain BatchNorm), or both NULL for a pure copy / channel slice / upsample. */
+int b2_ccbn_act_ndhwc(const void* x, int ldx, void* y, int ldy, const float* scale, const float* shift, int lda, int N,
+                      int H, int W, int C, int up, int relu, void* stream);
+/* y[n][c][s] = tanh(x[n*S + s][c]): fp16 channels-last (pitch ldx) -> NCHW planes, fp32 (out_f32) or fp16. */
+int b2_tanh_nhwc_to_nchw(const void* x, int ldx, void* y, int N, int C, long long S, int out_f32, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,4 +20,6 @@ from .models.r2plus1d import (r2plus1d10, r2plus1d18, r2plus1d34, r2plus1d50, r2
                               r2plus1d152, r2plus1d200)
 from .models.trn import Relation, MultiScaleRelation, HierarchicalRelation  # noqa: F401
 from .models.utils import Identity  # noqa: F401
+# BigGAN-deep generator (BASELINE.json configs[4]; not in the reference tree -- see models/biggan_deep.py)
+from .models.biggan_deep import biggan_deep, biggan_deep128, biggan_deep256, biggan_deep512  # noqa: F401
 from .models import slowfast  # noqa: F401  (module, as in pretorched/__init__.py:83)

@@ -32,7 +32,7 @@ class ConvArgs(ctypes.Structure):
         ("kt", c_i32), ("kh", c_i32), ("kw", c_i32),
         ("st", c_i32), ("sh", c_i32), ("sw", c_i32),
         ("pt", c_i32), ("ph", c_i32), ("pw", c_i32),
-        ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32),
+        ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32), ("aff_ld", c_i32),
     ]
 
 
@@ -44,6 +44,7 @@ class GemmArgs(ctypes.Structure):
         ("M", c_i32), ("N", c_i32), ("Kd", c_i32),
         ("lda", c_i32), ("ldb", c_i32), ("ldd", c_i32), ("ldr", c_i32),
         ("per_row", c_i32), ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32),
+        ("aff_ld", c_i32), ("aff_rows", c_i32),
     ]
 
 
@@ -69,6 +70,9 @@ SYMBOLS = {
     "b2_shortcut_a_ndhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "b2_concat_channels": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_longlong, c_void_p]),
     "b2_gather_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2_embed_concat": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
+    "b2_ccbn_act_ndhwc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "b2_tanh_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, ctypes.c_longlong, c_int, c_void_p]),
 }
 
 

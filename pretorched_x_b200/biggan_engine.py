@@ -1,0 +1,222 @@
+"""BigGAN-deep generator forward on the B200 kernels (BASELINE.json configs[4]).
+
+There is no reference code for this path: the block bodies below implement the published
+GBlock / SAGAN-attention / class-conditional-BN arithmetic restated in ``oracle/biggan.py`` (test infrastructure), on the
+same hand-written kernels as the video path -- the persistent 1x1 GEMM, the slab 3x3 convolution, the fused attention --
+plus three HBM-bound helpers in ``csrc/b2_gan.cu``.
+
+How the pieces map:
+
+* **All 48+ class-conditional BatchNorms of a forward come out of ONE GEMM.**  ``ccbn(x, y) = (x - mu) * rstd * (1 + Wg y)
+  + Wb y`` is an affine map per (sample, channel): ``scale = rstd + (rstd * Wg) y`` and ``shift = (Wb - m * rstd * Wg) y
+  - m * rstd`` are both linear in the conditioning vector y, so the (spectrally normalised) gain / bias matrices of every
+  ccbn are stacked, with ``rstd`` and the mean folded in, into one fp16 matrix ``[2 * sum(C)][256]`` and a single
+  tcgen05 GEMM with fp32 output produces every scale and shift of the network: ``aff[B][2 * sum(C)]``.
+* ccbn -> ReLU that FOLLOWS a convolution is that convolution's epilogue (per-sample affine, ``b2_conv_args.aff_ld``):
+  conv2 carries bn3, conv3 carries bn4, conv1 carries bn2 in the non-upsampling blocks; the conv bias is folded into the
+  shift (``m = mean - bias``).  bn1 (its input also feeds the skip path) and the bn2 + nearest-2x-upsample of the
+  upsampling blocks are one ``b2_ccbn_act_ndhwc`` pass each.
+* conv4's epilogue adds the skip path (channel-dropped via the residual pitch; upsampled copy for the second block).
+* Spectral norm: weights are divided by sigma (one power iteration from the stored ``u0``) when they are packed.
+* Self-attention: theta and phi|g projections (zero-padded to the 64-column granularity of the attention kernel),
+  2x2 max-pool of phi|g, the fused softmax(theta^T phi) g kernel, and the output 1x1 GEMM with gamma as its scale and x
+  as its residual.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .ops import Act, _round_up
+
+
+def _sn_sigma(weight, u, eps):
+    wm = weight.detach().double().reshape(weight.shape[0], -1)
+    u = u.detach().double()
+    v = F.normalize(u @ wm, eps=eps)
+    u2 = F.normalize(v @ wm.t(), eps=eps)
+    return ((v @ wm.t()) @ u2.t()).squeeze()
+
+
+def _sn_weight(mod, eps):
+    """fp64 weight / sigma of a spectrally normalised layer (eval mode: no update of u0)."""
+    return mod.weight.detach().double() / _sn_sigma(mod.weight, mod.u0, eps)
+
+
+class _NS:
+    pass
+
+
+def _pack_conv(conv, eps, in_pitch):
+    w = _sn_weight(conv, eps).float()
+    pad = conv.padding
+    return ops.PackedConv(w, conv.bias, None, (1, 1, 1), (0, int(pad[0]), int(pad[1])), in_pitch=in_pitch)
+
+
+def _pack(model, dev):
+    """Everything derived from the parameters: packed filters, the stacked ccbn GEMM, attention matrices."""
+    eps_sn = model.SN_eps
+    cond = model.dim_z + model.shared_dim
+    pk = _NS()
+    pk.cond_pitch = _round_up(cond, 8)
+    rows_w, rows_scale, rows_shift = [], [], []       # of the stacked ccbn GEMM
+    col = [0]
+
+    def add_ccbn(bn, prev_bias):
+        """Append this ccbn's scale and shift columns; returns (scale offset, shift offset, C)."""
+        C = bn.output_size
+        rstd = torch.rsqrt(bn.stored_var.detach().double() + bn.eps)
+        m = bn.stored_mean.detach().double()
+        if prev_bias is not None:
+            m = m - prev_bias.detach().double()                     # ccbn(acc + bias) == affine of acc with mean - bias
+        wg = _sn_weight(bn.gain, eps_sn)                           # [C][cond]
+        wb = _sn_weight(bn.bias, eps_sn)
+        rows_w.append(wg * rstd[:, None]);                   rows_scale.append(torch.ones_like(rstd)); rows_shift.append(rstd)
+        rows_w.append(wb - (m * rstd)[:, None] * wg);        rows_scale.append(torch.ones_like(rstd)); rows_shift.append(-m * rstd)
+        o = col[0]
+        col[0] += 2 * C
+        return (o, o + C, C)
+
+    # first linear: rows re-ordered so that the GEMM output [B][16 * C0] is already channels-last [B * 16][C0]
+    C0 = model.arch['in_channels'][0]
+    bw2 = model.bottom_width ** 2
+    wl = _sn_weight(model.linear, eps_sn).reshape(C0, bw2, cond).permute(1, 0, 2).reshape(bw2 * C0, cond)
+    pk.lin_w = torch.zeros((bw2 * C0, pk.cond_pitch), dtype=torch.float16, device=dev)
+    pk.lin_w[:, :cond] = wl.to(torch.float16)
+    pk.lin_b = model.linear.bias.detach().reshape(C0, bw2).t().reshape(-1).float().contiguous()
+    pk.lin_ones = torch.ones_like(pk.lin_b)
+
+    pk.blocks, pk.att = {}, {}
+    res = model.bottom_width
+    for stage in model.blocks:
+        for blk in stage:
+            if hasattr(blk, 'conv4'):
+                bp = _NS()
+                hw_in = res * res
+                h8, in8 = _round_up(blk.hidden_channels, 8), _round_up(blk.in_channels, 8)
+                if blk.hidden_channels % 8 or blk.in_channels % 8 or blk.out_channels % 8:
+                    raise NotImplementedError("GBlock channel counts must be multiples of 8 (got %d / %d / %d)" %
+                                              (blk.in_channels, blk.hidden_channels, blk.out_channels))
+                # bn2 rides in conv1's epilogue when no upsampling sits between them and a 128-row tile stays in one image
+                bp.fuse2 = (not blk.upsample) and hw_in % 128 == 0
+                bp.bn = [add_ccbn(blk.bn1, None),
+                         add_ccbn(blk.bn2, blk.conv1.bias if bp.fuse2 else None),
+                         add_ccbn(blk.bn3, blk.conv2.bias),
+                         add_ccbn(blk.bn4, blk.conv3.bias)]
+                bp.conv = [_pack_conv(blk.conv1, eps_sn, in8), _pack_conv(blk.conv2, eps_sn, h8),
+                           _pack_conv(blk.conv3, eps_sn, h8), _pack_conv(blk.conv4, eps_sn, h8)]
+                pk.blocks[id(blk)] = bp
+                if blk.upsample:
+                    res *= 2
+            else:
+                C = blk.ch
+                d, dv = C // 8, C // 2
+                ap = _NS()
+                ap.d, ap.dv = _round_up(d, 64), _round_up(dv, 64)        # attention kernel granularity; padding is zero weights
+                ld = _round_up(C, 8)
+                ap.wq = torch.zeros((ap.d, ld), dtype=torch.float16, device=dev)
+                ap.wq[:d, :C] = _sn_weight(blk.theta, eps_sn).reshape(d, C).to(torch.float16)
+                ap.wkv = torch.zeros((ap.d + ap.dv, ld), dtype=torch.float16, device=dev)
+                ap.wkv[:d, :C] = _sn_weight(blk.phi, eps_sn).reshape(d, C).to(torch.float16)
+                ap.wkv[ap.d:ap.d + dv, :C] = _sn_weight(blk.g, eps_sn).reshape(dv, C).to(torch.float16)
+                ap.wo = torch.zeros((C, ap.dv), dtype=torch.float16, device=dev)
+                ap.wo[:, :dv] = _sn_weight(blk.o, eps_sn).reshape(C, dv).to(torch.float16)
+                ap.ones = torch.ones(max(ap.d + ap.dv, C), dtype=torch.float32, device=dev)
+                ap.zeros = torch.zeros_like(ap.ones)
+                ap.gamma = (torch.ones(C, dtype=torch.float32, device=dev) * blk.gamma.detach().float()).contiguous()
+                pk.att[id(blk)] = ap
+
+    # output layer: plain BN (shared by all samples) + ReLU pass, then 3x3 conv to RGB
+    obn, oconv = model.output_layer[0], model.output_layer[2]
+    rstd = torch.rsqrt(obn.stored_var.detach().double() + obn.eps)
+    sc = obn.gain.detach().double() * rstd
+    pk.out_scale = sc.float().reshape(1, -1).contiguous()
+    pk.out_shift = (obn.bias.detach().double() - obn.stored_mean.detach().double() * sc).float().reshape(1, -1).contiguous()
+    pk.out_conv = _pack_conv(oconv, eps_sn, _round_up(obn.output_size, 8))
+
+    pk.ncols = col[0]
+    pk.cond_w = torch.zeros((pk.ncols, pk.cond_pitch), dtype=torch.float16, device=dev)
+    pk.cond_w[:, :cond] = torch.cat(rows_w, 0).to(torch.float16)
+    pk.cond_scale = torch.cat(rows_scale).float().contiguous()
+    pk.cond_shift = torch.cat(rows_shift).float().contiguous()
+    return pk
+
+
+def _packed(model, dev):
+    tensors = list(model.parameters()) + list(model.buffers())
+    sig = tuple((t.data_ptr(), t._version) for t in tensors) + (str(dev),)
+    hit = model.__dict__.get('_b2_pack')
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    with torch.no_grad():
+        pk = _pack(model, dev)
+    model.__dict__['_b2_pack'] = (sig, pk)
+    return pk
+
+
+def _aff(aff, slot):
+    o_scale, o_shift, C = slot
+    return aff[:, o_scale:o_scale + C], aff[:, o_shift:o_shift + C]
+
+
+def run_gblock(blk, a, aff, pk):
+    """One GBlock: h = conv4(relu(bn4(conv3(relu(bn3(conv2(up(relu(bn2(conv1(relu(bn1(x))))))))))))) + up(x[:, :out])."""
+    bp = pk.blocks[id(blk)]
+    up = 2 if blk.upsample else 1
+    s1, t1 = _aff(aff, bp.bn[0])
+    t = ops.ccbn_act(a, s1, t1)                                              # relu(bn1(x))
+    if bp.fuse2:
+        t = ops.conv(t, bp.conv[0], relu=True, sample_affine=_aff(aff, bp.bn[1]))     # relu(bn2(conv1(.)))
+    else:
+        t = ops.conv(t, bp.conv[0])                                          # conv1 + bias
+        s2, t2 = _aff(aff, bp.bn[1])
+        t = ops.ccbn_act(t, s2, t2, up=up)                                   # relu(bn2(.)), nearest 2x upsampling
+    t = ops.conv(t, bp.conv[1], relu=True, sample_affine=_aff(aff, bp.bn[2]))          # relu(bn3(conv2(.)))
+    t = ops.conv(t, bp.conv[2], relu=True, sample_affine=_aff(aff, bp.bn[3]))          # relu(bn4(conv3(.)))
+    if up == 1 and blk.in_channels == blk.out_channels:
+        skip = a
+    else:
+        skip = ops.ccbn_act(a, None, None, channels=blk.out_channels, up=up, relu=False)   # up(x[:, :out])
+    return ops.conv(t, bp.conv[3], residual=skip)                            # conv4(.) + skip
+
+
+def run_attention(att, a, pk):
+    """SAGAN self-attention with 2x2 max-pooled keys / values: gamma * o(softmax(theta^T phi) g) + x."""
+    ap = pk.att[id(att)]
+    C, M = att.ch, a.M
+    nkv = ap.d + ap.dv
+    q = ops.gemm(a.data, ap.wq, ap.ones[:ap.d], ap.zeros[:ap.d], M, ap.d, a.ld)
+    kv = ops.gemm(a.data, ap.wkv, ap.ones[:nkv], ap.zeros[:nkv], M, nkv, a.ld)
+    kvp = ops.maxpool3d(Act(kv, a.N, 1, a.H, a.W, nkv), (1, 2, 2), (1, 2, 2), (0, 0, 0))
+    o = ops.attention(q, kvp.data, kvp.data[:, ap.d:], ap.d, ap.dv, a.N, a.H * a.W, kvp.positions)
+    z = ops.gemm(o, ap.wo, ap.gamma, ap.zeros[:C], M, C, ap.dv, residual=a.data)
+    return Act(z, a.N, 1, a.H, a.W, C)
+
+
+def generator_forward(model, z, y, out_dtype=torch.float32, stages=None):
+    """z fp32 [B, dim_z] (CUDA), y int64 [B] class indices or fp32 [B, shared_dim] embeddings -> images [B, 3, R, R]."""
+    if model.training:
+        raise RuntimeError("the B200 engine is inference-only: call model.eval() (standing statistics, no SN update)")
+    if not z.is_cuda:
+        raise RuntimeError("the generator runs on a CUDA (sm_100a) device only: this engine has no CPU path")
+    dev = z.device
+    pk = _packed(model, dev)
+    B = z.shape[0]
+    cond = model.dim_z + model.shared_dim
+    y16 = ops.embed_concat(z, y.to(dev), model.shared.weight, ldy=pk.cond_pitch)
+    aff = ops.gemm(y16, pk.cond_w, pk.cond_scale, pk.cond_shift, B, pk.ncols, cond, out_f32=True)     # every ccbn at once
+    C0, bw = model.arch['in_channels'][0], model.bottom_width
+    h = ops.gemm(y16, pk.lin_w, pk.lin_ones, pk.lin_b, B, bw * bw * C0, cond)
+    a = Act(h.view(B * bw * bw, C0), B, 1, bw, bw, C0)
+    if stages is not None:
+        stages['linear'] = a
+    for i, stage in enumerate(model.blocks):
+        for blk in stage:
+            a = run_gblock(blk, a, aff, pk) if hasattr(blk, 'conv4') else run_attention(blk, a, pk)
+        if stages is not None:
+            stages['stage%d' % i] = a
+    t = ops.ccbn_act(a, pk.out_scale, pk.out_shift)
+    t = ops.conv(t, pk.out_conv)
+    if stages is not None:
+        stages['pre_tanh'] = t
+    return ops.tanh_to_nchw(t, out_dtype)

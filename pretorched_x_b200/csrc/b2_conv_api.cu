@@ -210,6 +210,7 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   p.y = reinterpret_cast<__half*>(a->y);
   p.ldy = a->ldy;
   p.relu = a->relu;
+  p.aff_ld = a->aff_ld;
   p.naff = slab_naff(a->ldy);
   p.tiles_n = (a->ldy + BN - 1) / BN;
   p.tiles_q = (p.P + MT * 128 - 1) / (MT * 128);
@@ -465,6 +466,7 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.scale = ip.scale; p.shift = ip.shift;
   p.has_residual = ip.residual != nullptr;
   p.relu = ip.relu;
+  p.aff_ld = ip.aff_ld; p.aff_rows = ip.aff_rows;
   const int grid = p.tiles_total < sm_count() ? p.tiles_total : sm_count();
   B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN>, dim3(grid), dim3(kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, p));
   B2_CHECK_LAUNCH("pgemm_kernel");
@@ -475,6 +477,8 @@ static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (g_gemm_algo == 0 && L.p.amode == AMODE_TMA && L.p.epi == EPI_TMA_F16 && !L.p.per_row) {
     return L.p.ldy <= 64 ? launch_pgemm<64>(L, stream) : launch_pgemm<128>(L, stream);
   }
+  if (L.p.aff_ld)
+    return set_error(B2_ERR_UNSUPPORTED, "per-sample affine is implemented by the slab convolution and the persistent GEMM only");
   // 64-wide tiles for narrow outputs, 128 otherwise
   const int width = (L.p.epi == EPI_TMA_F16) ? L.p.ldy : L.p.Ncols;
   if (width <= 64) return launch_igemm<64>(L, stream);
@@ -521,6 +525,8 @@ static int validate_conv(const b2_conv_args* a) {
     B2_CHECK_ARG(a->mode == B2_CONV_AUTO, "unknown conv mode %d", a->mode);
     B2_CHECK_ARG(a->C % 8 == 0, "channel pitch %d is not a multiple of 8", a->C);
   }
+  B2_CHECK_ARG(a->aff_ld >= 0 && (a->aff_ld == 0 || (a->aff_ld >= a->K && !a->out_f32 && a->mode == B2_CONV_AUTO)),
+               "bad per-sample affine pitch %d", a->aff_ld);
   if (!a->out_f32) {
     B2_CHECK_ARG(a->ldy % 8 == 0, "ldy %d is not a multiple of 8", a->ldy);
     B2_CHECK_ARG(a->residual == nullptr || a->ldr % 8 == 0, "ldr %d is not a multiple of 8", a->ldr);
@@ -557,6 +563,10 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   p.y = a->y; p.ldy = a->ldy;
   p.relu = a->relu; p.per_row = 0; p.accumulate = a->accumulate;
   p.epi = a->out_f32 ? EPI_DIRECT_F32 : EPI_TMA_F16;
+  p.aff_ld = a->aff_ld;
+  p.aff_rows = p.To * p.Ho * p.Wo;
+  if (a->aff_ld && p.aff_rows % 128 != 0)
+    return set_error(B2_ERR_UNSUPPORTED, "per-sample affine on a 1x1x1 convolution needs To*Ho*Wo %% 128 == 0 (got %d)", p.aff_rows);
   L.w = a->w;
 
   const int taps = a->kt * a->kh * a->kw;
@@ -621,6 +631,10 @@ static int gemm_common(const b2_gemm_args* g, const void* a2, int lda2, const vo
   p.y = g->d; p.ldy = g->ldd;
   p.relu = g->relu; p.per_row = g->per_row; p.accumulate = g->accumulate;
   p.epi = g->out_f32 ? EPI_DIRECT_F32 : EPI_TMA_F16;
+  B2_CHECK_ARG(g->aff_ld >= 0 && (g->aff_ld == 0 || (g->aff_ld >= g->N && g->aff_rows > 0 && g->aff_rows % 128 == 0 &&
+                                                     !g->out_f32 && !g->per_row)),
+               "bad per-sample affine (pitch %d, rows per sample %d)", g->aff_ld, g->aff_rows);
+  p.aff_ld = g->aff_ld; p.aff_rows = g->aff_rows;
   p.x = reinterpret_cast<const __half*>(g->a);
   L.a_mat = g->a; L.lda = g->lda; L.a_cols = g->Kd;
   L.w = g->b; L.ldb = g->ldb; L.b_cols = g->Kd;

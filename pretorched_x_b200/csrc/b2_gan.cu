@@ -1,0 +1,159 @@
+// b2_gan.cu -- HBM-bound helper kernels of the BigGAN-deep generator path (BASELINE.json configs[4]; the architecture
+// is absent from /root/reference, see oracle/biggan.py): conditioning-vector assembly, the class-conditional
+// BatchNorm + ReLU (+ nearest 2x upsampling) pass, and the final tanh + NHWC -> NCHW image write.  Same conventions
+// as b2_aux.cu: fp16 channels-last rows, 16 bytes per thread per access, channel index fastest.
+#include "b2_host.h"
+
+#include <cuda_fp16.h>
+
+namespace b2 {
+
+static inline int gan_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// y[b] = [ table[label[b]][0:ds] | z[b][0:dz] | 0 ... ]  as fp16 with pitch ldy
+__global__ void embed_concat_kernel(const float* __restrict__ z, const long long* __restrict__ labels,
+                                    const float* __restrict__ table, const float* __restrict__ embedded, __half* __restrict__ y,
+                                    int B, int dz, int ds, int n_classes, int ldy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * ldy) return;
+  const int b = i / ldy, c = i - b * ldy;
+  float v = 0.f;
+  if (c < ds) {
+    if (embedded) v = embedded[(long long)b * ds + c];
+    else {
+      long long l = labels[b];
+      l = l < 0 ? 0 : (l >= n_classes ? n_classes - 1 : l);
+      v = table[l * ds + c];
+    }
+  } else if (c < ds + dz) {
+    v = z[(long long)b * dz + (c - ds)];
+  }
+  y[i] = __float2half_rn(v);
+}
+
+// y[n, up*h + i, up*w + j, c] = act(x[n, h, w, c] * scale[n*lda + c] + shift[n*lda + c]),  i, j < up, c < C;
+// channels [C, ldy) of y are written as zero.  scale == nullptr: identity (pure channel-slice / upsample copy).
+template <int UP>
+__global__ void __launch_bounds__(256)
+ccbn_act_kernel(const __half* __restrict__ x, int ldx8, __half* __restrict__ y, int ldy8, const float* __restrict__ scale,
+                const float* __restrict__ shift, int lda, int H, int W, int C8, int relu, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % ldy8);
+  long long q = i / ldy8;                    // input pixel index n*H*W + h*W + w
+  const int w = (int)(q % W);
+  const long long q2 = q / W;
+  const int h = (int)(q2 % H);
+  const long long n = q2 / H;
+  uint4 out = make_uint4(0, 0, 0, 0);
+  if (c8 < C8) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + q * ldx8 + c8);
+    if (scale) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + n * lda + c8 * 8));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + n * lda + c8 * 8) + 1);
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift + n * lda + c8 * 8));
+      const float4 t1 = __ldg(reinterpret_cast<const float4*>(shift + n * lda + c8 * 8) + 1);
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+      const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[e]));
+        float a0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
+        float a1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+        if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+        const __half2 hv = __floats2half2_rn(a0, a1);
+        o[e] = *reinterpret_cast<const uint32_t*>(&hv);
+      }
+      out = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      out = v;
+      if (relu) {
+        __half2* hp = reinterpret_cast<__half2*>(&out);
+        const __half2 zero = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hp[e] = __hmax2(hp[e], zero);
+      }
+    }
+  }
+  const long long Wo = (long long)W * UP;
+  uint4* yo = reinterpret_cast<uint4*>(y) + ((n * H * UP + (long long)h * UP) * Wo + (long long)w * UP) * ldy8 + c8;
+#pragma unroll
+  for (int a = 0; a < UP; ++a)
+#pragma unroll
+    for (int b = 0; b < UP; ++b) yo[(a * Wo + b) * ldy8] = out;
+}
+
+// y[n][c][s] = tanh(x[n*S + s][c])  (fp16 NHWC with pitch ldx -> NCHW, fp32 or fp16): 32 x 32 smem transpose is not
+// needed for C = 3; each thread handles one pixel (one 16-byte load) and writes C scalars to C planes, consecutive
+// threads -> consecutive addresses within each plane.
+template <typename TOut>
+__global__ void tanh_nhwc_to_nchw_kernel(const __half* __restrict__ x, int ldx, TOut* __restrict__ y, int C, long long S,
+                                         long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / S, s = i - n * S;
+  const __half* xr = x + i * ldx;
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + c0));
+    const __half* hv = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (c0 + e < C) {
+        // tanh(v) = 1 - 2 / (exp(2v) + 1); |v| clamped so that exp stays finite (tanh(15) == 1 in fp32)
+        const float v2 = 2.f * fminf(fmaxf(__half2float(hv[e]), -15.f), 15.f);
+        y[(n * C + c0 + e) * S + s] = static_cast<TOut>(1.f - __fdividef(2.f, __expf(v2) + 1.f));
+      }
+  }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+int b2_embed_concat(const float* z, const long long* labels, const float* table, const float* embedded, void* y, int B,
+                    int dz, int ds, int n_classes, int ldy, void* stream) {
+  B2_CHECK_ARG(z && y && (embedded || (labels && table)), "null pointer");
+  B2_CHECK_ARG(B > 0 && dz >= 0 && ds >= 0 && ldy >= dz + ds && ldy % 8 == 0, "bad dimensions");
+  embed_concat_kernel<<<gan_div_up((long long)B * ldy, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      z, labels, table, embedded, (__half*)y, B, dz, ds, n_classes, ldy);
+  B2_CHECK_LAUNCH("embed_concat");
+  return B2_OK;
+}
+
+int b2_ccbn_act_ndhwc(const void* x, int ldx, void* y, int ldy, const float* scale, const float* shift, int lda, int N,
+                      int H, int W, int C, int up, int relu, void* stream) {
+  B2_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0, "bad argument");
+  B2_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && C % 8 == 0 && ldx >= C && ldy >= C, "channel counts / pitches must be multiples of 8");
+  B2_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift go together");
+  B2_CHECK_ARG(lda % 4 == 0 && (reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0,
+               "affine arrays must be 16-byte aligned with a pitch that is a multiple of 4");
+  if (up != 1 && up != 2) return set_error(B2_ERR_UNSUPPORTED, "nearest upsampling by %d is not implemented (1 or 2)", up);
+  const long long total = (long long)N * H * W * (ldy / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (up == 1)
+    ccbn_act_kernel<1><<<gan_div_up(total, 256), 256, 0, st>>>((const __half*)x, ldx / 8, (__half*)y, ldy / 8, scale, shift, lda, H, W,
+                                                             C / 8, relu, total);
+  else
+    ccbn_act_kernel<2><<<gan_div_up(total, 256), 256, 0, st>>>((const __half*)x, ldx / 8, (__half*)y, ldy / 8, scale, shift, lda, H, W,
+                                                             C / 8, relu, total);
+  B2_CHECK_LAUNCH("ccbn_act");
+  return B2_OK;
+}
+
+int b2_tanh_nhwc_to_nchw(const void* x, int ldx, void* y, int N, int C, long long S, int out_f32, void* stream) {
+  B2_CHECK_ARG(x && y && N > 0 && C > 0 && S > 0 && ldx % 8 == 0 && ldx >= C, "bad argument");
+  const long long total = (long long)N * S;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_f32)
+    tanh_nhwc_to_nchw_kernel<float><<<gan_div_up(total, 256), 256, 0, st>>>((const __half*)x, ldx, (float*)y, C, S, total);
+  else
+    tanh_nhwc_to_nchw_kernel<__half><<<gan_div_up(total, 256), 256, 0, st>>>((const __half*)x, ldx, (__half*)y, C, S, total);
+  B2_CHECK_LAUNCH("tanh_nhwc_to_nchw");
+  return B2_OK;
+}
+
+}  // extern "C"

@@ -50,6 +50,7 @@ struct IgemmParams {
   int accumulate;          // EPI_DIRECT_F32: y += result
   int amode;
   int epi;
+  int aff_ld, aff_rows;    // per-sample affine (persistent GEMM only): scale/shift row (m / aff_rows), pitch aff_ld; 0 = off
 };
 
 template <int BN>

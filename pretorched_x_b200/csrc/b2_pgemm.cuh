@@ -36,6 +36,7 @@ struct PgemmParams {
   const float* shift;
   int has_residual;
   int relu;
+  int aff_ld, aff_rows;     // > 0: scale/shift are [M / aff_rows][aff_ld] (per-sample affine; aff_rows % 128 == 0)
 };
 
 template <int BN>
@@ -171,8 +172,10 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       asm volatile("bar.sync 1, 256;" ::: "memory");     // (also: everyone is done with the previous tile's affine)
       if (tid < BN) {
         const int c = n0 + tid;
-        s_scale[tid] = (c < p.Ncols) ? __ldg(&p.scale[c]) : 0.f;
-        s_shift[tid] = (c < p.Ncols) ? __ldg(&p.shift[c]) : 0.f;
+        // per-sample affine (class-conditional BN of the consumer): a 128-row tile never straddles two samples
+        const size_t arow = p.aff_ld ? static_cast<size_t>(m0 / p.aff_rows) * p.aff_ld : 0;
+        s_scale[tid] = (c < p.Ncols) ? __ldg(&p.scale[arow + c]) : 0.f;
+        s_shift[tid] = (c < p.Ncols) ? __ldg(&p.shift[arow + c]) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll 1

@@ -73,6 +73,7 @@ struct SlabParams {
   int ldy;
   int relu;
   int naff;                // scale/shift entries staged in smem (>= every column an epilogue chunk can touch)
+  int aff_ld;              // > 0: scale/shift are per-sample [N][aff_ld] arrays read from global memory per work item
 };
 
 // scale/shift live in smem for all (padded) output channels: SlabParams::naff = round_up(ldy, 32) + 32 entries each
@@ -138,8 +139,8 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
   }
   if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   for (int i = tid; i < p.naff; i += kSlabThreads) {
-    s_scale[i] = (i < p.Ncols) ? __ldg(&p.scale[i]) : 0.f;
-    s_shift[i] = (i < p.Ncols) ? __ldg(&p.shift[i]) : 0.f;
+    s_scale[i] = (i < p.Ncols && !p.aff_ld) ? __ldg(&p.scale[i]) : 0.f;
+    s_shift[i] = (i < p.Ncols && !p.aff_ld) ? __ldg(&p.shift[i]) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -284,10 +285,22 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
         // folded-BN scale/shift of these 32 channels: registers, reused by every M tile of the item
         float sc[32], sh[32];
         const int c0 = w.n0 + jc * 32;
+        if (p.aff_ld) {
+          // per-sample affine (class-conditional BN of the consumer): the item lies in one image, every lane reads
+          // the same 32 + 32 floats (L1/L2 broadcast)
+          const size_t arow = static_cast<size_t>(w.plane_o / p.To) * p.aff_ld;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          sc[c] = s_scale[c0 + c];
-          sh[c] = s_shift[c0 + c];
+          for (int c = 0; c < 32; ++c) {
+            const bool in = c0 + c < p.Ncols;
+            sc[c] = in ? __ldg(p.scale + arow + c0 + c) : 0.f;
+            sh[c] = in ? __ldg(p.shift + arow + c0 + c) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            sc[c] = s_scale[c0 + c];
+            sh[c] = s_shift[c0 + c];
+          }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -9,27 +9,39 @@ import torch
 
 
 class GraphedForward:
-    """``g = GraphedForward(model, example); y = g(x)`` with ``x`` of ``example``'s shape (device or pinned host)."""
+    """``g = GraphedForward(model, example); y = g(x)`` with ``x`` of ``example``'s shape (device or pinned host).
+    ``example`` may be a tuple of tensors for models that take several inputs (the BigGAN generator's ``(z, y)``);
+    ``**kwargs`` are passed to every ``model(...)`` call."""
 
-    def __init__(self, model, example_input, warmup=2):
-        if not example_input.is_cuda:
-            raise RuntimeError("GraphedForward needs a CUDA example input: the engine has no CPU path")
+    def __init__(self, model, example_input, warmup=2, **kwargs):
+        self.multi = isinstance(example_input, (tuple, list))
+        examples = tuple(example_input) if self.multi else (example_input,)
+        if not all(e.is_cuda for e in examples):
+            raise RuntimeError("GraphedForward needs CUDA example inputs: the engine has no CPU path")
         self.model = model
-        self.static_in = example_input.detach().clone()
+        self.static_ins = tuple(e.detach().clone() for e in examples)
+        self.static_in = self.static_ins if self.multi else self.static_ins[0]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(max(1, warmup)):          # packs weights, sets kernel attributes, warms the allocator
-                model(self.static_in)
+                model(*self.static_ins, **kwargs)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
-            self.static_out = model(self.static_in)
+            self.static_out = model(*self.static_ins, **kwargs)
+
+    def load(self, x):
+        """Copy new input(s) into the static buffers (asynchronously on the current stream)."""
+        xs = tuple(x) if self.multi else (x,)
+        for dst, src in zip(self.static_ins, xs):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
 
     def __call__(self, x=None):
-        if x is not None and x.data_ptr() != self.static_in.data_ptr():
-            self.static_in.copy_(x, non_blocking=True)
+        if x is not None:
+            self.load(x)
         self.graph.replay()
         return self.static_out
 
@@ -43,8 +55,8 @@ class PipelinedForward:
     sum -- with fp32 NCDHW clips (the reference's input format) the PCIe copy is as long as the forward itself.
     """
 
-    def __init__(self, model, example_input, depth=2):
-        self.graphs = [GraphedForward(model, example_input) for _ in range(depth)]
+    def __init__(self, model, example_input, depth=2, **kwargs):
+        self.graphs = [GraphedForward(model, example_input, **kwargs) for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream()
         self.compute_stream = torch.cuda.Stream()
         self.copied = [torch.cuda.Event() for _ in range(depth)]
@@ -61,7 +73,7 @@ class PipelinedForward:
         g = self.graphs[d]
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.done[d])          # slot's previous forward (and D2H) finished
-            g.static_in.copy_(host_batch, non_blocking=True)
+            g.load(host_batch)
             self.copied[d].record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.copied[d])

@@ -186,9 +186,12 @@ def _out_dim(i, k, s, p):
 # ---------------------------------------------------------------------------------------------
 # convolution / dense
 # ---------------------------------------------------------------------------------------------
-def conv(a, pc, residual=None, relu=False, simt=False):
+def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None):
     """nn.Conv3d -> BatchNorm3d -> (+residual) -> ReLU in one kernel
-    (resnet3D.py:91-106, 125-143, 176-185; r2plus1d.py:85-88; torchvision_models.py:449-451)."""
+    (resnet3D.py:91-106, 125-143, 176-185; r2plus1d.py:85-88; torchvision_models.py:449-451).
+
+    ``sample_affine=(scale, shift)``: fp32 ``[N][pitch]`` views -- a per-SAMPLE epilogue affine instead of the packed
+    per-channel one (class-conditional BatchNorm of the layer that follows the convolution, BigGAN GBlock)."""
     if a.ld != pc.C:
         raise ValueError("activation pitch %d != packed filter pitch %d" % (a.ld, pc.C))
     kt, kh, kw = pc.k
@@ -210,6 +213,11 @@ def conv(a, pc, residual=None, relu=False, simt=False):
     args.st, args.sh, args.sw = pc.s
     args.pt, args.ph, args.pw = pc.p
     args.relu, args.out_f32, args.accumulate, args.mode = int(relu), 0, 0, pc.mode
+    if sample_affine is not None:
+        sc, sh = sample_affine
+        if simt or sc.shape != sh.shape or sc.shape[0] != a.N or sc.stride(0) != sh.stride(0) or sc.shape[1] < pc.K:
+            raise ValueError("per-sample affine must be two fp32 [N][>=K] views with the same pitch")
+        args.scale, args.shift, args.aff_ld = _ptr(sc), _ptr(sh), sc.stride(0)
     lib = _lib.load()
     fn = lib.b2_conv_ndhwc_fprop_simt if simt else lib.b2_conv_ndhwc_fprop
     taps = kt * kh * kw
@@ -222,7 +230,7 @@ def conv(a, pc, residual=None, relu=False, simt=False):
 
 
 def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=False, out=None, out_f32=False,
-         accumulate=False, second=None):
+         accumulate=False, second=None, aff_rows=0):
     """D[M][N] = act(scale * A[M][Kd] . B[N][Kd]^T + shift + residual) on tcgen05 (b2_gemm_f16).
     ``second=(A2, B2, K2)`` adds A2[M][K2] . B2[N][K2]^T into the same accumulator (b2_gemm2_f16)."""
     dev = a2d.device
@@ -237,6 +245,8 @@ def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=Fa
     g.lda, g.ldb, g.ldd = a2d.stride(0), b2d.stride(0), out.stride(0)
     g.ldr = residual.stride(0) if residual is not None else 0
     g.per_row, g.relu, g.out_f32, g.accumulate = int(per_row), int(relu), int(out_f32), int(accumulate)
+    if aff_rows:                      # per-sample affine: scale/shift are fp32 [M / aff_rows][pitch] views
+        g.aff_ld, g.aff_rows = scale.stride(0), int(aff_rows)
     if second is not None:
         a2, b2, k2 = second
         with _timed("gemm", "gemm2 M=%d N=%d K=%d+%d" % (M, N, Kd, k2), 2.0 * M * N * (Kd + k2),
@@ -367,3 +377,59 @@ def attention(q2d, k2d, v2d, d, dv, B, Nq, Nk, dot_product=False):
 def nonlocal_attention(qkv, d, dv, B, Npos):
     """Embedded-gaussian core on one fused projection: qkv fp16 [B*Npos][>= 2d + dv] = theta | phi | g."""
     return attention(qkv, qkv[:, d:], qkv[:, 2 * d:], d, dv, B, Npos, Npos)
+
+
+# ---------------------------------------------------------------------------------------------
+# BigGAN-deep generator helpers (architecture absent from the reference tree; see models/biggan_deep.py)
+# ---------------------------------------------------------------------------------------------
+def embed_concat(z, labels, table, ldy=None):
+    """fp16 [B][ldy] = [table[labels] | z | 0]: the conditioning vector every ccbn of the generator consumes.
+    ``labels`` int64 [B] class indices, or an fp32 [B][shared_dim] tensor that is already embedded."""
+    _require_cuda(z, "z")
+    z = z.contiguous().float()
+    B, dz = z.shape
+    ds = table.shape[1]
+    ldy = _round_up(dz + ds, 8) if ldy is None else ldy
+    y = torch.empty((B, ldy), dtype=torch.float16, device=z.device)
+    if labels.dtype in (torch.int64, torch.int32, torch.int16, torch.uint8) and labels.dim() == 1:
+        lab, emb = labels.to(torch.int64).contiguous(), None
+    else:
+        lab, emb = None, labels.contiguous().float()
+        if emb.shape != (B, ds):
+            raise ValueError("embedded class vectors must be [B, %d], got %s" % (ds, tuple(emb.shape)))
+    _lib.check(_lib.load().b2_embed_concat(_ptr(z), _ptr(lab), _ptr(table), _ptr(emb), _ptr(y), B, dz, ds, table.shape[0],
+                                          ldy, _stream()), "b2_embed_concat")
+    return y
+
+
+def ccbn_act(a, scale=None, shift=None, channels=None, up=1, relu=True):
+    """act(x * scale[n] + shift[n]) with optional nearest 2x upsampling: the ccbn -> ReLU (-> F.interpolate) chain of a
+    GBlock in one HBM pass.  ``scale``/``shift``: fp32 [N][pitch] views (per sample), [1][pitch] (shared), or None
+    (pure copy: channel slice x[:, :channels] and/or upsampling of the skip path)."""
+    C = a.C if channels is None else channels
+    ldy = _round_up(C, 8)
+    y = torch.empty((a.N * a.T * a.H * up * a.W * up, ldy), dtype=torch.float16, device=a.data.device)
+    if a.T != 1:
+        raise ValueError("ccbn_act works on images (T == 1)")
+    lda = 0
+    if scale is not None:
+        lda = scale.stride(0) if scale.shape[0] > 1 else 0
+        if scale.shape[0] not in (1, a.N) or scale.shape[1] < C or shift.shape != scale.shape or (
+                scale.shape[0] > 1 and shift.stride(0) != lda):
+            raise ValueError("ccbn affine must be fp32 [N or 1][>=C] views with one pitch")
+    with _timed("ccbn", "ccbn_act C%d px=%d up%d" % (C, a.M, up), 0.0, 2.0 * C * a.M * (1 + up * up)):
+        _lib.check(_lib.load().b2_ccbn_act_ndhwc(_ptr(a.data), a.ld, _ptr(y), ldy, _ptr(scale), _ptr(shift), lda, a.N, a.H,
+                                                a.W, C, up, int(relu), _stream()), "b2_ccbn_act_ndhwc")
+    return Act(y, a.N, 1, a.H * up, a.W * up, C)
+
+
+def tanh_to_nchw(a, out_dtype=torch.float32):
+    """torch.tanh + channels-last -> NCHW: the generator's image write (fp32 like the public model, or fp16)."""
+    if out_dtype not in (torch.float32, torch.float16):
+        raise ValueError("images are written as fp32 or fp16")
+    y = torch.empty((a.N, a.C, a.H, a.W), dtype=out_dtype, device=a.data.device)
+    S = a.T * a.H * a.W
+    with _timed("tanh", "tanh->nchw C%d px=%d" % (a.C, a.M), 0.0, a.M * (2.0 * a.ld + y.element_size() * a.C)):
+        _lib.check(_lib.load().b2_tanh_nhwc_to_nchw(_ptr(a.data), a.ld, _ptr(y), a.N, a.C, S, int(out_dtype == torch.float32),
+                                                   _stream()), "b2_tanh_nhwc_to_nchw")
+    return y

@@ -1,0 +1,169 @@
+"""GPU (-m gpu): BigGAN-deep generator path (BASELINE.json configs[4]) against oracle/biggan.py.
+
+PARITY UNPINNED: the reference tree holds no GAN code, so the checker is our own CPU
+restatement of the published architecture, not an output of the reference.
+
+Stated tolerances (fp16 activations and weights, fp32 accumulation; relative to max|restatement| of the tensor):
+  helper kernels 2e-3 (one fp16 rounding), convolutions with a per-sample epilogue 3e-3, per-stage activations of the
+  whole generator 2e-2 (13 residual blocks, 48 conditional BatchNorms whose gains come from an fp16 GEMM), final images
+  (tanh output in (-1, 1)) 2e-2 absolute.
+"""
+import glob
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import biggan as OB
+import pretorched_x_b200 as P
+from pretorched_x_b200 import biggan_engine, ops
+from pretorched_x_b200.ops import Act
+
+pytestmark = pytest.mark.gpu
+FIX = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "biggan_*.pt")))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return torch.device("cuda:0")
+
+
+def nhwc(x16):
+    """fp16 NCHW (cpu or cuda) -> Act on cuda."""
+    N, C, H, W = x16.shape
+    return Act(x16.permute(0, 2, 3, 1).contiguous().view(N * H * W, C).cuda(), N, 1, H, W, C)
+
+
+def to_nchw(a):
+    return a.data[:, :a.C].float().view(a.N, a.H, a.W, a.C).permute(0, 3, 1, 2).cpu()
+
+
+def rel(got, want):
+    return (got.double() - want.double()).abs().max().item() / max(want.abs().max().item(), 1e-12)
+
+
+@pytest.mark.parametrize("up", [1, 2])
+@pytest.mark.parametrize("mode", ["sample", "shared", "copy"])
+def test_ccbn_act(dev, up, mode):
+    g = torch.Generator().manual_seed(5)
+    N, C, H, W = 3, 48, 6, 10
+    x = torch.randn(N, C, H, W, generator=g).half()
+    a = nhwc(x)
+    pitch = 104
+    aff = torch.randn(N, 2 * pitch, generator=g).cuda()
+    Cs = 24 if mode == "copy" else C
+    if mode == "sample":
+        sc, sh = aff[:, 8:8 + C], aff[:, pitch + 8:pitch + 8 + C]
+        want = F.relu(x.float() * sc.cpu().view(N, C, 1, 1) + sh.cpu().view(N, C, 1, 1))
+        out = ops.ccbn_act(a, sc, sh, up=up)
+    elif mode == "shared":
+        sc, sh = aff[:1, 8:8 + C].contiguous(), aff[:1, pitch + 8:pitch + 8 + C].contiguous()
+        want = F.relu(x.float() * sc.cpu().view(1, C, 1, 1) + sh.cpu().view(1, C, 1, 1))
+        out = ops.ccbn_act(a, sc, sh, up=up)
+    else:
+        want = x.float()[:, :Cs]
+        out = ops.ccbn_act(a, None, None, channels=Cs, up=up, relu=False)
+    if up == 2:
+        want = F.interpolate(want, scale_factor=2)
+    assert (out.H, out.W, out.C) == (H * up, W * up, Cs)
+    assert rel(to_nchw(out), want) <= (0.0 if mode == "copy" else 2e-3)
+    assert float(out.data[:, Cs:].abs().max()) == 0.0 if out.ld > Cs else True
+
+
+def test_embed_concat_and_tanh(dev):
+    g = torch.Generator().manual_seed(6)
+    z = torch.randn(5, 128, generator=g)
+    lab = torch.tensor([0, 9, 3, 3, 7])
+    table = torch.randn(10, 128, generator=g)
+    y = ops.embed_concat(z.cuda(), lab.cuda(), table.cuda())
+    want = torch.cat([table[lab], z], 1)
+    assert y.shape == (5, 256) and rel(y.float().cpu(), want) <= 1e-3
+    y2 = ops.embed_concat(z.cuda(), table[lab].cuda(), table.cuda())
+    assert torch.equal(y, y2)
+    x = (torch.randn(2, 3, 9, 14, generator=g) * 3).half()
+    a = nhwc(F.pad(x, (0, 0, 0, 0, 0, 5)))          # 3 channels in an 8-wide row
+    a.C = 3
+    for dt in (torch.float32, torch.float16):
+        img = ops.tanh_to_nchw(a, dt)
+        assert img.dtype == dt and img.shape == (2, 3, 9, 14)
+        assert (img.float().cpu() - torch.tanh(x.float())).abs().max().item() <= (1e-5 if dt == torch.float32 else 1e-3)
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 12, 20, 64), (2, 128, 16, 16, 128), (5, 32, 4, 4, 32), (2, 16, 40, 40, 8)])
+def test_conv3x3_with_per_sample_affine(dev, shape):
+    N, C, H, W, K = shape
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(N, C, H, W, generator=g).half()
+    w = (torch.randn(K, C, 3, 3, generator=g) / (3 * C ** 0.5))
+    aff = torch.randn(N, 2 * K + 16, generator=g).cuda()
+    sc, sh = aff[:, :K], aff[:, K + 16:]
+    pc = ops.PackedConv(w.cuda(), None, None, (1, 1, 1), (0, 1, 1), in_pitch=C)
+    out = ops.conv(nhwc(x), pc, relu=True, sample_affine=(sc, sh))
+    ref = F.conv2d(x.float(), w.half().float(), None, 1, 1)
+    want = F.relu(ref * sc.cpu().view(N, K, 1, 1) + sh.cpu().view(N, K, 1, 1))
+    assert rel(to_nchw(out), want) <= 3e-3
+
+
+@pytest.mark.parametrize("shape", [(3, 256, 16, 16, 64), (2, 64, 16, 8, 200)])
+def test_conv1x1_with_per_sample_affine(dev, shape):
+    N, C, H, W, K = shape
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(N, C, H, W, generator=g).half()
+    w = torch.randn(K, C, 1, 1, generator=g) / C ** 0.5
+    aff = torch.randn(N, 2 * K + 8, generator=g).cuda()
+    sc, sh = aff[:, :K], aff[:, K + 8:]
+    pc = ops.PackedConv(w.cuda(), None, None, (1, 1, 1), (0, 0, 0), in_pitch=C)
+    out = ops.conv(nhwc(x), pc, relu=True, sample_affine=(sc, sh))
+    want = F.relu(F.conv2d(x.float(), w.half().float()) * sc.cpu().view(N, K, 1, 1) + sh.cpu().view(N, K, 1, 1))
+    assert rel(to_nchw(out), want) <= 3e-3
+    # a tile that would straddle two samples is refused, not silently mis-scaled
+    x2 = torch.randn(2, C, 6, 6, generator=g).half()
+    with pytest.raises(RuntimeError, match="128"):
+        ops.conv(nhwc(x2), pc, relu=True, sample_affine=(sc[:2], sh[:2]))
+
+
+def run_case(model, sd, z, labels, res, ch, dev, tol_stage=2e-2, tol_img=2e-2):
+    want_stages = {}
+    with torch.no_grad():
+        want = OB.generator_forward(z, labels, sd, res, ch, stages=want_stages)
+        got_stages = {}
+        got = biggan_engine.generator_forward(model.to(dev), z.to(dev), labels.to(dev), stages=got_stages)
+    torch.cuda.synchronize()
+    errs = {k: rel(to_nchw(got_stages[k]), want_stages[k]) for k in want_stages}
+    errs["image"] = (got.cpu() - want).abs().max().item()
+    print("biggan %d ch%d B%d:" % (res, ch, z.shape[0]), " ".join("%s=%.2e" % kv for kv in errs.items()))
+    assert got.shape == want.shape and got.dtype == torch.float32
+    for k, e in errs.items():
+        assert e <= (tol_img if k == "image" else tol_stage), (k, e)
+    return got
+
+
+@pytest.mark.parametrize("path", FIX, ids=[os.path.basename(p)[:-3] for p in FIX])
+def test_generator_matches_restatement_on_fixture_cases(dev, path):
+    fx = torch.load(path, weights_only=False)
+    model, sd, z, labels = OB.build_case(P.biggan_deep, fx["resolution"], fx["ch"], fx["n_classes"], fx["batch"],
+                                         fx["seeds"]["init"], fx["seeds"]["input"], fx["init"])
+    got = run_case(model, sd, z, labels, fx["resolution"], fx["ch"], dev)
+    ref = fx["image"]                                  # the committed samples of the restatement's images
+    samp = got.cpu().reshape(-1)[::ref["step"]][:ref["sample"].numel()]
+    assert (samp - ref["sample"]).abs().max().item() <= 2e-2
+
+
+def test_full_size_biggan_deep_256(dev):
+    """BASELINE configs[4] architecture (ch = 128, 1000 classes, 55.7 M parameters) at a batch the CPU checks in seconds,
+    plus size-independent properties: a sample's image does not depend on its batch neighbours, fp16 output is the
+    rounding of the fp32 output, images stay inside (-1, 1)."""
+    model, sd, z, labels = OB.build_case(P.biggan_deep, 256, 128, 1000, 3, init="ortho")
+    got = run_case(model, sd, z, labels, 256, 128, dev)
+    assert float(got.abs().max()) <= 1.0
+    with torch.no_grad():
+        solo = model(z[1:2].to(dev), labels[1:2].to(dev))
+        half = model(z.to(dev), labels.to(dev), out_dtype=torch.float16)
+    assert (solo[0] - got[1]).abs().max().item() <= 1e-3
+    assert (half.float() - got).abs().max().item() <= 1e-3
+    # embedded class vectors in place of class indices give the same images
+    with torch.no_grad():
+        emb = model(z.to(dev), model.shared.weight[labels.to(dev)])
+    assert torch.equal(emb, got)
