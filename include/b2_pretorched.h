@@ -160,10 +160,12 @@ int b2_gather_frames(const void* x, void* y, const int32_t* idx_dev, int N, int 
  * F.interpolate(scale_factor=2) chain of the published GBlock, its embedding lookup + torch.cat, and the final
  * torch.tanh; see oracle/biggan.py for the restatement they are checked against.
  * ------------------------------------------------------------------------------------------- */
-/* y[b] = fp16 [ (embedded ? embedded[b] : table[labels[b]]) (ds) | z[b] (dz) | 0 ] with pitch ldy.  z, table, embedded
- * fp32; labels int64 (clamped to [0, n_classes)). */
+/* v[b] = [ (embedded ? embedded[b] : table[labels[b]]) (ds) | z[b] (dz) | 0 ], D = round_up(ds + dz, 8) entries.
+ * split == 0: y[b] = fp16(v), pitch ldy >= D.  split != 0: y[b] = [ hi | lo | hi ] (hi = fp16(v), lo = fp16(v - hi)),
+ * pitch ldy >= 3 * D -- the A operand of an fp16 GEMM against [ W_hi | W_hi | W_lo ] that reproduces v . W to ~fp32
+ * accuracy.  z, table, embedded fp32; labels int64 (clamped to [0, n_classes)). */
 int b2_embed_concat(const float* z, const long long* labels, const float* table, const float* embedded, void* y, int B,
-                    int dz, int ds, int n_classes, int ldy, void* stream);
+                    int dz, int ds, int n_classes, int ldy, int split, void* stream);
 /* y[n, up*h+i, up*w+j, c] = act(x[n,h,w,c] * scale[n*lda + c] + shift[n*lda + c]) for c < C, i,j < up (up = 1 or 2,
  * nearest-neighbour upsampling); channels [C, ldy) written as zero.  scale/shift fp32 [N][lda] (lda = 0: one row shared
  * by all samples, i.e. a plain BatchNorm), or both NULL for a pure copy / channel slice / upsample. */

@@ -55,12 +55,24 @@ def sn_sigma(w, u, eps=SN_EPS):
     return torch.squeeze(torch.matmul(torch.matmul(v, wm.t()), u2.t()))
 
 
-def sn_weight(sd, p):
-    return sd[p + '.weight'] / sn_sigma(sd[p + '.weight'], sd[p + '.u0'])
+def _ident(t):
+    return t
 
 
-def _sn_conv(x, sd, p, padding):
-    return F.conv2d(x, sn_weight(sd, p), sd.get(p + '.bias'), 1, padding)
+def fp16_storage(t):
+    """Round-trip through fp16: what ``storage=fp16_storage`` applies at every point where the CUDA engine keeps a tensor
+    in fp16 (weights, every activation it writes to HBM; accumulation, BN scale/shift and softmax stay fp32).  The
+    restatement run this way is the *expected-numerics* twin of the product path: its distance from the plain fp32
+    restatement is what fp16 storage costs by construction, and the GPU tests bound the product's error by it."""
+    return t.half().float()
+
+
+def sn_weight(sd, p, q=_ident):
+    return q(sd[p + '.weight'] / sn_sigma(sd[p + '.weight'], sd[p + '.u0']))
+
+
+def _sn_conv(x, sd, p, padding, q=_ident):
+    return F.conv2d(x, sn_weight(sd, p, q), sd.get(p + '.bias'), 1, padding)
 
 
 def ccbn(x, y, sd, p, eps=BN_EPS):
@@ -70,33 +82,31 @@ def ccbn(x, y, sd, p, eps=BN_EPS):
     return out * gain + bias
 
 
-def gblock(x, y, sd, p, out_channels, upsample, taps=None):
-    h = _sn_conv(F.relu(ccbn(x, y, sd, p + '.bn1')), sd, p + '.conv1', 0)
-    h = F.relu(ccbn(h, y, sd, p + '.bn2'))
+def gblock(x, y, sd, p, out_channels, upsample, q=_ident):
+    h = _sn_conv(q(F.relu(ccbn(x, y, sd, p + '.bn1'))), sd, p + '.conv1', 0, q)
+    h = q(F.relu(ccbn(h, y, sd, p + '.bn2')))
     if x.shape[1] != out_channels:
         x = x[:, :out_channels]
     if upsample:
         h = F.interpolate(h, scale_factor=2)          # nearest
         x = F.interpolate(x, scale_factor=2)
-    h = _sn_conv(h, sd, p + '.conv2', 1)
-    if taps is not None:
-        taps[p + '.conv2'] = h
-    h = _sn_conv(F.relu(ccbn(h, y, sd, p + '.bn3')), sd, p + '.conv3', 1)
-    h = _sn_conv(F.relu(ccbn(h, y, sd, p + '.bn4')), sd, p + '.conv4', 0)
-    return h + x
+    h = _sn_conv(h, sd, p + '.conv2', 1, q)
+    h = _sn_conv(q(F.relu(ccbn(h, y, sd, p + '.bn3'))), sd, p + '.conv3', 1, q)
+    h = _sn_conv(q(F.relu(ccbn(h, y, sd, p + '.bn4'))), sd, p + '.conv4', 0, q)
+    return q(h + x)
 
 
-def attention(x, sd, p):
+def attention(x, sd, p, q=_ident):
     B, C, H, W = x.shape
-    theta = _sn_conv(x, sd, p + '.theta', 0)
-    phi = F.max_pool2d(_sn_conv(x, sd, p + '.phi', 0), [2, 2])
-    g = F.max_pool2d(_sn_conv(x, sd, p + '.g', 0), [2, 2])
+    theta = q(_sn_conv(x, sd, p + '.theta', 0, q))
+    phi = F.max_pool2d(q(_sn_conv(x, sd, p + '.phi', 0, q)), [2, 2])
+    g = F.max_pool2d(q(_sn_conv(x, sd, p + '.g', 0, q)), [2, 2])
     theta = theta.view(B, C // 8, H * W)
     phi = phi.view(B, C // 8, H * W // 4)
     g = g.view(B, C // 2, H * W // 4)
-    beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)
-    o = _sn_conv(torch.bmm(g, beta.transpose(1, 2)).view(B, C // 2, H, W), sd, p + '.o', 0)
-    return sd[p + '.gamma'] * o + x
+    beta = q(F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1))
+    o = _sn_conv(q(torch.bmm(g, beta.transpose(1, 2)).view(B, C // 2, H, W)), sd, p + '.o', 0, q)
+    return q(sd[p + '.gamma'] * o + x)
 
 
 def condition(z, labels, sd):
@@ -104,25 +114,30 @@ def condition(z, labels, sd):
     return torch.cat([sd['shared.weight'][labels], z], 1)
 
 
-def generator_forward(z, labels, sd, resolution=256, ch=128, stages=None, eps=BN_EPS):
+def generator_forward(z, labels, sd, resolution=256, ch=128, stages=None, eps=BN_EPS, storage=None):
     """z fp32 [B, dim_z], labels int64 [B] -> images fp32 [B, 3, R, R] in (-1, 1).  ``stages``: optional dict that
-    receives the activation after every stage (and the linear / pre-tanh tensors) for stage-wise parity checks."""
+    receives the activation after every stage (and the linear / pre-tanh tensors) for stage-wise parity checks.
+    ``storage``: None = plain fp32 restatement; ``fp16_storage`` = the expected-numerics twin (see there)."""
+    q = storage or _ident
     y = condition(z, labels, sd)
     pl = plan(resolution, ch)
-    h = F.linear(y, sn_weight(sd, 'linear'), sd['linear.bias']).view(z.size(0), pl[0][0], 4, 4)
+    h = q(F.linear(q(y), sn_weight(sd, 'linear', q), sd['linear.bias'])).view(z.size(0), pl[0][0], 4, 4)
     if stages is not None:
         stages['linear'] = h
     for i, (cin, cout, res, att) in enumerate(pl):
-        h = gblock(h, y, sd, 'blocks.%d.0' % i, cin, False)
-        h = gblock(h, y, sd, 'blocks.%d.1' % i, cout, True)
+        h = gblock(h, y, sd, 'blocks.%d.0' % i, cin, False, q)
+        h = gblock(h, y, sd, 'blocks.%d.1' % i, cout, True, q)
         if att:
-            h = attention(h, sd, 'blocks.%d.2' % i)
+            h = attention(h, sd, 'blocks.%d.2' % i, q)
         if stages is not None:
             stages['stage%d' % i] = h
     p = 'output_layer'
     h = F.batch_norm(h, sd[p + '.0.stored_mean'], sd[p + '.0.stored_var'], sd[p + '.0.gain'], sd[p + '.0.bias'],
                      False, 0.1, eps)
-    h = _sn_conv(F.relu(h), sd, p + '.2', 1)
+    h = q(F.relu(h))
+    if stages is not None:
+        stages['out_act'] = h
+    h = q(_sn_conv(h, sd, p + '.2', 1, q))
     if stages is not None:
         stages['pre_tanh'] = h
     return torch.tanh(h)

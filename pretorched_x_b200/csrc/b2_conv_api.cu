@@ -161,7 +161,8 @@ static bool slab_geometry(const b2_conv_args* a, SlabParams* p, int wc_hint) {
   // W chunking: rows longer than a TMA box (256 pixels incl. halo) are cut into chunks of WC output columns.  For the
   // temporal remap (kw = 1, "rows" are H*W positions of one frame) a short chunk keeps MT+kt-1 frames in one slab.
   p->WC = p->Wo; p->wchunks = 1;
-  const int wc_max = wc_hint > 0 ? wc_hint : (ss == 1 ? 256 : 128) - p->halo_l - max_oj;   // TMA box <= 256 traversed pixels
+  const int wc_box = (ss == 1 ? 256 : 128) - p->halo_l - max_oj;                            // TMA box <= 256 traversed pixels
+  const int wc_max = (wc_hint > 0 && wc_hint < wc_box) ? wc_hint : wc_box;
   if (p->Wo > wc_max) {
     int best = 0;
     for (int c = wc_max; c >= (wc_max * 3) / 4; --c) if (p->Wo % c == 0) { best = c; break; }   // prefer an exact divisor
@@ -237,24 +238,9 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   return B2_OK;
 }
 
-// returns 1 when the slab kernel took the convolution, 0 when it does not apply, <0 on error
-static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
-  if (g_conv_algo == 1) return 0;
-  SlabParams p;
-  b2_conv_args remap = *a_in;
-  const b2_conv_args* a = a_in;
-  int wc_hint = 0;
-  if (a_in->kt > 1 && a_in->kh == 1 && a_in->kw == 1 && a_in->st == 1 && a_in->sh == 1 && a_in->sw == 1 &&
-      a_in->ph == 0 && a_in->pw == 0 && g_conv_algo != 3) {
-    // (kt,1,1) over [N][T][H][W] == (1,kt,1) over N images of T rows x (H*W) columns
-    remap.T = 1; remap.H = a_in->T; remap.W = a_in->H * a_in->W;
-    remap.kt = 1; remap.kh = a_in->kt; remap.kw = 1;
-    remap.pt = 0; remap.ph = a_in->pt; remap.pw = 0;
-    a = &remap;
-    wc_hint = 64;
-  }
-  if (!slab_geometry(a, &p, wc_hint)) return 0;
-  if (g_conv_algo == 2 && p.ss != 1) return 0;              // debug: strided convs through the gather kernel
+// Picks the N tile (fixed 64 / 128 or runtime), the M tiles per work item and the slab rows for a geometry; *best_mt == 0
+// when no configuration fits in shared memory.
+static void slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out, bool* flex_out, int* best_mt_out, int* best_R_out) {
   int BN = (a->ldy <= 64) ? 64 : 128;
   const int planes = a->N * p.To;
   int ntn = (a->ldy + BN - 1) / BN;
@@ -268,6 +254,11 @@ static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
       flex = true; BN = bn; ntn = tn;
       p.bn = bn; p.wbytes = (bn * 128 + 1023) / 1024 * 1024; p.accs = (bn + 31) / 32 * 32;
     }
+  } else if (a->ldy <= 16) {
+    // a handful of output channels (the generator's RGB head): the narrowest MMA (N = 16) instead of a 64-wide tile
+    // that is 95% padding -- the A operand still streams through shared memory once per tap, so this saves a third
+    flex = true; BN = 16; ntn = 1;
+    p.bn = 16; p.wbytes = 2048; p.accs = 32;
   }
   const int acc_stride = flex ? p.accs : BN;
   const int w_stage = flex ? p.wbytes : BN * 128;
@@ -305,6 +296,36 @@ static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
     }
     if (best_mt == 0 || cost < best_cost || (force_mt > 0 && MT == force_mt)) { best_mt = MT; best_R = R; best_cost = cost; }
     if (force_mt > 0 && MT == force_mt) break;
+  }
+  *BN_out = BN; *flex_out = flex; *best_mt_out = best_mt; *best_R_out = best_R;
+}
+
+// returns 1 when the slab kernel took the convolution, 0 when it does not apply, <0 on error
+static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
+  if (g_conv_algo == 1) return 0;
+  SlabParams p;
+  b2_conv_args remap = *a_in;
+  const b2_conv_args* a = a_in;
+  int wc_hint = 0;
+  if (a_in->kt > 1 && a_in->kh == 1 && a_in->kw == 1 && a_in->st == 1 && a_in->sh == 1 && a_in->sw == 1 &&
+      a_in->ph == 0 && a_in->pw == 0 && g_conv_algo != 3) {
+    // (kt,1,1) over [N][T][H][W] == (1,kt,1) over N images of T rows x (H*W) columns
+    remap.T = 1; remap.H = a_in->T; remap.W = a_in->H * a_in->W;
+    remap.kt = 1; remap.kh = a_in->kt; remap.kw = 1;
+    remap.pt = 0; remap.ph = a_in->pt; remap.pw = 0;
+    a = &remap;
+    wc_hint = 64;
+  }
+  // W chunking candidates: the default (row or <= 256-pixel chunks), then narrower chunks when no M-tile count fits the
+  // two slab stages in shared memory (256-pixel rows of a 256x256 image: 4 rows x 256 px x 128 B per slab).
+  const int wc_try[3] = {wc_hint, 128, 64};
+  int BN = 0, best_mt = 0, best_R = 0;
+  bool flex = false;
+  for (int attempt = 0; attempt < 3 && best_mt == 0; ++attempt) {
+    if (attempt > 0 && (wc_hint > 0 || wc_try[attempt] >= a->W)) continue;
+    if (!slab_geometry(a, &p, wc_try[attempt])) { if (attempt == 0) return 0; else continue; }
+    if (g_conv_algo == 2 && p.ss != 1) return 0;              // debug: strided convs through the gather kernel
+    slab_pick_tiles(a, p, &BN, &flex, &best_mt, &best_R);
   }
   if (best_mt == 0) return 0;
   int rc = flex ? launch_slab<0>(a, p, best_mt, best_R, stream)

@@ -10,13 +10,16 @@ namespace b2 {
 
 static inline int gan_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// y[b] = [ table[label[b]][0:ds] | z[b][0:dz] | 0 ... ]  as fp16 with pitch ldy
+// v[b] = [ table[label[b]][0:ds] | z[b][0:dz] | 0 ... ] (D = round_up(ds + dz, 8) entries).  split == 0: y[b] = fp16(v),
+// pitch ldy >= D.  split != 0: y[b] = [ hi | lo | hi ] with hi = fp16(v), lo = fp16(v - hi), pitch ldy >= 3 * D: against a
+// weight matrix stored as [ W_hi | W_hi | W_lo ] one fp16 GEMM of K = 3 * D evaluates v . W to ~fp32 accuracy (the
+// dropped lo x lo term is 2^-22 relative), which the stacked class-conditional BatchNorm gains need.
 __global__ void embed_concat_kernel(const float* __restrict__ z, const long long* __restrict__ labels,
                                     const float* __restrict__ table, const float* __restrict__ embedded, __half* __restrict__ y,
-                                    int B, int dz, int ds, int n_classes, int ldy) {
+                                    int B, int dz, int ds, int n_classes, int D, int ldy, int split) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * ldy) return;
-  const int b = i / ldy, c = i - b * ldy;
+  if (i >= B * D) return;
+  const int b = i / D, c = i - b * D;
   float v = 0.f;
   if (c < ds) {
     if (embedded) v = embedded[(long long)b * ds + c];
@@ -28,61 +31,85 @@ __global__ void embed_concat_kernel(const float* __restrict__ z, const long long
   } else if (c < ds + dz) {
     v = z[(long long)b * dz + (c - ds)];
   }
-  y[i] = __float2half_rn(v);
+  const __half hi = __float2half_rn(v);
+  __half* row = y + (long long)b * ldy;
+  row[c] = hi;
+  if (split) {
+    row[D + c] = __float2half_rn(v - __half2float(hi));
+    row[2 * D + c] = hi;
+  }
 }
 
 // y[n, up*h + i, up*w + j, c] = act(x[n, h, w, c] * scale[n*lda + c] + shift[n*lda + c]),  i, j < up, c < C;
 // channels [C, ldy) of y are written as zero.  scale == nullptr: identity (pure channel-slice / upsample copy).
+//
+// Thread (tx, ty) owns one 16-byte channel chunk (c8 = tx, tx + blockDim.x, ...) of kCcbnPix consecutive "pixel lanes":
+// the 8 + 8 affine floats of its chunk stay in registers across pixels (they only change with the sample), so the
+// kernel moves 16 B in + 16 B x up^2 out per iteration instead of re-reading 64 B of scale/shift for every 16 B of data.
+// blockDim.x = min(row chunks rounded up to a power of two, 32) keeps every warp on whole 128-byte lines.
+constexpr int kCcbnPix = 8;
+
 template <int UP>
 __global__ void __launch_bounds__(256)
 ccbn_act_kernel(const __half* __restrict__ x, int ldx8, __half* __restrict__ y, int ldy8, const float* __restrict__ scale,
-                const float* __restrict__ shift, int lda, int H, int W, int C8, int relu, long long total) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % ldy8);
-  long long q = i / ldy8;                    // input pixel index n*H*W + h*W + w
-  const int w = (int)(q % W);
-  const long long q2 = q / W;
-  const int h = (int)(q2 % H);
-  const long long n = q2 / H;
-  uint4 out = make_uint4(0, 0, 0, 0);
-  if (c8 < C8) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + q * ldx8 + c8);
-    if (scale) {
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + n * lda + c8 * 8));
-      const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + n * lda + c8 * 8) + 1);
-      const float4 t0 = __ldg(reinterpret_cast<const float4*>(shift + n * lda + c8 * 8));
-      const float4 t1 = __ldg(reinterpret_cast<const float4*>(shift + n * lda + c8 * 8) + 1);
-      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-      const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-      const uint32_t in[4] = {v.x, v.y, v.z, v.w};
-      uint32_t o[4];
+                const float* __restrict__ shift, int lda, int H, int W, int C8, int relu, long long pixels) {
+  const int HW = H * W;
+  const long long p0 = ((long long)blockIdx.x * blockDim.y + threadIdx.y) * kCcbnPix;
+  if (p0 >= pixels) return;
+  const long long Wo = (long long)W * UP;
+  const long long n0 = p0 / HW;
+  const int rem0 = (int)(p0 - n0 * HW);
+  const int h0 = rem0 / W, w0 = rem0 - h0 * W;
+  for (int c8 = threadIdx.x; c8 < ldy8; c8 += blockDim.x) {
+    float sc[8], sh[8];
+    long long n_cur = -1, n = n0;
+    int h = h0, w = w0 - 1;
+#pragma unroll 4
+    for (int j = 0; j < kCcbnPix; ++j) {
+      const long long q = p0 + j;
+      if (q >= pixels) break;
+      if (++w == W) { w = 0; if (++h == H) { h = 0; ++n; } }      // (n, h, w) of pixel q, without divisions
+      uint4 out = make_uint4(0, 0, 0, 0);
+      if (c8 < C8) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + q * ldx8 + c8);
+        if (scale) {
+          if (n != n_cur) {
+            n_cur = n;
+            const float4* sp = reinterpret_cast<const float4*>(scale + n * lda + c8 * 8);
+            const float4* tp = reinterpret_cast<const float4*>(shift + n * lda + c8 * 8);
+            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), t0 = __ldg(tp), t1 = __ldg(tp + 1);
+            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+            sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+          }
+          const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+          uint32_t o[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[e]));
-        float a0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
-        float a1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-        if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-        const __half2 hv = __floats2half2_rn(a0, a1);
-        o[e] = *reinterpret_cast<const uint32_t*>(&hv);
-      }
-      out = make_uint4(o[0], o[1], o[2], o[3]);
-    } else {
-      out = v;
-      if (relu) {
-        __half2* hp = reinterpret_cast<__half2*>(&out);
-        const __half2 zero = __floats2half2_rn(0.f, 0.f);
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[e]));
+            float a0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
+            float a1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            const __half2 hv = __floats2half2_rn(a0, a1);
+            o[e] = *reinterpret_cast<const uint32_t*>(&hv);
+          }
+          out = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+          out = v;
+          if (relu) {
+            __half2* hp = reinterpret_cast<__half2*>(&out);
+            const __half2 zero = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) hp[e] = __hmax2(hp[e], zero);
+            for (int e = 0; e < 4; ++e) hp[e] = __hmax2(hp[e], zero);
+          }
+        }
       }
+      uint4* yo = reinterpret_cast<uint4*>(y) + ((n * H * UP + (long long)h * UP) * Wo + (long long)w * UP) * ldy8 + c8;
+#pragma unroll
+      for (int a = 0; a < UP; ++a)
+#pragma unroll
+        for (int b = 0; b < UP; ++b) yo[(a * Wo + b) * ldy8] = out;
     }
   }
-  const long long Wo = (long long)W * UP;
-  uint4* yo = reinterpret_cast<uint4*>(y) + ((n * H * UP + (long long)h * UP) * Wo + (long long)w * UP) * ldy8 + c8;
-#pragma unroll
-  for (int a = 0; a < UP; ++a)
-#pragma unroll
-    for (int b = 0; b < UP; ++b) yo[(a * Wo + b) * ldy8] = out;
 }
 
 // y[n][c][s] = tanh(x[n*S + s][c])  (fp16 NHWC with pitch ldx -> NCHW, fp32 or fp16): 32 x 32 smem transpose is not
@@ -115,11 +142,12 @@ using namespace b2;
 extern "C" {
 
 int b2_embed_concat(const float* z, const long long* labels, const float* table, const float* embedded, void* y, int B,
-                    int dz, int ds, int n_classes, int ldy, void* stream) {
+                    int dz, int ds, int n_classes, int ldy, int split, void* stream) {
   B2_CHECK_ARG(z && y && (embedded || (labels && table)), "null pointer");
-  B2_CHECK_ARG(B > 0 && dz >= 0 && ds >= 0 && ldy >= dz + ds && ldy % 8 == 0, "bad dimensions");
-  embed_concat_kernel<<<gan_div_up((long long)B * ldy, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      z, labels, table, embedded, (__half*)y, B, dz, ds, n_classes, ldy);
+  const int D = (dz + ds + 7) / 8 * 8;
+  B2_CHECK_ARG(B > 0 && dz >= 0 && ds >= 0 && ldy % 8 == 0 && ldy >= (split ? 3 * D : D), "bad dimensions");
+  embed_concat_kernel<<<gan_div_up((long long)B * D, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      z, labels, table, embedded, (__half*)y, B, dz, ds, n_classes, D, ldy, split);
   B2_CHECK_LAUNCH("embed_concat");
   return B2_OK;
 }
@@ -132,14 +160,16 @@ int b2_ccbn_act_ndhwc(const void* x, int ldx, void* y, int ldy, const float* sca
   B2_CHECK_ARG(lda % 4 == 0 && (reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0,
                "affine arrays must be 16-byte aligned with a pitch that is a multiple of 4");
   if (up != 1 && up != 2) return set_error(B2_ERR_UNSUPPORTED, "nearest upsampling by %d is not implemented (1 or 2)", up);
-  const long long total = (long long)N * H * W * (ldy / 8);
+  const long long pixels = (long long)N * H * W;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int bx = 1;
+  while (bx < ldy / 8 && bx < 32) bx *= 2;
+  const dim3 block(bx, 256 / bx);
+  const int grid = gan_div_up(pixels, (long long)block.y * kCcbnPix);
   if (up == 1)
-    ccbn_act_kernel<1><<<gan_div_up(total, 256), 256, 0, st>>>((const __half*)x, ldx / 8, (__half*)y, ldy / 8, scale, shift, lda, H, W,
-                                                             C / 8, relu, total);
+    ccbn_act_kernel<1><<<grid, block, 0, st>>>((const __half*)x, ldx / 8, (__half*)y, ldy / 8, scale, shift, lda, H, W, C / 8, relu, pixels);
   else
-    ccbn_act_kernel<2><<<gan_div_up(total, 256), 256, 0, st>>>((const __half*)x, ldx / 8, (__half*)y, ldy / 8, scale, shift, lda, H, W,
-                                                             C / 8, relu, total);
+    ccbn_act_kernel<2><<<grid, block, 0, st>>>((const __half*)x, ldx / 8, (__half*)y, ldy / 8, scale, shift, lda, H, W, C / 8, relu, pixels);
   B2_CHECK_LAUNCH("ccbn_act");
   return B2_OK;
 }

@@ -382,14 +382,16 @@ def nonlocal_attention(qkv, d, dv, B, Npos):
 # ---------------------------------------------------------------------------------------------
 # BigGAN-deep generator helpers (architecture absent from the reference tree; see models/biggan_deep.py)
 # ---------------------------------------------------------------------------------------------
-def embed_concat(z, labels, table, ldy=None):
-    """fp16 [B][ldy] = [table[labels] | z | 0]: the conditioning vector every ccbn of the generator consumes.
-    ``labels`` int64 [B] class indices, or an fp32 [B][shared_dim] tensor that is already embedded."""
+def embed_concat(z, labels, table, split=False):
+    """The conditioning vector every ccbn of the generator consumes, v = [table[labels] | z | 0] (D = round_up(ds+dz, 8)):
+    fp16 [B][D], or with ``split`` fp16 [B][3D] = [hi | lo | hi] (v = hi + lo to ~2^-22) for the high-accuracy GEMM against
+    [W_hi | W_hi | W_lo].  ``labels`` int64 [B] class indices, or an fp32 [B][shared_dim] tensor that is already embedded."""
     _require_cuda(z, "z")
     z = z.contiguous().float()
     B, dz = z.shape
     ds = table.shape[1]
-    ldy = _round_up(dz + ds, 8) if ldy is None else ldy
+    D = _round_up(dz + ds, 8)
+    ldy = 3 * D if split else D
     y = torch.empty((B, ldy), dtype=torch.float16, device=z.device)
     if labels.dtype in (torch.int64, torch.int32, torch.int16, torch.uint8) and labels.dim() == 1:
         lab, emb = labels.to(torch.int64).contiguous(), None
@@ -398,7 +400,7 @@ def embed_concat(z, labels, table, ldy=None):
         if emb.shape != (B, ds):
             raise ValueError("embedded class vectors must be [B, %d], got %s" % (ds, tuple(emb.shape)))
     _lib.check(_lib.load().b2_embed_concat(_ptr(z), _ptr(lab), _ptr(table), _ptr(emb), _ptr(y), B, dz, ds, table.shape[0],
-                                          ldy, _stream()), "b2_embed_concat")
+                                          ldy, int(split), _stream()), "b2_embed_concat")
     return y
 
 
