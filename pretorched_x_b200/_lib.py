@@ -32,7 +32,7 @@ class ConvArgs(ctypes.Structure):
         ("kt", c_i32), ("kh", c_i32), ("kw", c_i32),
         ("st", c_i32), ("sh", c_i32), ("sw", c_i32),
         ("pt", c_i32), ("ph", c_i32), ("pw", c_i32),
-        ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32), ("aff_ld", c_i32),
+        ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32), ("aff_ld", c_i32), ("upsample", c_i32),
     ]
 
 
@@ -57,6 +57,7 @@ SYMBOLS = {
     "b2_conv_ndhwc_fprop_simt": (c_int, [ctypes.POINTER(ConvArgs), c_void_p]),
     "b2_pack_conv_weight_elems": (ctypes.c_size_t, [c_int] * 7),
     "b2_pack_conv_weight": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "b2_pack_upconv3x3_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2_gemm_f16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "b2_gemm2_f16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b2_nonlocal_attention": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,

@@ -193,6 +193,22 @@ static bool slab_geometry(const b2_conv_args* a, SlabParams* p, int wc_hint) {
       p->sub_w0[sidx] = pw_ - ss * p->halo_l;              // slab column 0 = sub-image column -halo_l
       ++p->n_sub;
     }
+  if (a->upsample) {
+    // 3x3 conv of the nearest-2x upsampled image: output (2h + py, 2w + px) reads low-res rows {h - 1, h} (py = 0) or
+    // {h, h + 1} (py = 1), same for columns; the folded 2x2 filters of phase ph are weight taps ph*4 .. ph*4 + 3
+    const int s_h0 = p->sub_h0[0], s_w0 = p->sub_w0[0];
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      for (int ai = 0; ai < 2; ++ai)
+        for (int bi = 0; bi < 2; ++bi) {
+          const int ro = ai - 1 + py, co = bi - 1 + px;
+          p->sub_off[ph][ai * 2 + bi] = (short)(ro * p->PW + co);
+          p->sub_tap[ph][ai * 2 + bi] = (unsigned char)(ph * 4 + ai * 2 + bi);
+        }
+      p->sub_ntaps[ph] = 4; p->sub_h0[ph] = s_h0; p->sub_w0[ph] = s_w0;
+    }
+    p->khw = 16; p->up = 1; p->n_sub = 1;
+  }
   return p->n_sub > 0 && p->PW <= 256;
 }
 
@@ -215,7 +231,7 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   p.naff = slab_naff(a->ldy);
   p.tiles_n = (a->ldy + BN - 1) / BN;
   p.tiles_q = (p.P + MT * 128 - 1) / (MT * 128);
-  const long long items = (long long)p.tiles_n * p.tiles_q * p.wchunks * a->N * p.To;
+  const long long items = (long long)p.tiles_n * p.tiles_q * p.wchunks * a->N * p.To * (p.up ? 4 : 1);
   if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "slab problem too large");
   p.items_total = (int)items;
   const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * p.wbytes + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
@@ -226,7 +242,7 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   }
   CUtensorMap tmX, tmB;
   int rc;
-  const int taps = a->kt * a->kh * a->kw;
+  const int taps = p.up ? 16 : a->kt * a->kh * a->kw;
   if ((rc = make_tmap_ndhwc_slab(&tmX, a->x, (uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N * a->T,
                                  (uint32_t)p.PW, (uint32_t)R, (uint32_t)p.ss)) != B2_OK)
     return rc;
@@ -281,7 +297,7 @@ static void slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out, b
     const long long smem = 2ll * slab_b + kSlabWStages * w_stage + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
     if (smem > 227 * 1024) continue;
     const long long tq = (p.P + MT * 128 - 1) / (MT * 128);
-    const long long items = (long long)ntn * tq * planes * p.wchunks;
+    const long long items = (long long)ntn * tq * planes * p.wchunks * (p.up ? 4 : 1);
     const double rounds = (double)((items + sm_count() - 1) / sm_count());
     const double tiles_per_item = (double)((p.P + 127) / 128) / (double)tq;          // average (the last item of a plane is short)
     const double mma = tiles_per_item * p.kt * taps_hw * ksteps * (40.0 + 0.5 * BN);
@@ -546,6 +562,10 @@ static int validate_conv(const b2_conv_args* a) {
     B2_CHECK_ARG(a->mode == B2_CONV_AUTO, "unknown conv mode %d", a->mode);
     B2_CHECK_ARG(a->C % 8 == 0, "channel pitch %d is not a multiple of 8", a->C);
   }
+  if (a->upsample)
+    B2_CHECK_ARG(a->upsample == 1 && a->mode == B2_CONV_AUTO && !a->out_f32 && a->kt == 1 && a->kh == 3 && a->kw == 3 && a->st == 1 &&
+                     a->sh == 1 && a->sw == 1 && a->pt == 0 && a->ph == 1 && a->pw == 1,
+                 "fused upsampling is implemented for 1x3x3 stride-1 'same' convolutions with fp16 output only");
   B2_CHECK_ARG(a->aff_ld >= 0 && (a->aff_ld == 0 || (a->aff_ld >= a->K && !a->out_f32 && a->mode == B2_CONV_AUTO)),
                "bad per-sample affine pitch %d", a->aff_ld);
   if (!a->out_f32) {
@@ -562,6 +582,7 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   if ((rc = require_sm100()) != B2_OK) return rc;
   rc = try_slab(a, reinterpret_cast<cudaStream_t>(stream));
   if (rc != 0) return rc < 0 ? rc : B2_OK;
+  if (a->upsample) return set_error(B2_ERR_UNSUPPORTED, "fused upsampling needs the slab kernel, which does not take this shape");
 
   IgemmLaunch L;
   memset(&L, 0, sizeof(L));

@@ -61,55 +61,77 @@ ccbn_act_kernel(const __half* __restrict__ x, int ldx8, __half* __restrict__ y, 
   const int rem0 = (int)(p0 - n0 * HW);
   const int h0 = rem0 / W, w0 = rem0 - h0 * W;
   for (int c8 = threadIdx.x; c8 < ldy8; c8 += blockDim.x) {
+    // all loads of the thread's pixels are issued before any is consumed (8 x 16 B in flight per thread)
+    uint4 v[kCcbnPix];
+#pragma unroll
+    for (int j = 0; j < kCcbnPix; ++j) {
+      v[j] = make_uint4(0, 0, 0, 0);
+      if (c8 < C8 && p0 + j < pixels) v[j] = __ldg(reinterpret_cast<const uint4*>(x) + (p0 + j) * ldx8 + c8);
+    }
     float sc[8], sh[8];
     long long n_cur = -1, n = n0;
     int h = h0, w = w0 - 1;
-#pragma unroll 4
+#pragma unroll
     for (int j = 0; j < kCcbnPix; ++j) {
       const long long q = p0 + j;
-      if (q >= pixels) break;
-      if (++w == W) { w = 0; if (++h == H) { h = 0; ++n; } }      // (n, h, w) of pixel q, without divisions
-      uint4 out = make_uint4(0, 0, 0, 0);
-      if (c8 < C8) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + q * ldx8 + c8);
-        if (scale) {
-          if (n != n_cur) {
-            n_cur = n;
-            const float4* sp = reinterpret_cast<const float4*>(scale + n * lda + c8 * 8);
-            const float4* tp = reinterpret_cast<const float4*>(shift + n * lda + c8 * 8);
-            const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), t0 = __ldg(tp), t1 = __ldg(tp + 1);
-            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-            sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
-          }
-          const uint32_t in[4] = {v.x, v.y, v.z, v.w};
-          uint32_t o[4];
+      if (q < pixels) {
+        if (++w == W) { w = 0; if (++h == H) { h = 0; ++n; } }      // (n, h, w) of pixel q, without divisions
+        uint4 out = v[j];
+        if (c8 < C8) {
+          if (scale) {
+            if (n != n_cur) {
+              n_cur = n;
+              const float4* sp = reinterpret_cast<const float4*>(scale + n * lda + c8 * 8);
+              const float4* tp = reinterpret_cast<const float4*>(shift + n * lda + c8 * 8);
+              const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1), t0 = __ldg(tp), t1 = __ldg(tp + 1);
+              sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+              sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+            }
+            const uint32_t in[4] = {out.x, out.y, out.z, out.w};
+            uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[e]));
-            float a0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
-            float a1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
-            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            const __half2 hv = __floats2half2_rn(a0, a1);
-            o[e] = *reinterpret_cast<const uint32_t*>(&hv);
-          }
-          out = make_uint4(o[0], o[1], o[2], o[3]);
-        } else {
-          out = v;
-          if (relu) {
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[e]));
+              float a0 = fmaf(f.x, sc[2 * e], sh[2 * e]);
+              float a1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+              if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+              const __half2 hv = __floats2half2_rn(a0, a1);
+              o[e] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            out = make_uint4(o[0], o[1], o[2], o[3]);
+          } else if (relu) {
             __half2* hp = reinterpret_cast<__half2*>(&out);
             const __half2 zero = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
             for (int e = 0; e < 4; ++e) hp[e] = __hmax2(hp[e], zero);
           }
         }
+        uint4* yo = reinterpret_cast<uint4*>(y) + ((n * H * UP + (long long)h * UP) * Wo + (long long)w * UP) * ldy8 + c8;
+#pragma unroll
+        for (int a = 0; a < UP; ++a)
+#pragma unroll
+          for (int b = 0; b < UP; ++b) yo[(a * Wo + b) * ldy8] = out;
       }
-      uint4* yo = reinterpret_cast<uint4*>(y) + ((n * H * UP + (long long)h * UP) * Wo + (long long)w * UP) * ldy8 + c8;
-#pragma unroll
-      for (int a = 0; a < UP; ++a)
-#pragma unroll
-        for (int b = 0; b < UP; ++b) yo[(a * Wo + b) * ldy8] = out;
     }
   }
+}
+
+// phase-folded filters of conv3x3(nearest_up2(x)): out[k][ph*4 + 2a + b][c] = sum_{dh in R(py,a)} sum_{dw in R(px,b)} w[k][c][dh][dw]
+// with R(0,0) = {0}, R(0,1) = {1,2}, R(1,0) = {0,1}, R(1,1) = {2}  (see b2_pack_upconv3x3_weight in the header)
+__global__ void pack_upconv3x3_kernel(const float* __restrict__ w, __half* __restrict__ out, int K, int Cin, int C, long long total) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int t = (int)((i / C) % 16);
+  const int k = (int)(i / ((long long)C * 16));
+  const int ph = t >> 2, a = (t >> 1) & 1, b = t & 1, py = ph >> 1, px = ph & 1;
+  const int h_lo = (py == 0) ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), h_hi = (py == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+  const int w_lo = (px == 0) ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), w_hi = (px == 0) ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+  float v = 0.f;
+  if (c < Cin)
+    for (int dh = h_lo; dh <= h_hi; ++dh)
+      for (int dw = w_lo; dw <= w_hi; ++dw) v += w[(((long long)k * Cin + c) * 3 + dh) * 3 + dw];
+  out[i] = __float2half_rn(v);
 }
 
 // y[n][c][s] = tanh(x[n*S + s][c])  (fp16 NHWC with pitch ldx -> NCHW, fp32 or fp16): 32 x 32 smem transpose is not
@@ -149,6 +171,14 @@ int b2_embed_concat(const float* z, const long long* labels, const float* table,
   embed_concat_kernel<<<gan_div_up((long long)B * D, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       z, labels, table, embedded, (__half*)y, B, dz, ds, n_classes, D, ldy, split);
   B2_CHECK_LAUNCH("embed_concat");
+  return B2_OK;
+}
+
+int b2_pack_upconv3x3_weight(const float* w_oihw, void* w_packed, int K, int Cin, int C, void* stream) {
+  B2_CHECK_ARG(w_oihw && w_packed && K > 0 && Cin > 0 && C >= Cin && C % 8 == 0, "bad argument");
+  const long long total = (long long)K * 16 * C;
+  pack_upconv3x3_kernel<<<gan_div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w_oihw, (__half*)w_packed, K, Cin, C, total);
+  B2_CHECK_LAUNCH("pack_upconv3x3");
   return B2_OK;
 }
 

@@ -74,16 +74,24 @@ struct SlabParams {
   int relu;
   int naff;                // scale/shift entries staged in smem (>= every column an epilogue chunk can touch)
   int aff_ld;              // > 0: scale/shift are per-sample [N][aff_ld] arrays read from global memory per work item
+  // Fused nearest-2x upsampling (3x3 conv of an upsampled image == four 2x2 "phase" convs of the low-res image): the
+  // geometry above is that of the LOW-res image, a work item additionally carries an output phase (py, px); phase ph
+  // uses the tap table row sub_*[ph] (4 taps, weights [K][ph*4 + i][C]) and writes output pixel (2h + py, 2w + px) of a
+  // (2 Ho) x (2 Wo) plane.  n_sub stays 1: all phases read the same slab.
+  int up;
 };
 
 // scale/shift live in smem for all (padded) output channels: SlabParams::naff = round_up(ldy, 32) + 32 entries each
 
 struct SlabItem {
   int n0, q0, wc, plane_o, plane_i0, r_lo, dt_lo, n_dt, n_slabs, mt_valid;   // plane_i0: input plane of temporal tap 0
+  int phase;                                                                  // output phase 2*py + px (SlabParams::up), else 0
 };
 __device__ __forceinline__ SlabItem slab_item(const SlabParams& p, int item, int BN) {
   SlabItem w;
   const int tn = item % p.tiles_n; item /= p.tiles_n;
+  w.phase = 0;
+  if (p.up) { w.phase = item & 3; item >>= 2; }
   const int tq = item % p.tiles_q; item /= p.tiles_q;
   w.wc = item % p.wchunks;
   w.plane_o = item / p.wchunks;
@@ -184,7 +192,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
       for (; item < p.items_total; item += gridDim.x) {
         cur = slab_item(p, item, bn);
         for (int si = 0; si < cur.n_slabs; ++si) {
-          const int sub = si % p.n_sub;
+          const int sub = p.up ? cur.phase : si % p.n_sub;          // tap-table row (== slab index unless p.up)
           const int r2 = si / p.n_sub;
           const int cc = r2 / cur.n_dt, dt = cur.dt_lo + (r2 - cc * cur.n_dt);
           const int ntaps = p.sub_ntaps[sub];
@@ -218,7 +226,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
       const uint32_t acc = tm + ab * acc_cols;
       int wl = 0;                                                // weight step within the item
       for (int si = 0; si < w.n_slabs; ++si, ++sg) {
-        const int sub = si % p.n_sub;
+        const int sub = p.up ? w.phase : si % p.n_sub;
         const int ntaps = p.sub_ntaps[sub];
         const int cc = (si / p.n_sub) / w.n_dt;
         const int ksteps = min(4, (p.C - cc * 64 + 15) >> 4);       // 16-channel K steps that hold real channels
@@ -278,7 +286,8 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
         const int h = q / p.PW, wp = q - h * p.PW;
         const int wo = w.wc * p.WC + wp - p.halo_l;       // output column
         ok[j] = (j < w.mt_valid) && (q < p.P) && (wp >= p.halo_l) && (wp < p.halo_l + p.WC) && (wo < p.Wo);
-        row[j] = (static_cast<size_t>(w.plane_o) * p.Ho + h) * p.Wo + wo;
+        row[j] = p.up ? (static_cast<size_t>(w.plane_o) * (2 * p.Ho) + 2 * h + (w.phase >> 1)) * (2 * p.Wo) + 2 * wo + (w.phase & 1)
+                      : (static_cast<size_t>(w.plane_o) * p.Ho + h) * p.Wo + wo;
       }
 #pragma unroll 1
       for (int jc = egroup; jc * 32 < ncols_here; jc += 2) {

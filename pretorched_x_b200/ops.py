@@ -139,9 +139,10 @@ class PackedConv:
     ``scale``/``shift`` fold the conv bias and the eval-mode BatchNorm that follows the convolution in
     the reference (y = (conv + bias - mean) / sqrt(var + eps) * gamma + beta).
     """
-    __slots__ = ("w", "scale", "shift", "K", "Cin", "C", "k", "s", "p", "mode")
+    __slots__ = ("w", "scale", "shift", "K", "Cin", "C", "k", "s", "p", "mode", "up")
 
-    def __init__(self, weight, bias=None, bn=None, stride=(1, 1, 1), padding=(0, 0, 0), in_pitch=None, stem=False):
+    def __init__(self, weight, bias=None, bn=None, stride=(1, 1, 1), padding=(0, 0, 0), in_pitch=None, stem=False,
+                 upsample=False):
         _require_cuda(weight, "conv weight")
         if weight.dim() == 4:       # Conv2d weight -> T = 1
             weight = weight.unsqueeze(2)
@@ -152,12 +153,20 @@ class PackedConv:
         self.p = tuple(int(v) for v in padding)
         self.mode = B2_CONV_STEM7 if stem else B2_CONV_AUTO
         self.C = 4 if stem else (in_pitch if in_pitch is not None else _round_up(Cin, 8))
+        self.up = bool(upsample)
         lib = _lib.load()
-        n = lib.b2_pack_conv_weight_elems(K, Cin, kt, kh, kw, self.C, self.mode)
-        self.w = torch.empty(n, dtype=torch.float16, device=weight.device)
         w32 = weight.detach().contiguous().float()
-        _lib.check(lib.b2_pack_conv_weight(_ptr(w32), _ptr(self.w), K, Cin, kt, kh, kw, self.C, self.mode, _stream()),
-                   "b2_pack_conv_weight")
+        if self.up:
+            # conv3x3(nearest_upsample_2x(x)) as four phase-specific 2x2 filters over the low-res image (GBlock conv2)
+            if (kt, kh, kw) != (1, 3, 3) or self.s != (1, 1, 1) or self.p != (0, 1, 1) or stem:
+                raise ValueError("fused upsampling needs a 3x3 stride-1 'same' convolution")
+            self.w = torch.empty(K * 16 * self.C, dtype=torch.float16, device=weight.device)
+            _lib.check(lib.b2_pack_upconv3x3_weight(_ptr(w32), _ptr(self.w), K, Cin, self.C, _stream()), "b2_pack_upconv3x3_weight")
+        else:
+            n = lib.b2_pack_conv_weight_elems(K, Cin, kt, kh, kw, self.C, self.mode)
+            self.w = torch.empty(n, dtype=torch.float16, device=weight.device)
+            _lib.check(lib.b2_pack_conv_weight(_ptr(w32), _ptr(self.w), K, Cin, kt, kh, kw, self.C, self.mode, _stream()),
+                       "b2_pack_conv_weight")
         self.scale, self.shift = fold_affine(K, bias, bn, weight.device)
 
 
@@ -197,6 +206,8 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None):
     kt, kh, kw = pc.k
     To, Ho, Wo = (_out_dim(a.T, kt, pc.s[0], pc.p[0]), _out_dim(a.H, kh, pc.s[1], pc.p[1]),
                   _out_dim(a.W, kw, pc.s[2], pc.p[2]))
+    if pc.up:                         # the kernel reads the low-res image and writes the 2x upsampled convolution
+        Ho, Wo = 2 * Ho, 2 * Wo
     M = a.N * To * Ho * Wo
     ldy = _round_up(pc.K, 8)
     y = torch.empty((M, ldy), dtype=torch.float16, device=a.data.device)
@@ -213,6 +224,9 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None):
     args.st, args.sh, args.sw = pc.s
     args.pt, args.ph, args.pw = pc.p
     args.relu, args.out_f32, args.accumulate, args.mode = int(relu), 0, 0, pc.mode
+    args.upsample = int(pc.up)
+    if pc.up and simt:
+        raise ValueError("the CUDA-core cross-check has no fused upsampling")
     if sample_affine is not None:
         sc, sh = sample_affine
         if simt or sc.shape != sh.shape or sc.shape[0] != a.N or sc.stride(0) != sh.stride(0) or sc.shape[1] < pc.K:
@@ -223,7 +237,7 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None):
     taps = kt * kh * kw
     flops = 2.0 * M * pc.K * pc.Cin * taps                     # algorithmic (padding taps included)
     nbytes = 2.0 * (a.M * a.C + M * pc.K * (2 if residual is not None else 1) + pc.K * pc.Cin * taps)
-    desc = "conv %dx%dx%d s%s C%d->%d M=%d" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, M)
+    desc = "conv %dx%dx%d s%s C%d->%d M=%d%s" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, M, " up2" if pc.up else "")
     with _timed("conv", desc, flops, nbytes):
         _lib.check(fn(ctypes.byref(args), _stream()), "b2_conv_ndhwc_fprop")
     return Act(y, a.N, To, Ho, Wo, pc.K)

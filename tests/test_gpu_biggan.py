@@ -114,6 +114,30 @@ def test_conv3x3_with_per_sample_affine(dev, shape):
     assert rel(to_nchw(out), want) <= 3e-3
 
 
+@pytest.mark.parametrize("shape", [(3, 64, 12, 20, 64), (2, 128, 16, 16, 128), (5, 512, 4, 4, 512), (2, 16, 40, 40, 8),
+                                   (2, 64, 10, 128, 64), (1, 256, 32, 32, 256), (3, 32, 7, 9, 24)])
+@pytest.mark.parametrize("affine", ["sample", "channel"])
+def test_conv3x3_of_upsampled_image_without_materialising_it(dev, shape, affine):
+    """b2_conv_args.upsample: conv3x3(nearest_up2(x)) from the low-res tensor (four folded 2x2 phase filters)."""
+    N, C, H, W, K = shape
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, C, H, W, generator=g).half()
+    w = torch.randn(K, C, 3, 3, generator=g) / (3 * C ** 0.5)
+    b = torch.randn(K, generator=g)
+    pc = ops.PackedConv(w.cuda(), b.cuda(), None, (1, 1, 1), (0, 1, 1), in_pitch=C, upsample=True)
+    ref = F.conv2d(F.interpolate(x.float(), scale_factor=2), w, None, 1, 1)
+    if affine == "sample":
+        aff = torch.randn(N, 2 * K + 16, generator=g).cuda()
+        sc, sh = aff[:, :K], aff[:, K + 16:]
+        out = ops.conv(nhwc(x), pc, relu=True, sample_affine=(sc, sh))
+        want = F.relu(ref * sc.cpu().view(N, K, 1, 1) + sh.cpu().view(N, K, 1, 1))
+    else:
+        out = ops.conv(nhwc(x), pc, relu=False)
+        want = ref + b.view(1, K, 1, 1)
+    assert (out.H, out.W, out.C) == (2 * H, 2 * W, K)
+    assert rel(to_nchw(out), want) <= 3e-3
+
+
 @pytest.mark.parametrize("shape", [(3, 256, 16, 16, 64), (2, 64, 16, 8, 200)])
 def test_conv1x1_with_per_sample_affine(dev, shape):
     N, C, H, W, K = shape
