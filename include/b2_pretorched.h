@@ -66,13 +66,19 @@ typedef struct b2_conv_args {
   int32_t out_f32;      /* y is fp32 (direct-store epilogue)                                       */
   int32_t accumulate;   /* out_f32 only: y += result                                               */
   int32_t mode;         /* B2_CONV_AUTO | B2_CONV_STEM7                                            */
-  int32_t aff_ld;       /* 0: scale/shift are [K].  > 0: per-SAMPLE affine, scale/shift are fp32 [N][aff_ld]
+  int32_t aff_ld;       /* 0: scale/shift are [K].  > 0: per-SAMPLE affine, scale/shift are fp32 [N][aff_ld], 16-byte aligned,
+                           aff_ld % 4 == 0
                            (class-conditional BatchNorm of the layer that FOLLOWS this convolution, BigGAN GBlock);
                            multi-tap "same" convolutions and 1x1x1 convolutions with To*Ho*Wo % 128 == 0 only      */
   int32_t upsample;     /* 1: y = conv3x3(nearest_upsample_2x(x)) without materialising the upsampled image (GBlock conv2):
                            x is the LOW-resolution input [N,1,H,W,C], y has (2H) x (2W) pixels per image, and w is the
                            phase-folded filter bank [K][16][C] written by b2_pack_upconv3x3_weight.  kt=1, kh=kw=3,
                            strides 1, padding (0,1,1) only                                                        */
+  int32_t residual_up;  /* 1: `residual` is the LOW-resolution tensor [N][H/2][W/2][ldr] of the skip path and is nearest-2x
+                           upsampled on the fly (GBlock: h + upsample(x[:, :out]); the channel drop is the pitch ldr).
+                           1x1 stride-1 2-D convolutions only                                                     */
+  int32_t residual_pre; /* 1: y = act(scale * (acc + residual) + shift) -- the residual joins BEFORE the affine (BatchNorm of
+                           the block output folded into its closing convolution).  1x1 convolutions only           */
 } b2_conv_args;
 
 int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream);

@@ -32,7 +32,7 @@ class ConvArgs(ctypes.Structure):
         ("kt", c_i32), ("kh", c_i32), ("kw", c_i32),
         ("st", c_i32), ("sh", c_i32), ("sw", c_i32),
         ("pt", c_i32), ("ph", c_i32), ("pw", c_i32),
-        ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32), ("aff_ld", c_i32), ("upsample", c_i32),
+        ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32), ("aff_ld", c_i32), ("upsample", c_i32), ("residual_up", c_i32), ("residual_pre", c_i32),
     ]
 
 

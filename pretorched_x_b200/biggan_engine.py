@@ -19,7 +19,8 @@ How the pieces map:
 * The nearest-2x upsampling in front of conv2 is never materialised: a 3x3 convolution of an upsampled image is four
   2x2 convolutions of the low-res image (one per output phase, filters summed when packed), which the slab kernel runs
   as 4 x 4 taps with a strided output write -- 2.25x fewer MACs and a quarter of the input bytes.
-* conv4's epilogue adds the skip path (channel-dropped via the residual pitch; upsampled copy for the second block).
+* conv4's epilogue adds the skip path: channel drop = the residual pitch, and for the upsampling block the epilogue reads
+  the LOW-res x and upsamples on the fly (``residual_up``), so ``upsample(x)`` is never written either.
 * Spectral norm: weights are divided by sigma (one power iteration from the stored ``u0``) when they are packed.
 * Self-attention: theta and phi|g projections (zero-padded to the 64-column granularity of the attention kernel),
   2x2 max-pool of phi|g, the fused softmax(theta^T phi) g kernel, and the output 1x1 GEMM with gamma as its scale and x
@@ -138,8 +139,8 @@ def _pack(model, dev):
     pk.out_shift = (obn.bias.detach().double() - obn.stored_mean.detach().double() * sc).float().reshape(1, -1).contiguous()
     pk.out_conv = _pack_conv(oconv, eps_sn, _round_up(obn.output_size, 8))
     # Output BN + ReLU folded into the LAST GBlock's closing convolution: relu(s * (acc + b4 + skip) + t) =
-    # relu(s * acc + (s * b4 + t) + s * skip), i.e. conv4 with per-channel scale s and shift s * b4 + t over a skip path
-    # that the (already needed) upsample copy pre-scales by s.  Removes one full read + write of the largest activation.
+    # relu(s * (acc + skip) + (s * b4 + t)), i.e. conv4 with per-channel scale s, shift s * b4 + t and the residual joining
+    # before the affine (residual_pre).  Removes one full read + write of the largest activation.
     last = [blk for stage in model.blocks for blk in stage][-1]
     pk.last_block = last if hasattr(last, 'conv4') else None
     if pk.last_block is not None:
@@ -148,7 +149,6 @@ def _pack(model, dev):
         pk.out_conv4.scale = pk.out_scale.reshape(-1).contiguous()
         pk.out_conv4.shift = (pk.out_scale.reshape(-1).double() * c4.bias.detach().double()
                               + pk.out_shift.reshape(-1).double()).float().contiguous()
-        pk.out_skip_zero = torch.zeros_like(pk.out_scale)
 
     # stacked ccbn matrix as [W_hi | W_hi | W_lo] against the conditioning vector stored as [y_hi | y_lo | y_hi]: the fp16
     # GEMM then carries ~22 mantissa bits (a plain fp16 W and y put a 5e-4 relative error on every gain, which 48 stacked
@@ -200,14 +200,11 @@ def run_gblock(blk, a, aff, pk, fuse_output_bn=False):
     # conv2; in the upsampling block it reads the LOW-res tensor: conv3x3(up2(.)) == four folded 2x2 phase filters
     t = ops.conv(t, bp.conv[1], relu=True, sample_affine=_aff(aff, bp.bn[2]))          # relu(bn3(conv2(up(.))))
     t = ops.conv(t, bp.conv[2], relu=True, sample_affine=_aff(aff, bp.bn[3]))          # relu(bn4(conv3(.)))
+    # conv4 + skip: the skip path x[:, :out] (channel drop = residual pitch) is read at LOW resolution by the epilogue and
+    # upsampled on the fly, so up(x) is never written; the last block also carries the output BN + ReLU (see _pack)
     if fuse_output_bn:
-        skip = ops.ccbn_act(a, pk.out_scale, pk.out_skip_zero, channels=blk.out_channels, up=up, relu=False)   # s * up(x[:, :out])
-        return ops.conv(t, pk.out_conv4, residual=skip, relu=True)           # relu(bn_out(conv4(.) + up(x)))
-    if up == 1 and blk.in_channels == blk.out_channels:
-        skip = a
-    else:
-        skip = ops.ccbn_act(a, None, None, channels=blk.out_channels, up=up, relu=False)   # up(x[:, :out])
-    return ops.conv(t, bp.conv[3], residual=skip)                            # conv4(.) + skip
+        return ops.conv(t, pk.out_conv4, residual=a, relu=True, residual_up=up == 2, residual_pre=True)
+    return ops.conv(t, bp.conv[3], residual=a, residual_up=up == 2)
 
 
 def run_attention(att, a, pk):

@@ -234,6 +234,10 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   const long long items = (long long)p.tiles_n * p.tiles_q * p.wchunks * a->N * p.To * (p.up ? 4 : 1);
   if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "slab problem too large");
   p.items_total = (int)items;
+  p.fd_tiles_n = make_fastdiv(p.tiles_n); p.fd_tiles_q = make_fastdiv(p.tiles_q); p.fd_wchunks = make_fastdiv(p.wchunks);
+  p.fd_To = make_fastdiv(p.To); p.fd_PW = make_fastdiv(p.PW);
+  if (a->aff_ld && ((a->aff_ld & 3) || (reinterpret_cast<uintptr_t>(a->scale) & 15) || (reinterpret_cast<uintptr_t>(a->shift) & 15)))
+    return set_error(B2_ERR_INVALID, "per-sample scale/shift must be 16-byte aligned with a pitch that is a multiple of 4 floats");
   const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * p.wbytes + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -256,7 +260,7 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
 
 // Picks the N tile (fixed 64 / 128 or runtime), the M tiles per work item and the slab rows for a geometry; *best_mt == 0
 // when no configuration fits in shared memory.
-static void slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out, bool* flex_out, int* best_mt_out, int* best_R_out) {
+static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out, bool* flex_out, int* best_mt_out, int* best_R_out) {
   int BN = (a->ldy <= 64) ? 64 : 128;
   const int planes = a->N * p.To;
   int ntn = (a->ldy + BN - 1) / BN;
@@ -314,6 +318,7 @@ static void slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out, b
     if (force_mt > 0 && MT == force_mt) break;
   }
   *BN_out = BN; *flex_out = flex; *best_mt_out = best_mt; *best_R_out = best_R;
+  return best_cost;
 }
 
 // returns 1 when the slab kernel took the convolution, 0 when it does not apply, <0 on error
@@ -332,17 +337,28 @@ static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
     a = &remap;
     wc_hint = 64;
   }
-  // W chunking candidates: the default (row or <= 256-pixel chunks), then narrower chunks when no M-tile count fits the
-  // two slab stages in shared memory (256-pixel rows of a 256x256 image: 4 rows x 256 px x 128 B per slab).
+  // W chunking candidates: the default (whole rows, or <= 256-pixel chunks) and narrower chunks.  Narrow chunks make the
+  // slab of a work item shorter, which (a) lets 256-pixel rows fit the two slab stages at all and (b) admits more M tiles
+  // per item for wide images -- with few-tap 2-D filters the per-item costs (decode, epilogue set-up, slab latency) are
+  // what the cycle model trades against the extra halo columns.  The cheapest modelled configuration wins.
   const int wc_try[3] = {wc_hint, 128, 64};
   int BN = 0, best_mt = 0, best_R = 0;
   bool flex = false;
-  for (int attempt = 0; attempt < 3 && best_mt == 0; ++attempt) {
+  double best_cost = 0.0;
+  SlabParams best_p;
+  for (int attempt = 0; attempt < 3; ++attempt) {
     if (attempt > 0 && (wc_hint > 0 || wc_try[attempt] >= a->W)) continue;
-    if (!slab_geometry(a, &p, wc_try[attempt])) { if (attempt == 0) return 0; else continue; }
-    if (g_conv_algo == 2 && p.ss != 1) return 0;              // debug: strided convs through the gather kernel
-    slab_pick_tiles(a, p, &BN, &flex, &best_mt, &best_R);
+    SlabParams q;
+    if (!slab_geometry(a, &q, wc_try[attempt])) { if (attempt == 0) return 0; else continue; }
+    if (attempt > 0 && q.wchunks == 1) continue;              // same geometry as the default
+    if (g_conv_algo == 2 && q.ss != 1) return 0;              // debug: strided convs through the gather kernel
+    int bn_c = 0, mt_c = 0, r_c = 0;
+    bool flex_c = false;
+    const double cost = slab_pick_tiles(a, q, &bn_c, &flex_c, &mt_c, &r_c);
+    if (mt_c == 0) continue;
+    if (best_mt == 0 || cost < best_cost) { best_p = q; BN = bn_c; flex = flex_c; best_mt = mt_c; best_R = r_c; best_cost = cost; }
   }
+  if (best_mt != 0) p = best_p;
   if (best_mt == 0) return 0;
   int rc = flex ? launch_slab<0>(a, p, best_mt, best_R, stream)
                 : (BN == 64) ? launch_slab<64>(a, p, best_mt, best_R, stream) : launch_slab<128>(a, p, best_mt, best_R, stream);
@@ -485,7 +501,7 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   if ((rc = make_tmap_2d_f16(&tmA, L.a_mat, (uint64_t)L.a_cols, (uint64_t)ip.M_total, (uint64_t)L.lda, 64, 128, true)) != B2_OK) return rc;
   if ((rc = make_tmap_2d_f16(&tmB, L.w, (uint64_t)L.b_cols, (uint64_t)ip.Ncols, (uint64_t)L.ldb, 64, BN, true)) != B2_OK) return rc;
   if ((rc = make_tmap_2d_f16(&tmC, ip.y, (uint64_t)ip.ldy, (uint64_t)ip.M_total, (uint64_t)ip.ldy, 64, 128, true)) != B2_OK) return rc;
-  if (ip.residual) {
+  if (ip.residual && !ip.res_up) {
     if ((rc = make_tmap_2d_f16(&tmR, ip.residual, (uint64_t)ip.ldr, (uint64_t)ip.M_total, (uint64_t)ip.ldr, 64, 128, true)) != B2_OK) return rc;
   } else {
     tmR = tmC;
@@ -501,9 +517,13 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.tiles_n = (ip.ldy + BN - 1) / BN;
   p.tiles_total = p.tiles_n * ((ip.M_total + 127) / 128);
   p.scale = ip.scale; p.shift = ip.shift;
-  p.has_residual = ip.residual != nullptr;
+  p.has_residual = ip.residual != nullptr && !ip.res_up;
   p.relu = ip.relu;
   p.aff_ld = ip.aff_ld; p.aff_rows = ip.aff_rows;
+  p.res_up = ip.res_up ? ip.residual : nullptr;
+  p.res_ld = ip.ldr; p.Wh = ip.up_W > 0 ? ip.up_W : 2; p.Hh = ip.up_H > 0 ? ip.up_H : 2;
+  p.fd_Wh = make_fastdiv(p.Wh); p.fd_Hh = make_fastdiv(p.Hh);
+  p.res_pre = ip.res_pre;
   const int grid = p.tiles_total < sm_count() ? p.tiles_total : sm_count();
   B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN>, dim3(grid), dim3(kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, p));
   B2_CHECK_LAUNCH("pgemm_kernel");
@@ -516,6 +536,8 @@ static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   }
   if (L.p.aff_ld)
     return set_error(B2_ERR_UNSUPPORTED, "per-sample affine is implemented by the slab convolution and the persistent GEMM only");
+  if (L.p.res_up || L.p.res_pre)
+    return set_error(B2_ERR_UNSUPPORTED, "upsampled / pre-scale residuals are implemented by the persistent GEMM (1x1 convolutions) only");
   // 64-wide tiles for narrow outputs, 128 otherwise
   const int width = (L.p.epi == EPI_TMA_F16) ? L.p.ldy : L.p.Ncols;
   if (width <= 64) return launch_igemm<64>(L, stream);
@@ -562,6 +584,12 @@ static int validate_conv(const b2_conv_args* a) {
     B2_CHECK_ARG(a->mode == B2_CONV_AUTO, "unknown conv mode %d", a->mode);
     B2_CHECK_ARG(a->C % 8 == 0, "channel pitch %d is not a multiple of 8", a->C);
   }
+  if (a->residual_up || a->residual_pre) {
+    B2_CHECK_ARG(a->residual != nullptr && a->kt * a->kh * a->kw == 1 && a->st == 1 && a->sh == 1 && a->sw == 1 && a->T == 1 &&
+                     !a->out_f32 && a->mode == B2_CONV_AUTO,
+                 "residual_up / residual_pre need a residual and a 1x1 stride-1 2-D convolution with fp16 output");
+    B2_CHECK_ARG(!a->residual_up || (a->H % 2 == 0 && a->W % 2 == 0), "residual_up needs even output height and width");
+  }
   if (a->upsample)
     B2_CHECK_ARG(a->upsample == 1 && a->mode == B2_CONV_AUTO && !a->out_f32 && a->kt == 1 && a->kh == 3 && a->kw == 3 && a->st == 1 &&
                      a->sh == 1 && a->sw == 1 && a->pt == 0 && a->ph == 1 && a->pw == 1,
@@ -606,6 +634,7 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   p.relu = a->relu; p.per_row = 0; p.accumulate = a->accumulate;
   p.epi = a->out_f32 ? EPI_DIRECT_F32 : EPI_TMA_F16;
   p.aff_ld = a->aff_ld;
+  p.res_up = a->residual_up; p.res_pre = a->residual_pre; p.up_H = p.Ho; p.up_W = p.Wo;
   p.aff_rows = p.To * p.Ho * p.Wo;
   if (a->aff_ld && p.aff_rows % 128 != 0)
     return set_error(B2_ERR_UNSUPPORTED, "per-sample affine on a 1x1x1 convolution needs To*Ho*Wo %% 128 == 0 (got %d)", p.aff_rows);

@@ -51,6 +51,8 @@ struct IgemmParams {
   int amode;
   int epi;
   int aff_ld, aff_rows;    // per-sample affine (persistent GEMM only): scale/shift row (m / aff_rows), pitch aff_ld; 0 = off
+  int res_up, res_pre;     // persistent GEMM only: residual is the low-res tensor of an (up_H x up_W) image / added before the scale
+  int up_H, up_W;
 };
 
 template <int BN>

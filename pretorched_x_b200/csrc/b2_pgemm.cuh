@@ -37,6 +37,13 @@ struct PgemmParams {
   int has_residual;
   int relu;
   int aff_ld, aff_rows;     // > 0: scale/shift are [M / aff_rows][aff_ld] (per-sample affine; aff_rows % 128 == 0)
+  // Residual read straight from a LOW-resolution tensor (nearest-2x upsampling on the fly; GBlock skip path): output
+  // row m = (n, h, w) of an Hh x Wh image adds res_up[((n * Hh/2 + h/2) * Wh/2 + w/2) * res_ld + column].  Replaces the
+  // TMA-staged residual tile (has_residual == 0); two neighbouring rows read the same 16 bytes (L1 broadcast).
+  const __half* res_up;
+  int res_ld, Wh, Hh;
+  FastDiv fd_Wh, fd_Hh;
+  int res_pre;              // 1: y = act(scale * (acc + residual) + shift) instead of act(scale * acc + shift + residual)
 };
 
 template <int BN>
@@ -163,6 +170,13 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
       const int m0 = (tile / p.tiles_n) * 128, n0 = (tile % p.tiles_n) * BN;
       const int ab = lt & 1;
+      const __half* up_row = nullptr;                    // this thread's row of the low-res residual (p.res_up)
+      if (p.res_up && m0 + r < p.M) {
+        const int m = m0 + r;
+        const int t1 = fdiv(m, p.fd_Wh), wq = m - t1 * p.Wh;
+        const int nq = fdiv(t1, p.fd_Hh), hq = t1 - nq * p.Hh;
+        up_row = p.res_up + (static_cast<size_t>(nq * (p.Hh >> 1) + (hq >> 1)) * (p.Wh >> 1) + (wq >> 1)) * p.res_ld + n0;
+      }
       mbar_wait(&acc_full[ab], (lt >> 1) & 1);
       tc_fence_after();
       const uint8_t* r_stage = smem + S::kResOff + ab * S::kTile;
@@ -191,15 +205,21 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t coff = (static_cast<uint32_t>(chunk0 + q) ^ swz) << 4;
           uint4 rv = make_uint4(0, 0, 0, 0);
           if (p.has_residual) rv = *reinterpret_cast<const uint4*>(rrow + coff);
+          else if (up_row && n0 + j * 32 + q * 8 < p.Ncols) rv = __ldg(reinterpret_cast<const uint4*>(up_row + j * 32 + q * 8));
           const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
           uint32_t out[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int ci = j * 32 + q * 8 + e * 2;
-            float a0 = __uint_as_float(v[q * 8 + e * 2]) * s_scale[ci] + s_shift[ci];
-            float a1 = __uint_as_float(v[q * 8 + e * 2 + 1]) * s_scale[ci + 1] + s_shift[ci + 1];
             const float2 rf = unpack_half2(rr[e]);
-            a0 += rf.x; a1 += rf.y;
+            float a0 = __uint_as_float(v[q * 8 + e * 2]), a1 = __uint_as_float(v[q * 8 + e * 2 + 1]);
+            if (p.res_pre) {
+              a0 = (a0 + rf.x) * s_scale[ci] + s_shift[ci];
+              a1 = (a1 + rf.y) * s_scale[ci + 1] + s_shift[ci + 1];
+            } else {
+              a0 = a0 * s_scale[ci] + s_shift[ci] + rf.x;
+              a1 = a1 * s_scale[ci + 1] + s_shift[ci + 1] + rf.y;
+            }
             if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
             out[e] = pack_half2(a0, a1);
           }

@@ -293,4 +293,22 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
   return __half22float2(h);
 }
 
+// Division by a run-time constant as a 64-bit multiply + shift (exact for 0 <= n < 2^31): the work-item decode and the
+// epilogue's position -> (row, column) split run once per item in every warp; with few-tap 2-D filters an item is short
+// enough that the ~25-instruction integer division sequences showed up in the issue-slot budget (profiles/NOTES_r01.md).
+struct FastDiv {
+  unsigned long long M;
+  int s, d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f; f.d = d; f.s = 0;
+  while ((1ll << f.s) < d) ++f.s;
+  const unsigned __int128 one = 1;
+  f.M = (unsigned long long)(((one << (32 + f.s)) + (unsigned)d - 1) / (unsigned)d);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(n)) * f.M) >> (32 + f.s));
+}
+
 }  // namespace b2

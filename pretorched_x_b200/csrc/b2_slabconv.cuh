@@ -79,6 +79,7 @@ struct SlabParams {
   // uses the tap table row sub_*[ph] (4 taps, weights [K][ph*4 + i][C]) and writes output pixel (2h + py, 2w + px) of a
   // (2 Ho) x (2 Wo) plane.  n_sub stays 1: all phases read the same slab.
   int up;
+  FastDiv fd_tiles_n, fd_tiles_q, fd_wchunks, fd_To, fd_PW;   // dividers of the item decode (set by launch_slab)
 };
 
 // scale/shift live in smem for all (padded) output channels: SlabParams::naff = round_up(ldy, 32) + 32 entries each
@@ -89,19 +90,21 @@ struct SlabItem {
 };
 __device__ __forceinline__ SlabItem slab_item(const SlabParams& p, int item, int BN) {
   SlabItem w;
-  const int tn = item % p.tiles_n; item /= p.tiles_n;
+  int t = fdiv(item, p.fd_tiles_n);
+  const int tn = item - t * p.tiles_n; item = t;
   w.phase = 0;
   if (p.up) { w.phase = item & 3; item >>= 2; }
-  const int tq = item % p.tiles_q; item /= p.tiles_q;
-  w.wc = item % p.wchunks;
-  w.plane_o = item / p.wchunks;
+  t = fdiv(item, p.fd_tiles_q);
+  const int tq = item - t * p.tiles_q; item = t;
+  w.plane_o = fdiv(item, p.fd_wchunks);
+  w.wc = item - w.plane_o * p.wchunks;
   w.n0 = tn * BN;
   w.q0 = tq * (p.MT * 128);
-  const int to = w.plane_o % p.To, n = w.plane_o / p.To;
+  const int n = fdiv(w.plane_o, p.fd_To), to = w.plane_o - n * p.To;
   const int t0 = to * p.st - p.pt;                  // input frame of temporal tap 0
   w.plane_i0 = n * p.T + t0;
   const int lo = w.q0 - p.reach;                    // lowest padded position any tap of this item touches
-  w.r_lo = (lo >= 0) ? lo / p.PW : -((-lo + p.PW - 1) / p.PW);
+  w.r_lo = (lo >= 0) ? fdiv(lo, p.fd_PW) : -fdiv(-lo + p.PW - 1, p.fd_PW);
   w.dt_lo = max(0, -t0);                            // temporal taps that stay inside the clip
   const int dt_hi = min(p.kt - 1, p.T - 1 - t0);
   w.n_dt = dt_hi - w.dt_lo + 1;
@@ -283,7 +286,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int q = w.q0 + j * 128 + erow;
-        const int h = q / p.PW, wp = q - h * p.PW;
+        const int h = fdiv(q, p.fd_PW), wp = q - h * p.PW;
         const int wo = w.wc * p.WC + wp - p.halo_l;       // output column
         ok[j] = (j < w.mt_valid) && (q < p.P) && (wp >= p.halo_l) && (wp < p.halo_l + p.WC) && (wo < p.Wo);
         row[j] = p.up ? (static_cast<size_t>(w.plane_o) * (2 * p.Ho) + 2 * h + (w.phase >> 1)) * (2 * p.Wo) + 2 * wo + (w.phase & 1)
@@ -295,14 +298,23 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
         float sc[32], sh[32];
         const int c0 = w.n0 + jc * 32;
         if (p.aff_ld) {
-          // per-sample affine (class-conditional BN of the consumer): the item lies in one image, every lane reads
-          // the same 32 + 32 floats (L1/L2 broadcast)
-          const size_t arow = static_cast<size_t>(w.plane_o / p.To) * p.aff_ld;
+          // per-sample affine (class-conditional BN of the consumer): the item lies in one image, every lane reads the
+          // same 32 + 32 floats (L1 broadcast) as 16-byte vectors; launch_slab checks the 16-byte alignment
+          const float* gs = p.scale + static_cast<size_t>(fdiv(w.plane_o, p.fd_To)) * p.aff_ld + c0;
+          const float* gt = p.shift + static_cast<size_t>(fdiv(w.plane_o, p.fd_To)) * p.aff_ld + c0;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const bool in = c0 + c < p.Ncols;
-            sc[c] = in ? __ldg(p.scale + arow + c0 + c) : 0.f;
-            sh[c] = in ? __ldg(p.shift + arow + c0 + c) : 0.f;
+          for (int g = 0; g < 8; ++g) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (c0 + 4 * g + 4 <= p.Ncols) {
+              a = __ldg(reinterpret_cast<const float4*>(gs) + g);
+              b = __ldg(reinterpret_cast<const float4*>(gt) + g);
+            } else if (c0 + 4 * g < p.Ncols) {              // ragged tail of a channel count that is not a multiple of 4
+              float* ap = reinterpret_cast<float*>(&a); float* bp = reinterpret_cast<float*>(&b);
+              for (int e = 0; e < 4; ++e)
+                if (c0 + 4 * g + e < p.Ncols) { ap[e] = __ldg(gs + 4 * g + e); bp[e] = __ldg(gt + 4 * g + e); }
+            }
+            sc[4 * g] = a.x; sc[4 * g + 1] = a.y; sc[4 * g + 2] = a.z; sc[4 * g + 3] = a.w;
+            sh[4 * g] = b.x; sh[4 * g + 1] = b.y; sh[4 * g + 2] = b.z; sh[4 * g + 3] = b.w;
           }
         } else {
 #pragma unroll
@@ -319,24 +331,43 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
             tmem_ld_wait();
             if (ok[j]) {
               __half* yrow = p.y + row[j] * p.ldy + c0;
-              const __half* rrow = p.residual ? p.residual + row[j] * p.ldr + c0 : nullptr;
+              if (p.residual) {                              // uniform: residual added in fp32 before the single rounding
+                const __half* rrow = p.residual + row[j] * p.ldr + c0;
 #pragma unroll
-              for (int c8 = 0; c8 < 4; ++c8) {
-                if (jc * 32 + c8 * 8 < ncols_here) {
-                  uint4 rv = make_uint4(0, 0, 0, 0);
-                  if (rrow) rv = __ldg(reinterpret_cast<const uint4*>(rrow + c8 * 8));
-                  const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-                  uint32_t o[4];
+                for (int c8 = 0; c8 < 4; ++c8) {
+                  if (jc * 32 + c8 * 8 < ncols_here) {
+                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + c8 * 8));
+                    const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+                    uint32_t o[4];
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int c = c8 * 8 + e * 2;
-                    const float2 rf = unpack_half2(rr[e]);
-                    float a0 = fmaf(__uint_as_float(v[c]), sc[c], sh[c]) + rf.x;
-                    float a1 = fmaf(__uint_as_float(v[c + 1]), sc[c + 1], sh[c + 1]) + rf.y;
-                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                    o[e] = pack_half2(a0, a1);
+                    for (int e = 0; e < 4; ++e) {
+                      const int c = c8 * 8 + e * 2;
+                      const float2 rf = unpack_half2(rr[e]);
+                      float a0 = fmaf(__uint_as_float(v[c]), sc[c], sh[c]) + rf.x;
+                      float a1 = fmaf(__uint_as_float(v[c + 1]), sc[c + 1], sh[c + 1]) + rf.y;
+                      if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                      o[e] = pack_half2(a0, a1);
+                    }
+                    *reinterpret_cast<uint4*>(yrow + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
                   }
-                  *reinterpret_cast<uint4*>(yrow + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+              } else {                                       // no residual: affine, round, ReLU on the packed pairs
+                const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                  if (jc * 32 + c8 * 8 < ncols_here) {
+                    uint4 ov;
+                    uint32_t* o = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const int c = c8 * 8 + e * 2;
+                      __half2 hv = __floats2half2_rn(fmaf(__uint_as_float(v[c]), sc[c], sh[c]),
+                                                     fmaf(__uint_as_float(v[c + 1]), sc[c + 1], sh[c + 1]));
+                      if (p.relu) hv = __hmax2(hv, zero2);
+                      o[e] = *reinterpret_cast<uint32_t*>(&hv);
+                    }
+                    *reinterpret_cast<uint4*>(yrow + c8 * 8) = ov;
+                  }
                 }
               }
             }

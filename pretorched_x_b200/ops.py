@@ -195,12 +195,15 @@ def _out_dim(i, k, s, p):
 # ---------------------------------------------------------------------------------------------
 # convolution / dense
 # ---------------------------------------------------------------------------------------------
-def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None):
+def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, residual_up=False, residual_pre=False):
     """nn.Conv3d -> BatchNorm3d -> (+residual) -> ReLU in one kernel
     (resnet3D.py:91-106, 125-143, 176-185; r2plus1d.py:85-88; torchvision_models.py:449-451).
 
     ``sample_affine=(scale, shift)``: fp32 ``[N][pitch]`` views -- a per-SAMPLE epilogue affine instead of the packed
-    per-channel one (class-conditional BatchNorm of the layer that follows the convolution, BigGAN GBlock)."""
+    per-channel one (class-conditional BatchNorm of the layer that follows the convolution, BigGAN GBlock).
+    ``residual_up``: ``residual`` is the skip tensor at HALF the output resolution, nearest-2x upsampled on the fly (its
+    first K channels are used: the GBlock's channel drop); ``residual_pre``: the residual joins before the affine,
+    y = act(scale * (conv + residual) + shift).  Both: 1x1 convolutions only."""
     if a.ld != pc.C:
         raise ValueError("activation pitch %d != packed filter pitch %d" % (a.ld, pc.C))
     kt, kh, kw = pc.k
@@ -218,8 +221,11 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None):
     args.N, args.T, args.H, args.W, args.C = a.N, a.T, a.H, a.W, a.ld
     args.K, args.ldy = pc.K, ldy
     args.ldr = residual.ld if residual is not None else 0
-    if residual is not None and residual.M != M:
-        raise ValueError("residual rows %d != output rows %d" % (residual.M, M))
+    if residual is not None and residual.M * (4 if residual_up else 1) != M:
+        raise ValueError("residual rows %d do not match output rows %d" % (residual.M, M))
+    if (residual_up or residual_pre) and (residual is None or simt):
+        raise ValueError("residual_up / residual_pre need a residual and the tensor-core path")
+    args.residual_up, args.residual_pre = int(residual_up), int(residual_pre)
     args.kt, args.kh, args.kw = kt, kh, kw
     args.st, args.sh, args.sw = pc.s
     args.pt, args.ph, args.pw = pc.p

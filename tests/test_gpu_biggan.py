@@ -105,8 +105,9 @@ def test_conv3x3_with_per_sample_affine(dev, shape):
     g = torch.Generator().manual_seed(7)
     x = torch.randn(N, C, H, W, generator=g).half()
     w = (torch.randn(K, C, 3, 3, generator=g) / (3 * C ** 0.5))
-    aff = torch.randn(N, 2 * K + 16, generator=g).cuda()
-    sc, sh = aff[:, :K], aff[:, K + 16:]
+    Kp = (K + 7) // 8 * 8                                   # per-sample affine rows: 16-byte aligned, pitch % 4 == 0
+    aff = torch.randn(N, 2 * Kp + 16, generator=g).cuda()
+    sc, sh = aff[:, :K], aff[:, Kp + 16:Kp + 16 + K]
     pc = ops.PackedConv(w.cuda(), None, None, (1, 1, 1), (0, 1, 1), in_pitch=C)
     out = ops.conv(nhwc(x), pc, relu=True, sample_affine=(sc, sh))
     ref = F.conv2d(x.float(), w.half().float(), None, 1, 1)
@@ -136,6 +137,28 @@ def test_conv3x3_of_upsampled_image_without_materialising_it(dev, shape, affine)
         want = ref + b.view(1, K, 1, 1)
     assert (out.H, out.W, out.C) == (2 * H, 2 * W, K)
     assert rel(to_nchw(out), want) <= 3e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16, 128, 200), (3, 32, 8, 8, 64, 64), (1, 128, 64, 128, 32, 96), (2, 16, 6, 10, 24, 24)])
+@pytest.mark.parametrize("pre", [False, True])
+def test_conv1x1_with_upsampled_skip(dev, shape, pre):
+    """GBlock closing convolution: conv1x1(t) + upsample(x[:, :K]) with x read at low resolution by the epilogue
+    (residual_up), optionally with the residual joining before the affine (residual_pre: folded output BatchNorm)."""
+    N, C, H, W, K, Cx = shape                              # t: [N, C, H, W]; x: [N, Cx >= K, H/2, W/2]
+    g = torch.Generator().manual_seed(10)
+    t = torch.randn(N, C, H, W, generator=g).half()
+    x = torch.randn(N, Cx, H // 2, W // 2, generator=g).half()
+    w = torch.randn(K, C, 1, 1, generator=g) / C ** 0.5
+    pc = ops.PackedConv(w.cuda(), None, None, (1, 1, 1), (0, 0, 0), in_pitch=C)
+    pc.scale = (torch.rand(K, generator=g) + 0.5).cuda()
+    pc.shift = torch.randn(K, generator=g).cuda()
+    out = ops.conv(nhwc(t), pc, residual=nhwc(x), relu=True, residual_up=True, residual_pre=pre)
+    acc = F.conv2d(t.float(), w.half().float())
+    skip = F.interpolate(x.float()[:, :K], scale_factor=2)
+    s_, b_ = pc.scale.cpu().view(1, K, 1, 1), pc.shift.cpu().view(1, K, 1, 1)
+    want = F.relu((acc + skip) * s_ + b_) if pre else F.relu(acc * s_ + b_ + skip)
+    assert rel(to_nchw(out), want) <= 3e-3
+    assert out.ld == (K + 7) // 8 * 8 and (out.ld == K or float(out.data[:, K:].abs().max()) == 0.0)
 
 
 @pytest.mark.parametrize("shape", [(3, 256, 16, 16, 64), (2, 64, 16, 8, 200)])
