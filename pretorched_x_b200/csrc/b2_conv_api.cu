@@ -487,12 +487,12 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
 
 static int g_gemm_algo = 0;   // 0 auto (persistent kernel where it applies), 1 force the per-tile kernel
 
-template <int BN>
+template <int BN, int GAN>
 static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   using S = PgemmSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(pgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(pgemm_kernel<BN, GAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
   const IgemmParams& ip = L.p;
@@ -517,7 +517,7 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.tiles_n = (ip.ldy + BN - 1) / BN;
   p.tiles_total = p.tiles_n * ((ip.M_total + 127) / 128);
   p.scale = ip.scale; p.shift = ip.shift;
-  p.has_residual = ip.residual != nullptr && !ip.res_up;
+  p.has_residual = ip.residual != nullptr;
   p.relu = ip.relu;
   p.aff_ld = ip.aff_ld; p.aff_rows = ip.aff_rows;
   p.res_up = ip.res_up ? ip.residual : nullptr;
@@ -525,14 +525,16 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.fd_Wh = make_fastdiv(p.Wh); p.fd_Hh = make_fastdiv(p.Hh);
   p.res_pre = ip.res_pre;
   const int grid = p.tiles_total < sm_count() ? p.tiles_total : sm_count();
-  B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN>, dim3(grid), dim3(kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, p));
+  B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN, GAN>, dim3(grid), dim3(kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, p));
   B2_CHECK_LAUNCH("pgemm_kernel");
   return B2_OK;
 }
 
 static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (g_gemm_algo == 0 && L.p.amode == AMODE_TMA && L.p.epi == EPI_TMA_F16 && !L.p.per_row) {
-    return L.p.ldy <= 64 ? launch_pgemm<64>(L, stream) : launch_pgemm<128>(L, stream);
+    if (L.p.res_up || L.p.res_pre)
+      return L.p.ldy <= 64 ? launch_pgemm<64, 1>(L, stream) : launch_pgemm<128, 1>(L, stream);
+    return L.p.ldy <= 64 ? launch_pgemm<64, 0>(L, stream) : launch_pgemm<128, 0>(L, stream);
   }
   if (L.p.aff_ld)
     return set_error(B2_ERR_UNSUPPORTED, "per-sample affine is implemented by the slab convolution and the persistent GEMM only");

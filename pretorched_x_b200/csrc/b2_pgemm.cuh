@@ -37,9 +37,10 @@ struct PgemmParams {
   int has_residual;
   int relu;
   int aff_ld, aff_rows;     // > 0: scale/shift are [M / aff_rows][aff_ld] (per-sample affine; aff_rows % 128 == 0)
-  // Residual read straight from a LOW-resolution tensor (nearest-2x upsampling on the fly; GBlock skip path): output
-  // row m = (n, h, w) of an Hh x Wh image adds res_up[((n * Hh/2 + h/2) * Wh/2 + w/2) * res_ld + column].  Replaces the
-  // TMA-staged residual tile (has_residual == 0); two neighbouring rows read the same 16 bytes (L1 broadcast).
+  // Residual gathered from a LOW-resolution tensor (nearest-2x upsampling on the fly; GBlock skip path): output row
+  // m = (n, h, w) of an Hh x Wh image adds res_up[((n * Hh/2 + h/2) * Wh/2 + w/2) * res_ld + column].  The producer warp
+  // fills the residual tile with 16-byte cp.async gathers (one tile ahead, like the TMA path it replaces), the epilogue
+  // is unchanged.  pgemm_kernel<BN, 1> only.
   const __half* res_up;
   int res_ld, Wh, Hh;
   FastDiv fd_Wh, fd_Hh;
@@ -60,7 +61,7 @@ struct PgemmSmem {
   static constexpr int kTotal = kAffOff + 2 * BN * 4 + 1024;
 };
 
-template <int BN>
+template <int BN, int GAN>   // GAN = 1: instance with the generator extras (res_up gather, res_pre); 0: the classic epilogue
 __global__ void __launch_bounds__(kPgThreads, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -82,7 +83,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < kPgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPgEpiWarps * 32);
-      mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], kPgEpiWarps * 32);
+      mbar_init(&res_full[i], (GAN && p.res_up) ? 32 : 1);   // gathered residual: one cp.async arrival per producer lane
+      mbar_init(&res_empty[i], kPgEpiWarps * 32);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
@@ -100,16 +102,18 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int it = 0, lt = 0;
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
       const int m0 = (tile / p.tiles_n) * 128, n0 = (tile % p.tiles_n) * BN;
+      const int rb = lt & 1;
       if (p.has_residual) {
-        const int rb = lt & 1;
         mbar_wait(&res_empty[rb], ((lt >> 1) & 1) ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(&res_full[rb], S::kTile);
+        if (!(GAN && p.res_up)) {
+          if (elect_one()) {
+            mbar_expect_tx(&res_full[rb], S::kTile);
 #pragma unroll
-          for (int b = 0; b < BN / 64; ++b)
-            tma_load_2d(smem + S::kResOff + rb * S::kTile + b * (128 * 128), &tmR, &res_full[rb], n0 + b * 64, m0);
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_2d(smem + S::kResOff + rb * S::kTile + b * (128 * 128), &tmR, &res_full[rb], n0 + b * 64, m0);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       for (int kb = 0; kb < p.nkb + p.nkb2; ++kb, ++it) {
         const int s = it % kPgStages;
@@ -126,6 +130,33 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         __syncwarp();
+      }
+      if (GAN && p.res_up) {
+        // residual tile of this output tile, gathered from the low-res skip tensor (after the operand loads were queued:
+        // the epilogue needs it last).  Lane l fills rows l, l + 32, l + 64, l + 96 in the SWIZZLE_128B box layout the
+        // epilogue reads; columns >= Ncols and rows >= M are zero-filled.
+        const int lane = tid & 31;
+        const uint32_t dst0 = smem_u32(smem + S::kResOff + rb * S::kTile);
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const int r = lane + 32 * k, m = m0 + r;
+          const bool ok = m < p.M;
+          const __half* src = p.res_up;
+          if (ok) {
+            const int t1 = fdiv(m, p.fd_Wh), wq = m - t1 * p.Wh;
+            const int nq = fdiv(t1, p.fd_Hh), hq = t1 - nq * p.Hh;
+            src = p.res_up + (static_cast<size_t>(nq * (p.Hh >> 1) + (hq >> 1)) * (p.Wh >> 1) + (wq >> 1)) * p.res_ld + n0;
+          }
+          const uint32_t drow = dst0 + static_cast<uint32_t>(r) * 128u;
+          const uint32_t swz = static_cast<uint32_t>(r & 7);
+#pragma unroll
+          for (int ch = 0; ch < BN / 8; ++ch) {
+            const bool okc = ok && (n0 + ch * 8 < p.Ncols);
+            cp_async_16_cg(drow + (ch >> 3) * (128u * 128u) + ((static_cast<uint32_t>(ch & 7) ^ swz) << 4),
+                           okc ? static_cast<const void*>(src + ch * 8) : static_cast<const void*>(p.res_up), okc ? 16u : 0u);
+          }
+        }
+        cp_async_mbar_arrive_noinc(&res_full[rb]);
       }
     }
   } else if (warp == kPgEpiWarps + 1) {
@@ -170,13 +201,6 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
       const int m0 = (tile / p.tiles_n) * 128, n0 = (tile % p.tiles_n) * BN;
       const int ab = lt & 1;
-      const __half* up_row = nullptr;                    // this thread's row of the low-res residual (p.res_up)
-      if (p.res_up && m0 + r < p.M) {
-        const int m = m0 + r;
-        const int t1 = fdiv(m, p.fd_Wh), wq = m - t1 * p.Wh;
-        const int nq = fdiv(t1, p.fd_Hh), hq = t1 - nq * p.Hh;
-        up_row = p.res_up + (static_cast<size_t>(nq * (p.Hh >> 1) + (hq >> 1)) * (p.Wh >> 1) + (wq >> 1)) * p.res_ld + n0;
-      }
       mbar_wait(&acc_full[ab], (lt >> 1) & 1);
       tc_fence_after();
       const uint8_t* r_stage = smem + S::kResOff + ab * S::kTile;
@@ -205,7 +229,6 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t coff = (static_cast<uint32_t>(chunk0 + q) ^ swz) << 4;
           uint4 rv = make_uint4(0, 0, 0, 0);
           if (p.has_residual) rv = *reinterpret_cast<const uint4*>(rrow + coff);
-          else if (up_row && n0 + j * 32 + q * 8 < p.Ncols) rv = __ldg(reinterpret_cast<const uint4*>(up_row + j * 32 + q * 8));
           const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
           uint32_t out[4];
 #pragma unroll
@@ -213,7 +236,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int ci = j * 32 + q * 8 + e * 2;
             const float2 rf = unpack_half2(rr[e]);
             float a0 = __uint_as_float(v[q * 8 + e * 2]), a1 = __uint_as_float(v[q * 8 + e * 2 + 1]);
-            if (p.res_pre) {
+            if (GAN && p.res_pre) {
               a0 = (a0 + rf.x) * s_scale[ci] + s_shift[ci];
               a1 = (a1 + rf.y) * s_scale[ci + 1] + s_shift[ci + 1];
             } else {
