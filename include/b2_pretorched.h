@@ -79,6 +79,12 @@ typedef struct b2_conv_args {
                            1x1 stride-1 2-D convolutions only                                                     */
   int32_t residual_pre; /* 1: y = act(scale * (acc + residual) + shift) -- the residual joins BEFORE the affine (BatchNorm of
                            the block output folded into its closing convolution).  1x1 convolutions only           */
+  void* y2;             /* nullable second output, fp16 [M][ldy]: y2 = relu(y * scale2[n] + shift2[n]) with y the fp32 value of
+                           the first output -- the class-conditional BatchNorm + ReLU that OPENS the next GBlock, produced
+                           while the tile is still on chip.  1x1 stride-1 convolutions with To*Ho*Wo % 128 == 0 only */
+  const float* scale2;  /* fp32 [N][aff2_ld] */
+  const float* shift2;
+  int32_t aff2_ld;
 } b2_conv_args;
 
 int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream);
@@ -121,6 +127,10 @@ typedef struct b2_gemm_args {
   int32_t aff_ld;   /* 0: scale/shift are [N] (or [M] when per_row).  > 0: per-sample affine, fp32 [M / aff_rows][aff_ld]:
                        row m uses scale[(m / aff_rows) * aff_ld + n]; fp16 output only, aff_rows % 128 == 0 */
   int32_t aff_rows;
+  void* d2;             /* nullable second output fp16 [M][ldd]: d2 = relu(d * scale2[m / aff2_rows] + shift2[...]) (see y2 above) */
+  const float* scale2;
+  const float* shift2;
+  int32_t aff2_ld, aff2_rows;
 } b2_gemm_args;
 int b2_gemm_f16(const b2_gemm_args* a, void* stream);
 /* D = act(scale * (A.B^T + A2.B2^T) + shift + residual): both products accumulate in the same TMEM tile.  Used to
@@ -187,6 +197,12 @@ int b2_embed_concat(const float* z, const long long* labels, const float* table,
  * by all samples, i.e. a plain BatchNorm), or both NULL for a pure copy / channel slice / upsample. */
 int b2_ccbn_act_ndhwc(const void* x, int ldx, void* y, int ldy, const float* scale, const float* shift, int lda, int N,
                       int H, int W, int C, int up, int relu, void* stream);
+/* RGB head of the generator (3x3 convolution to K <= 4 channels, + bias, tanh, NCHW write) split in two: a 1x1 GEMM
+ * (b2_gemm_f16) writes partial[q][(dh*3+dw)*4 + k] = sum_c x[q][c] * w[k][c][dh][dw] for every pixel q (36 columns, pitch
+ * ldp >= 36), and this call gathers y[n][k][h][w] = tanh(bias[k] + sum_taps partial[(n,h+dh-1,w+dw-1)][tap*4 + k]) with
+ * zero padding.  One pass of the tensor core over x instead of nine shifted passes that use 3 of 16 MMA columns. */
+int b2_rgb_head_gather_tanh(const void* partial, int ldp, const float* bias, void* y, int N, int H, int W, int K, int out_f32,
+                            void* stream);
 /* y[n][c][s] = tanh(x[n*S + s][c]): fp16 channels-last (pitch ldx) -> NCHW planes, fp32 (out_f32) or fp16. */
 int b2_tanh_nhwc_to_nchw(const void* x, int ldx, void* y, int N, int C, long long S, int out_f32, void* stream);
 

@@ -33,6 +33,7 @@ class ConvArgs(ctypes.Structure):
         ("st", c_i32), ("sh", c_i32), ("sw", c_i32),
         ("pt", c_i32), ("ph", c_i32), ("pw", c_i32),
         ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32), ("aff_ld", c_i32), ("upsample", c_i32), ("residual_up", c_i32), ("residual_pre", c_i32),
+        ("y2", c_void_p), ("scale2", c_void_p), ("shift2", c_void_p), ("aff2_ld", c_i32),
     ]
 
 
@@ -45,6 +46,7 @@ class GemmArgs(ctypes.Structure):
         ("lda", c_i32), ("ldb", c_i32), ("ldd", c_i32), ("ldr", c_i32),
         ("per_row", c_i32), ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32),
         ("aff_ld", c_i32), ("aff_rows", c_i32),
+        ("d2", c_void_p), ("scale2", c_void_p), ("shift2", c_void_p), ("aff2_ld", c_i32), ("aff2_rows", c_i32),
     ]
 
 
@@ -73,6 +75,7 @@ SYMBOLS = {
     "b2_gather_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2_embed_concat": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "b2_ccbn_act_ndhwc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
+    "b2_rgb_head_gather_tanh": (c_int, [c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "b2_tanh_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, ctypes.c_longlong, c_int, c_void_p]),
 }
 

@@ -19,6 +19,11 @@ How the pieces map:
 * The nearest-2x upsampling in front of conv2 is never materialised: a 3x3 convolution of an upsampled image is four
   2x2 convolutions of the low-res image (one per output phase, filters summed when packed), which the slab kernel runs
   as 4 x 4 taps with a strided output write -- 2.25x fewer MACs and a quarter of the input bytes.
+* bn1 + ReLU of block i+1 CAN be a second output of block i's conv4 (or of the attention's output GEMM): a second epilogue
+  pass over the accumulator that is still in TMEM writes relu(ccbn1_next(h + skip)) next to h + skip (``next_affine``,
+  ``dual_output=True``).  Measured on B200 it does not pay -- these layers are write-bound and the second 2-byte-per-element
+  stream costs the 1x1 kernel as much as the stand-alone read+write pass it replaces (27.3 vs 26.5 ms per 256 images) -- so
+  it is off by default; the stand-alone ``b2_ccbn_act_ndhwc`` pass runs at ~5 TB/s.
 * conv4's epilogue adds the skip path: channel drop = the residual pitch, and for the upsampling block the epilogue reads
   the LOW-res x and upsamples on the fly (``residual_up``), so ``upsample(x)`` is never written either.
 * Spectral norm: weights are divided by sigma (one power iteration from the stored ``u0``) when they are packed.
@@ -138,6 +143,20 @@ def _pack(model, dev):
     pk.out_scale = sc.float().reshape(1, -1).contiguous()
     pk.out_shift = (obn.bias.detach().double() - obn.stored_mean.detach().double() * sc).float().reshape(1, -1).contiguous()
     pk.out_conv = _pack_conv(oconv, eps_sn, _round_up(obn.output_size, 8))
+    # Split RGB head: the 3x3 conv to 3 channels as ONE 1x1 GEMM to 9 taps x (3 + 1 pad) partial-product columns followed
+    # by a gather-sum (+ bias, tanh, NCHW).  As a 3x3 slab convolution the layer streams x through the tensor core nine
+    # times using 3 of 16 MMA columns (2.1 ms at B = 256); as a GEMM it is one HBM-bound pass.
+    pk.head_w = None
+    if oconv.weight.shape[0] <= 4 and tuple(oconv.weight.shape[2:]) == (3, 3):
+        wo = _sn_weight(oconv, eps_sn)                                         # [K][C][3][3]
+        Kh, Ch = wo.shape[0], wo.shape[1]
+        hw_ = torch.zeros((40, _round_up(Ch, 8)), dtype=torch.float16, device=dev)
+        for tap in range(9):
+            hw_[tap * 4:tap * 4 + Kh, :Ch] = wo[:, :, tap // 3, tap % 3].to(torch.float16)
+        pk.head_w, pk.head_k = hw_, Kh
+        pk.head_ones = torch.ones(40, dtype=torch.float32, device=dev)
+        pk.head_zeros = torch.zeros(40, dtype=torch.float32, device=dev)
+        pk.head_bias = (oconv.bias.detach().float() if oconv.bias is not None else torch.zeros(Kh, device=dev)).contiguous()
     # Output BN + ReLU folded into the LAST GBlock's closing convolution: relu(s * (acc + b4 + skip) + t) =
     # relu(s * (acc + skip) + (s * b4 + t)), i.e. conv4 with per-channel scale s, shift s * b4 + t and the residual joining
     # before the affine (residual_pre).  Removes one full read + write of the largest activation.
@@ -184,13 +203,25 @@ def _aff(aff, slot):
     return aff[:, o_scale:o_scale + C], aff[:, o_shift:o_shift + C]
 
 
-def run_gblock(blk, a, aff, pk, fuse_output_bn=False):
+def _next_affine(nxt, a_out_hw, aff, pk):
+    """(scale, shift) of the ccbn that opens the GBlock ``nxt`` when the producer of its input may write it as a second
+    output (a 128-row tile must stay inside one image), else None."""
+    if nxt is None or not hasattr(nxt, 'conv4') or a_out_hw % 128 != 0:
+        return None
+    return _aff(aff, pk.blocks[id(nxt)].bn[0])
+
+
+def run_gblock(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None):
     """One GBlock: h = conv4(relu(bn4(conv3(relu(bn3(conv2(up(relu(bn2(conv1(relu(bn1(x))))))))))))) + up(x[:, :out]).
+    ``pre``: relu(bn1(x)) when the previous kernel already produced it; ``nxt``: the module that consumes the result --
+    if it is a GBlock its opening ccbn + ReLU is written as a second output of conv4 (returned as the second value).
     ``fuse_output_bn`` (last block only): returns relu(bn_out(h)) instead, see ``_pack``."""
     bp = pk.blocks[id(blk)]
     up = 2 if blk.upsample else 1
-    s1, t1 = _aff(aff, bp.bn[0])
-    t = ops.ccbn_act(a, s1, t1)                                              # relu(bn1(x))
+    if pre is None:
+        s1, t1 = _aff(aff, bp.bn[0])
+        pre = ops.ccbn_act(a, s1, t1)                                        # relu(bn1(x))
+    t = pre
     if bp.fuse2:
         t = ops.conv(t, bp.conv[0], relu=True, sample_affine=_aff(aff, bp.bn[1]))     # relu(bn2(conv1(.)))
     else:
@@ -203,12 +234,15 @@ def run_gblock(blk, a, aff, pk, fuse_output_bn=False):
     # conv4 + skip: the skip path x[:, :out] (channel drop = residual pitch) is read at LOW resolution by the epilogue and
     # upsampled on the fly, so up(x) is never written; the last block also carries the output BN + ReLU (see _pack)
     if fuse_output_bn:
-        return ops.conv(t, pk.out_conv4, residual=a, relu=True, residual_up=up == 2, residual_pre=True)
-    return ops.conv(t, bp.conv[3], residual=a, residual_up=up == 2)
+        return ops.conv(t, pk.out_conv4, residual=a, relu=True, residual_up=up == 2, residual_pre=True), None
+    nxt_aff = _next_affine(nxt, t.H * t.W, aff, pk)
+    out = ops.conv(t, bp.conv[3], residual=a, residual_up=up == 2, next_affine=nxt_aff)
+    return out if nxt_aff is not None else (out, None)
 
 
-def run_attention(att, a, pk):
-    """SAGAN self-attention with 2x2 max-pooled keys / values: gamma * o(softmax(theta^T phi) g) + x."""
+def run_attention(att, a, aff, pk, nxt=None):
+    """SAGAN self-attention with 2x2 max-pooled keys / values: gamma * o(softmax(theta^T phi) g) + x.  Returns (result,
+    relu(bn1_next(result)) or None) like ``run_gblock``."""
     ap = pk.att[id(att)]
     C, M = att.ch, a.M
     nkv = ap.d + ap.dv
@@ -216,15 +250,22 @@ def run_attention(att, a, pk):
     kv = ops.gemm(a.data, ap.wkv, ap.ones[:nkv], ap.zeros[:nkv], M, nkv, a.ld)
     kvp = ops.maxpool3d(Act(kv, a.N, 1, a.H, a.W, nkv), (1, 2, 2), (1, 2, 2), (0, 0, 0))
     o = ops.attention(q, kvp.data, kvp.data[:, ap.d:], ap.d, ap.dv, a.N, a.H * a.W, kvp.positions)
+    nxt_aff = _next_affine(nxt, a.H * a.W, aff, pk)
+    if nxt_aff is not None:
+        z, z2 = ops.gemm(o, ap.wo, ap.gamma, ap.zeros[:C], M, C, ap.dv, residual=a.data,
+                         next_affine=(nxt_aff[0], nxt_aff[1], a.H * a.W))
+        return Act(z, a.N, 1, a.H, a.W, C), Act(z2, a.N, 1, a.H, a.W, C)
     z = ops.gemm(o, ap.wo, ap.gamma, ap.zeros[:C], M, C, ap.dv, residual=a.data)
-    return Act(z, a.N, 1, a.H, a.W, C)
+    return Act(z, a.N, 1, a.H, a.W, C), None
 
 
-def generator_forward(model, z, y, out_dtype=torch.float32, stages=None, fuse_output_bn=True):
+def generator_forward(model, z, y, out_dtype=torch.float32, stages=None, fuse_output_bn=True, split_head=True,
+                      dual_output=False):
     """z fp32 [B, dim_z] (CUDA), y int64 [B] class indices or fp32 [B, shared_dim] embeddings -> images [B, 3, R, R].
     ``stages``: optional dict receiving the Act after the first linear, every stage, the output BN+ReLU ('out_act') and
     the RGB conv ('pre_tanh').  With ``fuse_output_bn`` (default) the last stage's raw output never exists (its closing
-    convolution writes relu(bn_out(.)) directly), so 'stage{last}' is only recorded when it is off."""
+    convolution writes relu(bn_out(.)) directly), so 'stage{last}' is only recorded when it is off; with ``split_head``
+    (default) the RGB convolution runs as a 1x1 GEMM + gather and 'pre_tanh' is only recorded when it is off."""
     if model.training:
         raise RuntimeError("the B200 engine is inference-only: call model.eval() (standing statistics, no SN update)")
     if not z.is_cuda:
@@ -241,18 +282,23 @@ def generator_forward(model, z, y, out_dtype=torch.float32, stages=None, fuse_ou
     if stages is not None:
         stages['linear'] = a
     fused_tail = False
-    for i, stage in enumerate(model.blocks):
-        for blk in stage:
-            if hasattr(blk, 'conv4'):
-                fused_tail = fuse_output_bn and blk is pk.last_block
-                a = run_gblock(blk, a, aff, pk, fuse_output_bn=fused_tail)
-            else:
-                a = run_attention(blk, a, pk)
-        if stages is not None and not fused_tail:
+    mods = [(i, blk) for i, stage in enumerate(model.blocks) for blk in stage]
+    pre = None                                  # relu(bn1(a)) of the upcoming GBlock when its producer already wrote it
+    for j, (i, blk) in enumerate(mods):
+        nxt = mods[j + 1][1] if (j + 1 < len(mods) and dual_output) else None
+        if hasattr(blk, 'conv4'):
+            fused_tail = fuse_output_bn and blk is pk.last_block
+            a, pre = run_gblock(blk, a, aff, pk, fuse_output_bn=fused_tail, pre=pre, nxt=nxt)
+        else:
+            a, pre = run_attention(blk, a, aff, pk, nxt=nxt)
+        if stages is not None and not fused_tail and (j + 1 == len(mods) or mods[j + 1][0] != i):
             stages['stage%d' % i] = a
     t = a if fused_tail else ops.ccbn_act(a, pk.out_scale, pk.out_shift)
     if stages is not None:
         stages['out_act'] = t
+    if split_head and pk.head_w is not None:
+        part = ops.gemm(t.data, pk.head_w, pk.head_ones, pk.head_zeros, t.M, 40, t.ld)      # per-tap partial products
+        return ops.rgb_head(part, pk.head_bias, t.N, t.H, t.W, pk.head_k, out_dtype)        # gather + bias + tanh + NCHW
     t = ops.conv(t, pk.out_conv)
     if stages is not None:
         stages['pre_tanh'] = t

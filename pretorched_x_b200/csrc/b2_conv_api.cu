@@ -501,11 +501,20 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   if ((rc = make_tmap_2d_f16(&tmA, L.a_mat, (uint64_t)L.a_cols, (uint64_t)ip.M_total, (uint64_t)L.lda, 64, 128, true)) != B2_OK) return rc;
   if ((rc = make_tmap_2d_f16(&tmB, L.w, (uint64_t)L.b_cols, (uint64_t)ip.Ncols, (uint64_t)L.ldb, 64, BN, true)) != B2_OK) return rc;
   if ((rc = make_tmap_2d_f16(&tmC, ip.y, (uint64_t)ip.ldy, (uint64_t)ip.M_total, (uint64_t)ip.ldy, 64, 128, true)) != B2_OK) return rc;
-  if (ip.residual && !ip.res_up) {
+  const int up_W = ip.up_W > 0 ? ip.up_W : 2;
+  const int res_rows = up_W >= 128 ? 64 : 32;
+  if (ip.residual && ip.res_up) {
+    // low-res skip tensor: a tile's 128 output rows read res_rows consecutive rows of it (see PgemmParams::res_up)
+    if (!(up_W % 128 == 0 || (up_W <= 64 && 64 % up_W == 0)))
+      return set_error(B2_ERR_UNSUPPORTED, "residual_up needs an output width that is a multiple of 128 or divides 64 (got %d)", up_W);
+    if ((rc = make_tmap_2d_f16(&tmR, ip.residual, (uint64_t)ip.ldr, (uint64_t)ip.M_total / 4, (uint64_t)ip.ldr, 64, res_rows, true)) != B2_OK) return rc;
+  } else if (ip.residual) {
     if ((rc = make_tmap_2d_f16(&tmR, ip.residual, (uint64_t)ip.ldr, (uint64_t)ip.M_total, (uint64_t)ip.ldr, 64, 128, true)) != B2_OK) return rc;
   } else {
     tmR = tmC;
   }
+  CUtensorMap tmC2 = tmC;
+  if (ip.y2 && (rc = make_tmap_2d_f16(&tmC2, ip.y2, (uint64_t)ip.ldy, (uint64_t)ip.M_total, (uint64_t)ip.ldy, 64, 128, true)) != B2_OK) return rc;
   CUtensorMap tmA2 = tmA, tmB2 = tmB;
   if (L.k2 > 0) {
     if ((rc = make_tmap_2d_f16(&tmA2, L.a2, (uint64_t)L.k2, (uint64_t)ip.M_total, (uint64_t)L.lda2, 64, 128, true)) != B2_OK) return rc;
@@ -521,25 +530,27 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.relu = ip.relu;
   p.aff_ld = ip.aff_ld; p.aff_rows = ip.aff_rows;
   p.res_up = ip.res_up ? ip.residual : nullptr;
-  p.res_ld = ip.ldr; p.Wh = ip.up_W > 0 ? ip.up_W : 2; p.Hh = ip.up_H > 0 ? ip.up_H : 2;
+  p.res_ld = ip.ldr; p.Wh = up_W; p.Hh = ip.up_H > 0 ? ip.up_H : 2; p.res_rows = res_rows;
   p.fd_Wh = make_fastdiv(p.Wh); p.fd_Hh = make_fastdiv(p.Hh);
   p.res_pre = ip.res_pre;
+  p.dual = ip.y2 != nullptr; p.scale2 = ip.scale2; p.shift2 = ip.shift2; p.aff2_ld = ip.aff2_ld; p.aff2_rows = ip.aff2_rows > 0 ? ip.aff2_rows : 128;
   const int grid = p.tiles_total < sm_count() ? p.tiles_total : sm_count();
-  B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN, GAN>, dim3(grid), dim3(kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, p));
+  B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN, GAN>, dim3(grid), dim3(kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, tmC2, p));
   B2_CHECK_LAUNCH("pgemm_kernel");
   return B2_OK;
 }
 
 static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (g_gemm_algo == 0 && L.p.amode == AMODE_TMA && L.p.epi == EPI_TMA_F16 && !L.p.per_row) {
+    if (L.p.y2) return launch_pgemm<64, 1>(L, stream);       // second output: the 64-wide instance has a second staging tile
     if (L.p.res_up || L.p.res_pre)
       return L.p.ldy <= 64 ? launch_pgemm<64, 1>(L, stream) : launch_pgemm<128, 1>(L, stream);
     return L.p.ldy <= 64 ? launch_pgemm<64, 0>(L, stream) : launch_pgemm<128, 0>(L, stream);
   }
   if (L.p.aff_ld)
     return set_error(B2_ERR_UNSUPPORTED, "per-sample affine is implemented by the slab convolution and the persistent GEMM only");
-  if (L.p.res_up || L.p.res_pre)
-    return set_error(B2_ERR_UNSUPPORTED, "upsampled / pre-scale residuals are implemented by the persistent GEMM (1x1 convolutions) only");
+  if (L.p.res_up || L.p.res_pre || L.p.y2)
+    return set_error(B2_ERR_UNSUPPORTED, "upsampled / pre-scale residuals and second outputs are implemented by the persistent GEMM (1x1 convolutions, fp16) only");
   // 64-wide tiles for narrow outputs, 128 otherwise
   const int width = (L.p.epi == EPI_TMA_F16) ? L.p.ldy : L.p.Ncols;
   if (width <= 64) return launch_igemm<64>(L, stream);
@@ -637,6 +648,13 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   p.epi = a->out_f32 ? EPI_DIRECT_F32 : EPI_TMA_F16;
   p.aff_ld = a->aff_ld;
   p.res_up = a->residual_up; p.res_pre = a->residual_pre; p.up_H = p.Ho; p.up_W = p.Wo;
+  p.y2 = a->y2; p.scale2 = a->scale2; p.shift2 = a->shift2; p.aff2_ld = a->aff2_ld; p.aff2_rows = p.To * p.Ho * p.Wo;
+  if (a->y2) {
+    B2_CHECK_ARG(a->scale2 && a->shift2 && a->aff2_ld >= a->K && !a->out_f32 && a->kt * a->kh * a->kw == 1,
+                 "second output needs scale2 / shift2 (fp32 [N][aff2_ld >= K]) and a 1x1 convolution with fp16 output");
+    if (p.aff2_rows % 128 != 0)
+      return set_error(B2_ERR_UNSUPPORTED, "second output with a per-sample affine needs To*Ho*Wo %% 128 == 0 (got %d)", p.aff2_rows);
+  }
   p.aff_rows = p.To * p.Ho * p.Wo;
   if (a->aff_ld && p.aff_rows % 128 != 0)
     return set_error(B2_ERR_UNSUPPORTED, "per-sample affine on a 1x1x1 convolution needs To*Ho*Wo %% 128 == 0 (got %d)", p.aff_rows);
@@ -708,6 +726,11 @@ static int gemm_common(const b2_gemm_args* g, const void* a2, int lda2, const vo
                                                      !g->out_f32 && !g->per_row)),
                "bad per-sample affine (pitch %d, rows per sample %d)", g->aff_ld, g->aff_rows);
   p.aff_ld = g->aff_ld; p.aff_rows = g->aff_rows;
+  if (g->d2) {
+    B2_CHECK_ARG(g->scale2 && g->shift2 && g->aff2_ld >= g->N && g->aff2_rows > 0 && g->aff2_rows % 128 == 0 && !g->out_f32 && !g->per_row,
+                 "second output needs scale2 / shift2 (fp32 [M / aff2_rows][aff2_ld >= N], aff2_rows %% 128 == 0) and fp16 output");
+    p.y2 = g->d2; p.scale2 = g->scale2; p.shift2 = g->shift2; p.aff2_ld = g->aff2_ld; p.aff2_rows = g->aff2_rows;
+  }
   p.x = reinterpret_cast<const __half*>(g->a);
   L.a_mat = g->a; L.lda = g->lda; L.a_cols = g->Kd;
   L.w = g->b; L.ldb = g->ldb; L.b_cols = g->Kd;

@@ -157,6 +157,41 @@ __global__ void tanh_nhwc_to_nchw_kernel(const __half* __restrict__ x, int ldx, 
   }
 }
 
+// RGB head, second half: the 3x3 convolution to K <= 4 channels was split into a 1x1 GEMM that produces, for every
+// pixel q and tap (dh, dw), the partial products P[q][(dh*3 + dw)*4 + k] = sum_c x[q][c] * w[k][c][dh][dw] (one tensor
+// core pass over x with 36 useful columns instead of 9 shifted passes with 3), and this gather:
+//   y[n][k][h][w] = tanh(bias[k] + sum_{dh,dw} P[(n, h + dh - 1, w + dw - 1)][(dh*3 + dw)*4 + k])      (zero padding)
+// One thread per output pixel, nine 8-byte loads (a tap's k-quadruple), neighbours share sectors through L1/L2.
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+rgb_head_gather_tanh_kernel(const __half* __restrict__ P, int ldp, const float* __restrict__ bias, TOut* __restrict__ y,
+                            int H, int W, int K) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y;
+  const long long n = blockIdx.z;
+  if (w >= W) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dh = 0; dh < 3; ++dh) {
+    const int hh = h + dh - 1;
+    if (hh < 0 || hh >= H) continue;
+#pragma unroll
+    for (int dw = 0; dw < 3; ++dw) {
+      const int ww = w + dw - 1;
+      if (ww < 0 || ww >= W) continue;
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(P + ((n * H + hh) * W + ww) * ldp + (dh * 3 + dw) * 4));
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+    }
+  }
+  const long long S = (long long)H * W;
+  for (int k = 0; k < K; ++k) {
+    const float v2 = 2.f * fminf(fmaxf(acc[k] + __ldg(bias + k), -15.f), 15.f);
+    y[(n * K + k) * S + (long long)h * W + w] = static_cast<TOut>(1.f - __fdividef(2.f, __expf(v2) + 1.f));
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -201,6 +236,21 @@ int b2_ccbn_act_ndhwc(const void* x, int ldx, void* y, int ldy, const float* sca
   else
     ccbn_act_kernel<2><<<grid, block, 0, st>>>((const __half*)x, ldx / 8, (__half*)y, ldy / 8, scale, shift, lda, H, W, C / 8, relu, pixels);
   B2_CHECK_LAUNCH("ccbn_act");
+  return B2_OK;
+}
+
+int b2_rgb_head_gather_tanh(const void* partial, int ldp, const float* bias, void* y, int N, int H, int W, int K, int out_f32,
+                            void* stream) {
+  B2_CHECK_ARG(partial && bias && y && N > 0 && H > 0 && W > 0 && K >= 1 && K <= 4, "bad argument");
+  B2_CHECK_ARG(ldp >= 36 && ldp % 4 == 0 && (reinterpret_cast<uintptr_t>(partial) & 7) == 0, "partial products need a pitch >= 36, multiple of 4");
+  B2_CHECK_ARG(H <= 65535 && N <= 65535, "image height / batch exceed the grid limits");
+  const dim3 block(W >= 256 ? 256 : (W + 31) / 32 * 32), grid((W + block.x - 1) / block.x, H, N);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_f32)
+    rgb_head_gather_tanh_kernel<float><<<grid, block, 0, st>>>((const __half*)partial, ldp, bias, (float*)y, H, W, K);
+  else
+    rgb_head_gather_tanh_kernel<__half><<<grid, block, 0, st>>>((const __half*)partial, ldp, bias, (__half*)y, H, W, K);
+  B2_CHECK_LAUNCH("rgb_head_gather_tanh");
   return B2_OK;
 }
 

@@ -53,6 +53,10 @@ struct IgemmParams {
   int aff_ld, aff_rows;    // per-sample affine (persistent GEMM only): scale/shift row (m / aff_rows), pitch aff_ld; 0 = off
   int res_up, res_pre;     // persistent GEMM only: residual is the low-res tensor of an (up_H x up_W) image / added before the scale
   int up_H, up_W;
+  void* y2;                // persistent GEMM only: second output relu(y * scale2[m / aff2_rows] + shift2[...]) (same pitch as y)
+  const float* scale2;
+  const float* shift2;
+  int aff2_ld, aff2_rows;
 };
 
 template <int BN>

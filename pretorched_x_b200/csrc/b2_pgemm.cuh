@@ -37,14 +37,23 @@ struct PgemmParams {
   int has_residual;
   int relu;
   int aff_ld, aff_rows;     // > 0: scale/shift are [M / aff_rows][aff_ld] (per-sample affine; aff_rows % 128 == 0)
-  // Residual gathered from a LOW-resolution tensor (nearest-2x upsampling on the fly; GBlock skip path): output row
-  // m = (n, h, w) of an Hh x Wh image adds res_up[((n * Hh/2 + h/2) * Wh/2 + w/2) * res_ld + column].  The producer warp
-  // fills the residual tile with 16-byte cp.async gathers (one tile ahead, like the TMA path it replaces), the epilogue
-  // is unchanged.  pgemm_kernel<BN, 1> only.
+  // Residual taken from a LOW-resolution tensor (nearest-2x upsampling on the fly; GBlock skip path): output row
+  // m = (n, h, w) of an Hh x Wh image adds res_up[((n * Hh/2 + h/2) * Wh/2 + w/2) * res_ld + column].  The 128 output rows
+  // of a tile are a segment of one image row (Wh >= 128) or whole pairs of image rows (Wh <= 64), so their sources are
+  // res_rows = 64 (resp. 32) CONSECUTIVE rows of the low-res matrix: one TMA box per 64 columns, loaded a tile ahead like
+  // the plain residual, and the epilogue thread of row r reads row src(r) of that box.  pgemm_kernel<BN, 1> only.
   const __half* res_up;
   int res_ld, Wh, Hh;
+  int res_rows;             // rows of the low-res residual box: 64 (Wh >= 128) or 32
   FastDiv fd_Wh, fd_Hh;
   int res_pre;              // 1: y = act(scale * (acc + residual) + shift) instead of act(scale * acc + shift + residual)
+  // Second output (pgemm_kernel<BN, 1>): y2 = relu(y * scale2[m / aff2_rows][n] + shift2[...]) -- the class-conditional
+  // BatchNorm + ReLU of the NEXT block applied to this block's fp32 result, written through tmC2 in a second epilogue pass
+  // over the same accumulator (the HBM-bound tile loop has the issue slots to spare; no extra shared memory).
+  int dual;
+  const float* scale2;
+  const float* shift2;
+  int aff2_ld, aff2_rows;
 };
 
 template <int BN>
@@ -56,16 +65,19 @@ struct PgemmSmem {
   static constexpr int kRing = kPgStages * kStage;
   static constexpr int kResOff = kRing;                      // 2 residual tiles
   static constexpr int kCOff = kResOff + 2 * kTile;          // 1 C tile
-  static constexpr int kBarOff = kCOff + kTile;
-  static constexpr int kAffOff = kBarOff + 256;              // scale[BN], shift[BN] of the current tile
-  static constexpr int kTotal = kAffOff + 2 * BN * 4 + 1024;
+  static constexpr int kC2Off = kCOff + kTile;               // second C tile (second output; 64-wide instance only: the
+                                                             // 128-wide one has no room and falls back to re-using C)
+  static constexpr int kBarOff = kC2Off + (BN == 64 ? kTile : 0);
+  static constexpr int kAffOff = kBarOff + 256;              // scale[BN], shift[BN] (+ scale2[BN], shift2[BN]) of the current tile
+  static constexpr int kTotal = kAffOff + 4 * BN * 4 + 1024;
 };
 
 template <int BN, int GAN>   // GAN = 1: instance with the generator extras (res_up gather, res_pre); 0: the classic epilogue
 __global__ void __launch_bounds__(kPgThreads, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const PgemmParams p) {
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+             const __grid_constant__ CUtensorMap tmC2, const PgemmParams p) {
   using S = PgemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align<1024>(smem_raw);
@@ -83,8 +95,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < kPgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPgEpiWarps * 32);
-      mbar_init(&res_full[i], (GAN && p.res_up) ? 32 : 1);   // gathered residual: one cp.async arrival per producer lane
-      mbar_init(&res_empty[i], kPgEpiWarps * 32);
+      mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], kPgEpiWarps * 32);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
@@ -105,15 +116,21 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int rb = lt & 1;
       if (p.has_residual) {
         mbar_wait(&res_empty[rb], ((lt >> 1) & 1) ^ 1);
-        if (!(GAN && p.res_up)) {
-          if (elect_one()) {
-            mbar_expect_tx(&res_full[rb], S::kTile);
-#pragma unroll
-            for (int b = 0; b < BN / 64; ++b)
-              tma_load_2d(smem + S::kResOff + rb * S::kTile + b * (128 * 128), &tmR, &res_full[rb], n0 + b * 64, m0);
-          }
-          __syncwarp();
+        int r0 = m0;                                       // first row of the residual box
+        uint32_t rbytes = S::kTile;
+        if (GAN && p.res_up) {
+          const int t1 = fdiv(m0, p.fd_Wh), wq = m0 - t1 * p.Wh;
+          const int nq = fdiv(t1, p.fd_Hh), hq = t1 - nq * p.Hh;
+          r0 = (nq * (p.Hh >> 1) + (hq >> 1)) * (p.Wh >> 1) + (wq >> 1);
+          rbytes = static_cast<uint32_t>(p.res_rows) * BN * 2;
         }
+        if (elect_one()) {
+          mbar_expect_tx(&res_full[rb], rbytes);
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_2d(smem + S::kResOff + rb * S::kTile + b * (128 * 128), &tmR, &res_full[rb], n0 + b * 64, r0);
+        }
+        __syncwarp();
       }
       for (int kb = 0; kb < p.nkb + p.nkb2; ++kb, ++it) {
         const int s = it % kPgStages;
@@ -130,33 +147,6 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         __syncwarp();
-      }
-      if (GAN && p.res_up) {
-        // residual tile of this output tile, gathered from the low-res skip tensor (after the operand loads were queued:
-        // the epilogue needs it last).  Lane l fills rows l, l + 32, l + 64, l + 96 in the SWIZZLE_128B box layout the
-        // epilogue reads; columns >= Ncols and rows >= M are zero-filled.
-        const int lane = tid & 31;
-        const uint32_t dst0 = smem_u32(smem + S::kResOff + rb * S::kTile);
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-          const int r = lane + 32 * k, m = m0 + r;
-          const bool ok = m < p.M;
-          const __half* src = p.res_up;
-          if (ok) {
-            const int t1 = fdiv(m, p.fd_Wh), wq = m - t1 * p.Wh;
-            const int nq = fdiv(t1, p.fd_Hh), hq = t1 - nq * p.Hh;
-            src = p.res_up + (static_cast<size_t>(nq * (p.Hh >> 1) + (hq >> 1)) * (p.Wh >> 1) + (wq >> 1)) * p.res_ld + n0;
-          }
-          const uint32_t drow = dst0 + static_cast<uint32_t>(r) * 128u;
-          const uint32_t swz = static_cast<uint32_t>(r & 7);
-#pragma unroll
-          for (int ch = 0; ch < BN / 8; ++ch) {
-            const bool okc = ok && (n0 + ch * 8 < p.Ncols);
-            cp_async_16_cg(drow + (ch >> 3) * (128u * 128u) + ((static_cast<uint32_t>(ch & 7) ^ swz) << 4),
-                           okc ? static_cast<const void*>(src + ch * 8) : static_cast<const void*>(p.res_up), okc ? 16u : 0u);
-          }
-        }
-        cp_async_mbar_arrive_noinc(&res_full[rb]);
       }
     }
   } else if (warp == kPgEpiWarps + 1) {
@@ -192,11 +182,14 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ================================ epilogue ==========================================
     float* s_scale = reinterpret_cast<float*>(smem + S::kAffOff);
     float* s_shift = s_scale + BN;
+    float* s_scale2 = s_shift + BN;
+    float* s_shift2 = s_scale2 + BN;
     const int r = (warp & 3) * 32 + (tid & 31);        // accumulator row == TMEM lane
     const int half = warp >> 2;                        // which half of the tile's columns this warp handles
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t swz = static_cast<uint32_t>(r & 7);
-    uint8_t* c_stage = smem + S::kCOff;
+    uint8_t* c_stage0 = smem + S::kCOff;
+    uint8_t* c_stage1 = smem + (BN == 64 ? S::kC2Off : S::kCOff);
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++lt) {
       const int m0 = (tile / p.tiles_n) * 128, n0 = (tile % p.tiles_n) * BN;
@@ -204,62 +197,91 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&acc_full[ab], (lt >> 1) & 1);
       tc_fence_after();
       const uint8_t* r_stage = smem + S::kResOff + ab * S::kTile;
+      int rsrc = r;                                        // row of the residual box this thread's output row adds
+      if (GAN && p.res_up) {
+        if (p.Wh >= 128) rsrc = r >> 1;
+        else { const int hr = fdiv(r, p.fd_Wh); rsrc = (hr >> 1) * (p.Wh >> 1) + ((r - hr * p.Wh) >> 1); }
+      }
+      const uint32_t rswz = static_cast<uint32_t>(rsrc & 7);
       if (p.has_residual) mbar_wait(&res_full[ab], (lt >> 1) & 1);
-      // the previous tile's TMA store must have finished reading the staging tile before we overwrite it
-      if (tid == 0) tma_store_wait_read0();
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // (also: everyone is done with the previous tile's affine)
-      if (tid < BN) {
-        const int c = n0 + tid;
-        // per-sample affine (class-conditional BN of the consumer): a 128-row tile never straddles two samples
-        const size_t arow = p.aff_ld ? static_cast<size_t>(m0 / p.aff_rows) * p.aff_ld : 0;
-        s_scale[tid] = (c < p.Ncols) ? __ldg(&p.scale[arow + c]) : 0.f;
-        s_shift[tid] = (c < p.Ncols) ? __ldg(&p.shift[arow + c]) : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int npass = (GAN && p.dual) ? 2 : 1;
 #pragma unroll 1
-      for (int j = half * (BN / 64); j < (half + 1) * (BN / 64); ++j) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + lane_off + ab * BN + j * 32, v);
-        tmem_ld_wait();
-        const int box = j >> 1, chunk0 = (j & 1) * 4;
-        uint8_t* crow = c_stage + box * (128 * 128) + r * 128;
-        const uint8_t* rrow = r_stage + box * (128 * 128) + r * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t coff = (static_cast<uint32_t>(chunk0 + q) ^ swz) << 4;
-          uint4 rv = make_uint4(0, 0, 0, 0);
-          if (p.has_residual) rv = *reinterpret_cast<const uint4*>(rrow + coff);
-          const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-          uint32_t out[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int ci = j * 32 + q * 8 + e * 2;
-            const float2 rf = unpack_half2(rr[e]);
-            float a0 = __uint_as_float(v[q * 8 + e * 2]), a1 = __uint_as_float(v[q * 8 + e * 2 + 1]);
-            if (GAN && p.res_pre) {
-              a0 = (a0 + rf.x) * s_scale[ci] + s_shift[ci];
-              a1 = (a1 + rf.y) * s_scale[ci + 1] + s_shift[ci + 1];
-            } else {
-              a0 = a0 * s_scale[ci] + s_shift[ci] + rf.x;
-              a1 = a1 * s_scale[ci + 1] + s_shift[ci + 1] + rf.y;
-            }
-            if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            out[e] = pack_half2(a0, a1);
-          }
-          *reinterpret_cast<uint4*>(crow + coff) = make_uint4(out[0], out[1], out[2], out[3]);
+      for (int pass = 0; pass < npass; ++pass) {
+        // the previous TMA store must have finished reading the staging tile before we overwrite it (the second pass of
+        // the 64-wide instance has its own tile: nothing to wait for)
+        // Without a residual the two residual tiles are free: the C staging tile alternates between them and its own slot, and
+        // only the store of two tiles ago has to have drained -- the TMA store of tile i then overlaps the epilogue math of
+        // tile i + 1 (write-dominated layers, e.g. the 64 -> 256 expansions, were serialised on that drain).
+        const bool alt = !p.has_residual && !(GAN && p.dual);
+        uint8_t* c_stage = pass == 0 ? ((alt && (lt & 1)) ? smem + S::kResOff : c_stage0) : c_stage1;
+        if (pass == 0 || BN != 64) {
+          if (tid == 0) { if (alt) tma_store_wait_read1(); else tma_store_wait_read0(); }
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // (also: everyone is done with the previous tile's affine)
         }
-      }
-      // accumulator and residual buffers are free for tile lt + 2
-      tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
-      if (p.has_residual) mbar_arrive(&res_empty[ab]);
-      fence_proxy_async();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid == 0) {
+        if (pass == 0 && tid < BN) {
+          const int c = n0 + tid;
+          // per-sample affine (class-conditional BN of the consumer): a 128-row tile never straddles two samples
+          const size_t arow = p.aff_ld ? static_cast<size_t>(m0 / p.aff_rows) * p.aff_ld : 0;
+          s_scale[tid] = (c < p.Ncols) ? __ldg(&p.scale[arow + c]) : 0.f;
+          s_shift[tid] = (c < p.Ncols) ? __ldg(&p.shift[arow + c]) : 0.f;
+          if (GAN && p.dual) {
+            const size_t arow2 = static_cast<size_t>(m0 / p.aff2_rows) * p.aff2_ld;
+            s_scale2[tid] = (c < p.Ncols) ? __ldg(&p.scale2[arow2 + c]) : 0.f;
+            s_shift2[tid] = (c < p.Ncols) ? __ldg(&p.shift2[arow2 + c]) : 0.f;
+          }
+        }
+        if (pass == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll 1
+        for (int j = half * (BN / 64); j < (half + 1) * (BN / 64); ++j) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_off + ab * BN + j * 32, v);
+          tmem_ld_wait();
+          const int box = j >> 1, chunk0 = (j & 1) * 4;
+          uint8_t* crow = c_stage + box * (128 * 128) + r * 128;
+          const uint8_t* rrow = r_stage + box * (128 * 128) + rsrc * 128;
 #pragma unroll
-        for (int b = 0; b < BN / 64; ++b)
-          if (n0 + b * 64 < p.ldy) tma_store_2d(&tmC, c_stage + b * (128 * 128), n0 + b * 64, m0);
-        tma_store_commit();
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t coff = (static_cast<uint32_t>(chunk0 + q) ^ swz) << 4;
+            uint4 rv = make_uint4(0, 0, 0, 0);
+            if (p.has_residual) rv = *reinterpret_cast<const uint4*>(rrow + ((static_cast<uint32_t>(chunk0 + q) ^ rswz) << 4));
+            const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+            uint32_t out[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int ci = j * 32 + q * 8 + e * 2;
+              const float2 rf = unpack_half2(rr[e]);
+              float a0 = __uint_as_float(v[q * 8 + e * 2]), a1 = __uint_as_float(v[q * 8 + e * 2 + 1]);
+              if (GAN && p.res_pre) {
+                a0 = (a0 + rf.x) * s_scale[ci] + s_shift[ci];
+                a1 = (a1 + rf.y) * s_scale[ci + 1] + s_shift[ci + 1];
+              } else {
+                a0 = a0 * s_scale[ci] + s_shift[ci] + rf.x;
+                a1 = a1 * s_scale[ci + 1] + s_shift[ci + 1] + rf.y;
+              }
+              if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+              if (GAN && pass == 1) {                          // second output: next block's ccbn + ReLU on the fp32 value
+                a0 = fmaxf(a0 * s_scale2[ci] + s_shift2[ci], 0.f);
+                a1 = fmaxf(a1 * s_scale2[ci + 1] + s_shift2[ci + 1], 0.f);
+              }
+              out[e] = pack_half2(a0, a1);
+            }
+            *reinterpret_cast<uint4*>(crow + coff) = make_uint4(out[0], out[1], out[2], out[3]);
+          }
+        }
+        if (pass == npass - 1) {
+          // accumulator and residual buffers are free for tile lt + 2
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
+          if (p.has_residual) mbar_arrive(&res_empty[ab]);
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid == 0) {
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            if (n0 + b * 64 < p.ldy) tma_store_2d(pass == 0 ? &tmC : &tmC2, c_stage + b * (128 * 128), n0 + b * 64, m0);
+          tma_store_commit();
+        }
       }
     }
     if (tid == 0) tma_store_wait_read0();

@@ -195,7 +195,8 @@ def _out_dim(i, k, s, p):
 # ---------------------------------------------------------------------------------------------
 # convolution / dense
 # ---------------------------------------------------------------------------------------------
-def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, residual_up=False, residual_pre=False):
+def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, residual_up=False, residual_pre=False,
+         next_affine=None):
     """nn.Conv3d -> BatchNorm3d -> (+residual) -> ReLU in one kernel
     (resnet3D.py:91-106, 125-143, 176-185; r2plus1d.py:85-88; torchvision_models.py:449-451).
 
@@ -203,7 +204,9 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     per-channel one (class-conditional BatchNorm of the layer that follows the convolution, BigGAN GBlock).
     ``residual_up``: ``residual`` is the skip tensor at HALF the output resolution, nearest-2x upsampled on the fly (its
     first K channels are used: the GBlock's channel drop); ``residual_pre``: the residual joins before the affine,
-    y = act(scale * (conv + residual) + shift).  Both: 1x1 convolutions only."""
+    y = act(scale * (conv + residual) + shift).  ``next_affine=(scale2, shift2)`` (fp32 [N][pitch] views): also return
+    relu(y * scale2[n] + shift2[n]) -- the ccbn + ReLU that opens the next GBlock -- as a second Act, written by the same
+    kernel.  All three: 1x1 convolutions only."""
     if a.ld != pc.C:
         raise ValueError("activation pitch %d != packed filter pitch %d" % (a.ld, pc.C))
     kt, kh, kw = pc.k
@@ -226,6 +229,13 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     if (residual_up or residual_pre) and (residual is None or simt):
         raise ValueError("residual_up / residual_pre need a residual and the tensor-core path")
     args.residual_up, args.residual_pre = int(residual_up), int(residual_pre)
+    y2 = None
+    if next_affine is not None:
+        sc2, sh2 = next_affine
+        if simt or sc2.shape != sh2.shape or sc2.shape[0] != a.N or sc2.stride(0) != sh2.stride(0) or sc2.shape[1] < pc.K:
+            raise ValueError("next_affine must be two fp32 [N][>=K] views with the same pitch")
+        y2 = torch.empty_like(y)
+        args.y2, args.scale2, args.shift2, args.aff2_ld = _ptr(y2), _ptr(sc2), _ptr(sh2), sc2.stride(0)
     args.kt, args.kh, args.kw = kt, kh, kw
     args.st, args.sh, args.sw = pc.s
     args.pt, args.ph, args.pw = pc.p
@@ -242,15 +252,18 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     fn = lib.b2_conv_ndhwc_fprop_simt if simt else lib.b2_conv_ndhwc_fprop
     taps = kt * kh * kw
     flops = 2.0 * M * pc.K * pc.Cin * taps                     # algorithmic (padding taps included)
-    nbytes = 2.0 * (a.M * a.C + M * pc.K * (2 if residual is not None else 1) + pc.K * pc.Cin * taps)
-    desc = "conv %dx%dx%d s%s C%d->%d M=%d%s" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, M, " up2" if pc.up else "")
+    res_rows = 0 if residual is None else (M // 4 if residual_up else M)
+    nbytes = 2.0 * (a.M * a.C + M * pc.K * (2 if y2 is not None else 1) + res_rows * pc.K + pc.K * pc.Cin * taps)
+    desc = "conv %dx%dx%d s%s C%d->%d M=%d%s%s" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, M, " up2" if pc.up else "",
+                                                  " +next" if y2 is not None else "")
     with _timed("conv", desc, flops, nbytes):
         _lib.check(fn(ctypes.byref(args), _stream()), "b2_conv_ndhwc_fprop")
-    return Act(y, a.N, To, Ho, Wo, pc.K)
+    out = Act(y, a.N, To, Ho, Wo, pc.K)
+    return (out, Act(y2, a.N, To, Ho, Wo, pc.K)) if y2 is not None else out
 
 
 def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=False, out=None, out_f32=False,
-         accumulate=False, second=None, aff_rows=0):
+         accumulate=False, second=None, aff_rows=0, next_affine=None):
     """D[M][N] = act(scale * A[M][Kd] . B[N][Kd]^T + shift + residual) on tcgen05 (b2_gemm_f16).
     ``second=(A2, B2, K2)`` adds A2[M][K2] . B2[N][K2]^T into the same accumulator (b2_gemm2_f16)."""
     dev = a2d.device
@@ -267,6 +280,14 @@ def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=Fa
     g.per_row, g.relu, g.out_f32, g.accumulate = int(per_row), int(relu), int(out_f32), int(accumulate)
     if aff_rows:                      # per-sample affine: scale/shift are fp32 [M / aff_rows][pitch] views
         g.aff_ld, g.aff_rows = scale.stride(0), int(aff_rows)
+    if next_affine is not None:       # (scale2, shift2, rows per sample): second output relu(D * scale2 + shift2), returned too
+        sc2, sh2, rows2 = next_affine
+        out2 = torch.empty_like(out)
+        g.d2, g.scale2, g.shift2, g.aff2_ld, g.aff2_rows = _ptr(out2), _ptr(sc2), _ptr(sh2), sc2.stride(0), int(rows2)
+        with _timed("gemm", "gemm M=%d N=%d K=%d +next" % (M, N, Kd), 2.0 * M * N * Kd,
+                    2.0 * (M * Kd + N * Kd) + 2.0 * out.element_size() * M * N + (2.0 * M * N if residual is not None else 0.0)):
+            _lib.check(_lib.load().b2_gemm_f16(ctypes.byref(g), _stream()), "b2_gemm_f16")
+        return out, out2
     if second is not None:
         a2, b2, k2 = second
         with _timed("gemm", "gemm2 M=%d N=%d K=%d+%d" % (M, N, Kd, k2), 2.0 * M * N * (Kd + k2),
@@ -454,4 +475,17 @@ def tanh_to_nchw(a, out_dtype=torch.float32):
     with _timed("tanh", "tanh->nchw C%d px=%d" % (a.C, a.M), 0.0, a.M * (2.0 * a.ld + y.element_size() * a.C)):
         _lib.check(_lib.load().b2_tanh_nhwc_to_nchw(_ptr(a.data), a.ld, _ptr(y), a.N, a.C, S, int(out_dtype == torch.float32),
                                                    _stream()), "b2_tanh_nhwc_to_nchw")
+    return y
+
+
+def rgb_head(partial, bias, N, H, W, K=3, out_dtype=torch.float32):
+    """Second half of the split RGB head: gather the per-tap partial products of the 1x1 GEMM (fp16 [N*H*W][>=36], column
+    tap*4 + k), add the bias, tanh, write NCHW images (see b2_rgb_head_gather_tanh)."""
+    if out_dtype not in (torch.float32, torch.float16):
+        raise ValueError("images are written as fp32 or fp16")
+    y = torch.empty((N, K, H, W), dtype=out_dtype, device=partial.device)
+    M = N * H * W
+    with _timed("tanh", "rgb gather+tanh px=%d" % M, 0.0, M * (2.0 * 36 + y.element_size() * K)):
+        _lib.check(_lib.load().b2_rgb_head_gather_tanh(_ptr(partial), partial.stride(0), _ptr(bias), _ptr(y), N, H, W, K,
+                                                      int(out_dtype == torch.float32), _stream()), "b2_rgb_head_gather_tanh")
     return y

@@ -139,7 +139,8 @@ def test_conv3x3_of_upsampled_image_without_materialising_it(dev, shape, affine)
     assert rel(to_nchw(out), want) <= 3e-3
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 16, 16, 128, 200), (3, 32, 8, 8, 64, 64), (1, 128, 64, 128, 32, 96), (2, 16, 6, 10, 24, 24)])
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16, 128, 200), (3, 32, 8, 8, 64, 64), (1, 128, 64, 128, 32, 96), (2, 16, 6, 10, 24, 24),
+                                   (3, 64, 64, 64, 64, 72), (1, 32, 4, 256, 40, 40), (5, 16, 4, 4, 16, 16)])
 @pytest.mark.parametrize("pre", [False, True])
 def test_conv1x1_with_upsampled_skip(dev, shape, pre):
     """GBlock closing convolution: conv1x1(t) + upsample(x[:, :K]) with x read at low resolution by the epilogue
@@ -152,6 +153,10 @@ def test_conv1x1_with_upsampled_skip(dev, shape, pre):
     pc = ops.PackedConv(w.cuda(), None, None, (1, 1, 1), (0, 0, 0), in_pitch=C)
     pc.scale = (torch.rand(K, generator=g) + 0.5).cuda()
     pc.shift = torch.randn(K, generator=g).cuda()
+    if W % 128 != 0 and 64 % W != 0:          # a tile's sources must be consecutive low-res rows: refused, not mis-added
+        with pytest.raises(RuntimeError, match="multiple of 128 or divides 64"):
+            ops.conv(nhwc(t), pc, residual=nhwc(x), relu=True, residual_up=True, residual_pre=pre)
+        return
     out = ops.conv(nhwc(t), pc, residual=nhwc(x), relu=True, residual_up=True, residual_pre=pre)
     acc = F.conv2d(t.float(), w.half().float())
     skip = F.interpolate(x.float()[:, :K], scale_factor=2)
@@ -179,6 +184,46 @@ def test_conv1x1_with_per_sample_affine(dev, shape):
         ops.conv(nhwc(x2), pc, relu=True, sample_affine=(sc[:2], sh[:2]))
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 24, 40), (1, 64, 9, 300), (3, 16, 5, 7)])
+def test_split_rgb_head(dev, shape):
+    """3x3 conv to RGB as a 1x1 GEMM to per-tap partial products + gather-sum + bias + tanh (b2_rgb_head_gather_tanh)."""
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, C, H, W, generator=g).half()
+    w = torch.randn(3, C, 3, 3, generator=g) / (3 * C ** 0.5)
+    b = torch.randn(3, generator=g)
+    hw = torch.zeros(40, C, dtype=torch.float16)
+    for tap in range(9):
+        hw[tap * 4:tap * 4 + 3] = w[:, :, tap // 3, tap % 3].half()
+    a = nhwc(x)
+    part = ops.gemm(a.data, hw.cuda(), torch.ones(40).cuda(), torch.zeros(40).cuda(), a.M, 40, a.ld)
+    want = torch.tanh(F.conv2d(x.float(), w.half().float(), b, 1, 1))
+    for dt in (torch.float32, torch.float16):
+        img = ops.rgb_head(part, b.cuda(), N, H, W, 3, dt)
+        assert img.shape == (N, 3, H, W) and img.dtype == dt
+        assert (img.float().cpu() - want).abs().max().item() <= 3e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 16, 16, 128), (3, 256, 16, 8, 64), (1, 32, 32, 32, 200)])
+@pytest.mark.parametrize("up", [False, True])
+def test_conv1x1_with_second_output(dev, shape, up):
+    """conv4 of a GBlock writing h + skip AND relu(ccbn1_next(h + skip)) (b2_conv_args.y2) from one accumulator."""
+    N, C, H, W, K = shape
+    g = torch.Generator().manual_seed(12)
+    t = torch.randn(N, C, H, W, generator=g).half()
+    x = torch.randn(N, K + 8, H // 2, W // 2, generator=g).half() if up else torch.randn(N, K, H, W, generator=g).half()
+    w = torch.randn(K, C, 1, 1, generator=g) / C ** 0.5
+    b = torch.randn(K, generator=g)
+    aff = torch.randn(N, 2 * K + 8, generator=g).cuda()
+    sc2, sh2 = aff[:, :K], aff[:, K + 8:]
+    pc = ops.PackedConv(w.cuda(), b.cuda(), None, (1, 1, 1), (0, 0, 0), in_pitch=C)
+    out, nxt = ops.conv(nhwc(t), pc, residual=nhwc(x), residual_up=up, next_affine=(sc2, sh2))
+    skip = F.interpolate(x.float()[:, :K], scale_factor=2) if up else x.float()
+    want = F.conv2d(t.float(), w.half().float(), b) + skip
+    want2 = F.relu(want * sc2.cpu().view(N, K, 1, 1) + sh2.cpu().view(N, K, 1, 1))
+    assert rel(to_nchw(out), want) <= 3e-3 and rel(to_nchw(nxt), want2) <= 3e-3
+
+
 def rms(got, want):
     return ((got.double() - want.double()).pow(2).mean().sqrt() / want.double().pow(2).mean().sqrt().clamp_min(1e-12)).item()
 
@@ -189,12 +234,14 @@ def run_case(model, sd, z, labels, res, ch, dev, fuse_output_bn=True):
         want = OB.generator_forward(z, labels, sd, res, ch, stages=want_stages)
         twin = OB.generator_forward(z, labels, sd, res, ch, stages=twin_stages, storage=OB.fp16_storage)
         got = biggan_engine.generator_forward(model.to(dev), z.to(dev), labels.to(dev), stages=got_stages,
-                                              fuse_output_bn=fuse_output_bn)
+                                              fuse_output_bn=fuse_output_bn, split_head=fuse_output_bn,
+                                              dual_output=not fuse_output_bn)
     torch.cuda.synchronize()
     assert got.shape == want.shape and got.dtype == torch.float32
     report = []
     last = "stage%d" % (len(model.blocks) - 1)
-    assert set(want_stages) - set(got_stages) == ({last} if fuse_output_bn else set())   # fused tail: raw last stage never exists
+    # fused tail: the raw last stage and the pre-tanh tensor never exist (output BN in conv4's epilogue, split RGB head)
+    assert set(want_stages) - set(got_stages) == ({last, "pre_tanh"} if fuse_output_bn else set())
     for k in got_stages:
         g = to_nchw(got_stages[k])
         e_max, e_rms = rel(g, want_stages[k]), rms(g, want_stages[k])
