@@ -258,7 +258,11 @@ def run_ours(args, rank, world, local):
     second = None
     if not args.no_biggan:
         torch.cuda.empty_cache()
-        second = run_biggan(args, rank, world, local, emit=False, steps=max(5, min(args.steps, 20)))
+        try:
+            second = run_biggan(args, rank, world, local, emit=False, steps=max(5, min(args.steps, 20)))
+        except Exception as exc:          # the contract's line (resnet3d50) must survive a failure of the secondary workload
+            second = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            print("secondary BigGAN measurement failed: %s" % second["error"], file=sys.stderr)
         torch.cuda.empty_cache()
     if rank != 0:
         return
@@ -336,8 +340,9 @@ def run_ours(args, rank, world, local):
     }
     if second is not None:
         # the other half of BASELINE.json's metric, measured in the same run (full line: --workload biggan256)
-        line["biggan256"] = {k: second[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "e2e", "gpu_launches",
-                                                    "roofline", "cpu_baseline", "config")}
+        line["biggan256"] = second if "error" in second else {
+            k: second[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "e2e", "gpu_launches", "roofline",
+                                   "cpu_baseline", "config")}
     print(json.dumps(line), flush=True)
 
 
