@@ -39,10 +39,22 @@ def short(name):
     return n.replace("(int)", "")[:44]
 
 
+_SCALE = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+
+
 def raw_metrics(path):
+    """metric -> value of the first profiled launch, bytes normalised to MB and times to us (ncu picks the unit per column)."""
     rows = list(csv.reader(open(path)))
-    hdr, vals = rows[0], rows[2]
-    return dict(zip(hdr, vals))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    out = {}
+    for h, u, v in zip(hdr, units, vals):
+        if u in _SCALE:
+            try:
+                v = "%.6f" % (float(v.replace(",", "")) * _SCALE[u])
+            except ValueError:
+                pass
+        out[h] = v
+    return out
 
 
 def fnum(x):
@@ -88,13 +100,17 @@ def main():
             ("sm_throughput_pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
             ("l2_hit_pct", "lts__t_sector_hit_rate.pct"), ("l1tex_pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed")]
     top_lines = []
-    traffic = {}
+    traffic, gan_traffic = {}, {}
     captures = [("ncu_stem", "stemconv<64>  conv 7x7x7 s122 C3->64, B=32 16x224x224", "conv 7x7x7 s122 C3->64 M=6422528"),
                 ("ncu_slab64", "slabconv<64>  conv 3x3x3 C64->64, 32x8x56x56", "conv 3x3x3 s111 C64->64 M=802816"),
                 ("ncu_slab128", "slabconv<128> conv 3x3x3 C128->128, 32x4x28x28", "conv 3x3x3 s111 C128->128 M=100352"),
                 ("ncu_pgemm_64_256", "pgemm<128>    conv 1x1x1 C64->256, 32x8x56x56 (no residual)", "conv 1x1x1 s111 C64->256 M=802816"),
                 ("ncu_slab_r2p1d_144", "slabconv<0>   conv 1x3x3 C64->144 (runtime N=144), 16x16x28x28", None),
-                ("ncu_attention", "attention_online<256>  B=8 N=6272 d=256 dv=256", None)]
+                ("ncu_attention", "attention_online<256>  B=8 N=6272 d=256 dv=256", None),
+                ("ncu_gan_conv64", "slabconv<64>  BigGAN conv 3x3 C64->64 at 256x256, 64 images, per-sample affine", "gan:conv 1x3x3 s111 C64->64 M=16777216"),
+                ("ncu_gan_upconv64", "slabconv<64>  BigGAN conv 3x3 of the upsampled image (4 folded 2x2 phases) C64->64, 128->256, 64 images", "gan:conv 1x3x3 s111 C64->64 M=16777216 up2"),
+                ("ncu_gan_conv128", "slabconv<128> BigGAN conv 3x3 C128->128 at 128x128, 64 images", "gan:conv 1x3x3 s111 C128->128 M=4194304"),
+                ("ncu_gan_pgemm_64_128", "pgemm<128>    BigGAN conv 1x1 C64->128 at 256x256, 64 images", "gan:conv 1x1x1 s111 C64->128 M=16777216")]
     with open(os.path.join(PR, "ncu_top_%s.csv" % TAG), "w") as f:
         f.write("capture," + ",".join(k for k, _ in want) + "\n")
         for fn, label, desc in captures:
@@ -108,11 +124,14 @@ def main():
             top_lines.append("%-62s %8.1f us  dram R %7.1f W %7.1f MB (%4.1f%%)  tensor-pipe %4.1f%%  L2 hit %4.1f%%  regs %3d" % (
                 label, d["duration_us"], d["dram_read_MB"], d["dram_write_MB"], d["dram_pct"], d["tensor_pipe_active_pct"],
                 d["l2_hit_pct"], int(d["regs"])))
-            if desc:
+            if desc and desc.startswith("gan:"):      # captured on 64 images; the bench runs 256: per-launch traffic x 4
+                gan_traffic[desc[4:]] = int((d["dram_read_MB"] + d["dram_write_MB"]) * 1e6) * 4
+            elif desc:
                 traffic[desc] = int((d["dram_read_MB"] + d["dram_write_MB"]) * 1e6)
     json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full --clock-control none` "
-                           "captures of single layers at the BASELINE shapes (tools/conv_micro.py, tools/evidence.sh)",
-               "B=32": traffic}, open(os.path.join(PR, "ncu_traffic_%s.json" % TAG), "w"), indent=1)
+                           "captures of single layers at the BASELINE shapes (tools/conv_micro.py, tools/gan_micro.py, "
+                           "tools/evidence.sh); the BigGAN layers were captured on 64 images and scaled x4 to the B=256 launch",
+               "B=32": traffic, "biggan B=256": gan_traffic}, open(os.path.join(PR, "ncu_traffic_%s.json" % TAG), "w"), indent=1)
 
     # ---- README body (numbers only; prose lives in profiles/README_<tag>.md, regenerated here) ----
     rl, e2e, cb = bench["roofline"], bench["e2e"], bench.get("cpu_baseline") or {}
@@ -148,6 +167,33 @@ def main():
     out.extend(launch_txt)
     out.append("```\n\n## ncu --set full, one launch per kernel at the BASELINE shapes\n\n```")
     out.extend(top_lines)
+    # ---- BigGAN-deep-256 (BASELINE configs[4]) ----
+    try:
+        bg = last_json_line(read("biggan.json"))
+        json.dump(bg, open(os.path.join(PR, "bench_biggan256_%s.json" % TAG), "w"), indent=1)
+        shutil.copy(os.path.join(EV, "biggan_layers.txt"), os.path.join(PR, "layers_biggan256_%s.txt" % TAG))
+        bref = last_json_line(read("biggan_reference.json"))
+        json.dump(bref, open(os.path.join(PR, "bench_biggan256_reference_%s.json" % TAG), "w"), indent=1)
+        brl, be = bg["roofline"], bg["e2e"]
+        out.append("```\n\n## BigGAN-deep-256 generator (`python bench.py --workload biggan256`; also the `biggan256` key of the default line)\n")
+        out.append("* value **%.0f images/s** (%.2f ms per %d-image step, CUDA-graph replay), e2e **%.0f images/s** (%.0f KB H2D + "
+                   "%.0f MB D2H per step); %.1f GFLOP/image algorithmic -> %.0f TFLOP/s = %.1f %% of the sustained tensor peak for the "
+                   "whole step." % (bg["value"], bg["ms_per_step"], bg["config"]["global_batch"], be["value"], be["h2d_bytes_per_step"] / 1e3,
+                                    be["d2h_bytes_per_step"] / 1e6, brl["whole_step_tflops"] * 1e3 / bg["value"], brl["whole_step_tflops"],
+                                    100 * brl["whole_step_frac"]))
+        out.append("* dominant kernel `%s`: %.0f TFLOP/s = %.1f %% of peak, %.1f %% of the step, DRAM traffic %s B for %.0f B algorithmic; "
+                   "HBM-bound helper passes (%s): %.0f GB/s of %.0f, %.1f %% of the step." % (
+                       brl["kernel"], brl["achieved"], 100 * brl["frac"], 100 * brl["share_of_step"], brl["traffic"], brl["algorithmic_bytes"],
+                       brl["hbm_passes"]["kernels"], brl["hbm_passes"]["achieved_gbs"] or 0, brl["hbm_passes"]["peak_gbs"],
+                       100 * brl["hbm_passes"]["share_of_step"]))
+        cbb = bg.get("cpu_baseline") or {}
+        if cbb:
+            out.append("* cpu_baseline: %.2f %s on %s host threads (%s); reference arm: %.2f %s." % (
+                cbb["value"], cbb["unit"], cbb["cores"], cbb["sample"], bref["value"], bref["unit"]))
+        out.append("\n```")
+        out.append(read("biggan_layers.txt").rstrip())
+    except (OSError, KeyError, SystemExit) as exc:
+        out.append("```\n\n(BigGAN evidence missing: %s)\n\n```" % exc)
     out.append("```\n\n## Other BASELINE configs (parity-test cases; device-resident, CUDA-graph replay, 1 GPU)\n\n```")
     out.append(read("others.jsonl").rstrip())
     out.append("```\n\nPer-layer tables of those runs: `others_layers_%s.txt`.\n" % TAG)
