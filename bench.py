@@ -581,6 +581,9 @@ def main():
             run_reference_arm(args, rank, world)
         return
     if world > 1:
+        # the box exports NCCL_DEBUG=VERSION, which makes NCCL print its version banner on stdout in front of the JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         from pretorched_x_b200 import parallel
         parallel.init_from_env(backend="nccl")
     if args.workload == "biggan256":
