@@ -181,9 +181,13 @@ def main():
                    "whole step." % (bg["value"], bg["ms_per_step"], bg["config"]["global_batch"], be["value"], be["h2d_bytes_per_step"] / 1e3,
                                     be["d2h_bytes_per_step"] / 1e6, brl["whole_step_tflops"] * 1e3 / bg["value"], brl["whole_step_tflops"],
                                     100 * brl["whole_step_frac"]))
-        out.append("* dominant kernel `%s`: %.0f TFLOP/s = %.1f %% of peak, %.1f %% of the step, DRAM traffic %s B for %.0f B algorithmic; "
-                   "HBM-bound helper passes (%s): %.0f GB/s of %.0f, %.1f %% of the step." % (
-                       brl["kernel"], brl["achieved"], 100 * brl["frac"], 100 * brl["share_of_step"], brl["traffic"], brl["algorithmic_bytes"],
+        if brl["bound"] == "tensor" and brl["algorithmic_bytes"] / (brl["ms_per_launch"] * 1e-3) / 1e9 > 0.25 * brl["hbm_passes"]["peak_gbs"]:
+            # line produced before bench.py classified the dominant kernel by its arithmetic intensity: a 1x1 layer is HBM-bound
+            gbs = brl["algorithmic_bytes"] / (brl["ms_per_launch"] * 1e-3) / 1e9
+            brl = dict(brl, bound="hbm", achieved=gbs, unit="GB/s", frac=gbs / brl["hbm_passes"]["peak_gbs"])
+        out.append("* dominant kernel `%s` (%s-bound): %.0f %s = %.1f %% of the measured peak, %.1f %% of the step, DRAM traffic %s B for %.0f B "
+                   "algorithmic; HBM-bound helper passes (%s): %.0f GB/s of %.0f, %.1f %% of the step." % (
+                       brl["kernel"], brl["bound"], brl["achieved"], brl["unit"], 100 * brl["frac"], 100 * brl["share_of_step"], brl["traffic"], brl["algorithmic_bytes"],
                        brl["hbm_passes"]["kernels"], brl["hbm_passes"]["achieved_gbs"] or 0, brl["hbm_passes"]["peak_gbs"],
                        100 * brl["hbm_passes"]["share_of_step"]))
         cbb = bg.get("cpu_baseline") or {}
