@@ -496,7 +496,6 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
         a = agg.setdefault(r["desc"], dict(kind=r["kind"], ms=0.0, flops=0.0, bytes=0.0, n=0))
         a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["n"] += 1
     top_desc, top = max(((d, a) for d, a in agg.items() if a["kind"] in ("conv", "gemm", "attention")), key=lambda kv: kv[1]["ms"])
-    top_tflops = top["flops"] / (top["ms"] * 1e-3) / 1e12
     hbm_rows = [r for r in rows if r["kind"] in ("ccbn", "tanh", "maxpool")]
     hbm_ms = sum(r["ms"] for r in hbm_rows)
     traffic = None

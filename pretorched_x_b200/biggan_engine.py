@@ -32,7 +32,6 @@ How the pieces map:
   as its residual.
 """
 import torch
-import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops

@@ -124,3 +124,49 @@ def test_no_cpu_path():
         m.train()(torch.randn(1, 128), torch.zeros(1, dtype=torch.long))
     with pytest.raises(RuntimeError):
         m.blocks[0][0].conv1(torch.randn(1, 256, 4, 4))
+
+
+def test_stacked_ccbn_gemm_algebra(monkeypatch):
+    """Host logic of biggan_engine._pack, checked without a GPU: every conditional BatchNorm of the generator is an affine
+    map per (sample, channel) that ONE GEMM of the conditioning vector against the stacked, pre-folded gain / bias matrices
+    produces -- incl. the conv bias folded into the mean when the ccbn rides in a convolution's epilogue, and the fp16
+    hi/lo operand split ([y_hi | y_lo | y_hi] . [W_hi | W_hi | W_lo]^T) that keeps the gains at ~fp32 accuracy."""
+    from pretorched_x_b200 import biggan_engine as BE
+
+    class FakePacked:                                   # ops.PackedConv needs the CUDA library; the algebra under test does not
+        def __init__(self, w, bias, bn, stride, padding, in_pitch=None, upsample=False):
+            self.K, self.scale, self.shift = w.shape[0], None, None
+    monkeypatch.setattr(BE.ops, "PackedConv", FakePacked)
+
+    res, ch, ncls, B = 128, 16, 10, 3
+    model, sd, z, labels = OB.build_case(P.biggan_deep, res, ch, ncls, B)
+    with torch.no_grad():
+        pk = BE._pack(model, torch.device("cpu"))
+        y = OB.condition(z, labels, sd)                                      # [B][256] fp32
+        y_hi = y.half()
+        y_lo = (y - y_hi.float()).half()
+        y3 = torch.cat([y_hi, y_lo, y_hi], 1).double()                       # what b2_embed_concat(split=1) writes
+        aff = y3 @ pk.cond_w.double().t() * pk.cond_scale.double() + pk.cond_shift.double()      # the GEMM + its epilogue
+        assert pk.cond_w.shape == (pk.ncols, 3 * 256) and pk.ncols == 2 * sum(
+            b.bn1.output_size + 3 * b.bn2.output_size for st in model.blocks for b in st if hasattr(b, "conv4"))
+        g = torch.Generator().manual_seed(4)
+        worst = 0.0
+        for st_i, stage in enumerate(model.blocks):
+            for b_i, blk in enumerate(stage):
+                if not hasattr(blk, "conv4"):
+                    continue
+                bp = pk.blocks[id(blk)]
+                prev = [None, blk.conv1.bias if bp.fuse2 else None, blk.conv2.bias, blk.conv3.bias]
+                for k, (bn, pb) in enumerate(zip((blk.bn1, blk.bn2, blk.bn3, blk.bn4), prev)):
+                    o_s, o_t, C = bp.bn[k]
+                    x = torch.randn(B, C, 3, 3, generator=g) * 2 + 1                 # "accumulator" (before the conv bias)
+                    xin = x + (pb.detach().view(1, C, 1, 1) if pb is not None else 0)
+                    want = OB.ccbn(xin, y, sd, "blocks.%d.%d.bn%d" % (st_i, b_i, k + 1)).double()
+                    got = x.double() * aff[:, o_s:o_s + C].view(B, C, 1, 1) + aff[:, o_t:o_t + C].view(B, C, 1, 1)
+                    worst = max(worst, ((got - want).abs().max() / want.abs().max()).item())
+        assert worst <= 2e-5, worst                     # fp32 reference arithmetic is the floor; plain fp16 operands give ~1e-3
+        # first linear: rows permuted so that the GEMM output is already channels-last [B*16][C0]
+        C0 = model.arch["in_channels"][0]
+        h = (y.half().double() @ pk.lin_w.double()[:, :256].t() + pk.lin_b.double()).view(B, 16, C0).permute(0, 2, 1).reshape(B, C0, 4, 4)
+        want_h = torch.nn.functional.linear(y, OB.sn_weight(sd, "linear"), sd["linear.bias"]).view(B, C0, 4, 4)
+        assert ((h - want_h.double()).abs().max() / want_h.abs().max()).item() <= 2e-3
