@@ -3,19 +3,19 @@
 There is no reference code for this path: the block bodies below implement the published
 GBlock / SAGAN-attention / class-conditional-BN arithmetic restated in ``oracle/biggan.py`` (test infrastructure), on the
 same hand-written kernels as the video path -- the persistent 1x1 GEMM, the slab 3x3 convolution, the fused attention --
-plus three HBM-bound helpers in ``csrc/b2_gan.cu``.
+plus the HBM-bound helpers in ``csrc/b2_gan.cu``.
 
 How the pieces map:
 
 * **All 48+ class-conditional BatchNorms of a forward come out of ONE GEMM.**  ``ccbn(x, y) = (x - mu) * rstd * (1 + Wg y)
   + Wb y`` is an affine map per (sample, channel): ``scale = rstd + (rstd * Wg) y`` and ``shift = (Wb - m * rstd * Wg) y
   - m * rstd`` are both linear in the conditioning vector y, so the (spectrally normalised) gain / bias matrices of every
-  ccbn are stacked, with ``rstd`` and the mean folded in, into one fp16 matrix ``[2 * sum(C)][256]`` and a single
+  ccbn are stacked, with ``rstd`` and the mean folded in, into one fp16 matrix ``[2 * sum(C)][3 * 256]`` and a single
   tcgen05 GEMM with fp32 output produces every scale and shift of the network: ``aff[B][2 * sum(C)]`` (operands split
   into fp16 hi + lo parts, K = 3 x 256, so the gains carry ~22 bits).
 * ccbn -> ReLU that FOLLOWS a convolution is that convolution's epilogue (per-sample affine, ``b2_conv_args.aff_ld``):
-  conv2 carries bn3, conv3 carries bn4, conv1 carries bn2 in the non-upsampling blocks; the conv bias is folded into the
-  shift (``m = mean - bias``).  bn1 (its input also feeds the skip path) is one ``b2_ccbn_act_ndhwc`` pass.
+  conv2 carries bn3, conv3 carries bn4, conv1 carries bn2 (from 16x16 images on: a 128-row tile must stay inside one
+  image); the conv bias is folded into the shift (``m = mean - bias``).  bn1 (its input also feeds the skip path) is one ``b2_ccbn_act_ndhwc`` pass.
 * The nearest-2x upsampling in front of conv2 is never materialised: a 3x3 convolution of an upsampled image is four
   2x2 convolutions of the low-res image (one per output phase, filters summed when packed), which the slab kernel runs
   as 4 x 4 taps with a strided output write -- 2.25x fewer MACs and a quarter of the input bytes.
@@ -26,6 +26,9 @@ How the pieces map:
   it is off by default; the stand-alone ``b2_ccbn_act_ndhwc`` pass runs at ~5 TB/s.
 * conv4's epilogue adds the skip path: channel drop = the residual pitch, and for the upsampling block the epilogue reads
   the LOW-res x and upsamples on the fly (``residual_up``), so ``upsample(x)`` is never written either.
+* Tail: the output BatchNorm + ReLU is folded into the last block's conv4 (``residual_pre``: the skip joins before the
+  affine), and the 3x3 convolution to RGB runs as one 1x1 GEMM to 9 taps x 4 partial-product columns followed by a gather
+  that also adds the bias, applies tanh and writes NCHW (``b2_rgb_head_gather_tanh``).
 * Spectral norm: weights are divided by sigma (one power iteration from the stored ``u0``) when they are packed.
 * Self-attention: theta and phi|g projections (zero-padded to the 64-column granularity of the attention kernel),
   2x2 max-pool of phi|g, the fused softmax(theta^T phi) g kernel, and the output 1x1 GEMM with gamma as its scale and x
