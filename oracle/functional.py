@@ -44,6 +44,9 @@ ARCHS = {
                                nonlocal_blocks=[0, 2, 3, 0]),
     # torchvision_models.py:484-492 (torchvision BasicBlock body)
     'resnet18': dict(family='resnet2d', block='basic', layers=[2, 2, 2, 2], shortcut='B'),
+    # resnext3D.py:224-252 (ResNeXtBottleneck: grouped 3x3x3 conv, expansion 2, planes 128..1024, head `fc`)
+    'resnext3d50': dict(family='resnext3d', block='resnext', layers=[3, 4, 6, 3], shortcut='B', cardinality=32),
+    'resnext3d101': dict(family='resnext3d', block='resnext', layers=[3, 4, 23, 3], shortcut='B', cardinality=32),
 }
 
 
@@ -122,6 +125,17 @@ def bottleneck(x, sd, p, family, shortcut, planes, stride, has_downsample):
     return F.relu(out)
 
 
+def resnext_bottleneck(x, sd, p, shortcut, planes, cardinality, stride, has_downsample):
+    """ResNeXtBottleneck.forward (resnext3D.py:101-122): 1x1x1 -> grouped 3x3x3 (groups = cardinality, stride s) -> 1x1x1
+    to planes * 2, BN after each, residual (type A / B as in resnet3D), ReLU."""
+    out = F.relu(_bn(_conv(x, sd, p + '.conv1'), sd, p + '.bn1'))
+    out = F.conv3d(out, sd[p + '.conv2.weight'], None, stride, 1, 1, cardinality)
+    out = F.relu(_bn(out, sd, p + '.bn2'))
+    out = _bn(_conv(out, sd, p + '.conv3'), sd, p + '.bn3')
+    out = out + _residual(x, sd, p, 'resnext3d', shortcut, planes * 2, stride, has_downsample)
+    return F.relu(out)
+
+
 def nonlocal_block(x, sd, p):
     """_NonLocalBlockND._embedded_gaussian (nonlocalnet.py:143-166), 3-D, no sub-sampling."""
     b, c = x.shape[0], x.shape[1]
@@ -192,17 +206,22 @@ def trunk(x, sd, arch, stages=None):
     spec = ARCHS[arch] if isinstance(arch, str) else arch
     family, shortcut = spec['family'], spec['shortcut']
     block_fn = bottleneck if spec['block'] == 'bottleneck' else basic_block
-    expansion = 4 if spec['block'] == 'bottleneck' else 1
+    expansion = {'bottleneck': 4, 'resnext': 2}.get(spec['block'], 1)
+    widths = (128, 256, 512, 1024) if spec['block'] == 'resnext' else (64, 128, 256, 512)     # resnext3D.py:134-137
     nl = nonlocal_positions(spec['layers'], spec['nonlocal_blocks']) if 'nonlocal_blocks' in spec else [[]] * 4
     x = stem(x, sd, family)
     if stages is not None:
         stages['maxpool'] = x
     inplanes = 64
-    for li, (planes, nblocks) in enumerate(zip((64, 128, 256, 512), spec['layers'])):
+    for li, (planes, nblocks) in enumerate(zip(widths, spec['layers'])):
         for bi in range(nblocks):
             stride = 2 if (li > 0 and bi == 0) else 1
             has_ds = bi == 0 and (stride != 1 or inplanes != planes * expansion)
             p = 'layer%d.%d' % (li + 1, bi)
+            if spec['block'] == 'resnext':
+                x = resnext_bottleneck(x, sd, p, shortcut, planes, spec['cardinality'], stride, has_ds)
+                inplanes = planes * expansion
+                continue
             x = block_fn(x, sd, p, 'resnet3d' if family in ('nonlocal', 'resnet2d') else family, shortcut, planes,
                          stride, has_ds)
             if bi in nl[li]:

@@ -98,6 +98,45 @@ def run_model_case(name, arch, kwargs, shape):
                                                          ",".join(hooked)))
 
 
+def run_resnext_cases():
+    """ResNeXt-3D (resnext3D.py; exported by pretorched/__init__.py:66-72): plain ``**kwargs`` factories and an ``fc`` head, so
+    the fixtures get their own kind and their own tests (tests/test_oracle_golden.py, tests/test_gpu_resnext.py)."""
+    for name, (arch, kwargs, shape) in {
+            "resnext3d50_b1_t8_64": ("resnext3d50", dict(num_classes=400), (1, 3, 8, 64, 64)),
+            # (cardinality != 32 is broken upstream: fc is sized cardinality * 32 * expansion, the trunk ends with 2048 channels)
+            "resnext3d18_a_b2_t8_64": ("resnext3d18", dict(num_classes=10, shortcut_type='A'), (2, 3, 8, 64, 64)),
+    }.items():
+        RL.load()
+        torch.manual_seed(SEED_INIT)
+        ref = RL.build(arch, **kwargs)
+        OF.randomize_bn_(ref, SEED_BN)
+        ref.eval()
+        x = OF.seeded_input(shape, SEED_INPUT)
+        hooked, handles = {}, []
+        for stage in ("maxpool", "layer1", "layer2", "layer3", "layer4"):
+            handles.append(getattr(ref, stage).register_forward_hook(
+                lambda m, i, o, stage=stage: hooked.__setitem__(stage, o.detach().clone())))
+        with torch.no_grad():
+            logits = ref(x)
+        for h in handles:
+            h.remove()
+        hooked["logits"] = logits
+        sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+        spec = dict(OF.ARCHS["resnext3d50"], layers={"resnext3d50": [3, 4, 6, 3], "resnext3d18": [2, 2, 2, 2]}[arch],
+                    shortcut=kwargs.get("shortcut_type", "B"), cardinality=kwargs.get("cardinality", 32))
+        stages = {}
+        with torch.no_grad():
+            out = OF.forward(x, sd, spec, stages)
+        for k, v in hooked.items():
+            assert torch.equal(stages[k], v), "oracle restatement differs from the reference at %s/%s" % (name, k)
+        assert torch.equal(out, logits)
+        torch.save(dict(kind="resnext", arch=arch, kwargs=kwargs, spec=spec, input_shape=tuple(shape),
+                        seeds=dict(init=SEED_INIT, bn=SEED_BN, input=SEED_INPUT), logits=logits.clone(),
+                        stages={k: summarize(v) for k, v in hooked.items()}, weight_digest=OF.state_digest(sd), n_state=len(sd),
+                        torch_version=torch.__version__), os.path.join(GOLDEN_DIR, name + ".pt"))
+        print("%-32s logits %s absmax %.4f  stages ok: %s" % (name, tuple(logits.shape), logits.abs().max(), ",".join(hooked)))
+
+
 def run_relation_cases():
     trn = RL.load_trn()
     # (a) single Relation, small and at the TRN-wired size (trn.py:230-233: T=8, F=2048, bottleneck 512)
@@ -215,6 +254,7 @@ def main():
     run_relation_cases()
     run_slowfast_cases()
     run_nlblock_cases()
+    run_resnext_cases()
 
 
 if __name__ == "__main__":

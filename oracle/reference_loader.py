@@ -69,6 +69,8 @@ def build(arch, **kwargs):
     pt = load()
     if arch.startswith("r2plus1d"):
         return getattr(load_r2plus1d(), arch)(**kwargs)
+    if arch.startswith("resnext3d"):                     # resnext3D.py:224-252: plain **kwargs factories, no `pretrained`
+        return getattr(pt, arch)(**kwargs)
     if arch.startswith("nonlocal"):
         return getattr(pt.models.nonlocalnet, arch)(pretrained=None, **kwargs)
     return getattr(pt, arch)(pretrained=None, **kwargs)

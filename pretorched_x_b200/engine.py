@@ -60,14 +60,18 @@ def _conv_geometry(conv):
 
 def packed_conv(conv, bn, in_pitch, stem=False, stride=None):
     """PackedConv for a plain nn.Conv3d / nn.Conv2d followed (optionally) by BatchNorm ``bn``."""
-    if conv.groups != 1 or any(d != 1 for d in conv.dilation):
-        raise NotImplementedError("grouped / dilated convolutions are outside the engine's scope")
+    if any(d != 1 for d in conv.dilation):
+        raise NotImplementedError("dilated convolutions are outside the engine's scope")
+    if conv.groups != 1 and stem:
+        raise NotImplementedError("grouped stem convolutions are outside the engine's scope")
     sig = _sig(conv.weight, conv.bias, *_bn_tensors(bn)) + (in_pitch, stem, id(bn), stride)
     cstride, padding = _conv_geometry(conv)
     if stride is None:
         stride = cstride
+    # grouped convolution (ResNeXt-3D, resnext3D.py:86-93): packed as the block-diagonal dense filter, see ops.dense_from_grouped
     return _cached(conv, "pc", sig,
-                   lambda: ops.PackedConv(conv.weight, conv.bias, bn, stride, padding, in_pitch=in_pitch, stem=stem))
+                   lambda: ops.PackedConv(ops.dense_from_grouped(conv.weight.detach(), conv.groups), conv.bias, bn, stride, padding,
+                                          in_pitch=in_pitch, stem=stem))
 
 
 def _is_stem_shape(conv):

@@ -3,8 +3,9 @@ restricted to the model families this engine implements."""
 from .resnet3d import pretrained_settings as resnet3d_settings
 from .nonlocalnet import pretrained_settings as nonlocal_settings
 from .resnet2d import pretrained_settings as resnet2d_settings
+from .resnext3d import pretrained_settings as resnext3d_settings      # settings.py:18,36 of the reference
 
-all_settings = [resnet2d_settings, resnet3d_settings, nonlocal_settings]
+all_settings = [resnet2d_settings, resnet3d_settings, resnext3d_settings, nonlocal_settings]
 
 model_names = []
 pretrained_settings = {}

@@ -170,6 +170,23 @@ class PackedConv:
         self.scale, self.shift = fold_affine(K, bias, bn, weight.device)
 
 
+def dense_from_grouped(weight, groups):
+    """Grouped-convolution filter [K][C/groups][...] -> the block-diagonal dense filter [K][C][...] (zeros off the diagonal).
+    Output channel k belongs to group k // (K / groups) and reads input channels [g * C/groups, (g + 1) * C/groups)
+    (nn.Conv3d semantics, resnext3D.py:86-93).  Groups of the ResNeXt-3D nets are 4..32 channels wide -- far below an MMA
+    tile -- so the tensor-core path runs the dense filter; the product with the zero blocks is exact."""
+    K, cg = weight.shape[0], weight.shape[1]
+    if groups == 1:
+        return weight
+    if K % groups:
+        raise ValueError("output channels %d not divisible by groups %d" % (K, groups))
+    dense = weight.new_zeros((K, cg * groups) + tuple(weight.shape[2:]))
+    kg = K // groups
+    for g in range(groups):
+        dense[g * kg:(g + 1) * kg, g * cg:(g + 1) * cg] = weight[g * kg:(g + 1) * kg]
+    return dense
+
+
 def fold_affine(K, bias, bn, device):
     """Per-output-channel (scale, shift) in fp32 for conv(+bias) followed by eval-mode BatchNorm."""
     if bn is not None:

@@ -145,3 +145,77 @@ def test_nonlocal_block_modes_init_and_oracle_match_reference(path):
     with torch.no_grad():
         y = OF.nonlocal_block_nd(x, blk.state_dict(), "", fx["dimension"], fx["mode"], fx["sub_sample"], fx["bn_layer"])
     assert (y - fx["output"]).abs().max().item() <= 1e-5 * fx["output"].abs().max().item()
+
+
+# ---------------------------------------------------------------------------------------------
+# ResNeXt-3D (resnext3D.py; exported by pretorched/__init__.py:66-72)
+# ---------------------------------------------------------------------------------------------
+RX_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "resnext"]
+
+
+def build_resnext(fx):
+    torch.manual_seed(fx["seeds"]["init"])
+    m = getattr(P, fx["arch"])(**fx["kwargs"])
+    OF.randomize_bn_(m, fx["seeds"]["bn"])
+    return m.eval()
+
+
+@pytest.mark.parametrize("path", RX_FIX, ids=[os.path.basename(p)[:-3] for p in RX_FIX])
+def test_resnext3d_init_and_oracle_match_reference(path):
+    fx = torch.load(path, weights_only=False)
+    sd = build_resnext(fx).state_dict()
+    assert len(sd) == fx["n_state"] and list(sd) == list(fx["weight_digest"])
+    assert "fc.weight" in sd and "last_linear.weight" not in sd            # no modify_resnets on this family
+    assert OF.digests_match(OF.state_digest(sd), fx["weight_digest"])
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"])
+    stages = {}
+    with torch.no_grad():
+        out = OF.forward(x, sd, fx["spec"], stages)
+    assert (out - fx["logits"]).abs().max().item() <= 1e-5 * fx["logits"].abs().max().item()
+    for name, ref in fx["stages"].items():
+        samp = stages[name].reshape(-1)[::ref["step"]][:ref["sample"].numel()]
+        assert tuple(stages[name].shape) == ref["shape"]
+        assert (samp - ref["sample"]).abs().max().item() <= 1e-5 * max(ref["absmax"], 1e-6), name
+
+
+def test_resnext_fixtures_present():
+    assert len(RX_FIX) >= 2
+
+
+@pytest.mark.skipif(not RL.available(), reason="/root/reference not present (GPU box)")
+def test_resnext3d_state_dict_identical_to_live_reference():
+    import warnings
+    RL.load()
+    for arch, kw in [("resnext3d50", dict(num_classes=400)), ("resnext3d18", dict(num_classes=10, shortcut_type="A")),
+                     ("resnext3d101", dict())]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            torch.manual_seed(5)
+            ref = RL.build(arch, **kw)
+        torch.manual_seed(5)
+        ours = getattr(P, arch)(**kw)
+        a, b = ref.state_dict(), ours.state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (arch, k)
+    assert P.models.resnext3d.pretrained_settings["resnext3d101"]["kinetics-400"]["url"].endswith("resnext3d101_kinetics-8e57b772.pth")
+    assert P.models.resnext3d.pretrained_settings["resnext3d50"]["kinetics-400"]["url"] is None
+
+
+def test_grouped_filter_as_block_diagonal_dense_filter():
+    """Host logic behind the engine's grouped convolution: the dense filter built by ops.dense_from_grouped gives exactly the
+    grouped convolution (the products with the zero blocks vanish)."""
+    import torch.nn.functional as F
+    from pretorched_x_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    for K, C, groups, k in ((64, 64, 32, 3), (24, 12, 4, 3), (16, 16, 1, 1), (128, 128, 32, 3)):
+        w = torch.randn(K, C // groups, k, k, k, generator=g)
+        x = torch.randn(2, C, 4, 6, 5, generator=g)
+        dense = ops.dense_from_grouped(w, groups)
+        assert dense.shape == (K, C, k, k, k)
+        want = F.conv3d(x, w, None, 1, k // 2, 1, groups)
+        got = F.conv3d(x, dense, None, 1, k // 2)
+        assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+        assert float((dense != 0).double().mean()) <= 1.0 / groups + 1e-9
+    with pytest.raises(ValueError):
+        ops.dense_from_grouped(torch.zeros(10, 4, 1, 1, 1), 4)
