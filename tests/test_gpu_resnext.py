@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 FIX = [g for g in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "resnext3d*.pt")))]
 
 
+@pytest.mark.timeout(240, method="thread")        # first hardware run of this family: a stuck kernel must fail, not hang the tier
 @pytest.mark.parametrize("path", FIX, ids=[os.path.basename(p)[:-3] for p in FIX])
 def test_resnext3d_forward_matches_reference_golden(path):
     assert torch.cuda.is_available(), "GPU tests need a B200"
