@@ -569,7 +569,7 @@ using namespace b2;
 
 extern "C" {
 
-int b2_version(void) { return 101; }
+int b2_version(void) { return 102; }   // 102: b2_conv_args / b2_gemm_args grew the generator fields (aff_ld ... y2)
 /* debug knob (not in the public header): 0 = auto, 1 = never use the slab kernel */
 int b2_debug_set_conv_algo(int algo) { g_conv_algo = algo; return B2_OK; }
 int b2_debug_set_gemm_algo(int algo) { g_gemm_algo = algo; return B2_OK; }
