@@ -144,6 +144,9 @@ int b2_gemm2_f16(const b2_gemm_args* a, const void* a2, int lda2, const void* b2
  *     mode 0:  O[b] = softmax_rows(Q[b] . K[b]^T) . V[b]   (`_embedded_gaussian` :143-166, `_gaussian` :168-190;
  *                                                          unscaled logits, softmax over keys)
  *     mode 1:  O[b] = (Q[b] . K[b]^T / Nk) . V[b]          (`_dot_product` :192-211)
+ *     mode 2:  O[b] = (relu(Q[b] . K[b]^T) / Nk) . V[b]    (`_concatenation` :213-243: concat_project's 1x1 conv over
+ *                                                          [theta_i ; phi_j] is a_i + b_j, which the caller encodes as the
+ *                                                          rank-2 product Q_i = [a_i, 1, 0..], K_j = [1, b_j, 0..])
  * Q: fp16 [B*Nq][ldq] (d columns used); K, V: fp16 [B*Nk][ld] (d resp. dv columns; Nk < Nq when phi and g were
  * max-pooled, `sub_sample=True` :126-131); O: fp16 [B*Nq][ldo].  One fused kernel, the Nq x Nk matrix is never
  * materialised.
@@ -179,6 +182,29 @@ int b2_concat_channels(const void* a, int lda, int Ca, const void* b, int ldb, i
 /* y[n][j*F + f] = x[n][idx[j]][f]: frame-tuple gather of MultiScaleRelation (trn.py:108), fp16. */
 int b2_gather_frames(const void* x, void* y, const int32_t* idx_dev, int N, int T, int F, int n_idx,
                      void* stream);
+/* All tuples of one scale at once: y[n * n_tuples + t][j*F + f] = x[n][idx[t][j]][f], idx_dev int32 [n_tuples][n_idx] on the
+ * device (one table for the whole forward, filled by a single host->device copy: trn.py:100-110 without a copy per tuple). */
+int b2_gather_frame_tuples(const void* x, void* y, const int32_t* idx_dev, int N, int T, int F, int n_idx, int n_tuples,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Image preprocessing on the device -- TransformImage (pretorched/transforms/utils.py:34-81; used by
+ * examples/imagenet_logits.py:38-43): transforms.Resize (Pillow 8-bit BILINEAR: horizontal pass then vertical pass,
+ * 22-bit fixed-point coefficients, each pass rounds to uint8) -> Center/RandomCrop -> flips -> ToTensor -> ToSpaceBGR ->
+ * ToRange255 -> Normalize, bit-exact with the Pillow + torchvision pipeline the reference composes.
+ *   img       uint8 [H][W][3] RGB on the device
+ *   hbounds/hk  int32 [Wr][2] (first source column, count) and [Wr][hksize] coefficients of the horizontal pass (null when Wr == W)
+ *   vbounds/vk  the same for the vertical pass to Hr rows (null when Hr == H);  tmp: uint8 [H][Wr][3] scratch (horizontal result)
+ *   top/left/crop_h/crop_w  crop window inside the resized [Hr][Wr] image
+ *   flags     bit 0 horizontal flip, bit 1 vertical flip, bit 2 BGR, bit 3 range 255
+ *   mean/stdv HOST pointers to 3 floats each
+ *   out_f32   nullable fp32 [3][crop_h][crop_w] (what the reference returns); out_h4: nullable fp16 [crop_h*crop_w][4]
+ *             (NDHWC4: the stem convolution's input layout, channel 3 zero)
+ * ------------------------------------------------------------------------------------------- */
+int b2_transform_image_u8(const uint8_t* img, int H, int W, const int32_t* hbounds, const int32_t* hk, int hksize, int Wr,
+                          const int32_t* vbounds, const int32_t* vk, int vksize, int Hr, uint8_t* tmp, int top, int left,
+                          int crop_h, int crop_w, int flags, const float* mean, const float* stdv, float* out_f32,
+                          void* out_h4, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BigGAN-deep generator helpers (BASELINE.json configs[4]).  The architecture is NOT in the reference tree

@@ -44,10 +44,35 @@ ARCHS = {
                                nonlocal_blocks=[0, 2, 3, 0]),
     # torchvision_models.py:484-492 (torchvision BasicBlock body)
     'resnet18': dict(family='resnet2d', block='basic', layers=[2, 2, 2, 2], shortcut='B'),
+    # pre_act_resnet3D.py:100-139 (ResNet3D subclass: default shortcut 'B', head `fc`)
+    'preact_resnet3d18': dict(family='resnet3d', block='preact_basic', layers=[2, 2, 2, 2], shortcut='B'),
+    'preact_resnet3d50': dict(family='resnet3d', block='preact_bottleneck', layers=[3, 4, 6, 3], shortcut='B'),
     # resnext3D.py:224-252 (ResNeXtBottleneck: grouped 3x3x3 conv, expansion 2, planes 128..1024, head `fc`)
     'resnext3d50': dict(family='resnext3d', block='resnext', layers=[3, 4, 6, 3], shortcut='B', cardinality=32),
     'resnext3d101': dict(family='resnext3d', block='resnext', layers=[3, 4, 23, 3], shortcut='B', cardinality=32),
 }
+
+
+def arch_spec(arch, kwargs=None):
+    """Architecture row for a factory call: ``shortcut_type=`` in the factory kwargs overrides the table's default."""
+    spec = ARCHS[arch]
+    st = (kwargs or {}).get('shortcut_type')
+    return dict(spec, shortcut=st) if st and st != spec['shortcut'] else spec
+
+
+def build_package_model(pkg, fx):
+    """The package-under-test's model for a ``kind == 'model'`` fixture: same factory call, seeds and BN / non-local
+    conditioning as oracle/make_golden.py applied to the reference."""
+    torch.manual_seed(fx["seeds"]["init"])
+    arch = fx["arch"]
+    if arch.startswith(("r2plus1d", "preact_")):             # plain **kwargs factories upstream (no `pretrained`)
+        m = getattr(pkg, arch)(**fx["kwargs"])
+    else:
+        m = getattr(pkg, arch)(pretrained=None, **fx["kwargs"])
+    randomize_bn_(m, fx["seeds"]["bn"])
+    if fx.get("nl_factors"):
+        apply_nonlocal_factors_(m, fx["nl_factors"])
+    return m.eval()
 
 
 def nonlocal_positions(layers, nonlocal_blocks):
@@ -125,6 +150,21 @@ def bottleneck(x, sd, p, family, shortcut, planes, stride, has_downsample):
     return F.relu(out)
 
 
+def preact_basic_block(x, sd, p, family, shortcut, planes, stride, has_downsample):
+    """PreActivationBasicBlock.forward (pre_act_resnet3D.py:41-57): BN-ReLU-conv twice, + shortcut(x), no final ReLU."""
+    out = _conv(F.relu(_bn(x, sd, p + '.bn1')), sd, p + '.conv1', stride, 1)
+    out = _conv(F.relu(_bn(out, sd, p + '.bn2')), sd, p + '.conv2', 1, 1)
+    return out + _residual(x, sd, p, family, shortcut, planes, stride, has_downsample)
+
+
+def preact_bottleneck(x, sd, p, family, shortcut, planes, stride, has_downsample):
+    """PreActivationBottleneck.forward (pre_act_resnet3D.py:76-96)."""
+    out = _conv(F.relu(_bn(x, sd, p + '.bn1')), sd, p + '.conv1')
+    out = _conv(F.relu(_bn(out, sd, p + '.bn2')), sd, p + '.conv2', stride, 1)
+    out = _conv(F.relu(_bn(out, sd, p + '.bn3')), sd, p + '.conv3')
+    return out + _residual(x, sd, p, family, shortcut, planes * 4, stride, has_downsample)
+
+
 def resnext_bottleneck(x, sd, p, shortcut, planes, cardinality, stride, has_downsample):
     """ResNeXtBottleneck.forward (resnext3D.py:101-122): 1x1x1 -> grouped 3x3x3 (groups = cardinality, stride s) -> 1x1x1
     to planes * 2, BN after each, residual (type A / B as in resnet3D), ReLU."""
@@ -151,7 +191,7 @@ def nonlocal_block(x, sd, p):
 
 
 def nonlocal_block_nd(x, sd, p, dimension, mode, sub_sample, bn_layer=True):
-    """_NonLocalBlockND.forward for the three softmax / dot-product modes (nonlocalnet.py:143-211), any of 1/2/3
+    """_NonLocalBlockND.forward for the softmax / dot-product / concatenation modes (nonlocalnet.py:143-243), any of 1/2/3
     position axes, with optional max-pooled phi / g (:126-131).  ``p`` is the key prefix ('' for a bare block)."""
     key = (lambda k: p + '.' + k) if p else (lambda k: k)
     conv = (None, F.conv1d, F.conv2d, F.conv3d)[dimension]
@@ -173,8 +213,18 @@ def nonlocal_block_nd(x, sd, p, dimension, mode, sub_sample, bn_layer=True):
         if sub_sample:
             phi_x = pool(phi_x, 2)
         phi_x = phi_x.reshape(b, d, -1)
-    f = torch.matmul(theta_x, phi_x)
-    f_div_c = f / f.size(-1) if mode == 'dot_product' else F.softmax(f, dim=-1)
+    if mode == 'concatenation':
+        # _concatenation (nonlocalnet.py:213-243): [theta_i ; phi_j] on an N x N grid -> bias-free 1x1 Conv2d to one
+        # channel -> ReLU -> / N.  Same tensor ops as the reference (repeat + cat + conv2d) so the result is bit-identical.
+        th = cw('theta').reshape(b, d, -1, 1)
+        ph = phi_x.reshape(b, d, 1, -1)
+        h, w = th.size(2), ph.size(3)
+        feat = torch.cat([th.repeat(1, 1, 1, w), ph.repeat(1, 1, h, 1)], dim=1)
+        f = F.relu(F.conv2d(feat, sd[key('concat_project.0.weight')])).view(b, h, w)
+        f_div_c = f / f.size(-1)
+    else:
+        f = torch.matmul(theta_x, phi_x)
+        f_div_c = f / f.size(-1) if mode == 'dot_product' else F.softmax(f, dim=-1)
     y = torch.matmul(f_div_c, g_x).permute(0, 2, 1).contiguous().view(b, d, *x.shape[2:])
     if bn_layer:
         w_y = conv(y, sd[key('W.0.weight')], sd[key('W.0.bias')])
@@ -205,8 +255,9 @@ def trunk(x, sd, arch, stages=None):
     """``features`` (torchvision_models.py:448-458).  If ``stages`` is a dict it receives every stage output."""
     spec = ARCHS[arch] if isinstance(arch, str) else arch
     family, shortcut = spec['family'], spec['shortcut']
-    block_fn = bottleneck if spec['block'] == 'bottleneck' else basic_block
-    expansion = {'bottleneck': 4, 'resnext': 2}.get(spec['block'], 1)
+    block_fn = {'bottleneck': bottleneck, 'preact_basic': preact_basic_block,
+                'preact_bottleneck': preact_bottleneck}.get(spec['block'], basic_block)
+    expansion = {'bottleneck': 4, 'preact_bottleneck': 4, 'resnext': 2}.get(spec['block'], 1)
     widths = (128, 256, 512, 1024) if spec['block'] == 'resnext' else (64, 128, 256, 512)     # resnext3D.py:134-137
     nl = nonlocal_positions(spec['layers'], spec['nonlocal_blocks']) if 'nonlocal_blocks' in spec else [[]] * 4
     x = stem(x, sd, family)
@@ -333,9 +384,9 @@ def relation(x, sd, p, num_inputs, in_features):
     return out.view(x.size(0), -1, out.shape[-1])
 
 
-def multiscale_relation(x, sd, num_input, in_features, num_relations=3, tuples=None):
+def multiscale_relation(x, sd, num_input, in_features, num_relations=3, tuples=None, p=''):
     """MultiScaleRelation.forward (trn.py:100-110).  ``tuples`` (per scale) overrides the np.random.choice draw;
-    when None the draw is made exactly as the reference does, from NumPy's global RNG."""
+    when None the draw is made exactly as the reference does, from NumPy's global RNG.  ``p``: state_dict key prefix."""
     scales = list(range(num_input, 1, -1))
     sets = [list(itertools.combinations(range(num_input), s)) for s in scales]
     outs = []
@@ -346,9 +397,36 @@ def multiscale_relation(x, sd, num_input, in_features, num_relations=3, tuples=N
         else:
             chosen = tuples[si]
         for tup in chosen:
-            outs.append(relation(x[..., list(tup), :], sd, 'relations.%d.' % si, s, in_features))
+            outs.append(relation(x[..., list(tup), :], sd, p + 'relations.%d.' % si, s, in_features))
     total = torch.stack(outs).sum(0)
     return total.view(x.size(0), -1, total.shape[-1])
+
+
+def trn_forward(x, sd, arch, consensus, num_segments, stages=None):
+    """TRN.forward (trn.py:246-263) in eval mode: frames folded into the batch of the 2-D backbone (``base_model.*`` keys, whose
+    ``last_linear`` is a Dropout == identity, :211-212), pooled frame features regrouped [B, 1, T, F] (:249-254), consensus
+    module (``Relation`` for 'TRN', the degenerate depth-0 ``HierarchicalRelation`` == its ``final_relation`` for 'HTRN'
+    (:155-158 with no hierarchy levels), ``MultiScaleRelation`` for 'MSTRN'), ``.squeeze()``, final Linear (:257-258)."""
+    base = {k[len('base_model.'):]: v for k, v in sd.items() if k.startswith('base_model.')}
+    b = x.size(0)
+    frames = x.view((-1, 3) + tuple(x.shape[-2:]))
+    feat = trunk(frames, base, arch)
+    rep = feat.mean(dim=(2, 3))                                   # avgpool + view; Dropout (eval) is the identity
+    fdim = rep.size(-1)
+    rep = rep.view(b, -1, num_segments, fdim)
+    t_in = rep.view(-1, rep.size(1), num_segments, fdim)
+    if consensus == 'TRN':
+        v = relation(t_in, sd, 'temporal_relation.', num_segments, fdim)
+    elif consensus == 'HTRN':
+        v = relation(t_in.view(-1, num_segments, fdim), sd, 'temporal_relation.final_relation.', num_segments, fdim)
+    elif consensus == 'MSTRN':
+        v = multiscale_relation(t_in, sd, num_segments, fdim, p='temporal_relation.')
+    else:
+        raise ValueError(consensus)
+    v = v.squeeze()
+    if stages is not None:
+        stages['features'] = v
+    return F.linear(v, sd['last_linear.weight'], sd['last_linear.bias'])
 
 
 # ---------------------------------------------------------------------------------------------

@@ -34,6 +34,14 @@ MODEL_CASES = {
     "resnet18_b2_64": ("resnet18", dict(num_classes=1000), (2, 3, 64, 64)),
     # same net with theta/phi rescaled into a trained-like logit regime (oracle.functional.calibrate_nonlocal_)
     "nonlocalresnet3d50_tamed_b1_t16_96": ("nonlocalresnet3d50", dict(), (1, 3, 16, 96, 96)),
+    # ---- the BASELINE.json clip sizes themselves (configs[1], [2], [3]): what bench.py times.  Same recipe, the
+    #      reference's CPU forward takes seconds per clip; fixtures stay small (strided samples + logits).
+    "resnet3d50_b2_t16_224": ("resnet3d50", dict(num_classes=400), (2, 3, 16, 224, 224)),
+    "r2plus1d34_b1_t32_112": ("r2plus1d34", dict(num_classes=400), (1, 3, 32, 112, 112)),
+    "nonlocalresnet3d50_tamed_b1_t32_224": ("nonlocalresnet3d50", dict(), (1, 3, 32, 224, 224)),
+    # pre-activation blocks (pre_act_resnet3D.py:27-96), SURVEY 8f n3
+    "preact_resnet3d50_b2_t8_64": ("preact_resnet3d50", dict(num_classes=174), (2, 3, 8, 64, 64)),
+    "preact_resnet3d18_b1_t8_64": ("preact_resnet3d18", dict(num_classes=174, shortcut_type='A'), (1, 3, 8, 64, 64)),
 }
 SEED_INIT, SEED_BN, SEED_INPUT = 0, 1, 2
 
@@ -67,8 +75,8 @@ def run_model_case(name, arch, kwargs, shape):
         handles.append(getattr(ref, stage).register_forward_hook(
             lambda m, i, o, stage=stage: hooked.__setitem__(stage, o.detach().clone())))
     with torch.no_grad():
-        if arch.startswith("r2plus1d"):
-            # R2Plus1D inherits ResNet3D.forward, which modify_resnets may have patched at class level to need
+        if arch.startswith("r2plus1d") or arch.startswith("preact_"):
+            # R2Plus1D / PreActivationResNet3D inherit ResNet3D.forward, which modify_resnets may have patched at class level to need
             # `last_linear`.  The unpatched body is conv1..layer4 -> avgpool -> fc:
             feat = ref.layer4(ref.layer3(ref.layer2(ref.layer1(ref.maxpool(ref.relu(ref.bn1(ref.conv1(x))))))))
             logits = ref.fc(ref.avgpool(feat).view(feat.size(0), -1))
@@ -80,8 +88,11 @@ def run_model_case(name, arch, kwargs, shape):
 
     sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
     stages = {}
+    spec = arch
+    if kwargs.get("shortcut_type") and OF.ARCHS[arch]["shortcut"] != kwargs["shortcut_type"]:
+        spec = dict(OF.ARCHS[arch], shortcut=kwargs["shortcut_type"])
     with torch.no_grad():
-        out = OF.forward(x, sd, arch, stages)
+        out = OF.forward(x, sd, spec, stages)
     for k, v in hooked.items():
         assert torch.equal(stages[k], v), "oracle restatement differs from the reference at %s/%s" % (name, k)
     assert torch.equal(out, logits)
@@ -172,6 +183,101 @@ def run_relation_cases():
     print("%-32s out %s" % ("msrelation_small", tuple(y.shape)))
 
 
+TRN_CASES = {
+    # name -> (consensus, backbone, segments, batch, frame size, relation kwargs, numpy seed)
+    "trn_resnet18_TRN": ("TRN", "resnet18", 8, 2, 64, dict(frame_bottleneck_dim=128, video_feature_dim=64), None),
+    "trn_resnet18_HTRN": ("HTRN", "resnet18", 8, 2, 64, dict(), None),
+    "trn_resnet18_MSTRN": ("MSTRN", "resnet18", 8, 2, 64, dict(frame_bottleneck_dim=128, video_feature_dim=64), 321),
+}
+
+
+def run_trn_cases():
+    """The full TRN wrapper (trn.py:192-338).  Upstream cannot construct it offline: the backbone
+    factory must download a checkpoint to get its preprocessing attributes.  The ONLY patch applied here is to that
+    factory: build the same backbone with ``pretrained=None`` and attach the registry's attributes (what
+    ``load_pretrained`` does after the download, torchvision_models.py:162-166).  TRN.__init__/features/logits/forward run
+    unmodified."""
+    import contextlib, io
+    trn = RL.load_trn()
+    pt = RL.load()
+    for name, (consensus, arch, T, B, hw, kw, np_seed) in TRN_CASES.items():
+        orig = pt.__dict__[arch]
+
+        def offline(num_classes=1000, pretrained=None, _orig=orig, _arch=arch):
+            m = _orig(num_classes=num_classes, pretrained=None)
+            for k, v in pt.pretrained_settings[_arch]['imagenet'].items():
+                if k in ('input_space', 'input_size', 'input_range', 'mean', 'std'):
+                    setattr(m, k, v)
+            return m
+        pt.__dict__[arch] = offline
+        try:
+            torch.manual_seed(SEED_INIT)
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref = trn.TRN(10, num_segments=T, arch=arch, consensus=consensus, pretrained=None, **kw)
+        finally:
+            pt.__dict__[arch] = orig
+        OF.randomize_bn_(ref, SEED_BN)
+        ref.eval()
+        x = OF.seeded_input((B, T, 3, hw, hw), SEED_INPUT)
+        with torch.no_grad():
+            if np_seed is not None:
+                np.random.seed(np_seed)
+            feats = ref.features(x)
+            logits = ref.logits(feats)
+            sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+            if np_seed is not None:
+                np.random.seed(np_seed)
+            st = {}
+            out = OF.trn_forward(x, sd, arch, consensus, T, st)
+        assert torch.equal(st['features'], feats) and torch.equal(out, logits), "oracle restatement differs from the reference TRN (%s)" % name
+        torch.save(dict(kind="trn", consensus=consensus, arch=arch, segments=T, kwargs=kw, input_shape=(B, T, 3, hw, hw), np_seed=np_seed,
+                        seeds=dict(init=SEED_INIT, bn=SEED_BN, input=SEED_INPUT), features=feats.clone(), logits=logits.clone(),
+                        weight_digest=OF.state_digest(sd), n_state=len(sd)), os.path.join(GOLDEN_DIR, name + ".pt"))
+        print("%-32s logits %s absmax %.4f" % (name, tuple(logits.shape), logits.abs().max()))
+
+
+def run_image_case():
+    """BASELINE.json configs[0]: resnet18 on the reference's own test image through the reference's own preprocessing
+    (examples/imagenet_logits.py:38-43: LoadImage -> TransformImage(model) -> model; weights random-init, as offline).
+    Stores the decoded image (the GPU box has no /root/reference), the preprocessed tensor and the logits."""
+    utils = RL.load_transforms()
+    pt = RL.load()
+    from oracle import image as OI
+    torch.manual_seed(SEED_INIT)
+    ref = RL.build("resnet18", num_classes=1000)
+    OF.randomize_bn_(ref, SEED_BN)
+    ref.eval()
+    settings = pt.pretrained_settings["resnet18"]["imagenet"]
+    img = utils.LoadImage()(os.path.join(RL.REFERENCE_ROOT, "data", "cat.jpg"))
+    x = utils.TransformImage(settings)(img)                       # the reference's Compose (transforms/utils.py:53-77)
+    u8 = torch.from_numpy(np.array(img, copy=True))
+    restated = torch.from_numpy(OI.transform_image(u8.numpy(), settings["input_size"], settings["input_space"],
+                                                   settings["input_range"], settings["mean"], settings["std"]))
+    assert torch.equal(restated, x), "oracle/image.py differs from the reference's TransformImage"
+    hooked, handles = {}, []
+    for stage in ("maxpool", "layer1", "layer2", "layer3", "layer4"):
+        handles.append(getattr(ref, stage).register_forward_hook(
+            lambda m, i, o, stage=stage: hooked.__setitem__(stage, o.detach().clone())))
+    with torch.no_grad():
+        logits = ref(x.unsqueeze(0))
+    for h in handles:
+        h.remove()
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    stages = {}
+    with torch.no_grad():
+        out = OF.forward(x.unsqueeze(0), sd, "resnet18", stages)
+    for k, v in hooked.items():
+        assert torch.equal(stages[k], v), k
+    assert torch.equal(out, logits)
+    hooked["logits"] = logits
+    torch.save(dict(kind="image", arch="resnet18", kwargs=dict(num_classes=1000), settings={k: settings[k] for k in
+                    ("input_size", "input_space", "input_range", "mean", "std")}, image_u8=u8, input=summarize(x), input_sha=OF.state_digest({"x": x})["x"],
+                    seeds=dict(init=SEED_INIT, bn=SEED_BN), logits=logits.clone(),
+                    stages={k: summarize(v) for k, v in hooked.items()}, weight_digest=OF.state_digest(sd), n_state=len(sd)),
+               os.path.join(GOLDEN_DIR, "resnet18_cat_224.pt"))
+    print("%-32s image %s -> %s, logits absmax %.4f" % ("resnet18_cat_224", tuple(u8.shape), tuple(x.shape), logits.abs().max()))
+
+
 NLBLOCK_CASES = {
     # name -> (dimension, mode, sub_sample, bn_layer, channels, input shape)
     "nlblock3d_gaussian_sub": (3, "gaussian", True, True, 128, (2, 128, 4, 8, 8)),
@@ -180,6 +286,11 @@ NLBLOCK_CASES = {
     "nlblock2d_embedded": (2, "embedded_gaussian", False, True, 128, (2, 128, 12, 12)),
     "nlblock2d_dot_sub_nobn": (2, "dot_product", True, False, 128, (2, 128, 12, 12)),
     "nlblock1d_gaussian": (1, "gaussian", False, True, 128, (3, 128, 50)),
+    # concatenation mode (nonlocalnet.py:213-243), plain and with max-pooled phi / g; and a block whose inter_channels (32)
+    # is below the attention kernel's 64-wide granule (the nonlocalresnet3d18/34 placement: C = 64, d = 32)
+    "nlblock3d_concat": (3, "concatenation", False, True, 128, (2, 128, 2, 6, 6)),
+    "nlblock2d_concat_sub": (2, "concatenation", True, True, 128, (2, 128, 12, 12)),
+    "nlblock3d_embedded_c64": (3, "embedded_gaussian", False, True, 64, (2, 64, 2, 8, 8)),
 }
 
 
@@ -197,9 +308,11 @@ def condition_nlblock_(blk, seed):
     return blk
 
 
-def run_nlblock_cases():
+def run_nlblock_cases(only=None):
     ref_nl = RL.load().models.nonlocalnet
     for name, (dim, mode, sub, bn, C, shape) in NLBLOCK_CASES.items():
+        if only is not None and name not in only:
+            continue
         cls = getattr(ref_nl, "NonLocalBlock%dD" % dim)
         torch.manual_seed(SEED_INIT)
         ref = condition_nlblock_(cls(C, mode=mode, sub_sample=sub, bn_layer=bn), SEED_BN).eval()
@@ -244,17 +357,30 @@ def run_slowfast_cases():
         print("%-32s logits %s absmax %.4f" % (name, tuple(y.shape), y.abs().max()))
 
 
-def main():
+def main(argv=None):
+    """``python -m oracle.make_golden`` regenerates everything; ``... name [name ...]`` only the named model / nlblock cases
+    or groups (``relations``, ``slowfast``, ``nlblocks``, ``resnext``, ``image``, ``preact``, ``trn``)."""
+    argv = list(sys.argv[1:] if argv is None else argv)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    want = (lambda n: True) if not argv else (lambda n: n in argv)
     # R(2+1)D first: see reference_loader.load_r2plus1d
     order = sorted(MODEL_CASES, key=lambda n: 0 if MODEL_CASES[n][0].startswith("r2plus1d") else 1)
     for name in order:
-        run_model_case(name, *MODEL_CASES[name])
-    run_relation_cases()
-    run_slowfast_cases()
-    run_nlblock_cases()
-    run_resnext_cases()
+        if want(name):
+            run_model_case(name, *MODEL_CASES[name])
+    if want("relations"):
+        run_relation_cases()
+    if want("slowfast"):
+        run_slowfast_cases()
+    if want("nlblocks") or any(a in NLBLOCK_CASES for a in argv):
+        run_nlblock_cases(None if want("nlblocks") else [a for a in argv if a in NLBLOCK_CASES])
+    if want("resnext"):
+        run_resnext_cases()
+    if want("trn"):
+        run_trn_cases()
+    if want("image"):
+        run_image_case()
 
 
 if __name__ == "__main__":

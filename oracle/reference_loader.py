@@ -51,6 +51,36 @@ def load_r2plus1d():
         sys.dont_write_bytecode = old
 
 
+def load_preact():
+    """pretorched.models.pre_act_resnet3D (same absolute ``import resnet3D`` defect as r2plus1d.py: pre_act_resnet3D.py:8)."""
+    pt = load()
+    sys.modules.setdefault("resnet3D", pt.models.resnet3D)
+    old = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        return importlib.import_module("pretorched.models.pre_act_resnet3D")
+    finally:
+        sys.dont_write_bytecode = old
+
+
+def load_transforms():
+    """pretorched.transforms.utils.  transforms/utils.py:7 imports ``munchify`` from the ``munch`` package, which is not
+    installed here; it is only used to turn a settings dict into an attribute bag (utils.py:39-40), so a two-line stand-in
+    module is registered before the import.  Nothing else is patched."""
+    import types
+    load()
+    if "munch" not in sys.modules:
+        stub = types.ModuleType("munch")
+        stub.munchify = lambda d: types.SimpleNamespace(**d)
+        sys.modules["munch"] = stub
+    old = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        return importlib.import_module("pretorched.transforms.utils")
+    finally:
+        sys.dont_write_bytecode = old
+
+
 def load_trn():
     pt = load()
     sys.modules.setdefault("pretrainedmodels", pt)
@@ -69,6 +99,8 @@ def build(arch, **kwargs):
     pt = load()
     if arch.startswith("r2plus1d"):
         return getattr(load_r2plus1d(), arch)(**kwargs)
+    if arch.startswith("preact_"):
+        return getattr(load_preact(), arch)(**kwargs)
     if arch.startswith("resnext3d"):                     # resnext3D.py:224-252: plain **kwargs factories, no `pretrained`
         return getattr(pt, arch)(**kwargs)
     if arch.startswith("nonlocal"):

@@ -18,9 +18,11 @@ from .models.nonlocalnet import (nonlocalresnet3d18, nonlocalresnet3d34, nonloca
 # not exported by the reference's __init__ (r2plus1d.py / trn.py are import-broken upstream); offered here
 from .models.r2plus1d import (r2plus1d10, r2plus1d18, r2plus1d34, r2plus1d50, r2plus1d101,  # noqa: F401
                               r2plus1d152, r2plus1d200)
+from .models.pre_act_resnet3d import (preact_resnet3d10, preact_resnet3d18, preact_resnet3d34, preact_resnet3d50,  # noqa: F401
+                                      preact_resnet3d101, preact_resnet3d152, preact_resnet3d200)   # pre_act_resnet3D.py:100-139
 from .models.resnext3d import (resnext3d10, resnext3d18, resnext3d34, resnext3d50, resnext3d101,  # noqa: F401
                                resnext3d152, resnext3d200)          # pretorched/__init__.py:66-72
-from .models.trn import Relation, MultiScaleRelation, HierarchicalRelation  # noqa: F401
+from .models.trn import Relation, MultiScaleRelation, HierarchicalRelation, TRN, trn  # noqa: F401
 from .models.utils import Identity  # noqa: F401
 # BigGAN-deep generator (BASELINE.json configs[4]; not in the reference tree -- see models/biggan_deep.py)
 from .models.biggan_deep import biggan_deep, biggan_deep128, biggan_deep256, biggan_deep512  # noqa: F401

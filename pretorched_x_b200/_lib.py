@@ -14,6 +14,9 @@ _lock = threading.Lock()
 _lib = None
 
 B2_OK = 0
+# The ABI revision this binding was written against (b2_version() of csrc/b2_conv_api.cu).  The argument structs below
+# mirror that revision; a library from another checkout would silently ignore / misread fields, so load() insists on it.
+EXPECTED_ABI = 103
 B2_CONV_AUTO = 0
 B2_CONV_STEM7 = 1
 
@@ -73,6 +76,9 @@ SYMBOLS = {
     "b2_shortcut_a_ndhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "b2_concat_channels": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, ctypes.c_longlong, c_void_p]),
     "b2_gather_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2_gather_frame_tuples": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b2_transform_image_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                      c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2_embed_concat": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "b2_ccbn_act_ndhwc": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "b2_rgb_head_gather_tanh": (c_int, [c_void_p, c_int, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
@@ -92,10 +98,18 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(_LIB_PATH):
-            from .csrc.build import build
-            build()  # raises if nvcc is missing: the product path must not degrade silently
+        from .csrc import build as _build
+        if _build.sources_present() and _build.have_nvcc():
+            _build.build()    # digest check: rebuilds only when a source, header or flag changed since the .so was linked
+        elif not os.path.exists(_LIB_PATH):
+            raise RuntimeError("libb2pretorched.so is missing and cannot be built here (no nvcc / no sources): the engine has "
+                               "no CPU or library fallback")
         lib = ctypes.CDLL(_LIB_PATH)
+        lib.b2_version.restype = c_int
+        got = lib.b2_version()
+        if got != EXPECTED_ABI:
+            raise RuntimeError("libb2pretorched.so reports ABI %d, this binding needs %d: stale library from another checkout -- "
+                               "run `python -m pretorched_x_b200.csrc.build --force`" % (got, EXPECTED_ABI))
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
             fn.restype = res

@@ -214,6 +214,15 @@ def _next_affine(nxt, a_out_hw, aff, pk):
 
 
 def run_gblock(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None):
+    """One GBlock through its torch.autograd.Function (functions.GBlockFunction: forward = the launch sequence of
+    ``_gblock_body``, outputs non-differentiable).  Returns (block output, relu(bn1_next(output)) or None)."""
+    from .functions import GBlockFunction
+    d0, g0, d1, g1 = GBlockFunction.apply(a.data, (a.N, a.T, a.H, a.W, a.C), blk, aff, pk,
+                                          dict(fuse_output_bn=fuse_output_bn, pre=pre, nxt=nxt))
+    return Act(d0, *g0), (Act(d1, *g1) if d1 is not None else None)
+
+
+def _gblock_body(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None):
     """One GBlock: h = conv4(relu(bn4(conv3(relu(bn3(conv2(up(relu(bn2(conv1(relu(bn1(x))))))))))))) + up(x[:, :out]).
     ``pre``: relu(bn1(x)) when the previous kernel already produced it; ``nxt``: the module that consumes the result --
     if it is a GBlock its opening ccbn + ReLU is written as a second output of conv4 (returned as the second value).
@@ -236,10 +245,9 @@ def run_gblock(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None):
     # conv4 + skip: the skip path x[:, :out] (channel drop = residual pitch) is read at LOW resolution by the epilogue and
     # upsampled on the fly, so up(x) is never written; the last block also carries the output BN + ReLU (see _pack)
     if fuse_output_bn:
-        return ops.conv(t, pk.out_conv4, residual=a, relu=True, residual_up=up == 2, residual_pre=True), None
+        return ops.conv(t, pk.out_conv4, residual=a, relu=True, residual_up=up == 2, residual_pre=True)
     nxt_aff = _next_affine(nxt, t.H * t.W, aff, pk)
-    out = ops.conv(t, bp.conv[3], residual=a, residual_up=up == 2, next_affine=nxt_aff)
-    return out if nxt_aff is not None else (out, None)
+    return ops.conv(t, bp.conv[3], residual=a, residual_up=up == 2, next_affine=nxt_aff)    # Act, or (Act, Act) with nxt_aff
 
 
 def run_attention(att, a, aff, pk, nxt=None):

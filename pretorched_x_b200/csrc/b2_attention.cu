@@ -32,7 +32,8 @@ struct AttParams {
   int Nk;         // key / value positions per sample (== Nq unless phi and g were sub-sampled)
   int nkb;        // d / 64
   int nkv;        // ceil(Nk / 64)
-  int mode;       // 0: softmax over keys (embedded gaussian / gaussian); 1: f / Nk without softmax (dot product)
+  int mode;       // 0: softmax over keys (embedded gaussian / gaussian); 1: f / Nk without softmax (dot product);
+                  // 2: relu(f) / Nk (concatenation mode: the caller encodes f_ij = a_i + b_j as a rank-2 product, see engine.run_nonlocal)
   float scale;    // mode 1: 1 / Nk
   __half* o;
   int ldo;
@@ -155,6 +156,7 @@ nonlocal_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
             } else {                                   // dot-product mode: f / N (nonlocalnet.py:203-204)
               p0 = (key < nvalid) ? __uint_as_float(v[i]) * p.scale : 0.f;
               p1 = (key + 1 < nvalid) ? __uint_as_float(v[i + 1]) * p.scale : 0.f;
+              if (p.mode == 2) { p0 = fmaxf(p0, 0.f); p1 = fmaxf(p1, 0.f); }   // concatenation mode: ReLU(.) / N (nonlocalnet.py:231-237)
             }
             o4[e] = pack_half2(p0, p1);
           }
@@ -559,11 +561,7 @@ template <int DVT>
 static int launch_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                             int B, int Nq, int Nk, int d, int dv, int mode, cudaStream_t stream) {
   using S = AttSmem<DVT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(nonlocal_attention_kernel<DVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  B2_OPT_IN_SMEM(nonlocal_attention_kernel<DVT>, S::kTotal);
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   const uint64_t qrows = (uint64_t)B * Nq, krows = (uint64_t)B * Nk;
@@ -584,11 +582,7 @@ template <int DVT>
 static int launch_attention_online(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                                    int B, int Nq, int Nk, int d, int dv, cudaStream_t stream) {
   using S = OnSmem<DVT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(nonlocal_attention_online_kernel<DVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  B2_OPT_IN_SMEM(nonlocal_attention_online_kernel<DVT>, S::kTotal);
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   const uint64_t qrows = (uint64_t)B * Nq, krows = (uint64_t)B * Nk;
@@ -616,7 +610,7 @@ extern "C" int b2_nonlocal_attention(const void* q, int ldq, const void* k, int 
                                      int ldo, int B, int Nq, int Nk, int d, int dv, int mode, void* stream) {
   B2_CHECK_ARG(q && k && v && o, "null pointer");
   B2_CHECK_ARG(B > 0 && Nq > 0 && Nk > 0 && d > 0 && dv > 0, "non-positive dimension");
-  B2_CHECK_ARG(mode == 0 || mode == 1, "unknown attention mode %d", mode);
+  B2_CHECK_ARG(mode >= 0 && mode <= 2, "unknown attention mode %d", mode);
   B2_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "pitches must be multiples of 8");
   B2_CHECK_ARG(ldq >= d && ldk >= d && ldo >= dv && ldv >= dv, "pitch smaller than extent");
   if (d % 64 != 0 || dv % 64 != 0)

@@ -331,15 +331,19 @@ __global__ void concat_channels_kernel(const __half* __restrict__ a, int lda8, i
   reinterpret_cast<uint4*>(y)[i] = v;
 }
 
+// y[(n * n_tuples + t)][j * F + f] = x[n][idx[t * n_idx + j]][f]: all frame tuples of one scale in one pass; the output row
+// index has the tuple fastest, so the hidden layer of the relation MLP comes out as [n][n_tuples * bottleneck]
 __global__ void gather_frames_kernel(const __half* __restrict__ x, __half* __restrict__ y, const int* __restrict__ idx,
-                                     int T, int F8, int n_idx, long long total) {
+                                     int T, int F8, int n_idx, int n_tuples, long long total) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int f8 = (int)(i % F8);
   long long q = i / F8;
   const int j = (int)(q % n_idx);
-  const long long n = q / n_idx;
-  reinterpret_cast<uint4*>(y)[i] = __ldg(reinterpret_cast<const uint4*>(x + (n * T + idx[j]) * (long long)(F8 * 8)) + f8);
+  q /= n_idx;
+  const int t = (int)(q % n_tuples);
+  const long long n = q / n_tuples;
+  reinterpret_cast<uint4*>(y)[i] = __ldg(reinterpret_cast<const uint4*>(x + (n * T + idx[t * n_idx + j]) * (long long)(F8 * 8)) + f8);
 }
 
 }  // namespace b2
@@ -483,13 +487,18 @@ int b2_concat_channels(const void* a, int lda, int Ca, const void* b, int ldb, i
   return B2_OK;
 }
 
-int b2_gather_frames(const void* x, void* y, const int32_t* idx_dev, int N, int T, int F, int n_idx, void* stream) {
-  B2_CHECK_ARG(x && y && idx_dev && F % 8 == 0 && n_idx > 0 && T > 0, "bad argument");
-  const long long total = (long long)N * n_idx * (F / 8);
+int b2_gather_frame_tuples(const void* x, void* y, const int32_t* idx_dev, int N, int T, int F, int n_idx, int n_tuples,
+                           void* stream) {
+  B2_CHECK_ARG(x && y && idx_dev && F % 8 == 0 && n_idx > 0 && n_tuples > 0 && T > 0, "bad argument");
+  const long long total = (long long)N * n_tuples * n_idx * (F / 8);
   gather_frames_kernel<<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const __half*)x, (__half*)y, idx_dev, T, F / 8, n_idx, total);
+      (const __half*)x, (__half*)y, idx_dev, T, F / 8, n_idx, n_tuples, total);
   B2_CHECK_LAUNCH("gather_frames");
   return B2_OK;
+}
+
+int b2_gather_frames(const void* x, void* y, const int32_t* idx_dev, int N, int T, int F, int n_idx, void* stream) {
+  return b2_gather_frame_tuples(x, y, idx_dev, N, T, F, n_idx, 1, stream);
 }
 
 }  // extern "C"

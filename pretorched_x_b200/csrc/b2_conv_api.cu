@@ -41,12 +41,19 @@ int require_sm100() {
   return B2_OK;
 }
 
-static int sm_count() {
-  static int n = 0;
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+int sm_count() {               // per device ordinal (a process may drive several GPUs)
+  static std::atomic<int> cache[64];
+  const int dev = current_device() & 63;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -239,11 +246,7 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   if (a->aff_ld && ((a->aff_ld & 3) || (reinterpret_cast<uintptr_t>(a->scale) & 15) || (reinterpret_cast<uintptr_t>(a->shift) & 15)))
     return set_error(B2_ERR_INVALID, "per-sample scale/shift must be 16-byte aligned with a pitch that is a multiple of 4 floats");
   const int smem_bytes = kSlabSStages * p.slab_bytes + kSlabWStages * p.wbytes + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(slabconv_kernel<BNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  B2_OPT_IN_SMEM(slabconv_kernel<BNT>, 227 * 1024);
   CUtensorMap tmX, tmB;
   int rc;
   const int taps = p.up ? 16 : a->kt * a->kh * a->kw;
@@ -411,11 +414,7 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
   p.ldy = a->ldy;
   p.relu = a->relu;
   const int smem_bytes = p.nstages * p.stage_bytes + tail_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(stemconv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  B2_OPT_IN_SMEM(stemconv_kernel<BN>, 227 * 1024);
   // input viewed as 8-byte pixels (W, H, N*T); box (256, rows, 1); no swizzle -> dense 2 KB rows in smem
   CUtensorMap tmX;
   cuuint64_t dims[3] = {(cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N * a->T};
@@ -450,11 +449,7 @@ struct IgemmLaunch {
 template <int BN>
 static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   using S = IgemmSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotalBytes));
-    attr_set = true;
-  }
+  B2_OPT_IN_SMEM(igemm_kernel<BN>, S::kTotalBytes);
   const IgemmParams& p = L.p;
   CUtensorMap tmA, tmB, tmC, tmR;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmC, 0, sizeof(tmC)); memset(&tmR, 0, sizeof(tmR));
@@ -490,11 +485,7 @@ static int g_gemm_algo = 0;   // 0 auto (persistent kernel where it applies), 1 
 template <int BN, int GAN>
 static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   using S = PgemmSmem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(pgemm_kernel<BN, GAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  B2_OPT_IN_SMEM((pgemm_kernel<BN, GAN>), S::kTotal);
   const IgemmParams& ip = L.p;
   CUtensorMap tmA, tmB, tmC, tmR;
   int rc;
@@ -569,7 +560,7 @@ using namespace b2;
 
 extern "C" {
 
-int b2_version(void) { return 102; }   // 102: b2_conv_args / b2_gemm_args grew the generator fields (aff_ld ... y2)
+int b2_version(void) { return 103; }   // 103: split-K / fused (2+1)D / pooled-stem entry points (round 2); 102: generator fields
 /* debug knob (not in the public header): 0 = auto, 1 = never use the slab kernel */
 int b2_debug_set_conv_algo(int algo) { g_conv_algo = algo; return B2_OK; }
 int b2_debug_set_gemm_algo(int algo) { g_gemm_algo = algo; return B2_OK; }

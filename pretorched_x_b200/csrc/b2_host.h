@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/b2_pretorched.h"
 
 namespace b2 {
@@ -35,6 +37,21 @@ void count_launch(int n = 1);
     if (e__ != cudaSuccess)                                                                          \
       return ::b2::set_error(B2_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
     ::b2::count_launch();                                                                            \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: a single process that drives several
+// GPUs (nn.DataParallel -- the reference's only multi-GPU construct -- or model.to('cuda:1')) must opt in on each of them.
+// One bit per device ordinal, set after the first successful call on that device.
+int current_device();
+int sm_count();          // SM count of the current device (cached per ordinal)
+#define B2_OPT_IN_SMEM(kernel, bytes)                                                                          \
+  do {                                                                                                         \
+    static std::atomic<unsigned long long> done__{0};                                                          \
+    const unsigned long long bit__ = 1ull << (::b2::current_device() & 63);                                    \
+    if (!(done__.load(std::memory_order_relaxed) & bit__)) {                                                   \
+      B2_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+      done__.fetch_or(bit__, std::memory_order_relaxed);                                                       \
+    }                                                                                                          \
   } while (0)
 
 // 2-D fp16 tensor map: `inner` contiguous elements per row, `outer` rows of pitch `pitch_elems`;

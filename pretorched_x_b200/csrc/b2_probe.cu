@@ -126,12 +126,8 @@ extern "C" int b2_debug_umma_probe(const void* a, const void* b, float* out, int
   B2_CHECK_ARG(a && b && out, "null pointer");
   int rc;
   if ((rc = require_sm100()) != B2_OK) return rc;
-  static bool attr_set = false;
   const int smem_bytes = 32768 + 8192 + 64 + 1024;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = true;
-  }
+  B2_OPT_IN_SMEM(umma_probe_kernel, smem_bytes);
   CUtensorMap tmA, tmB;
   memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
   if (mode == 0) {

@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["b2_conv_api.cu", "b2_aux.cu", "b2_attention.cu", "b2_gan.cu", "b2_probe.cu"]
+SOURCES = ["b2_conv_api.cu", "b2_aux.cu", "b2_attention.cu", "b2_gan.cu", "b2_image.cu", "b2_probe.cu"]
 HEADERS = ["b2_ptx.cuh", "b2_igemm.cuh", "b2_pgemm.cuh", "b2_slabconv.cuh", "b2_stemconv.cuh", "b2_host.h", "../../include/b2_pretorched.h"]
 LIB = os.path.join(HERE, "libb2pretorched.so")
 STAMP = os.path.join(HERE, ".build_stamp")
@@ -31,6 +31,18 @@ def _nvcc():
         if cand and os.path.exists(cand):
             return cand
     raise RuntimeError("nvcc not found; cannot build the sm_100a extension")
+
+
+def have_nvcc():
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+def sources_present():
+    return all(os.path.exists(os.path.join(HERE, f)) for f in SOURCES + HEADERS)
 
 
 def _digest():

@@ -11,13 +11,23 @@ layout; nothing in them computes.  This file holds the block bodies:
 * ``run_stem`` / ``run_head``   stem conv+BN+ReLU+maxpool, global average + last_linear
                          (torchvision_models.py:448-464)
 
-Packed fp16 filters and folded BN affines are cached on the owning module and rebuilt whenever a
-source tensor changes (``load_state_dict``, in-place edits), so checkpoints stay drop-in.
+Packed fp16 filters and folded BN affines are cached on the owning module.  The cache key is
+``(data_ptr, _version, shape)`` of every source tensor, so ``load_state_dict`` and in-place edits of the
+parameter itself (``p.copy_()``, ``p.mul_()`` under ``no_grad``) rebuild the packed copy.  Edits made through
+``p.data`` (the reference's own init style, ``m.weight.data.fill_``) bump a *different* version counter and are
+NOT seen: ``model.invalidate()`` / ``engine.invalidate(model)`` drops every packed copy, and it runs by itself on
+``train()`` / ``eval()`` and on ``.to()`` / ``.half()`` / ``.cuda()`` (``_apply``).
+
+Every block body is entered through a ``torch.autograd.Function`` (``functions.py``): the
+Function's ``forward`` is the ctypes call sequence, its outputs are marked non-differentiable (frozen-backbone
+semantics: the engine has no backward for the convolutional trunk), and the dense heads (``last_linear``, the TRN
+relation MLPs) have a real backward on the same tcgen05 GEMM so that a head can be trained on engine features.
 """
 import torch
 import torch.nn as nn
 
 from . import ops
+from . import functions as Fn
 from .ops import Act
 
 
@@ -42,6 +52,30 @@ def _cached(owner, slot, sig, build):
     val = build()
     cache[slot] = (sig, val)
     return val
+
+
+def invalidate(root):
+    """Drop every packed filter / folded affine cached under ``root`` (call after editing parameters through ``.data``)."""
+    for m in root.modules():
+        m.__dict__.pop("_b2_cache", None)
+        m.__dict__.pop("_b2_pack", None)
+    return root
+
+
+class CacheOwner:
+    """Mixin for engine-backed nn.Modules: packed copies are dropped whenever the module is moved, cast or switched
+    between train / eval, and on request (``invalidate()``)."""
+
+    def invalidate(self):
+        return invalidate(self)
+
+    def train(self, mode=True):
+        invalidate(self)
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        invalidate(self)
+        return super()._apply(fn, *args, **kwargs)
 
 
 def _triple(v):
@@ -81,13 +115,17 @@ def _is_stem_shape(conv):
     return w.shape[1] <= 4 and kw == 7 and stride[2] == 2 and padding[2] == 3
 
 
+def _st_conv_body(conv, bn, a, residual, relu, simt):
+    """(2+1)D factorised conv (r2plus1d.py:85-88): spatial conv + its own BN + ReLU, then the temporal conv whose
+    epilogue carries the *outer* BN / residual / ReLU."""
+    mid = conv_bn_act(conv.spatial_conv, conv.bn, a, relu=True, simt=simt)
+    return conv_bn_act(conv.temporal_conv, bn, mid, residual=residual, relu=relu, simt=simt)
+
+
 def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False):
     """Run ``conv`` (Conv3d / Conv2d / SpatioTemporalConv-like) -> ``bn`` -> (+residual) -> (ReLU)."""
     if hasattr(conv, "spatial_conv") and hasattr(conv, "temporal_conv"):
-        # (2+1)D factorised conv (r2plus1d.py:85-88): spatial conv + its own BN + ReLU, then the temporal
-        # conv whose epilogue carries the *outer* BN / residual / ReLU.
-        mid = conv_bn_act(conv.spatial_conv, conv.bn, a, relu=True, simt=simt)
-        return conv_bn_act(conv.temporal_conv, bn, mid, residual=residual, relu=relu, simt=simt)
+        return Fn.SpatioTemporalConvFunction.run(conv, a, bn, residual, relu, simt)
     stem = a.ld == 4
     if stem and not _is_stem_shape(conv):
         raise NotImplementedError("NDHWC4 inputs are only supported by 7-wide stride-2 stem convolutions")
@@ -121,6 +159,10 @@ def _shortcut(block, a, simt):
 
 def run_basic(block, a, simt=False):
     """conv-BN-ReLU-conv-BN-(+shortcut)-ReLU (resnet3D.py:91-106)."""
+    return Fn.BasicBlockFunction.run(block, a, simt)
+
+
+def _basic_body(block, a, simt=False):
     res = _shortcut(block, a, simt)
     out = conv_bn_act(block.conv1, block.bn1, a, relu=True, simt=simt)
     out = conv_bn_act(block.conv2, block.bn2, out, residual=res, relu=True, simt=simt)
@@ -163,6 +205,10 @@ def _fused_close_with_projection(block, a, h):
 
 def run_bottleneck(block, a, simt=False):
     """1x1x1-BN-ReLU, 3x3x3(stride)-BN-ReLU, 1x1x1-BN-(+shortcut)-ReLU (resnet3D.py:125-143)."""
+    return Fn.BottleneckFunction.run(block, a, simt)
+
+
+def _bottleneck_body(block, a, simt=False):
     ds = block.downsample
     if (not simt and isinstance(ds, nn.Sequential) and len(ds) == 2 and _plain_1x1(ds[0]) and _plain_1x1(block.conv3)
             and not ds[1].training and len(set(_conv_geometry(ds[0])[0])) == 1 and (a.T > 1 or _conv_geometry(ds[0])[0][0] == 1)
@@ -177,8 +223,34 @@ def run_bottleneck(block, a, simt=False):
     return out
 
 
+def _bn_relu(bn, a):
+    """Stand-alone eval-mode BatchNorm + ReLU over an activation (the pre-activation that opens a pre-act block): one
+    element-wise HBM pass with the folded per-channel affine."""
+    dev = a.data.device
+    sc, sh = _cached(bn, "aff1", _sig(*_bn_tensors(bn)) + (a.ld,),
+                     lambda: tuple(t.reshape(1, -1).contiguous() for t in ops.fold_affine(bn.num_features, None, bn, dev)))
+    flat = ops.ccbn_act(Act(a.data, a.N, 1, a.T * a.H, a.W, a.C), sc, sh, relu=True)
+    return Act(flat.data, a.N, a.T, a.H, a.W, a.C)
+
+
+def _preact_body(block, a, simt=False):
+    """PreActivationBasicBlock / PreActivationBottleneck (pre_act_resnet3D.py:41-57, 76-96):
+    out = conv1(relu(bn1(x))); out = conv2(relu(bn2(out))); [out = conv3(relu(bn3(out)))]; out += shortcut(x); no ReLU.
+    bn_{k+1} + ReLU run in conv_k's epilogue; the last convolution's epilogue adds the shortcut of the RAW x."""
+    res = _shortcut(block, a, simt)
+    h = _bn_relu(block.bn1, a)
+    h = conv_bn_act(block.conv1, block.bn2, h, relu=True, simt=simt)
+    if hasattr(block, "conv3"):
+        h = conv_bn_act(block.conv2, block.bn3, h, relu=True, simt=simt)
+        return conv_bn_act(block.conv3, None, h, residual=res, relu=False, simt=simt)
+    return conv_bn_act(block.conv2, None, h, residual=res, relu=False, simt=simt)
+
+
 def run_block(block, a, simt=False):
-    out = run_bottleneck(block, a, simt) if hasattr(block, "conv3") else run_basic(block, a, simt)
+    if getattr(block, "preactivation", False):
+        out = Fn.PreActBlockFunction.run(block, a, simt)
+    else:
+        out = run_bottleneck(block, a, simt) if hasattr(block, "conv3") else run_basic(block, a, simt)
     nl = getattr(block, "nonlocalblock", None)
     if nl is not None and getattr(block, "nonlocal_layer", True):
         out = run_nonlocal(nl, out, simt=simt)
@@ -196,55 +268,133 @@ def _first(m):
     return m[0] if isinstance(m, nn.Sequential) else m
 
 
+def _pad_cols(x2d, cols):
+    """fp16 [rows][ld] -> [rows][cols] with zero columns appended (glue for operands whose K extent must be a multiple of 64)."""
+    if x2d.shape[1] == cols:
+        return x2d
+    y = x2d.new_zeros((x2d.shape[0], cols))
+    y[:, :x2d.shape[1]] = x2d
+    return y
+
+
 def run_nonlocal(nl, a, simt=False):
+    return Fn.NonLocalFunction.run(nl, a, simt)
+
+
+def _nonlocal_body(nl, a, simt=False):
     """z = W(y) + x with y = softmax(theta^T phi) g  (embedded gaussian, nonlocalnet.py:143-166),
-    y = softmax(x^T phi(x)) g (gaussian, :168-190) or y = (theta^T phi / N) g (dot product, :192-211); phi and g are
-    max-pooled when ``sub_sample`` (:126-131)."""
-    if nl.mode not in ("embedded_gaussian", "gaussian", "dot_product"):
-        raise NotImplementedError("non-local mode %r is outside the engine's scope" % (nl.mode,))
+    y = softmax(x^T phi(x)) g (gaussian, :168-190), y = (theta^T phi / N) g (dot product, :192-211) or
+    y = (relu(w . [theta_i ; phi_j]) / N) g (concatenation, :213-243); phi and g are max-pooled when ``sub_sample``
+    (:126-131).
+
+    The attention kernel takes d and dv in multiples of 64: the theta / phi / g projections are packed with zero rows up
+    to ``dp = round_up(inter_channels, 64)`` (zero logit contributions, zero output columns -- exact), so any width the
+    reference accepts runs (nonlocalresnet3d18/34 put a block on C = 64, d = 32).
+
+    Concatenation mode: ``concat_project`` is a bias-free 1x1 Conv2d over the 2d channels of [theta_i ; phi_j] followed
+    by ReLU, i.e. f_ij = relu(a_i + b_j) with a_i = w_theta . theta_i and b_j = w_phi . phi_j.  The N x N x 2d tensor the
+    reference materialises is never built: a_i + b_j is the rank-2 product of Q_i = [a_i, 1, 0, ...] and K_j = [1, b_j, 0, ...]
+    (64-wide), which goes through the same fused kernel with ReLU in place of the softmax (mode 2)."""
+    mode = nl.mode
+    if mode not in ("embedded_gaussian", "gaussian", "dot_product", "concatenation"):
+        raise NotImplementedError("non-local mode %r is outside the engine's scope" % (mode,))
     d, C = nl.inter_channels, nl.in_channels
+    dp = ops._round_up(d, 64)
     dev = a.data.device
     w_conv, w_bn = (nl.W[0], nl.W[1]) if isinstance(nl.W, nn.Sequential) else (nl.W, None)
     g_conv = _first(nl.g)
-    projected = [g_conv] if nl.mode == "gaussian" else [nl.theta, _first(nl.phi), g_conv]   # column order of the GEMM
+    concat = mode == "concatenation"
+    sub = bool(nl.sub_sample)
+    if mode == "gaussian":
+        projected = [g_conv]
+    elif concat:
+        projected = [nl.theta, _first(nl.phi), g_conv]
+    else:
+        projected = [nl.theta, _first(nl.phi), g_conv]           # column order of the GEMM
+    cp_w = nl.concat_project[0].weight if concat else None
+
+    def block(conv):                                             # [dp][ld] fp16 weight rows + fp32 bias of one projection
+        w = torch.zeros((dp, a.ld), dtype=torch.float32, device=dev)
+        w[:d, :C] = _conv1x1_matrix(conv).float()
+        b = torch.zeros(dp, dtype=torch.float32, device=dev)
+        if conv.bias is not None:
+            b[:d] = conv.bias.detach().float()
+        return w, b
+
+    def scalar_block(conv, wvec, slot):
+        """64 projection columns [.., wvec . conv(x), ..] with the scalar in column ``slot`` and a constant 1 in the other
+        of the first two columns: Q_i = [a_i, 1, 0..] (slot 0) resp. K_j = [1, b_j, 0..] (slot 1)."""
+        w = torch.zeros((64, a.ld), dtype=torch.float64, device=dev)
+        b = torch.zeros(64, dtype=torch.float64, device=dev)
+        w[slot, :C] = wvec.double() @ _conv1x1_matrix(conv).double()
+        b[slot] = (wvec.double() @ conv.bias.detach().double()) if conv.bias is not None else 0.0
+        b[1 - slot] = 1.0
+        return w.float(), b.float()
 
     def build():
-        n = len(projected) * d
-        w = torch.zeros((n, a.ld), dtype=torch.float16, device=dev)
-        for i, conv in enumerate(projected):
-            w[i * d:(i + 1) * d, :C] = _conv1x1_matrix(conv).to(torch.float16)
-        b = torch.cat([conv.bias.detach() for conv in projected]).float().contiguous()
-        wo = torch.zeros((C, ops._round_up(d, 8)), dtype=torch.float16, device=dev)
+        if concat:
+            wv = cp_w.detach().reshape(-1)
+            q_w, q_b = scalar_block(nl.theta, wv[:d], 0)
+            g_w, g_b = block(g_conv)
+            if sub:      # phi must be pooled before w_phi is applied (max is not linear): full-resolution phi | g, then a small GEMM
+                p_w, p_b = block(_first(nl.phi))
+                ws, bs = [q_w, p_w, g_w], [q_b, p_b, g_b]
+                kw = torch.zeros((64, dp), dtype=torch.float16, device=dev)
+                kw[1, :d] = wv[d:].to(torch.float16)
+                kshift = torch.zeros(64, dtype=torch.float32, device=dev)
+                kshift[0] = 1.0
+                extra = (kw, torch.ones(64, dtype=torch.float32, device=dev), kshift)
+            else:
+                k_w, k_b = scalar_block(_first(nl.phi), wv[d:], 1)
+                ws, bs, extra = [q_w, k_w, g_w], [q_b, k_b, g_b], None
+        else:
+            pairs = [block(conv) for conv in projected]
+            ws, bs, extra = [w for w, _ in pairs], [b for _, b in pairs], None
+        w = torch.cat(ws).to(torch.float16).contiguous()
+        b = torch.cat(bs).contiguous()
+        wo = torch.zeros((C, dp), dtype=torch.float16, device=dev)
         wo[:, :d] = _conv1x1_matrix(w_conv).to(torch.float16)
         so, bo = ops.fold_affine(C, w_conv.bias, w_bn, dev)
-        return w, b, torch.ones(n, dtype=torch.float32, device=dev), wo, so, bo
+        return w, b, torch.ones(w.shape[0], dtype=torch.float32, device=dev), wo, so, bo, extra
 
-    sig = _sig(*[t for conv in projected for t in (conv.weight, conv.bias)], w_conv.weight, w_conv.bias,
-               *_bn_tensors(w_bn)) + (a.ld, nl.mode)
-    wp, bp, ones, wo, so, bo = _cached(nl, "proj", sig, build)
+    srcs = [t for conv in projected for t in (conv.weight, conv.bias)]
+    sig = _sig(*srcs, w_conv.weight, w_conv.bias, cp_w, *_bn_tensors(w_bn)) + (a.ld, mode, sub)
+    wp, bp, ones, wo, so, bo, extra = _cached(nl, "proj", sig, build)
 
     pool = {3: (2, 2, 2), 2: (1, 2, 2), 1: (1, 1, 2)}[nl.dimension]
     B, Nq = a.N, a.positions
-    dot = nl.mode == "dot_product"
-    if nl.mode == "gaussian":
-        gv = ops.gemm(a.data, wp, ones, bp, a.M, d, a.ld)                       # g(x): [M][d]
-        if nl.sub_sample:
+    amode = {"dot_product": 1, "concatenation": 2}.get(mode, 0)
+    if mode == "gaussian":
+        gv = ops.gemm(a.data, wp, ones, bp, a.M, dp, a.ld)                      # g(x): [M][dp]
+        Cq = ops._round_up(C, 64)
+        xq = _pad_cols(a.data, Cq)                                               # theta = x itself
+        if sub:
             xk = ops.maxpool3d(a, pool, pool, (0, 0, 0))                           # phi = max_pool(x)
-            gk = ops.maxpool3d(Act(gv, a.N, a.T, a.H, a.W, d), pool, pool, (0, 0, 0))
-            k2d, v2d, Nk = xk.data, gk.data, xk.positions
+            gk = ops.maxpool3d(Act(gv, a.N, a.T, a.H, a.W, dp), pool, pool, (0, 0, 0))
+            k2d, v2d, Nk = _pad_cols(xk.data, Cq), gk.data, xk.positions
         else:
-            k2d, v2d, Nk = a.data, gv, Nq
-        y = ops.attention(a.data, k2d, v2d, C, d, B, Nq, Nk)                      # theta = x itself
-    elif not nl.sub_sample:
-        qkv = ops.gemm(a.data, wp, ones, bp, a.M, 3 * d, a.ld)                   # [M][3d]: theta | phi | g
-        y = ops.attention(qkv, qkv[:, d:], qkv[:, 2 * d:], d, d, B, Nq, Nq, dot_product=dot)
+            k2d, v2d, Nk = xq, gv, Nq
+        y = ops.attention(xq, k2d, v2d, Cq, dp, B, Nq, Nk)
+    elif concat and sub:
+        q = ops.gemm(a.data, wp[:64], ones[:64], bp[:64], a.M, 64, a.ld)        # [a_i, 1, 0..]
+        kv = ops.gemm(a.data, wp[64:], ones[64:], bp[64:], a.M, 2 * dp, a.ld)   # phi | g at full resolution
+        kvp = ops.maxpool3d(Act(kv, a.N, a.T, a.H, a.W, 2 * dp), pool, pool, (0, 0, 0))
+        kw, kones, kshift = extra
+        k = ops.gemm(kvp.data, kw, kones, kshift, kvp.M, 64, dp)                 # [1, w_phi . phi_j, 0..]
+        y = ops.attention(q, k, kvp.data[:, dp:], 64, dp, B, Nq, kvp.positions, mode=2)
+    elif concat:
+        qkv = ops.gemm(a.data, wp, ones, bp, a.M, 128 + dp, a.ld)               # [a_i,1,0..] | [1,b_j,0..] | g
+        y = ops.attention(qkv, qkv[:, 64:], qkv[:, 128:], 64, dp, B, Nq, Nq, mode=2)
+    elif not sub:
+        qkv = ops.gemm(a.data, wp, ones, bp, a.M, 3 * dp, a.ld)                  # [M][3dp]: theta | phi | g
+        y = ops.attention(qkv, qkv[:, dp:], qkv[:, 2 * dp:], dp, dp, B, Nq, Nq, mode=amode)
     else:
-        q = ops.gemm(a.data, wp[:d], ones[:d], bp[:d], a.M, d, a.ld)             # theta at full resolution
-        kv = ops.gemm(a.data, wp[d:], ones[d:], bp[d:], a.M, 2 * d, a.ld)        # phi | g ...
-        kvp = ops.maxpool3d(Act(kv, a.N, a.T, a.H, a.W, 2 * d), pool, pool, (0, 0, 0))   # ... max-pooled together
-        y = ops.attention(q, kvp.data, kvp.data[:, d:], d, d, B, Nq, kvp.positions, dot_product=dot)
+        q = ops.gemm(a.data, wp[:dp], ones[:dp], bp[:dp], a.M, dp, a.ld)         # theta at full resolution
+        kv = ops.gemm(a.data, wp[dp:], ones[dp:], bp[dp:], a.M, 2 * dp, a.ld)    # phi | g ...
+        kvp = ops.maxpool3d(Act(kv, a.N, a.T, a.H, a.W, 2 * dp), pool, pool, (0, 0, 0))   # ... max-pooled together
+        y = ops.attention(q, kvp.data, kvp.data[:, dp:], dp, dp, B, Nq, kvp.positions, mode=amode)
     # W (1x1 conv with bias) + BN + residual x, no ReLU
-    z = ops.gemm(y, wo, so, bo, a.M, C, d, residual=a.data)
+    z = ops.gemm(y, wo, so, bo, a.M, C, dp, residual=a.data)
     return Act(z, a.N, a.T, a.H, a.W, C)
 
 
@@ -263,6 +413,10 @@ def _pool_args(mp):
 def run_stem(model, x, simt=False):
     """conv1 -> bn1 -> relu -> maxpool (torchvision_models.py:449-452)."""
     a = x if isinstance(x, Act) else ops.from_ncdhw(x)
+    return Fn.StemFunction.run(model, a, simt)
+
+
+def _stem_body(model, a, simt=False):
     a = conv_bn_act(model.conv1, model.bn1, a, relu=True, simt=simt)
     k, s, p = _pool_args(model.maxpool)
     return ops.maxpool3d(a, k, s, p)
@@ -279,6 +433,9 @@ def run_trunk(model, x, simt=False):
 def run_head(model, a, head):
     """avgpool -> view(B,-1) -> last_linear (torchvision_models.py:460-464).  Returns fp32 [N][classes]."""
     pooled = ops.avgpool_global(a)                     # fp16 [N][ld]
+    if isinstance(head, nn.Linear) and torch.is_grad_enabled() and any(p.requires_grad for p in head.parameters()):
+        # trainable head on frozen engine features: differentiable GEMM (functions.LinearFunction), same kernel
+        return Fn.linear(pooled[:, :head.in_features], head.weight, head.bias)
     if isinstance(head, nn.Linear):
         pl = _cached(head, "pl", _sig(head.weight, head.bias), lambda: ops.PackedLinear(head.weight, head.bias))
         return ops.linear(pooled, pl, out_f32=True)

@@ -19,6 +19,8 @@ power-iteration step off the stored ``u0`` (no update).
 import torch
 import torch.nn as nn
 
+from .. import engine as _engine
+
 __all__ = ['Generator', 'biggan_deep', 'biggan_deep128', 'biggan_deep256', 'biggan_deep512', 'G_ARCH']
 
 # resolution -> (in multipliers, out multipliers, resolutions with attention); channels = multiplier * ch
@@ -109,7 +111,7 @@ class Attention(nn.Module):
         self.gamma = nn.Parameter(torch.tensor(0.))
 
 
-class Generator(nn.Module):
+class Generator(_engine.CacheOwner, nn.Module):
     def __init__(self, G_ch=128, dim_z=128, bottom_width=4, resolution=256, n_classes=1000, shared_dim=128,
                  G_attn='64', BN_eps=1e-5, SN_eps=1e-12, G_init='ortho', hier=True, **unused):
         super().__init__()

@@ -38,15 +38,13 @@ class _NonLocalBlockND(EngineModule):
 
     Modes on the engine: ``embedded_gaussian`` (:143-166), ``gaussian`` (:168-190), ``dot_product`` (:192-211), each
     with or without ``sub_sample`` (max-pooled phi / g, :126-131) and with or without the output BatchNorm.
-    ``concatenation`` (:213-243) is not implemented."""
+    ``concatenation`` (:213-243) runs on the same fused kernel through a rank-2 encoding of a_i + b_j (engine.run_nonlocal)."""
 
     def __init__(self, in_channels, inter_channels=None, dimension=3, mode='embedded_gaussian', sub_sample=False,
                  bn_layer=True):
         super().__init__()
         assert dimension in [1, 2, 3]
         assert mode in ['embedded_gaussian', 'gaussian', 'dot_product', 'concatenation']
-        if mode == 'concatenation':
-            raise NotImplementedError("the 'concatenation' non-local mode is outside the engine's scope")
         self.mode, self.dimension, self.sub_sample = mode, dimension, sub_sample
         self.in_channels = in_channels
         self.inter_channels = inter_channels if inter_channels is not None else max(in_channels // 2, 1)
@@ -66,9 +64,11 @@ class _NonLocalBlockND(EngineModule):
         self.theta = None
         self.phi = None
         self.concat_project = None
-        if mode in ('embedded_gaussian', 'dot_product'):
+        if mode in ('embedded_gaussian', 'dot_product', 'concatenation'):
             self.theta = conv_nd(in_channels, d, kernel_size=1, stride=1, padding=0)
             self.phi = conv_nd(in_channels, d, kernel_size=1, stride=1, padding=0)
+            if mode == 'concatenation':        # nonlocalnet.py:117-121
+                self.concat_project = nn.Sequential(nn.Conv2d(d * 2, 1, 1, 1, 0, bias=False), nn.ReLU())
         if sub_sample:
             self.g = nn.Sequential(self.g, max_pool(kernel_size=2))
             self.phi = max_pool(kernel_size=2) if self.phi is None else nn.Sequential(self.phi, max_pool(kernel_size=2))
@@ -140,7 +140,7 @@ class NonLocalBottleneck(_NLBlockBase):
             self.nonlocalblock = NonLocalBlock3D(planes * 4)
 
 
-class NonLocalResNet3D(nn.Module):
+class NonLocalResNet3D(engine.CacheOwner, nn.Module):
     Conv3d = nn.Conv3d
     head_name = 'last_linear'
 

@@ -35,7 +35,7 @@ pretrained_settings['resnet18']['places365'] = _row('http://pretorched-x.csail.m
 pretrained_settings['resnet50']['places365'] = _row('http://pretorched-x.csail.mit.edu/models/resnet50_places365-a570fcfc.pth', 365)
 
 
-class ResNet2D(tvresnet.ResNet):
+class ResNet2D(engine.CacheOwner, tvresnet.ResNet):
     """torchvision ResNet parameters + engine forward; ``last_linear`` replaces ``fc``."""
 
     def __init__(self, block, layers, num_classes=1000):

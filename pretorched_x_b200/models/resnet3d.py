@@ -60,7 +60,7 @@ pretrained_settings = _make_settings([n for n in __all__ if n not in ('ResNet3D'
 # ---------------------------------------------------------------------------------------------
 # shared behaviour of every engine-backed module
 # ---------------------------------------------------------------------------------------------
-class EngineModule(nn.Module):
+class EngineModule(engine.CacheOwner, nn.Module):
     """Accepts either an engine ``Act`` (inside a network) or a plain NCDHW tensor (standalone use, as the
     reference's blocks allow) and returns the same kind."""
 
@@ -131,7 +131,7 @@ class Bottleneck(EngineModule):
 Bottleneck3D = Bottleneck   # the name BASELINE.json's north_star uses
 
 
-class ResNet3D(nn.Module):
+class ResNet3D(engine.CacheOwner, nn.Module):
     """conv1(7x7x7, s(1,2,2)) - bn - relu - maxpool - layer1..4 - avgpool - last_linear."""
 
     Conv3d = nn.Conv3d

@@ -94,7 +94,7 @@ def _subsample_frames(x, stride):
     return x[:, :, ::stride]
 
 
-class Slow(nn.Module):
+class Slow(engine.CacheOwner, nn.Module):
     """Slow pathway with lateral inputs (slowfast.py:104-180)."""
     lateral_factor = 2            # channels gained from the fast pathway: out // 8 * 2
 
@@ -148,7 +148,7 @@ class SlowOnly(Slow):
         return engine.run_head(self, a, self.last_linear)
 
 
-class Fast(nn.Module):
+class Fast(engine.CacheOwner, nn.Module):
     """Fast pathway + the lateral projections (slowfast.py:244-345)."""
 
     def __init__(self, block=Bottleneck, layers=(2, 2, 2, 2)):
@@ -203,7 +203,7 @@ class FastOnly(Fast):
         return engine.run_head(self, a, self.last_linear)
 
 
-class SlowFast(nn.Module):
+class SlowFast(engine.CacheOwner, nn.Module):
     def __init__(self, block=Bottleneck, layers=(2, 2, 2, 2), num_classes=400, dropout=0.5, slow_stride=16,
                  fast_stride=2):
         super().__init__()

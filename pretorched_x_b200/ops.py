@@ -415,20 +415,33 @@ def gather_frames(x3d, idx_dev):
     return y
 
 
+def gather_frame_tuples(x3d, idx_dev, n_tuples, n_idx):
+    """x3d fp16 [N][T][F], idx int32 [n_tuples][n_idx] on device -> [N * n_tuples][n_idx * F], tuple index fastest
+    (trn.py:100-110: every sampled tuple of one scale in one launch)."""
+    N, T, F = x3d.shape
+    y = torch.empty((N * n_tuples, n_idx * F), dtype=torch.float16, device=x3d.device)
+    _lib.check(_lib.load().b2_gather_frame_tuples(_ptr(x3d), _ptr(y), _ptr(idx_dev), N, T, F, n_idx, n_tuples, _stream()),
+               "b2_gather_frame_tuples")
+    return y
+
+
 # ---------------------------------------------------------------------------------------------
 # non-local attention
 # ---------------------------------------------------------------------------------------------
-def attention(q2d, k2d, v2d, d, dv, B, Nq, Nk, dot_product=False):
-    """softmax(Q K^T) V, or (Q K^T / Nk) V when ``dot_product`` (nonlocalnet.py:143-211).
+def attention(q2d, k2d, v2d, d, dv, B, Nq, Nk, dot_product=False, mode=None):
+    """softmax(Q K^T) V (mode 0), (Q K^T / Nk) V (mode 1, ``dot_product``) or (relu(Q K^T) / Nk) V (mode 2, the
+    concatenation mode's rank-2 encoding) -- nonlocalnet.py:143-243.
 
     q2d: fp16 [B*Nq][>= d]; k2d: fp16 [B*Nk][>= d]; v2d: fp16 [B*Nk][>= dv] (row views of projection outputs, 16-byte
     aligned).  Returns fp16 [B*Nq][dv]."""
+    if mode is None:
+        mode = 1 if dot_product else 0
     o = torch.empty((B * Nq, _round_up(dv, 8)), dtype=torch.float16, device=q2d.device)
     with _timed("attention", "attention B=%d Nq=%d Nk=%d d=%d dv=%d" % (B, Nq, Nk, d, dv), 2.0 * B * Nq * Nk * (d + dv),
                 2.0 * B * (Nq * (d + dv) + Nk * (d + dv))):
         _lib.check(_lib.load().b2_nonlocal_attention(_ptr(q2d), q2d.stride(0), _ptr(k2d), k2d.stride(0), _ptr(v2d),
                                                     v2d.stride(0), _ptr(o), o.stride(0), B, Nq, Nk, d, dv,
-                                                    int(dot_product), _stream()), "b2_nonlocal_attention")
+                                                    int(mode), _stream()), "b2_nonlocal_attention")
     return o
 
 

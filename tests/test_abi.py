@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), "libb2pretorched.so does not export %s" % name
     assert set(declared_symbols()) == set(_lib.SYMBOLS), "ctypes table and header disagree"
-    assert lib.b2_version() >= 100
+    assert lib.b2_version() == _lib.EXPECTED_ABI == 103
 
 
 def test_ctypes_structs_match_c_layout(tmp_path):

@@ -33,13 +33,7 @@ def dev():
 
 
 def build(fx, dev):
-    torch.manual_seed(fx["seeds"]["init"])
-    arch = fx["arch"]
-    m = getattr(P, arch)(**fx["kwargs"]) if arch.startswith("r2") else getattr(P, arch)(pretrained=None, **fx["kwargs"])
-    OF.randomize_bn_(m, fx["seeds"]["bn"])
-    if fx.get("nl_factors"):
-        OF.apply_nonlocal_factors_(m, fx["nl_factors"])
-    return m.eval().to(dev)
+    return OF.build_package_model(P, fx).to(dev)
 
 
 def stage_errors(m, x, fx):
@@ -225,3 +219,106 @@ def test_nonlocal_block_modes_match_reference_golden(dev, path):
     assert tuple(y.shape) == tuple(fx["output"].shape)
     err = (y.cpu().double() - fx["output"].double()).abs().max().item() / fx["output"].abs().max().item()
     assert err <= 5e-3, err
+
+
+TRN_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "trn"]
+
+
+@pytest.mark.parametrize("path", TRN_FIX, ids=[os.path.basename(p)[:-3] for p in TRN_FIX])
+def test_trn_wrapper_matches_reference_golden(dev, path):
+    """Full TRN (frames -> 2-D backbone -> relation -> Linear, trn.py:246-263) against the reference's own outputs."""
+    from tests.test_oracle_golden import build_trn
+    fx = torch.load(path, weights_only=False)
+    m = build_trn(fx).to(dev)
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"]).to(dev)
+    if fx["np_seed"] is not None:
+        np.random.seed(fx["np_seed"])
+    with torch.no_grad():
+        feats = m.features(x)
+        y = m.logits(feats)
+    assert tuple(y.shape) == tuple(fx["logits"].shape)
+    ef = (feats.cpu().double() - fx["features"].double()).abs().max().item() / fx["features"].abs().max().item()
+    el = (y.cpu().double() - fx["logits"].double()).abs().max().item() / fx["logits"].abs().max().item()
+    assert ef <= 1e-2 and el <= 1e-2, (ef, el)
+
+
+def test_multiscale_relation_is_graph_capturable(dev):
+    """The tuple table lives in one persistent device buffer: a CUDA graph over forward_tuples replays with NEW tuples after
+    a single host->device copy (no per-tuple copies, no host work inside the graph)."""
+    from pretorched_x_b200 import ops
+    torch.manual_seed(0)
+    r = P.MultiScaleRelation(8, 256, 64, bottleneck_dim=128).to(dev).eval()
+    x = OF.seeded_input((4, 8, 256), 5).to(dev)
+    with torch.no_grad():
+        x16 = ops.cast_rows(x.view(4, -1), relu=True).view(4, 8, -1)
+        np.random.seed(7)
+        picks_a = r.sample_tuples()
+        picks_b = r.sample_tuples()
+        table = r.upload_tuples(picks_a, dev)
+        total = torch.empty((4, 64), dtype=torch.float32, device=dev)
+        r.forward_tuples(x16, table, total)                      # warm-up (packs weights)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            r.forward_tuples(x16, table, total)
+        g.replay()
+        torch.cuda.synchronize()
+        got_a = total.clone()
+        r.upload_tuples(picks_b, dev)
+        g.replay()
+        torch.cuda.synchronize()
+        got_b = total.clone()
+        sd = {k: v.cpu() for k, v in r.state_dict().items()}
+        want_a = OF.multiscale_relation(x.cpu(), sd, 8, 256, tuples=picks_a).view(4, 64)
+        want_b = OF.multiscale_relation(x.cpu(), sd, 8, 256, tuples=picks_b).view(4, 64)
+    assert (got_a.cpu() - want_a).abs().max().item() <= 5e-3 * want_a.abs().max().item()
+    assert (got_b.cpu() - want_b).abs().max().item() <= 5e-3 * want_b.abs().max().item()
+    assert not torch.equal(got_a, got_b)
+
+
+def test_trainable_head_on_frozen_engine_features(dev):
+    """torch.autograd.Function boundary: the trunk is a frozen feature extractor (non-differentiable outputs), the dense head has
+    a real backward on the tcgen05 GEMM.  Gradients of last_linear match torch's fp32 autograd on the same pooled features."""
+    torch.manual_seed(0)
+    m = OF.randomize_bn_(P.resnet3d18(num_classes=7, pretrained=None), 1).eval().to(dev)
+    x = OF.seeded_input((3, 3, 8, 64, 64), 4).to(dev).requires_grad_(True)
+    target = torch.tensor([1, 5, 2], device=dev)
+    logits = m(x)                                                   # grad mode on, head parameters require grad
+    assert logits.requires_grad
+    loss = torch.nn.functional.cross_entropy(logits, target)
+    loss.backward()
+    assert x.grad is None                                           # frozen trunk: nothing flows to the input
+    assert all(p.grad is None for n, p in m.named_parameters() if not n.startswith("last_linear"))
+    gw, gb = m.last_linear.weight.grad.clone(), m.last_linear.bias.grad.clone()
+    with torch.no_grad():
+        from pretorched_x_b200 import ops
+        pooled = ops.avgpool_global(m.features_act(x))[:, :512].float()
+    w = m.last_linear.weight.detach().clone().requires_grad_(True)
+    b = m.last_linear.bias.detach().clone().requires_grad_(True)
+    ref_loss = torch.nn.functional.cross_entropy(pooled @ w.t() + b, target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3 * max(1.0, abs(ref_loss.item()))
+    assert (gw - w.grad).abs().max().item() <= 5e-3 * w.grad.abs().max().item()
+    assert (gb - b.grad).abs().max().item() <= 5e-3 * b.grad.abs().max().item()
+    # an optimiser step changes the head's output (the packed copy follows the parameter's version counter)
+    opt = torch.optim.SGD(m.last_linear.parameters(), lr=0.5)
+    opt.step()
+    with torch.no_grad():
+        assert not torch.equal(m(x), logits.detach())
+
+
+def test_relation_mlp_backward_matches_torch(dev):
+    torch.manual_seed(0)
+    r = P.Relation(4, 64, 16, bottleneck_dim=32).to(dev)
+    x = OF.seeded_input((5, 4, 64), 3).to(dev).requires_grad_(True)
+    y = r(x)
+    y.square().mean().backward()
+    got = {n: p.grad.clone() for n, p in r.named_parameters()}
+    gx = x.grad.clone()
+    ref = torch.nn.Sequential(torch.nn.ReLU(), torch.nn.Linear(256, 32), torch.nn.ReLU(), torch.nn.Linear(32, 16)).to(dev)
+    ref.load_state_dict({k.replace("relate.", ""): v for k, v in r.state_dict().items()})
+    x2 = x.detach().clone().requires_grad_(True)
+    ref(x2.view(5, -1)).square().mean().backward()
+    for n, p in ref.named_parameters():
+        assert (got["relate." + n] - p.grad).abs().max().item() <= 1e-2 * p.grad.abs().max().item() + 1e-6, n
+    assert (gx - x2.grad).abs().max().item() <= 1e-2 * x2.grad.abs().max().item() + 1e-6

@@ -72,8 +72,8 @@ def test_nonlocal_quirks():
     assert nl == ["layer2.0", "layer2.2", "layer3.0", "layer3.2", "layer3.4"]
     assert float(m.layer2[0].nonlocalblock.W[1].weight.abs().mean()) == 1.0   # init_weights overrides the zero init
     assert OF.nonlocal_positions([3, 4, 6, 3], [0, 2, 3, 0]) == [[], [0, 2], [0, 2, 4], []]
-    with pytest.raises(NotImplementedError):
-        nonlocalnet.NonLocalBlock3D(64, mode="concatenation")
+    cat = nonlocalnet.NonLocalBlock3D(64, mode="concatenation")               # nonlocalnet.py:117-121: 2d -> 1 projection, no bias
+    assert tuple(cat.state_dict()["concat_project.0.weight"].shape) == (1, 64, 1, 1) and "concat_project.0.bias" not in cat.state_dict()
     sub = nonlocalnet.NonLocalBlock2D(64, mode="gaussian", sub_sample=True)     # reference layout with sub_sample
     assert set(sub.state_dict()) >= {"g.0.weight", "g.0.bias", "W.0.weight", "W.1.running_mean"}
     assert "theta.weight" not in sub.state_dict()

@@ -16,16 +16,7 @@ MODEL_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "
 
 
 def build_ours(fx):
-    torch.manual_seed(fx["seeds"]["init"])
-    arch = fx["arch"]
-    if arch.startswith("r2plus1d"):
-        m = getattr(P, arch)(**fx["kwargs"])
-    else:
-        m = getattr(P, arch)(pretrained=None, **fx["kwargs"])
-    OF.randomize_bn_(m, fx["seeds"]["bn"])
-    if fx.get("nl_factors"):
-        OF.apply_nonlocal_factors_(m, fx["nl_factors"])
-    return m.eval()
+    return OF.build_package_model(P, fx)
 
 
 def test_fixtures_present():
@@ -48,7 +39,7 @@ def test_oracle_reproduces_reference_outputs(path):
     x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"])
     stages = {}
     with torch.no_grad():
-        out = OF.forward(x, sd, fx["arch"], stages)
+        out = OF.forward(x, sd, OF.arch_spec(fx["arch"], fx["kwargs"]), stages)
     scale = fx["logits"].abs().max().item()
     assert (out - fx["logits"]).abs().max().item() <= 1e-5 * scale
     for name, ref in fx["stages"].items():
@@ -219,3 +210,31 @@ def test_grouped_filter_as_block_diagonal_dense_filter():
         assert float((dense != 0).double().mean()) <= 1.0 / groups + 1e-9
     with pytest.raises(ValueError):
         ops.dense_from_grouped(torch.zeros(10, 4, 1, 1, 1), 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# TRN wrapper (trn.py:192-338): fixtures come from the reference with only its backbone factory patched for offline use
+# ---------------------------------------------------------------------------------------------
+TRN_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "trn"]
+
+
+def build_trn(fx):
+    torch.manual_seed(fx["seeds"]["init"])
+    m = P.TRN(10, num_segments=fx["segments"], arch=fx["arch"], consensus=fx["consensus"], pretrained=None, **fx["kwargs"])
+    OF.randomize_bn_(m, fx["seeds"]["bn"])
+    return m.eval()
+
+
+@pytest.mark.parametrize("path", TRN_FIX, ids=[os.path.basename(p)[:-3] for p in TRN_FIX])
+def test_trn_wrapper_init_and_oracle_match_reference(path):
+    fx = torch.load(path, weights_only=False)
+    sd = build_trn(fx).state_dict()
+    assert list(sd) == list(fx["weight_digest"]) and OF.digests_match(OF.state_digest(sd), fx["weight_digest"])
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"])
+    if fx["np_seed"] is not None:
+        np.random.seed(fx["np_seed"])
+    st = {}
+    with torch.no_grad():
+        y = OF.trn_forward(x, sd, fx["arch"], fx["consensus"], fx["segments"], st)
+    assert (st["features"] - fx["features"]).abs().max().item() <= 1e-5 * fx["features"].abs().max().item()
+    assert (y - fx["logits"]).abs().max().item() <= 1e-5 * fx["logits"].abs().max().item()
