@@ -1,17 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- clips/sec of the resnet3d50 forward (B=32 clips of 16x224x224 per GPU), BASELINE.json config[1].
+"""bench.py -- throughput of the forward hot path on B200, one BASELINE.json config per --workload.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A step = one forward pass of the hot path over one batch of synthetic clips per GPU (weak scaling: every rank
-runs B=32; clips shard with no data-path collective, one all-gather of the [B,400] logits per step).  Prints ONE
-JSON line (rank 0).  ``value`` times CUDA-graph replays with the input resident in HBM; ``e2e`` times the same
-forward through the public API with pinned HOST input (H2D inside) and a D2H read of the logits every step.
+Workloads (BASELINE.json ``configs``):
+    resnet3d50  configs[1]  resnet3d50, B=32 clips of 16x224x224 per GPU, weak scaling   (default: the contract's line)
+    r2plus1d34  configs[2]  r2plus1d34 (R(2+1)D-34), B=16 clips of 32x112x112 IN TOTAL, strong scaling over 1 -> 8 GPUs
+    nonlocal50  configs[3]  nonlocalresnet3d50 (5 non-local blocks), 8 clips of 32x224x224 per GPU (B=64 on 8), weak scaling
+    biggan256   configs[4]  BigGAN-deep-256 generator, B=256 z+class -> fp16 images per GPU, weak scaling
+    resnet18    configs[0]  resnet18 224x224 images (the reference's CPU-runnable anchor), B=256 per GPU
 
-``--impl reference`` times the reference's CPU fp32 forward (the oracle port of it; /root/reference itself when
-the tree is present) on the box's host cores, on a bounded sample of the same workload.
+A step = one forward pass of the hot path over one batch of synthetic input per GPU.  Clips shard with no data-path
+collective; one all-gather of the [B, classes] logits per step.  Prints ONE JSON line (rank 0):
+  value      CUDA-event time of K CUDA-graph replays, input resident in HBM, max over ranks
+  e2e        the same forward through the public API from pinned HOST memory: fp32 NCDHW clips (the reference's input dtype)
+             -> H2D -> forward -> D2H logits, every step (copies overlap the previous step's compute); the fp16-host rate beside it
+  parity     logits of the timed graph for the first clips of the timed batch against the CPU oracle (asserted before timing)
+  roofline   dominant kernel of the step: algorithmic FLOP (or bytes) / its CUDA-event time vs the measured peak
+  cpu_baseline  the reference's own CPU forward on the host cores (oracle/_ref = the byte-compiled reference), bounded sample
+
+``--impl reference`` times the reference's CPU fp32 forward itself (rank 0 only) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -25,12 +35,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-ARCH = "resnet3d50"
-NUM_CLASSES = 400
-CLIP = (3, 16, 224, 224)
-BATCH_PER_GPU = 32
-GFLOP_PER_CLIP = 79.69          # algorithmic, padding taps included (SURVEY.md section 8a / BASELINE.md section 2)
-METRIC = "clips/sec resnet3d50 16x224x224 forward"
+# algorithmic GFLOP per sample: padding taps included, exactly what hooking the reference's modules yields
+WORKLOADS = {
+    "resnet3d50": dict(arch="resnet3d50", kwargs=dict(num_classes=400), sample=(3, 16, 224, 224), batch=32, scaling="weak",
+                       gflop=79.69, classes=400, unit="clips/s", metric="clips/sec resnet3d50 16x224x224 forward",
+                       config="configs[1]", check_clips=2, cpu_sample=2, act_elems=127.9e6),
+    "r2plus1d34": dict(arch="r2plus1d34", kwargs=dict(num_classes=400), sample=(3, 32, 112, 112), batch=16, scaling="strong",
+                       gflop=51.48, classes=400, unit="clips/s", metric="clips/sec r2plus1d34 32x112x112 forward",
+                       config="configs[2]", check_clips=2, cpu_sample=2, act_elems=79.2e6),
+    "nonlocal50": dict(arch="nonlocalresnet3d50", kwargs=dict(), sample=(3, 32, 224, 224), batch=8, scaling="weak",
+                       gflop=262.22, classes=339, unit="clips/s", metric="clips/sec nonlocalresnet3d50 32x224x224 forward",
+                       config="configs[3]", check_clips=1, cpu_sample=1, act_elems=289.3e6,
+                       nl_fixture="nonlocalresnet3d50_tamed_b1_t32_224.pt"),
+    "resnet18": dict(arch="resnet18", kwargs=dict(num_classes=1000), sample=(3, 224, 224), batch=256, scaling="weak",
+                     gflop=3.63, classes=1000, unit="images/s", metric="images/sec resnet18 224x224 forward",
+                     config="configs[0]", check_clips=4, cpu_sample=16, act_elems=4.7e6),
+}
+DEFAULT_WORKLOAD = "resnet3d50"
 
 
 def load_peaks():
@@ -62,7 +83,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.1)
 
     def stop(self):
         self._stop_evt.set()
@@ -79,35 +100,63 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm (reference's own implementation of the path on host cores)
+# model construction shared by both arms (same seeds => same weights on the reference, the port and the engine)
 # ------------------------------------------------------------------------------------------------
-def cpu_forward_fn():
-    """Returns (callable(x) -> logits, kind).  Uses the unmodified reference when /root/reference exists (build
-    container), else the oracle port of it (GPU box)."""
+def condition_(model, spec):
+    """Non-trivial BN statistics; for the non-local net the theta/phi rescale recorded in the committed reference fixture (a
+    trained-like logit regime: raw Kaiming-initialised logits reach 1e4..1e8 and make softmax an arg-max)."""
+    import torch
+    from oracle import functional as OF
+    OF.randomize_bn_(model, 1)
+    if spec.get("nl_fixture"):
+        fx = torch.load(os.path.join(ROOT, "tests", "golden", spec["nl_fixture"]), weights_only=False)
+        OF.apply_nonlocal_factors_(model, fx["nl_factors"])
+    return model
+
+
+def build_ours(spec):
+    import torch
+    import pretorched_x_b200 as P
+    torch.manual_seed(0)
+    arch = spec["arch"]
+    m = getattr(P, arch)(**spec["kwargs"]) if arch.startswith("r2plus1d") else getattr(P, arch)(pretrained=None, **spec["kwargs"])
+    return condition_(m, spec).eval()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (the reference's own implementation of the path on the host cores)
+# ------------------------------------------------------------------------------------------------
+def cpu_forward_fn(spec):
+    """Returns (callable(x) -> logits, kind).  ``reference``: the unmodified reference modules (source tree in the build
+    container, byte-compiled oracle/_ref on the GPU box); ``port``: the oracle restatement, only when neither exists."""
     import torch
     from oracle import functional as OF
     from oracle import reference_loader as RL
-    torch.set_num_threads(os.cpu_count() or 1)
+    arch = spec["arch"]
     if RL.available():
         RL.load()
         torch.manual_seed(0)
-        model = RL.build(ARCH, num_classes=NUM_CLASSES)
-        OF.randomize_bn_(model, 1)
-        model.eval()
+        model = condition_(RL.build(arch, **spec["kwargs"]), spec).eval()
+        if arch.startswith("r2plus1d"):
+            # R2Plus1D inherits ResNet3D.forward, which a resnet3d* factory call may have patched at class level to need
+            # `last_linear` (SURVEY.md section 0.1); its own unpatched body is conv1..layer4 -> avgpool -> fc
+            def fwd(x, m=model):
+                f = m.layer4(m.layer3(m.layer2(m.layer1(m.maxpool(m.relu(m.bn1(m.conv1(x))))))))
+                return m.fc(m.avgpool(f).view(f.size(0), -1))
+            return fwd, "reference"
         return (lambda x: model(x)), "reference"
-    import pretorched_x_b200 as P
-    torch.manual_seed(0)
-    sd = OF.randomize_bn_(P.resnet3d50(num_classes=NUM_CLASSES, pretrained=None), 1).state_dict()
-    return (lambda x: OF.forward(x, sd, ARCH)), "port"
+    sd = build_ours(spec).state_dict()
+    return (lambda x: OF.forward(x, sd, arch)), "port"
 
 
-def time_cpu(steps, warmup, sample_clips=2):
+def time_cpu(spec, steps, warmup):
     import torch
     from oracle import functional as OF
-    fn, kind = cpu_forward_fn()
-    x = OF.seeded_input((sample_clips,) + CLIP, 2)
-    # "all the host threads it can use": torch's default is every core, which oversubscribes badly on large
-    # shared hosts -- probe a few thread counts with one forward each and keep the fastest.
+    fn, kind = cpu_forward_fn(spec)
+    n = spec["cpu_sample"]
+    x = OF.seeded_input((n,) + spec["sample"], 2)
+    # "all the host threads it can use": torch's default is every core, which oversubscribes badly on large shared hosts --
+    # probe a few thread counts with one forward each and keep the fastest
     ncpu = os.cpu_count() or 1
     best = None
     with torch.no_grad():
@@ -119,65 +168,67 @@ def time_cpu(steps, warmup, sample_clips=2):
             dt = time.perf_counter() - t0
             if best is None or dt < best[0]:
                 best = (dt, nt)
-    torch.set_num_threads(best[1])
-    with torch.no_grad():
+        torch.set_num_threads(best[1])
         for _ in range(warmup):
             fn(x)
         t0 = time.perf_counter()
         for _ in range(steps):
             fn(x)
         dt = time.perf_counter() - t0
-    return dict(value=sample_clips * steps / dt, unit="clips/s", cores=torch.get_num_threads(), kind=kind,
-                sample="%d steps x %d clips of %s fp32 on %d host threads (torch %s)" % (
-                    steps, sample_clips, "x".join(map(str, CLIP)), torch.get_num_threads(), torch.__version__),
+    return dict(value=n * steps / dt, unit=spec["unit"], cores=torch.get_num_threads(), kind=kind,
+                sample="%d steps x %d samples of %s fp32 on %d host threads (torch %s; %s)" % (
+                    steps, n, "x".join(map(str, spec["sample"])), torch.get_num_threads(), torch.__version__,
+                    "unmodified reference modules" if kind == "reference" else "oracle restatement"),
                 ms_per_step=dt / steps * 1e3)
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, spec, rank):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 6))
-    cb = time_cpu(steps, max(1, min(args.warmup, 1)))
-    line = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded randn clips, random-init weights)",
-        "config": {"workload": "resnet3d50 forward, clips of 16x224x224 (bounded CPU sample: 2 clips per step)",
-                   "parallelism": "cpu"},
+    cb = time_cpu(spec, steps, 1)
+    print(json.dumps({
+        "impl": "reference", "metric": spec["metric"], "value": cb["value"], "unit": spec["unit"], "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": spec["scaling"],
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded randn input, random-init weights)",
+        "config": {"workload": "%s forward, %s (bounded CPU sample: %d per step; BASELINE.json %s)" % (
+            spec["arch"], "x".join(map(str, spec["sample"])), spec["cpu_sample"], spec["config"]), "parallelism": "cpu"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
+        "e2e": {"value": cb["value"], "unit": spec["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
-# GPU arm
+# GPU arm, video / image classifiers
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local):
+def run_ours(args, spec, rank, world, local):
     import torch
     import torch.distributed as dist
-    import pretorched_x_b200 as P
     from pretorched_x_b200 import ops, parallel, _lib
     from pretorched_x_b200.graph import GraphedForward, PipelinedForward
-    from oracle import functional as OF           # BN conditioning + cpu_baseline leg only
+    from oracle import functional as OF           # checker (parity) + cpu_baseline leg only; never on the timed path
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    B = args.batch
-    torch.manual_seed(0)
-    model = P.resnet3d50(num_classes=NUM_CLASSES, pretrained=None)
-    OF.randomize_bn_(model, 1)
-    model = model.eval().to(dev)
+    strong = spec["scaling"] == "strong"
+    per_gpu = args.batch if args.batch else spec["batch"]
+    if strong:
+        total = per_gpu                               # the whole job's batch is fixed; ranks split it
+        lo, hi = parallel.shard_bounds(total, world, rank)
+        B = hi - lo
+        if total % world:
+            raise SystemExit("strong scaling of B=%d needs a GPU count that divides it" % total)
+    else:
+        B, total = per_gpu, per_gpu * world
+    model = build_ours(spec).to(dev)
     if world > 1:
         parallel.broadcast_parameters(model)
 
     g = torch.Generator().manual_seed(1000 + rank)
-    host_in = [torch.randn((B,) + CLIP, generator=g).pin_memory() for _ in range(2)]   # fp32 NCDHW, as the reference takes
+    host_in = [torch.randn((B,) + spec["sample"], generator=g).pin_memory() for _ in range(2)]   # fp32, as the reference takes
     x_dev = host_in[0].to(dev)
     h2d_bytes = host_in[0].numel() * 4
-    host_out = torch.empty((B, NUM_CLASSES), dtype=torch.float32).pin_memory()
-    d2h_bytes = host_out.numel() * 4
+    d2h_bytes = B * spec["classes"] * 4
 
     # launches per forward, counted on one eager pass (graph replays re-issue exactly these kernels)
     with torch.no_grad():
@@ -190,6 +241,22 @@ def run_ours(args, rank, world, local):
 
     graphed = GraphedForward(model, x_dev, warmup=2)
 
+    # ---- parity of the timed configuration itself (outside the timed region): the graph's logits for the first clips of the
+    #      timed batch against the CPU oracle (pinned bit-exact to the reference, tests/test_oracle_golden.py) ----
+    parity = None
+    if rank == 0 and not args.no_check:
+        k = min(spec["check_clips"], B)
+        sd = {n_: v.detach().cpu() for n_, v in model.state_dict().items()}
+        with torch.no_grad():
+            want = OF.forward(host_in[0][:k], sd, spec["arch"])
+            got = graphed()[:k].float().cpu()
+        scale = want.abs().max().item()
+        err = (got.double() - want.double()).abs().max().item() / scale
+        agree = bool((got.argmax(1) == want.argmax(1)).all())
+        parity = {"clips": k, "max_rel_err": err, "argmax_agree": agree, "tolerance": 5e-3,
+                  "checker": "oracle/functional.py on the host (pinned bit-exact to the reference's outputs), same weights, same clips"}
+        assert err <= 5e-3 and agree, "timed configuration does not match the CPU oracle: %r" % (parity,)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -199,7 +266,7 @@ def run_ours(args, rank, world, local):
     for _ in range(args.warmup):
         out = graphed()
         if world > 1:
-            parallel.gather_logits(out, B * world)     # also brings the NCCL communicator up outside the timed region
+            parallel.gather_logits(out, total)     # also brings the NCCL communicator up outside the timed region
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -209,7 +276,7 @@ def run_ours(args, rank, world, local):
     for _ in range(args.steps):
         out = graphed()
         if world > 1:
-            gathered = parallel.gather_logits(out, B * world)
+            parallel.gather_logits(out, total)
     e1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -218,11 +285,10 @@ def run_ours(args, rank, world, local):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    value = B * world * args.steps / (ms_total / 1e3)
+    value = total * args.steps / (ms_total / 1e3)
 
-    # ---- end-to-end through the public API (pretorched_x_b200.graph.PipelinedForward): pinned HOST clips -> H2D ->
-    #      forward -> D2H logits every step; the copy of batch i+1 overlaps the forward of batch i.  Measured for
-    #      fp16 host clips (what the engine computes in; the headline e2e) and for fp32 clips (the reference's dtype).
+    # ---- end to end through the public API (pretorched_x_b200.graph.PipelinedForward): pinned HOST clips -> H2D -> forward ->
+    #      D2H logits every step; the copy of batch i+1 overlaps the forward of batch i ----
     del graphed
     torch.cuda.empty_cache()
 
@@ -247,20 +313,20 @@ def run_ours(args, rank, world, local):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         del pipe
         torch.cuda.empty_cache()
-        return B * world * args.steps / (float(tt.item()) / 1e3)
+        sec = float(tt.item()) / 1e3
+        return total * args.steps / sec, sec
 
+    e2e_fp32, sec32 = run_e2e(host_in, x_dev)
     host_in16 = [h.half().pin_memory() for h in host_in]
-    e2e_value = run_e2e(host_in16, x_dev.half())
-    e2e_fp32 = run_e2e(host_in, x_dev)
-    h2d_bytes16 = host_in16[0].numel() * 2
+    e2e_fp16, _ = run_e2e(host_in16, x_dev.half())
 
-    # ---- second workload of BASELINE.json's metric (images/sec, BigGAN-deep-256, configs[4]) on the same ranks ----
+    # ---- second half of BASELINE.json's metric on the same ranks (images/sec, BigGAN-deep-256) ----
     second = None
-    if not args.no_biggan:
+    if args.workload == DEFAULT_WORKLOAD and not args.no_biggan:
         torch.cuda.empty_cache()
         try:
             second = run_biggan(args, rank, world, local, emit=False, steps=max(5, min(args.steps, 20)))
-        except Exception as exc:          # the contract's line (resnet3d50) must survive a failure of the secondary workload
+        except Exception as exc:          # the contract's line must survive a failure of the secondary workload
             second = {"error": "%s: %s" % (type(exc).__name__, exc)}
             print("secondary BigGAN measurement failed: %s" % second["error"], file=sys.stderr)
         torch.cuda.empty_cache()
@@ -269,86 +335,89 @@ def run_ours(args, rank, world, local):
 
     # ---- per-launch profile (eager, CUDA events on the launching stream) -> roofline of the dominant kernel ----
     peaks = load_peaks()
+    nrep = 2
     with torch.no_grad():
         model(x_dev)
         with ops.profile() as prof:
-            for _ in range(2):
+            for _ in range(nrep):
                 model(x_dev)
     rows = prof.rows
-    nrep = 2
-    conv_rows = [r for r in rows if r["kind"] in ("conv", "gemm")]
+    conv_rows = [r for r in rows if r["kind"] in ("conv", "gemm", "attention")]
     conv_ms = sum(r["ms"] for r in conv_rows) / nrep
     conv_flops = sum(r["flops"] for r in conv_rows) / nrep
     all_ms = sum(r["ms"] for r in rows) / nrep
     family_tflops = conv_flops / (conv_ms * 1e-3) / 1e12
-    # dominant kernel = the conv/GEMM layer group with the largest share of the step (the 7x7x7 stem at the BASELINE config)
     groups = {}
     for r in conv_rows:
-        g = groups.setdefault(r["desc"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
-        g["ms"] += r["ms"]; g["flops"] += r["flops"]; g["bytes"] += r["bytes"]; g["n"] += 1
+        gr = groups.setdefault(r["desc"], dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+        gr["ms"] += r["ms"]; gr["flops"] += r["flops"]; gr["bytes"] += r["bytes"]; gr["n"] += 1
     top_desc, top = max(groups.items(), key=lambda kv: kv[1]["ms"])
-    top_tflops = top["flops"] / (top["ms"] * 1e-3) / 1e12
-    traffic = None
-    try:       # DRAM bytes per launch from the committed `ncu --set full` capture of the same shape (profiles/)
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
-            traffic = json.load(f).get("B=%d" % B, {}).get(top_desc)
-    except OSError:
-        pass
-    roofline = {
-        "bound": "tensor", "kernel": "%s (%d launch per forward; %s)" % (top_desc, top["n"] // nrep, kernel_of(top_desc)),
-        "achieved": top_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": top_tflops / peaks["tflops"],
-        "traffic": traffic, "algorithmic_bytes": top["bytes"] / top["n"],
+    roofline = dominant_roofline(top, peaks)
+    whole = spec["gflop"] * 1e9 * value / world / 1e12
+    roofline.update({
+        "kernel": "%s (%d launch per forward; %s)" % (top_desc, top["n"] // nrep, kernel_of(top_desc)),
+        "traffic": None,      # dram bytes need an ncu pass (profiles/ncu_traffic_r02.json); not measurable inside an un-profiled run
+        "algorithmic_bytes": top["bytes"] / top["n"], "algorithmic_flop": top["flops"] / top["n"],
         "ms_per_launch": top["ms"] / top["n"], "share_of_step": top["ms"] / nrep / all_ms,
-        "peak_source": peaks["source"] + ", sustained bf16/fp16 GEMM",
-        "family": {"kernels": "all %d tcgen05 conv/GEMM launches of one forward (stemconv, slabconv, pgemm, igemm)" % (len(conv_rows) // nrep),
+        "family": {"kernels": "all %d tcgen05 conv / GEMM / attention launches of one forward" % (len(conv_rows) // nrep),
                    "achieved": family_tflops, "frac": family_tflops / peaks["tflops"], "share_of_step": conv_ms / all_ms},
-        "whole_step_tflops": GFLOP_PER_CLIP * 1e9 * value / world / 1e12,
-        "whole_step_frac": GFLOP_PER_CLIP * 1e9 * value / world / 1e12 / peaks["tflops"],
+        "whole_step_tflops": whole, "whole_step_frac": whole / peaks["tflops"],
         "mixed": mixed_roofline(rows, nrep, peaks, ms_total / args.steps),
-    }
+    })
     if args.layers:
-        agg = {}
-        for r in rows:
-            a = agg.setdefault(r["desc"], dict(kind=r["kind"], ms=0.0, flops=0.0, bytes=0.0, n=0))
-            a["ms"] += r["ms"] / nrep; a["flops"] += r["flops"] / nrep; a["bytes"] += r["bytes"] / nrep; a["n"] += 1
-        print("%-52s %4s %9s %9s %8s %8s" % ("layer", "n", "ms", "TFLOP/s", "GB/s", "%step"), file=sys.stderr)
-        for d, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-            print("%-52s %4d %9.3f %9.1f %8.0f %7.1f%%" % (d, a["n"] // nrep, a["ms"], a["flops"] / a["ms"] / 1e9 if a["ms"] else 0,
-                                                          a["bytes"] / a["ms"] / 1e6 if a["ms"] else 0, 100 * a["ms"] / all_ms), file=sys.stderr)
-        print("eager per-launch total %.3f ms/forward (graph replay: %.3f ms)" % (all_ms, ms_total / args.steps), file=sys.stderr)
+        print_layers(rows, nrep, all_ms, ms_total / args.steps)
 
     cpu = None
     if not args.no_cpu:
-        cb = time_cpu(steps=3, warmup=1)
+        cb = time_cpu(spec, steps=3, warmup=1)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16", "data": "synthetic (seeded randn clips, random-init weights, randomised BN statistics)",
-        "config": {"workload": "resnet3d50 forward, B=%d clips of 16x224x224 per GPU (BASELINE.json configs[1])" % B,
-                   "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "l2": "inputs (%.0f MB fp32 clips, %.0f MB of activations per step) exceed the 126 MB L2; no flush needed"
-                         % (h2d_bytes / 1e6, 127.9e6 * 2 * B / 1e6),
+        "metric": spec["metric"], "value": value, "unit": spec["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic (seeded randn input, random-init weights, randomised BN statistics)",
+        "config": {"workload": "%s forward, %s of %s (BASELINE.json %s)" % (
+                       spec["arch"], ("B=%d in total (%d per GPU)" % (total, B)) if strong else ("B=%d per GPU" % B),
+                       "x".join(map(str, spec["sample"])), spec["config"]),
+                   "global_batch": total, "parallelism": "dp%d" % world,
+                   "l2": "input (%.0f MB fp32) and the activations of one step (%.0f MB) exceed the 126 MB L2; no flush needed"
+                         % (h2d_bytes / 1e6, spec["act_elems"] * 2 * B / 1e6),
                    "timing": "CUDA events around %d CUDA-graph replays, max over ranks" % args.steps},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes16 * world, "d2h_bytes_per_step": d2h_bytes * world,
-                "input": "fp16 NCDHW clips in pinned host memory; logits read back to pinned host memory every step",
-                "fp32_input_value": e2e_fp32, "fp32_input_h2d_bytes_per_step": h2d_bytes * world},
+        "e2e": {"value": e2e_fp32, "unit": spec["unit"], "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
+                "input": "fp32 NCDHW input in pinned host memory (the reference's dtype and layout); logits read back to pinned host "
+                         "memory every step; H2D of step i+1 overlaps the forward of step i",
+                "h2d_gbs_per_gpu": h2d_bytes * args.steps / sec32 / 1e9,
+                "fp16_input_value": e2e_fp16, "fp16_input_h2d_bytes_per_step": h2d_bytes // 2 * world},
         "gpu_launches": int(launches_per_fwd * args.steps),
+        "parity": parity,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
     if second is not None:
-        # the other half of BASELINE.json's metric, measured in the same run (full line: --workload biggan256)
         line["biggan256"] = second if "error" in second else {
             k: second[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "e2e", "gpu_launches", "roofline",
-                                   "cpu_baseline", "config")}
+                                   "cpu_baseline", "config", "parity")}
     print(json.dumps(line), flush=True)
 
 
+def print_layers(rows, nrep, all_ms, step_ms):
+    agg = {}
+    for r in rows:
+        a = agg.setdefault(r["desc"], dict(kind=r["kind"], ms=0.0, flops=0.0, bytes=0.0, n=0))
+        a["ms"] += r["ms"] / nrep; a["flops"] += r["flops"] / nrep; a["bytes"] += r["bytes"] / nrep; a["n"] += 1
+    peaks = load_peaks()
+    print("%-52s %4s %9s %9s %8s %8s %6s" % ("layer", "n", "ms", "TFLOP/s", "GB/s", "%step", "roof"), file=sys.stderr)
+    for d, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        roof = max(a["flops"] / (peaks["tflops"] * 1e12), a["bytes"] / (peaks["hbm_gbs"] * 1e9)) * 1e3
+        print("%-52s %4d %9.3f %9.1f %8.0f %7.1f%% %6.2f" % (d, a["n"] // nrep, a["ms"], a["flops"] / a["ms"] / 1e9 if a["ms"] else 0,
+                                                            a["bytes"] / a["ms"] / 1e6 if a["ms"] else 0, 100 * a["ms"] / all_ms,
+                                                            roof / a["ms"] if a["ms"] else 0), file=sys.stderr)
+    print("eager per-launch total %.3f ms/forward (graph replay: %.3f ms)" % (all_ms, step_ms), file=sys.stderr)
+
+
 # ------------------------------------------------------------------------------------------------
-# second workload of BASELINE.json's metric: BigGAN-deep-256 generator, images/sec (configs[4])
+# BASELINE.json configs[4]: BigGAN-deep-256 generator, images/sec
 # ------------------------------------------------------------------------------------------------
 BIGGAN_RES, BIGGAN_CH, BIGGAN_CLASSES, BIGGAN_BATCH = 256, 128, 1000, 256
 BIGGAN_METRIC = "images/sec BigGAN-deep-256 generator forward"
@@ -405,14 +474,14 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
     import pretorched_x_b200 as P
     from pretorched_x_b200 import ops, parallel, _lib
     from pretorched_x_b200.graph import GraphedForward, PipelinedForward
-    from oracle import biggan as OB                 # standing-statistics conditioning + cpu_baseline leg only
+    from oracle import biggan as OB                 # standing-statistics conditioning, checker, cpu_baseline leg only
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     steps = steps or args.steps
-    B = args.batch if args.batch != BATCH_PER_GPU else BIGGAN_BATCH
+    B = args.batch if args.batch else BIGGAN_BATCH
     # random-init generator with calibrated standing statistics (a tiny CPU pass of the restatement: O(1) activations)
-    model, _, _, _ = OB.build_case(P.biggan_deep, BIGGAN_RES, BIGGAN_CH, BIGGAN_CLASSES, 4, init="ortho")
+    model, sd_cpu, _, _ = OB.build_case(P.biggan_deep, BIGGAN_RES, BIGGAN_CH, BIGGAN_CLASSES, 4, init="ortho")
     model = model.to(dev)
     if world > 1:
         parallel.broadcast_parameters(model)
@@ -433,6 +502,20 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
         torch.cuda.synchronize()
         launches_per_fwd = _lib.launch_count() - c0
     graphed = GraphedForward(model, (z_dev, l_dev), warmup=1, out_dtype=torch.float16)
+
+    parity = None
+    if rank == 0 and not args.no_check and emit:
+        # the timed generator's first images against the CPU restatement and its fp16-storage twin (tests/test_gpu_biggan.py's bound)
+        k = 2
+        with torch.no_grad():
+            want = OB.generator_forward(host[0][0][:k], host[0][1][:k], sd_cpu)
+            twin = OB.generator_forward(host[0][0][:k], host[0][1][:k], sd_cpu, storage=OB.fp16_storage)
+            got = graphed()[:k].float().cpu()
+        e_rms = (got - want).pow(2).mean().sqrt().item()
+        t_rms = (twin - want).pow(2).mean().sqrt().item()
+        parity = {"images": k, "rms_err": e_rms, "fp16_storage_twin_rms_err": t_rms, "bound": "rms <= 1.5 x twin + 5e-4 on (-1, 1) images",
+                  "checker": "oracle/biggan.py restatement of the published architecture (parity unpinned: no GAN code in the reference tree)"}
+        assert e_rms <= 1.5 * t_rms + 5e-4, "timed generator does not match the CPU restatement: %r" % (parity,)
 
     def barrier():
         if world > 1:
@@ -499,30 +582,23 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
     top_desc, top = max(((d, a) for d, a in agg.items() if a["kind"] in ("conv", "gemm", "attention")), key=lambda kv: kv[1]["ms"])
     hbm_rows = [r for r in rows if r["kind"] in ("ccbn", "tanh", "maxpool")]
     hbm_ms = sum(r["ms"] for r in hbm_rows)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
-            traffic = json.load(f).get("biggan B=%d" % B, {}).get(top_desc)
-    except OSError:
-        pass
     roofline = dominant_roofline(top, peaks)
+    exec_flops = sum(r.get("exec_flops", r["flops"]) for r in rows)
     roofline.update({
         "kernel": "%s (%d launches per forward; %s)" % (top_desc, top["n"], kernel_of(top_desc)),
-        "traffic": traffic, "algorithmic_bytes": top["bytes"] / top["n"], "ms_per_launch": top["ms"] / top["n"],
-        "share_of_step": top["ms"] / all_ms,
+        "traffic": None, "algorithmic_bytes": top["bytes"] / top["n"], "algorithmic_flop": top["flops"] / top["n"],
+        "ms_per_launch": top["ms"] / top["n"], "share_of_step": top["ms"] / all_ms,
         "hbm_passes": {"kernels": "ccbn_act / tanh / maxpool passes (%d launches)" % len(hbm_rows),
                        "achieved_gbs": sum(r["bytes"] for r in hbm_rows) / (hbm_ms * 1e-3) / 1e9 if hbm_ms else None,
                        "peak_gbs": peaks["hbm_gbs"], "share_of_step": hbm_ms / all_ms},
         "whole_step_tflops": gflop * 1e9 * value / world / 1e12,
         "whole_step_frac": gflop * 1e9 * value / world / 1e12 / peaks["tflops"],
+        "executed_gflop_per_image": exec_flops / B / 1e9, "algorithmic_gflop_per_image": gflop,
         "mixed": mixed_roofline(rows, 1, peaks, ms_total / steps),
+        "mixed_executed": mixed_roofline(rows, 1, peaks, ms_total / steps, key="exec_flops"),
     })
     if args.layers:
-        print("%-52s %4s %9s %9s %8s %8s" % ("layer", "n", "ms", "TFLOP/s", "GB/s", "%step"), file=sys.stderr)
-        for d, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-            print("%-52s %4d %9.3f %9.1f %8.0f %7.1f%%" % (d, a["n"], a["ms"], a["flops"] / a["ms"] / 1e9 if a["ms"] else 0,
-                                                          a["bytes"] / a["ms"] / 1e6 if a["ms"] else 0, 100 * a["ms"] / all_ms), file=sys.stderr)
-        print("eager per-launch total %.3f ms/forward (graph replay: %.3f ms)" % (all_ms, ms_total / steps), file=sys.stderr)
+        print_layers(rows, 1, all_ms, ms_total / steps)
     cpu = None
     if not args.no_cpu:
         cb = biggan_cpu(steps=2 if not emit else 3, warmup=1)
@@ -540,22 +616,25 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "input": "fp32 z + int64 class ids in pinned host memory; fp16 NCHW images copied back to pinned host memory every step"},
-        "gpu_launches": int(launches_per_fwd * steps), "roofline": roofline, "cpu_baseline": cpu})
+        "gpu_launches": int(launches_per_fwd * steps), "parity": parity, "roofline": roofline, "cpu_baseline": cpu})
     if emit:
         print(json.dumps(line), flush=True)
     return line
 
 
-def mixed_roofline(rows, nrep, peaks, step_ms):
+def mixed_roofline(rows, nrep, peaks, step_ms, key="flops"):
     """Per-launch ("implicit-GEMM") roofline of one step: sum over the profiled launches of max(FLOP / P_tensor, bytes / BW_hbm)
-    with each launch's ALGORITHMIC work and the measured peaks; ``frac`` = that time / the measured step."""
+    with each launch's ALGORITHMIC work (``key='exec_flops'``: the FLOPs the kernel actually executes where
+    that is less -- the phase-folded upsampling convolutions) and the measured peaks; ``frac`` = that time / the measured step."""
     p_flops, p_bytes = peaks["tflops"] * 1e12, peaks["hbm_gbs"] * 1e9
-    t = sum(max(r["flops"] / p_flops, r["bytes"] / p_bytes) for r in rows) / nrep
+    fl = lambda r: r.get(key, r["flops"])
+    t = sum(max(fl(r) / p_flops, r["bytes"] / p_bytes) for r in rows) / nrep
     return {"ms_per_step": t * 1e3, "frac": t * 1e3 / step_ms,
-            "compute_only_ms": sum(r["flops"] for r in rows) / nrep / p_flops * 1e3,
+            "compute_only_ms": sum(fl(r) for r in rows) / nrep / p_flops * 1e3,
             "memory_only_ms": sum(r["bytes"] for r in rows) / nrep / p_bytes * 1e3,
-            "definition": "sum_l max(FLOP_l / %.0f TFLOP/s, bytes_l / %.0f GB/s) over the launches of one step (algorithmic work per "
-                          "launch) / measured ms_per_step" % (peaks["tflops"], peaks["hbm_gbs"])}
+            "definition": "sum_l max(FLOP_l / %.0f TFLOP/s, bytes_l / %.0f GB/s) over the launches of one step (%s work per "
+                          "launch) / measured ms_per_step" % (peaks["tflops"], peaks["hbm_gbs"],
+                                                              "executed" if key != "flops" else "algorithmic")}
 
 
 def dominant_roofline(top, peaks):
@@ -577,6 +656,8 @@ def kernel_of(desc):
     """Kernel that the C ABI dispatches a profiled layer description to (see csrc/b2_conv_api.cu)."""
     if desc.startswith("conv 7x7x7") or desc.startswith("conv 1x7x7"):
         return "stemconv_kernel"
+    if desc.startswith("st2p1d"):
+        return "st2p1d_kernel (fused (2+1)D pair)"
     if desc.startswith("conv 1x1x1 s111") or desc.startswith("gemm"):
         return "pgemm_kernel"
     if desc.startswith("attention"):
@@ -590,23 +671,25 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (default: the BASELINE config)")
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU (weak) / in total (strong); default: the BASELINE config")
     ap.add_argument("--layers", action="store_true", help="print the per-layer table to stderr")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-check", action="store_true", help="skip the in-bench parity check against the CPU oracle")
     ap.add_argument("--no-biggan", action="store_true", help="skip the secondary BigGAN-deep-256 measurement of the default line")
-    ap.add_argument("--workload", default="resnet3d50", choices=["resnet3d50", "biggan256"],
-                    help="resnet3d50 = BASELINE configs[1] (default, the contract's line); biggan256 = configs[4], images/sec")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["biggan256"],
+                    help="which BASELINE.json config to time (default resnet3d50 = configs[1], the contract's line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    spec = WORKLOADS.get(args.workload)
     if args.impl == "reference":
         if args.workload == "biggan256":
             run_biggan_reference_arm(args, rank)
         else:
-            run_reference_arm(args, rank, world)
+            run_reference_arm(args, spec, rank)
         return
     if world > 1:
         # the box exports NCCL_DEBUG=VERSION, which makes NCCL print its version banner on stdout in front of the JSON line
@@ -617,7 +700,7 @@ def main():
     if args.workload == "biggan256":
         run_biggan(args, rank, world, local)
     else:
-        run_ours(args, rank, world, local)
+        run_ours(args, spec, rank, world, local)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -14,11 +14,20 @@ import os
 import sys
 import warnings
 
-REFERENCE_ROOT = os.environ.get("B2_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the source tree (build container) or, where that does not exist (GPU box), its byte-compiled image under oracle/_ref
+# (oracle/build_ref.py): the same unmodified modules either way
+_CANDIDATES = [os.environ.get("B2_REFERENCE_ROOT", "/root/reference"), os.path.join(_HERE, "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "pretorched"))), _CANDIDATES[0])
 
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "pretorched"))
+
+
+def is_source_tree():
+    """True when the unmodified SOURCE tree is mounted (fixture generation needs data/ files that oracle/_ref does not carry)."""
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "pretorched", "__init__.py"))
 
 
 def load():
