@@ -292,8 +292,8 @@ def run_ours(args, spec, rank, world, local):
     del graphed
     torch.cuda.empty_cache()
 
-    def run_e2e(batches, example):
-        pipe = PipelinedForward(model, example, depth=2)
+    def run_e2e(batches, example, fwd=None):
+        pipe = PipelinedForward(fwd if fwd is not None else model, example, depth=2)
         for i in range(3):
             pipe.submit(batches[i % 2])
         pipe.drain()
@@ -319,6 +319,15 @@ def run_ours(args, spec, rank, world, local):
     e2e_fp32, sec32 = run_e2e(host_in, x_dev)
     host_in16 = [h.half().pin_memory() for h in host_in]
     e2e_fp16, _ = run_e2e(host_in16, x_dev.half())
+    # decoded uint8 frames (3 bytes per pixel over PCIe), normalised on the device by ClipToStemInput (video workloads)
+    e2e_u8 = None
+    if len(spec["sample"]) == 4:
+        import pretorched_x_b200 as P
+        from pretorched_x_b200.transforms import ClipToStemInput
+        tf = ClipToStemInput(P.pretrained_settings["resnet3d50"]["kinetics-400"])
+        _, T_, H_, W_ = spec["sample"]
+        host_u8 = [torch.randint(0, 256, (B, T_, H_, W_, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        e2e_u8, _ = run_e2e(host_u8, host_u8[0].to(dev), fwd=lambda u8: model(tf(u8)))
 
     # ---- second half of BASELINE.json's metric on the same ranks (images/sec, BigGAN-deep-256) ----
     second = None
@@ -388,7 +397,11 @@ def run_ours(args, spec, rank, world, local):
                 "input": "fp32 NCDHW input in pinned host memory (the reference's dtype and layout); logits read back to pinned host "
                          "memory every step; H2D of step i+1 overlaps the forward of step i",
                 "h2d_gbs_per_gpu": h2d_bytes * args.steps / sec32 / 1e9,
-                "fp16_input_value": e2e_fp16, "fp16_input_h2d_bytes_per_step": h2d_bytes // 2 * world},
+                "fp16_input_value": e2e_fp16, "fp16_input_h2d_bytes_per_step": h2d_bytes // 2 * world,
+                "uint8_frames_value": e2e_u8, "uint8_frames_h2d_bytes_per_step": (h2d_bytes // 4 * world) if e2e_u8 else None,
+                "note": "fp32 clips need %.0f MB per step: at the measured H2D rate the copy alone is %.2f ms per step against %.2f ms of "
+                        "compute, so the fp32-host rate is the PCIe line rate; the uint8 / fp16 rows move 1/4 / 1/2 of the bytes"
+                        % (h2d_bytes / 1e6, sec32 / args.steps * 1e3, ms_total / args.steps)},
         "gpu_launches": int(launches_per_fwd * args.steps),
         "parity": parity,
         "roofline": roofline,

@@ -85,6 +85,11 @@ typedef struct b2_conv_args {
   const float* scale2;  /* fp32 [N][aff2_ld] */
   const float* shift2;
   int32_t aff2_ld;
+  int32_t pool_w;       /* B2_CONV_STEM7 only, needs relu: the MaxPool (k = 3, stride 2, padding 1 ALONG W) that follows the stem
+                           (resnet3D.py:156, torchvision_models.py:452) is applied in the epilogue.  y then has
+                           Wp = (Wo - 1) / 2 + 1 columns per output row ([N*To*Ho*Wp][ldy]); the H / T directions of the pool
+                           are a second b2_maxpool3d_ndhwc call with kernel (kt, kh, 1) -- max-pooling is separable -- over a
+                           tensor half the size.  Output rows of at most 120 columns                                   */
 } b2_conv_args;
 
 int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream);
@@ -201,6 +206,12 @@ int b2_gather_frame_tuples(const void* x, void* y, const int32_t* idx_dev, int N
  *   out_f32   nullable fp32 [3][crop_h][crop_w] (what the reference returns); out_h4: nullable fp16 [crop_h*crop_w][4]
  *             (NDHWC4: the stem convolution's input layout, channel 3 zero)
  * ------------------------------------------------------------------------------------------- */
+/* Decoded video frames, uint8 [N*T*H*W][3] (channels last, RGB) -> the stem's fp16 NDHWC4 input with ToTensor (/255), ToSpaceBGR,
+ * ToRange255 and Normalize applied per pixel (the per-frame tail of TransformImage, transforms/utils.py:72-75, for clips that are
+ * already at network resolution): a clip crosses PCIe as 3 bytes per pixel instead of 12.  flags: bit 2 BGR, bit 3 range 255;
+ * mean / stdv: HOST pointers to 3 floats. */
+int b2_u8_frames_to_ndhwc4_f16(const uint8_t* frames, void* y, long long pixels, int flags, const float* mean, const float* stdv,
+                               void* stream);
 int b2_transform_image_u8(const uint8_t* img, int H, int W, const int32_t* hbounds, const int32_t* hk, int hksize, int Wr,
                           const int32_t* vbounds, const int32_t* vk, int vksize, int Hr, uint8_t* tmp, int top, int left,
                           int crop_h, int crop_w, int flags, const float* mean, const float* stdv, float* out_f32,

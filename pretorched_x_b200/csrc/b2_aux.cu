@@ -202,6 +202,45 @@ maxpool3d_k3s2p1_kernel(const __half* __restrict__ x, __half* __restrict__ y, in
   reinterpret_cast<uint4*>(y)[i] = o;
 }
 
+// Second pass of the separable stem pool: (3, 3, 1) window, stride (2, 2, 1), padding (1, 1, 0) over a tensor whose W direction
+// was already pooled by the stem convolution's epilogue (b2_conv_args.pool_w).  Same branch-free clamping, 9 loads in flight.
+__global__ void __launch_bounds__(256)
+maxpool3d_k331s221_kernel(const __half* __restrict__ x, __half* __restrict__ y, int T, int H, int W, int C8, int To, int Ho,
+                          long long total) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  long long q = i / C8;
+  const int wo = (int)(q % W); q /= W;
+  const int ho = (int)(q % Ho); q /= Ho;
+  const int to = (int)(q % To);
+  const long long n = q / To;
+  const int tc = 2 * to, hc = 2 * ho;
+  const uint4* base = reinterpret_cast<const uint4*>(x) + c8;
+  uint4 v[9];
+#pragma unroll
+  for (int dt = -1; dt <= 1; ++dt) {
+    int ti = tc + dt; ti = ((unsigned)ti < (unsigned)T) ? ti : tc;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      int hi = hc + dh; hi = ((unsigned)hi < (unsigned)H) ? hi : hc;
+      v[(dt + 1) * 3 + dh + 1] = __ldg(base + (((n * T + ti) * H + hi) * (long long)W + wo) * C8);
+    }
+  }
+  __half2 m0 = __float2half2_rn(-65504.f), m1 = m0, m2 = m0, m3 = m0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    m0 = __hmax2(m0, *reinterpret_cast<const __half2*>(&v[k].x));
+    m1 = __hmax2(m1, *reinterpret_cast<const __half2*>(&v[k].y));
+    m2 = __hmax2(m2, *reinterpret_cast<const __half2*>(&v[k].z));
+    m3 = __hmax2(m3, *reinterpret_cast<const __half2*>(&v[k].w));
+  }
+  uint4 o;
+  o.x = *reinterpret_cast<uint32_t*>(&m0); o.y = *reinterpret_cast<uint32_t*>(&m1);
+  o.z = *reinterpret_cast<uint32_t*>(&m2); o.w = *reinterpret_cast<uint32_t*>(&m3);
+  reinterpret_cast<uint4*>(y)[i] = o;
+}
+
 // global average: grid (C8 chunks / 32, N), 1024 threads.  Lane = one 8-channel chunk (a warp reads 512 contiguous
 // bytes of a pixel), warp w walks positions w, w+32, ... ; the 32 partial sums meet in shared memory in a fixed order.
 __global__ void __launch_bounds__(1024) avgpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, int S, int C8) {
@@ -411,6 +450,9 @@ int b2_maxpool3d_ndhwc(const void* x, void* y, int N, int T, int H, int W, int C
   if (kt == 3 && kh == 3 && kw == 3 && st == 2 && sh == 2 && sw == 2 && pt == 1 && ph == 1 && pw == 1) {
     maxpool3d_k3s2p1_kernel<<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __half*)x, (__half*)y, T, H, W, C / 8, To, Ho, Wo, total);
+  } else if (kt == 3 && kh == 3 && kw == 1 && st == 2 && sh == 2 && sw == 1 && pt == 1 && ph == 1 && pw == 0) {
+    maxpool3d_k331s221_kernel<<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __half*)x, (__half*)y, T, H, W, C / 8, To, Ho, total);
   } else {
     maxpool3d_kernel<<<div_up(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __half*)x, (__half*)y, N, T, H, W, C / 8, To, Ho, Wo, kt, kh, kw, st, sh, sw, pt, ph, pw, total);

@@ -7,6 +7,7 @@
 
 #include "b2_host.h"
 #include "b2_igemm.cuh"
+#include "b2_densem.cuh"
 #include "b2_pgemm.cuh"
 #include "b2_slabconv.cuh"
 #include "b2_stemconv.cuh"
@@ -396,7 +397,7 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
   }
   p.w_bytes = a->kh * BN * 64;
   p.stage_bytes = ((p.rows * kStemPitch + p.w_bytes) + 127) / 128 * 128;
-  const int tail_bytes = 128 + 2048 + 256;
+  const int tail_bytes = 128 + 2048 + 512 + 256;      // barriers, scale / shift, W-pool exchange slots
   p.nstages = (227 * 1024 - tail_bytes) / p.stage_bytes;
   if (p.nstages > kStemMaxStages) p.nstages = kStemMaxStages;
   if (p.nstages < 1) return set_error(B2_ERR_UNSUPPORTED, "stem slab does not fit in shared memory (kh=%d)", a->kh);
@@ -405,7 +406,12 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
   if (p.ntiles_n * BN > 256) return set_error(B2_ERR_UNSUPPORTED, "stem convolution supports at most 256 output channels");
   p.tiles_w = (p.Wo + kStemTileW - 1) / kStemTileW;
   p.tiles_h = (p.Ho + p.G - 1) / p.G;
-  const long long items = (long long)p.tiles_w * p.tiles_h * p.ntiles_n * a->N * p.To;
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("B2_STEM_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
+  p.planes_total = a->N * p.To;
+  p.pair = (pair_env && a->kt == 1 && a->pt == 0 && p.Wo <= 60 && !a->pool_w && a->W <= 120) ? 1 : 0;
+  const long long plane_items = p.pair ? (p.planes_total + 1) / 2 : p.planes_total;
+  const long long items = (long long)p.tiles_w * p.tiles_h * p.ntiles_n * plane_items;
   if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "stem problem too large");
   p.items_total = (int)items;
   p.wimg = reinterpret_cast<const __half*>(a->w);
@@ -413,6 +419,9 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
   p.y = reinterpret_cast<__half*>(a->y);
   p.ldy = a->ldy;
   p.relu = a->relu;
+  p.pool_w = a->pool_w; p.Wp = (p.Wo - 1) / 2 + 1;
+  if (a->pool_w && (!a->relu || p.tiles_w != 1))
+    return set_error(B2_ERR_UNSUPPORTED, "fused W pooling needs ReLU and an output row of at most %d columns (got %d)", kStemTileW, p.Wo);
   const int smem_bytes = p.nstages * p.stage_bytes + tail_bytes;
   B2_OPT_IN_SMEM(stemconv_kernel<BN>, 227 * 1024);
   // input viewed as 8-byte pixels (W, H, N*T); box (256, rows, 1); no swizzle -> dense 2 KB rows in smem
@@ -420,6 +429,11 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
   cuuint64_t dims[3] = {(cuuint64_t)a->W, (cuuint64_t)a->H, (cuuint64_t)a->N * a->T};
   cuuint64_t strides[2] = {(cuuint64_t)a->W * 8, (cuuint64_t)a->H * a->W * 8};
   cuuint32_t box[3] = {(cuuint32_t)kStemRowPx, (cuuint32_t)p.rows, 1};
+  if (p.pair) {      // (W, plane, H): box (128 pixels, 2 planes, rows) -> smem [row][plane][1024 B]
+    dims[1] = (cuuint64_t)a->N * a->T; dims[2] = (cuuint64_t)a->H;
+    strides[0] = (cuuint64_t)a->H * a->W * 8; strides[1] = (cuuint64_t)a->W * 8;
+    box[0] = 128; box[1] = 2; box[2] = (cuuint32_t)p.rows;
+  }
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(a->x), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -480,6 +494,108 @@ static int launch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   return B2_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// small-M path: dense-M implicit GEMM, split-K over a thread-block cluster (b2_densem.cuh)
+// ------------------------------------------------------------------------------------------
+// Which layers take the dense-M kernel (measured with tools/conv_sweep.py as CUDA-graph replays, profiles/smallm_sweep_r02.txt):
+// it beats the slab kernel only where a plane fills a small part of a 128-row tile AND the K loop is long enough to split --
+// stride-1 multi-tap convolutions with M <= 1024 output positions (4x4 planes: 12% tile fill), strided multi-tap convolutions
+// (whose slab form needs four phase sub-images per tap) with M <= 8192.  1x1x1 convolutions stay on the persistent GEMM.
+// B2_DENSEM_MAXM = 0 disables the path, a positive value replaces BOTH thresholds (debug / sweeps).
+static int g_densem_maxm = -1;
+static int densem_maxm_env() {
+  if (g_densem_maxm < 0) {
+    const char* e = getenv("B2_DENSEM_MAXM");
+    g_densem_maxm = e ? atoi(e) : -2;               // -2: no override
+    if (g_densem_maxm == -1) g_densem_maxm = -2;
+  }
+  return g_densem_maxm;
+}
+static bool densem_wanted(long long M, int taps, bool strided) {
+  const int ov = densem_maxm_env();
+  if (ov >= 0) return ov > 0 && M <= ov;
+  if (taps <= 1) return false;
+  return strided ? M <= 8192 : M <= 1024;
+}
+
+// N tile (multiple of 32, <= 256, least padding then widest) and cluster size S (bn / S a multiple of 32, >= 2 K blocks per CTA):
+// the smallest S that gives every SM a work unit, else the largest admissible one.
+static bool densem_split_ok(int bn, int S, int nkb) {      // bn / S a multiple of 32 and every CTA of the cluster gets >= 1 K block
+  if (S < 1 || bn % (32 * S) != 0 || S > nkb) return false;
+  const int per = (nkb + S - 1) / S;
+  return (S - 1) * per < nkb;
+}
+static int g_densem_force_s = -1;
+static void densem_plan(int M, int ldy, int nkb, int* bn_out, int* S_out) {
+  int best_bn = 256, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 64; bn -= 32) {
+    const int tn = (ldy + bn - 1) / bn;
+    const int waste = tn * bn - ldy;
+    if (waste < best_waste) { best_waste = waste; best_bn = bn; }
+  }
+  if (ldy <= 32) best_bn = 32;
+  const int tiles = ((M + 127) / 128) * ((ldy + best_bn - 1) / best_bn);
+  if (g_densem_force_s < 0) { const char* e = getenv("B2_DENSEM_S"); g_densem_force_s = e ? atoi(e) : 0; }
+  int S = 1;
+  for (int cand = 1; cand <= 8; ++cand) {
+    if (!densem_split_ok(best_bn, cand, nkb) || (cand > 1 && nkb / cand < 2)) continue;
+    if (g_densem_force_s > 0) { if (cand <= g_densem_force_s) S = cand; continue; }
+    S = cand;
+    if (tiles * cand >= 64) break;                  // measured: beyond ~half the SMs the cluster / DSMEM cost outgrows the gain
+  }
+  *bn_out = best_bn; *S_out = S;
+}
+
+static int launch_densem(const IgemmLaunch& L, cudaStream_t stream) {
+  DensemParams dp;
+  memset(&dp, 0, sizeof(dp));
+  dp.g = L.p;
+  const IgemmParams& p = L.p;
+  const int width = (p.epi == EPI_DIRECT_F32) ? p.Ncols : p.ldy;
+  int bn = 0, S = 1;
+  densem_plan(p.M_total, width, p.nkb, &bn, &S);
+  dp.bn = bn; dp.bbytes = bn * 128; dp.stage_bytes = kBM * kBK * 2 + dp.bbytes;
+  dp.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+  dp.ksplit = S;
+  dp.kb_per = (p.nkb + S - 1) / S;
+  dp.nstages = (227 * 1024 - 256 - 1024) / dp.stage_bytes;
+  if (dp.nstages > kDmMaxStages) dp.nstages = kDmMaxStages;
+  const int smem_bytes = dp.nstages * dp.stage_bytes + 256 + 1024;
+  B2_OPT_IN_SMEM(densem_kernel, 227 * 1024);
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_2d_f16(&tmB, L.w, (uint64_t)L.b_cols, (uint64_t)p.Ncols, (uint64_t)L.ldb, kBK, (uint32_t)bn, true)) != B2_OK) return rc;
+  if (p.amode == AMODE_TMA) {
+    if ((rc = make_tmap_2d_f16(&tmA, L.a_mat, (uint64_t)L.a_cols, (uint64_t)p.M_total, (uint64_t)L.lda, kBK, kBM, true)) != B2_OK) return rc;
+  } else {
+    tmA = tmB;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((width + bn - 1) / bn, (p.M_total + kBM - 1) / kBM, dp.ksplit);
+  cfg.blockDim = dim3(kDmThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 1; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = dp.ksplit;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, densem_kernel, tmA, tmB, dp));
+  B2_CHECK_LAUNCH("densem_kernel");
+  return B2_OK;
+}
+
+// does the dense-M kernel take this launch?  (plain per-column affine, no generator extras, few output positions)
+static bool densem_applies(const IgemmParams& p, int k2) {
+  const bool gather = p.amode != AMODE_TMA;
+  const int taps = gather ? p.kt * p.kh * p.kw : 1;
+  const bool strided = gather && (p.st > 1 || p.sh > 1 || p.sw > 1);
+  return k2 == 0 && !p.aff_ld && !p.res_up && !p.res_pre && !p.y2 && densem_wanted(p.M_total, taps, strided) &&
+         (p.epi == EPI_DIRECT_F32 || !p.per_row);
+}
+
 static int g_gemm_algo = 0;   // 0 auto (persistent kernel where it applies), 1 force the per-tile kernel
 
 template <int BN, int GAN>
@@ -532,6 +648,7 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
 }
 
 static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
+  if (g_gemm_algo == 0 && densem_applies(L.p, L.k2)) return launch_densem(L, stream);
   if (g_gemm_algo == 0 && L.p.amode == AMODE_TMA && L.p.epi == EPI_TMA_F16 && !L.p.per_row) {
     if (L.p.y2) return launch_pgemm<64, 1>(L, stream);       // second output: the 64-wide instance has a second staging tile
     if (L.p.res_up || L.p.res_pre)
@@ -564,6 +681,8 @@ int b2_version(void) { return 103; }   // 103: split-K / fused (2+1)D / pooled-s
 /* debug knob (not in the public header): 0 = auto, 1 = never use the slab kernel */
 int b2_debug_set_conv_algo(int algo) { g_conv_algo = algo; return B2_OK; }
 int b2_debug_set_gemm_algo(int algo) { g_gemm_algo = algo; return B2_OK; }
+/* debug knobs of the small-M path: layers with M <= maxm take the dense-M kernel (0 = never); force_s > 0 caps the cluster size */
+int b2_debug_set_densem(int maxm, int force_s) { g_densem_maxm = maxm < 0 ? -2 : maxm; g_densem_force_s = force_s; return B2_OK; }
 const char* b2_last_error(void) { return g_err; }
 uint64_t b2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
@@ -580,6 +699,7 @@ static int validate_conv(const b2_conv_args* a) {
   B2_CHECK_ARG(conv_out_dim(a->T, a->kt, a->st, a->pt) > 0 && conv_out_dim(a->H, a->kh, a->sh, a->ph) > 0 &&
                    conv_out_dim(a->W, a->kw, a->sw, a->pw) > 0,
                "empty output");
+  B2_CHECK_ARG(!a->pool_w || a->mode == B2_CONV_STEM7, "pool_w is implemented by the stem convolution only");
   if (a->mode == B2_CONV_STEM7) {
     B2_CHECK_ARG(a->C == 4, "STEM7 needs NDHWC4 input (C == 4), got %d", a->C);
     B2_CHECK_ARG(a->kw == 7 && a->sw == 2 && a->pw == 3, "STEM7 needs kw=7, sw=2, pw=3");
@@ -612,7 +732,12 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   int rc = validate_conv(a);
   if (rc != B2_OK) return rc;
   if ((rc = require_sm100()) != B2_OK) return rc;
-  rc = try_slab(a, reinterpret_cast<cudaStream_t>(stream));
+  const long long M_out = (long long)a->N * conv_out_dim(a->T, a->kt, a->st, a->pt) * conv_out_dim(a->H, a->kh, a->sh, a->ph) *
+                          conv_out_dim(a->W, a->kw, a->sw, a->pw);
+  const bool small_m = a->mode == B2_CONV_AUTO && !a->upsample && !a->aff_ld && !a->out_f32 && !a->y2 && !a->residual_up &&
+                       !a->residual_pre && g_gemm_algo == 0 &&
+                       densem_wanted(M_out, a->kt * a->kh * a->kw, a->st > 1 || a->sh > 1 || a->sw > 1);
+  rc = small_m ? 0 : try_slab(a, reinterpret_cast<cudaStream_t>(stream));
   if (rc != 0) return rc < 0 ? rc : B2_OK;
   if (a->upsample) return set_error(B2_ERR_UNSUPPORTED, "fused upsampling needs the slab kernel, which does not take this shape");
 

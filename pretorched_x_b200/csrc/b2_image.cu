@@ -86,9 +86,53 @@ __global__ void resample_v_finish_kernel(const unsigned char* __restrict__ src, 
   }
 }
 
+// uint8 frames [pixels][3] (decoded video: N*T*H*W RGB pixels, channels last) -> fp16 NDHWC4 with ToTensor (/255), optional BGR
+// swap / x255 and Normalize: the clip-side counterpart of resample_v_finish_kernel.  4 pixels (12 bytes in, 32 bytes out) per thread.
+__global__ void u8_to_ndhwc4_norm_kernel(const unsigned char* __restrict__ src, __half* __restrict__ dst, long long npx, int bgr,
+                                         int range255, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;      // group of 4 pixels
+  const long long p0 = g * 4;
+  if (p0 >= npx) return;
+  unsigned char b[12];
+  if (p0 + 4 <= npx) {
+    const uint3 w = *reinterpret_cast<const uint3*>(src + p0 * 3);           // 12-byte aligned: p0 is a multiple of 4
+    *reinterpret_cast<uint3*>(b) = w;
+  } else {
+    for (int i = 0; i < 12; ++i) b[i] = (p0 * 3 + i < npx * 3) ? src[p0 * 3 + i] : 0;
+  }
+  const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (p0 + k >= npx) break;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int sc = bgr ? 2 - c : c;
+      float t = __fdiv_rn((float)b[k * 3 + sc], 255.0f);
+      if (range255) t = __fmul_rn(t, 255.0f);
+      v[c] = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);
+    }
+    const __half2 a = __floats2half2_rn(v[0], v[1]), c2 = __floats2half2_rn(v[2], 0.f);
+    uint2 w;
+    w.x = *reinterpret_cast<const unsigned*>(&a); w.y = *reinterpret_cast<const unsigned*>(&c2);
+    reinterpret_cast<uint2*>(dst)[p0 + k] = w;
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_u8_frames_to_ndhwc4_f16(const uint8_t* frames, void* y, long long pixels, int flags, const float* mean,
+                                          const float* stdv, void* stream) {
+  B2_CHECK_ARG(frames && y && pixels > 0 && mean && stdv, "bad argument");
+  B2_CHECK_ARG((reinterpret_cast<uintptr_t>(frames) & 3) == 0, "frame buffer must be 4-byte aligned");
+  const long long groups = (pixels + 3) / 4;
+  u8_to_ndhwc4_norm_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      frames, reinterpret_cast<__half*>(y), pixels, (flags >> 2) & 1, (flags >> 3) & 1, mean[0], mean[1], mean[2], stdv[0], stdv[1], stdv[2]);
+  B2_CHECK_LAUNCH("u8_to_ndhwc4_norm");
+  return B2_OK;
+}
 
 extern "C" int b2_transform_image_u8(const uint8_t* img, int H, int W, const int32_t* hbounds, const int32_t* hk, int hksize, int Wr,
                                      const int32_t* vbounds, const int32_t* vk, int vksize, int Hr, uint8_t* tmp, int top, int left,

@@ -55,6 +55,15 @@ struct StemParams {
   __half* y;               // [N*To*Ho*Wo][ldy]
   int ldy;
   int relu;
+  // pool_w: the MaxPool that follows the stem (k = 3, stride 2, padding 1 along W) is applied in the epilogue: y holds Wp = (Wo - 1) / 2 + 1
+  // columns per row, pooled column wp = max over output columns {2wp - 1, 2wp, 2wp + 1}.  Exact because max-pooling is
+  // separable; the H / T directions are pooled by a second pass over a tensor half the size (needs relu and one column tile per row).
+  int pool_w, Wp;
+  // pair: narrow images (Wo <= 60, kt == 1): an item covers TWO consecutive (n, t) planes.  The tensor map is declared with the
+  // plane index as its SECOND dimension, so a box (128 pixels, 2 planes, rows) lands in shared memory as [row][plane][1024 B]: the
+  // Toeplitz view of slab row i then shows plane 0 in tile rows 0..63 and plane 1 in rows 64..127 (rows r and r + 64 are exactly
+  // 64 x 16 B = 1024 B apart), and 112 of the 128 MMA rows carry output pixels instead of 56.
+  int pair, planes_total;
 };
 
 // slot of vertical tap dh inside one temporal tap of the weight image: even taps in decreasing order, then odd taps
@@ -103,6 +112,7 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_scale = reinterpret_cast<float*>(tail + 128);       // [256] (ntiles_n * BN <= 256 is enforced by the host)
   float* s_shift = s_scale + 256;
+  uint32_t* s_xchg = reinterpret_cast<uint32_t*>(s_shift + 256);   // [2][4][16]: lane 31 of each epilogue warp, for the W pool
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int slab_bytes = p.rows * kStemPitch;
@@ -138,7 +148,8 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
         if (elect_one()) {
           mbar_expect_tx(&full[s], static_cast<uint32_t>(slab_bytes + p.w_bytes));
           uint8_t* dst = smem + s * p.stage_bytes;
-          tma_load_3d(dst, &tmX, &full[s], 2 * w.w0 - 4, 2 * w.ho0 - p.ph, w.n * p.T + w.to + dt - p.pt);
+          if (p.pair) tma_load_3d(dst, &tmX, &full[s], 2 * w.w0 - 4, 2 * w.plane_o, 2 * w.ho0 - p.ph);
+          else tma_load_3d(dst, &tmX, &full[s], 2 * w.w0 - 4, 2 * w.ho0 - p.ph, w.n * p.T + w.to + dt - p.pt);
           const __half* wsrc = p.wimg + (static_cast<size_t>(w.ntile) * p.kt + dt) * (p.w_bytes / 2);
           bulk_load_1d(dst + slab_bytes, wsrc, static_cast<uint32_t>(p.w_bytes), &full[s]);
         }
@@ -200,13 +211,64 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
       const int ab = lt & 1;
       const int n0 = w.ntile * BN;
       const int ncols_here = min(BN, p.ldy - n0);
-      const int wo = w.w0 + tid;
-      const bool col_ok = (tid < kStemTileW) && (wo < p.Wo);
+      const int wo = p.pair ? (tid & 63) : w.w0 + tid;
+      const int plane_out = p.pair ? 2 * w.plane_o + (tid >> 6) : w.plane_o;
+      const bool col_ok = p.pair ? (wo < p.Wo && plane_out < p.planes_total) : ((tid < kStemTileW) && (wo < p.Wo));
       mbar_wait(&acc_full[ab], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_off + ab * kAccCols;
+      if (p.pool_w) {
+        // ---- BN + ReLU, then max over the 3-wide / stride-2 window along W before anything is written ----
+        // thread tid holds output column wo = tid (one column tile per row); even columns 2wp produce pooled column wp from
+        // their own value and both neighbours: lanes +-1 by shuffle, the left neighbour of lane 0 through shared memory.
+        // Post-ReLU values are >= 0, so a missing neighbour (image border, column >= Wo) contributes 0 without changing the max.
+        const int lane = tid & 31;
+        int xit = 0;
+        for (int g = 0; g < g_valid; ++g) {
+          const size_t prow = (static_cast<size_t>(w.plane_o) * p.Ho + (w.ho0 + g)) * p.Wp + (tid >> 1);
+          __half* yrow = p.y + prow * p.ldy + n0;
+#pragma unroll 1
+          for (int jc = 0; jc < BN / 32; ++jc, ++xit) {
+            uint32_t v[32];
+            tmem_ld32(acc + g * BN + jc * 32, v);
+            tmem_ld_wait();
+            uint32_t h[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int ci = n0 + jc * 32 + e * 2;
+              const float a0 = fmaxf(__uint_as_float(v[e * 2]) * s_scale[ci] + s_shift[ci], 0.f);
+              const float a1 = fmaxf(__uint_as_float(v[e * 2 + 1]) * s_scale[ci + 1] + s_shift[ci + 1], 0.f);
+              h[e] = col_ok ? pack_half2(a0, a1) : 0u;
+            }
+            uint32_t* xb = s_xchg + ((xit & 1) * 4 + warp) * 16;
+            if (lane == 31) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) xb[e] = h[e];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps (double-buffered slots: one barrier per chunk)
+            uint32_t m[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              uint32_t l = __shfl_up_sync(0xffffffffu, h[e], 1);
+              const uint32_t r = __shfl_down_sync(0xffffffffu, h[e], 1);
+              if (lane == 0) l = (warp > 0) ? (xb - 16)[e] : 0u;       // lane 31 of the previous warp; column -1 does not exist
+              __half2 mm = __hmax2(*reinterpret_cast<const __half2*>(&h[e]), *reinterpret_cast<const __half2*>(&l));
+              mm = __hmax2(mm, *reinterpret_cast<const __half2*>(&r));
+              m[e] = *reinterpret_cast<const uint32_t*>(&mm);
+            }
+            if (col_ok && (tid & 1) == 0) {
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8) {
+                const int col = jc * 32 + c8 * 8;
+                if (col < ncols_here)
+                  *reinterpret_cast<uint4*>(yrow + col) = make_uint4(m[c8 * 4], m[c8 * 4 + 1], m[c8 * 4 + 2], m[c8 * 4 + 3]);
+              }
+            }
+          }
+        }
+      } else
       for (int g = 0; g < g_valid; ++g) {
-        const size_t row = (static_cast<size_t>(w.plane_o) * p.Ho + (w.ho0 + g)) * p.Wo + wo;
+        const size_t row = (static_cast<size_t>(plane_out) * p.Ho + (w.ho0 + g)) * p.Wo + wo;
         __half* yrow = p.y + row * p.ldy + n0;
 #pragma unroll 1
         for (int jc = 0; jc < BN / 32; ++jc) {

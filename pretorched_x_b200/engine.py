@@ -23,6 +23,8 @@ Function's ``forward`` is the ctypes call sequence, its outputs are marked non-d
 semantics: the engine has no backward for the convolutional trunk), and the dense heads (``last_linear``, the TRN
 relation MLPs) have a real backward on the same tcgen05 GEMM so that a head can be trained on engine features.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -122,8 +124,9 @@ def _st_conv_body(conv, bn, a, residual, relu, simt):
     return conv_bn_act(conv.temporal_conv, bn, mid, residual=residual, relu=relu, simt=simt)
 
 
-def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False):
-    """Run ``conv`` (Conv3d / Conv2d / SpatioTemporalConv-like) -> ``bn`` -> (+residual) -> (ReLU)."""
+def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False, pool_w=False):
+    """Run ``conv`` (Conv3d / Conv2d / SpatioTemporalConv-like) -> ``bn`` -> (+residual) -> (ReLU).  ``pool_w``: stem only, see
+    ``_stem_body``."""
     if hasattr(conv, "spatial_conv") and hasattr(conv, "temporal_conv"):
         return Fn.SpatioTemporalConvFunction.run(conv, a, bn, residual, relu, simt)
     stem = a.ld == 4
@@ -140,7 +143,7 @@ def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False):
         pc = packed_conv(conv, bn, sub.ld, stride=(1, 1, 1))
         return ops.conv(sub, pc, residual=residual, relu=relu)
     pc = packed_conv(conv, bn, a.ld, stem=stem)
-    return ops.conv(a, pc, residual=residual, relu=relu, simt=simt)
+    return ops.conv(a, pc, residual=residual, relu=relu, simt=simt, pool_w=pool_w)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -417,8 +420,17 @@ def run_stem(model, x, simt=False):
 
 
 def _stem_body(model, a, simt=False):
-    a = conv_bn_act(model.conv1, model.bn1, a, relu=True, simt=simt)
+    """conv1 -> bn1 -> ReLU -> maxpool.  When the stem runs on the Toeplitz kernel and the pool is the usual 3-wide / stride-2 /
+    pad-1 window along W, that direction of the pool is taken in the convolution's epilogue (max-pooling is separable, so this is
+    exact): the stem writes half of its output and the remaining (kt, kh, 1) pool reads half as much."""
     k, s, p = _pool_args(model.maxpool)
+    conv = model.conv1
+    plain = isinstance(conv, (nn.Conv3d, nn.Conv2d))
+    if (plain and not simt and a.ld == 4 and _is_stem_shape(conv) and (k[2], s[2], p[2]) == (3, 2, 1)
+            and ops._out_dim(a.W, 7, 2, 3) <= 120 and os.environ.get("B2_STEM_POOLW", "1") != "0"):
+        a = conv_bn_act(conv, model.bn1, a, relu=True, pool_w=True)
+        return ops.maxpool3d(a, (k[0], k[1], 1), (s[0], s[1], 1), (p[0], p[1], 0))
+    a = conv_bn_act(conv, model.bn1, a, relu=True, simt=simt)
     return ops.maxpool3d(a, k, s, p)
 
 

@@ -213,7 +213,7 @@ def _out_dim(i, k, s, p):
 # convolution / dense
 # ---------------------------------------------------------------------------------------------
 def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, residual_up=False, residual_pre=False,
-         next_affine=None):
+         next_affine=None, pool_w=False):
     """nn.Conv3d -> BatchNorm3d -> (+residual) -> ReLU in one kernel
     (resnet3D.py:91-106, 125-143, 176-185; r2plus1d.py:85-88; torchvision_models.py:449-451).
 
@@ -231,6 +231,11 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
                   _out_dim(a.W, kw, pc.s[2], pc.p[2]))
     if pc.up:                         # the kernel reads the low-res image and writes the 2x upsampled convolution
         Ho, Wo = 2 * Ho, 2 * Wo
+    Wconv = Wo
+    if pool_w:                        # stem only: MaxPool (k 3, stride 2, pad 1) along W applied in the epilogue (b2_conv_args.pool_w)
+        if simt or not relu or pc.mode != B2_CONV_STEM7:
+            raise ValueError("pool_w needs the stem convolution kernel with ReLU")
+        Wo = (Wo - 1) // 2 + 1
     M = a.N * To * Ho * Wo
     ldy = _round_up(pc.K, 8)
     y = torch.empty((M, ldy), dtype=torch.float16, device=a.data.device)
@@ -258,6 +263,7 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     args.pt, args.ph, args.pw = pc.p
     args.relu, args.out_f32, args.accumulate, args.mode = int(relu), 0, 0, pc.mode
     args.upsample = int(pc.up)
+    args.pool_w = int(pool_w)
     if pc.up and simt:
         raise ValueError("the CUDA-core cross-check has no fused upsampling")
     if sample_affine is not None:
@@ -268,11 +274,11 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     lib = _lib.load()
     fn = lib.b2_conv_ndhwc_fprop_simt if simt else lib.b2_conv_ndhwc_fprop
     taps = kt * kh * kw
-    flops = 2.0 * M * pc.K * pc.Cin * taps                     # algorithmic (padding taps included)
+    flops = 2.0 * (a.N * To * Ho * Wconv) * pc.K * pc.Cin * taps        # algorithmic (padding taps included)
     res_rows = 0 if residual is None else (M // 4 if residual_up else M)
     nbytes = 2.0 * (a.M * a.C + M * pc.K * (2 if y2 is not None else 1) + res_rows * pc.K + pc.K * pc.Cin * taps)
-    desc = "conv %dx%dx%d s%s C%d->%d M=%d%s%s" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, M, " up2" if pc.up else "",
-                                                  " +next" if y2 is not None else "")
+    desc = "conv %dx%dx%d s%s C%d->%d M=%d%s%s%s" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, a.N * To * Ho * Wconv,
+                                                    " up2" if pc.up else "", " +next" if y2 is not None else "", " +poolW" if pool_w else "")
     with _timed("conv", desc, flops, nbytes):
         _lib.check(fn(ctypes.byref(args), _stream()), "b2_conv_ndhwc_fprop")
     out = Act(y, a.N, To, Ho, Wo, pc.K)

@@ -49,6 +49,10 @@ def _opt(opts, name):
     return opts[name] if isinstance(opts, dict) else getattr(opts, name)
 
 
+def _has(opts, name):
+    return (name in opts) if isinstance(opts, dict) else hasattr(opts, name)
+
+
 _COEFF_CACHE = {}
 
 
@@ -202,3 +206,33 @@ class LoadTransformImage(object):
 
     def __call__(self, path_img):
         return self.tf(self.load(path_img))
+
+
+class ClipToStemInput(object):
+    """Decoded video clips, uint8 ``[N, T, H, W, 3]`` (channels last, already at network resolution), to the fp16 NDHWC4 ``Act``
+    the 3-D stems consume: ToTensor, ToSpaceBGR, ToRange255 and Normalize of the model's settings (transforms/utils.py:72-75)
+    applied per pixel on the device.  The reference has no clip loader; what this adds is the transfer
+    format -- 3 bytes per pixel over PCIe instead of the 12 of an fp32 NCDHW tensor -- with the same arithmetic as
+    ``TransformImage``'s tail.  ``model(ClipToStemInput(model)(clips_u8))`` equals ``model(x)`` for
+    ``x = ((clips / 255 - mean) / std)`` permuted to NCDHW, bit for bit after the engine's fp16 rounding of the input."""
+
+    def __init__(self, opts):
+        self.input_space = _opt(opts, 'input_space') if _has(opts, 'input_space') else 'RGB'
+        self.input_range = list(_opt(opts, 'input_range')) if _has(opts, 'input_range') else [0, 1]
+        self.mean = list(_opt(opts, 'mean'))
+        self.std = list(_opt(opts, 'std'))
+        self._mean = (ctypes.c_float * 3)(*[float(np.float32(m)) for m in self.mean])
+        self._std = (ctypes.c_float * 3)(*[float(np.float32(s)) for s in self.std])
+
+    def __call__(self, clips_u8, out=None):
+        if clips_u8.dtype != torch.uint8 or clips_u8.dim() != 5 or clips_u8.shape[-1] != 3 or not clips_u8.is_cuda:
+            raise ValueError("expected a CUDA uint8 [N, T, H, W, 3] tensor, got %s %s" % (clips_u8.dtype, tuple(clips_u8.shape)))
+        clips_u8 = clips_u8.contiguous()
+        N, T, H, W, _ = clips_u8.shape
+        px = N * T * H * W
+        y = out if out is not None else torch.empty((px, 4), dtype=torch.float16, device=clips_u8.device)
+        flags = (int(self.input_space == 'BGR') << 2) | (int(max(self.input_range) == 255) << 3)
+        with torch.cuda.device(clips_u8.device):
+            _lib.check(_lib.load().b2_u8_frames_to_ndhwc4_f16(ops._ptr(clips_u8), ops._ptr(y), px, flags, self._mean, self._std,
+                                                             ops._stream()), "b2_u8_frames_to_ndhwc4_f16")
+        return ops.Act(y, N, T, H, W, 3)

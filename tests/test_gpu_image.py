@@ -74,3 +74,23 @@ def test_gpu_random_crop_and_flips_match_torchvision():
         torch.manual_seed(seed)
         got = tf(a).cpu()
         assert torch.equal(got, want), seed
+
+
+def test_uint8_clip_input_matches_fp32_pipeline():
+    """ClipToStemInput: uint8 THWC frames -> normalised fp16 NDHWC4 on the device == the fp32 NCDHW tensor a host pipeline would
+    build (ToTensor + Normalize per frame), so both give the same logits."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = OF.randomize_bn_(P.resnet3d18(num_classes=11, pretrained=None), 1).eval().to(dev)
+    s = P.pretrained_settings["resnet3d18"]["kinetics-400"]
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (2, 8, 64, 64, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(s["mean"], dtype=torch.float32).view(1, 1, 1, 1, 3)
+    std = torch.tensor(s["std"], dtype=torch.float32).view(1, 1, 1, 1, 3)
+    x = ((u8.float() / 255.0 - mean) / std).permute(0, 4, 1, 2, 3).contiguous()          # fp32 NCDHW, computed on the host
+    tf = TR.ClipToStemInput(s)
+    with torch.no_grad():
+        a = tf(u8.to(dev))
+        want_in = ops.from_ncdhw(x.to(dev))
+        assert torch.equal(a.data, want_in.data)                                          # identical fp16 NDHWC4 stem input
+        assert torch.equal(m(a), m(x.to(dev)))

@@ -75,6 +75,14 @@ CONV_CASES = [
     ("temporal3_14x14_from_576", 2, 576, 4, 14, 14, 256, (3, 1, 1), (1, 1, 1), (1, 0, 0), False, True, False, True),
     ("temporal5_ragged_positions", 1, 64, 7, 9, 11, 64, (5, 1, 1), (1, 1, 1), (2, 0, 0), False, True, False, True),
     ("projection_1x1x1_s2_subsample", 2, 256, 4, 8, 8, 512, (1, 1, 1), (2, 2, 2), (0, 0, 0), False, False, False, True),
+    # stem kernel, pair-of-planes mode (Wo <= 60, kt == 1): odd number of planes (the last pair is half empty), full 112-wide rows
+    ("stem_pair_odd_planes_112", 1, 3, 3, 20, 112, 110, (1, 7, 7), (1, 2, 2), (0, 3, 3), False, True, False, True),
+    ("stem_pair_2d_7x7_64ch", 3, 3, 1, 48, 96, 64, (1, 7, 7), (1, 2, 2), (0, 3, 3), False, True, False, True),
+    # dense-M split-K kernel (cluster / DSMEM reduction): 4x4 planes, long K, ragged M, residual; strided multi-tap convolutions
+    ("densem_4x4_1152_split", 5, 512, 2, 4, 4, 1152, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False, True),
+    ("densem_temporal_1152_512_res", 5, 1152, 2, 4, 4, 512, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
+    ("densem_3x3x3_s2_odd_200ch", 3, 200, 3, 9, 9, 328, (3, 3, 3), (2, 2, 2), (1, 1, 1), True, True, False, True),
+    ("densem_tiny_m_3", 3, 256, 1, 1, 1, 96, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, False, True, False),
 ]
 
 
@@ -268,3 +276,25 @@ def test_conv_linearity_at_full_layer_size(dev):
     ya, yb, ys = (engine.conv_bn_act(conv, None, ops.from_ncdhw(t.to(dev))).data.float() for t in (xa, xb, xs))
     scale = ys.abs().max().item()
     assert (ya + yb - ys).abs().max().item() <= 4e-3 * scale
+
+
+def test_stem_fused_w_pool_equals_separate_maxpool(dev):
+    """b2_conv_args.pool_w: conv 7x7x7 -> BN -> ReLU with the W direction of MaxPool3d(3, 2, 1) in the epilogue, then the (3, 3, 1)
+    pass, against (a) the same engine with the stand-alone pool (bit-exact: max-pooling is separable) and (b) the CPU oracle."""
+    from pretorched_x_b200 import ops, engine
+    g = torch.Generator().manual_seed(11)
+    for (N, T, H, W) in ((2, 5, 38, 224), (1, 4, 32, 64), (1, 3, 18, 30)):
+        x = h(torch.randn(N, 3, T, H, W, generator=g))
+        conv = nn.Conv3d(3, 64, 7, stride=(1, 2, 2), padding=3, bias=False)
+        with torch.no_grad():
+            conv.weight.copy_(h(torch.randn(conv.weight.shape, generator=g) / 32.0))
+        bn = OF.randomize_bn_(nn.BatchNorm3d(64), 7).eval()
+        with torch.no_grad():
+            want = F.max_pool3d(F.relu(bn(conv(x))), 3, 2, 1)
+        a = ops.from_ncdhw(x.to(dev))
+        conv, bn = conv.to(dev), bn.to(dev)
+        fused = ops.maxpool3d(engine.conv_bn_act(conv, bn, a, relu=True, pool_w=True), (3, 3, 1), (2, 2, 1), (1, 1, 0))
+        plain = ops.maxpool3d(engine.conv_bn_act(conv, bn, a, relu=True), (3, 3, 3), (2, 2, 2), (1, 1, 1))
+        assert (fused.N, fused.T, fused.H, fused.W) == (plain.N, plain.T, plain.H, plain.W) == (N,) + tuple(want.shape[2:])
+        assert torch.equal(fused.data, plain.data)
+        assert rel(ops.to_ncdhw(fused), want) <= TOL_F16
