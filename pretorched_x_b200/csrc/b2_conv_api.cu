@@ -125,6 +125,7 @@ int make_tmap_ndhwc_slab(CUtensorMap* out, const void* base, uint64_t C, uint64_
 // slab convolution launcher (stride 1, "same" padding)
 // ------------------------------------------------------------------------------------------
 static int g_conv_algo = 0;   // 0 auto, 1 force gather (debug / A-B comparisons)
+static int g_slab_force_mt = -1;   // M tiles per slab work item: -1 read B2_SLAB_MT once, 0 cost model, > 0 forced (tuning)
 
 static int slab_naff(int ldy) { return (ldy + 31) / 32 * 32 + 256; }   // chunk reads may run past ldy inside the last N tile
 
@@ -291,7 +292,7 @@ static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out,
   // from ncu: a 128xNx16 MMA retires in ~40 + N/2 cycles, TMA delivers ~48 B/cycle/SM out of L2.)
   int best_mt = 0, best_R = 0;
   double best_cost = 0.0;
-  static int force_mt = -1;
+  int& force_mt = g_slab_force_mt;
   if (force_mt < 0) { const char* e = getenv("B2_SLAB_MT"); force_mt = e ? atoi(e) : 0; }   // debug / tuning only
   int ksteps = 0;
   for (int cc = 0; cc < p.cchunks; ++cc) { const int k = (a->C - cc * 64 + 15) / 16; ksteps += k > 4 ? 4 : k; }
@@ -308,7 +309,12 @@ static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out,
     const long long items = (long long)ntn * tq * planes * p.wchunks * (p.up ? 4 : 1);
     const double rounds = (double)((items + sm_count() - 1) / sm_count());
     const double tiles_per_item = (double)((p.P + 127) / 128) / (double)tq;          // average (the last item of a plane is short)
-    const double mma = tiles_per_item * p.kt * taps_hw * ksteps * (40.0 + 0.5 * BN);
+    // the issuing warp spends ~650 cycles per weight tile (barrier wait, descriptor arithmetic, commits: measured on the
+    // (1,3,3) C64->144 layer of R(2+1)D, profiles/ncu_r02) -- with one M tile per item and a narrow N that, not the tensor pipe,
+    // is the floor; more tiles per item amortise it
+    const double mma_work = tiles_per_item * p.kt * taps_hw * ksteps * (40.0 + 0.5 * BN);
+    const double issue_floor = (double)p.kt * taps_hw * p.cchunks * 650.0;
+    const double mma = mma_work > issue_floor ? mma_work : issue_floor;
     const double load = (double)p.kt * p.n_sub * p.cchunks * slab_b / 48.0 + (double)p.kt * taps_hw * p.cchunks * w_stage / 48.0;
     const double epi = (MT * acc_stride <= 256) ? 0.0 : tiles_per_item * ((BN + 31) / 32) * 250.0;
     const double cost = rounds * ((mma > load ? mma : load) + epi + 1500.0);
@@ -681,7 +687,37 @@ int b2_version(void) { return 103; }   // 103: split-K / fused (2+1)D / pooled-s
 /* debug knob (not in the public header): 0 = auto, 1 = never use the slab kernel */
 int b2_debug_set_conv_algo(int algo) { g_conv_algo = algo; return B2_OK; }
 int b2_debug_set_gemm_algo(int algo) { g_gemm_algo = algo; return B2_OK; }
+/* host-only view of the slab kernel's tiling decision for a convolution (no launch, no GPU needed): out = {applies, BN, MT, R, PW,
+   WC, wchunks, items, flex, remapped}.  Used by tests/test_host_logic.py and by tuning scripts. */
+int b2_debug_slab_plan(const b2_conv_args* a_in, int* out) {
+  b2_conv_args remap = *a_in;
+  const b2_conv_args* a = a_in;
+  int wc_hint = 0, remapped = 0;
+  if (a_in->kt > 1 && a_in->kh == 1 && a_in->kw == 1 && a_in->st == 1 && a_in->sh == 1 && a_in->sw == 1 && a_in->ph == 0 && a_in->pw == 0) {
+    remap.T = 1; remap.H = a_in->T; remap.W = a_in->H * a_in->W; remap.kt = 1; remap.kh = a_in->kt; remap.kw = 1;
+    remap.pt = 0; remap.ph = a_in->pt; remap.pw = 0; a = &remap; wc_hint = 64; remapped = 1;
+  }
+  const int wc_try[3] = {wc_hint, 128, 64};
+  int BN = 0, best_mt = 0, best_R = 0; bool flex = false; double best_cost = 0.0; SlabParams best_p;
+  memset(&best_p, 0, sizeof(best_p));
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if (attempt > 0 && (wc_hint > 0 || wc_try[attempt] >= a->W)) continue;
+    SlabParams q;
+    if (!slab_geometry(a, &q, wc_try[attempt])) { if (attempt == 0) break; else continue; }
+    if (attempt > 0 && q.wchunks == 1) continue;
+    int bn_c = 0, mt_c = 0, r_c = 0; bool flex_c = false;
+    const double cost = slab_pick_tiles(a, q, &bn_c, &flex_c, &mt_c, &r_c);
+    if (mt_c == 0) continue;
+    if (best_mt == 0 || cost < best_cost) { best_p = q; BN = bn_c; flex = flex_c; best_mt = mt_c; best_R = r_c; best_cost = cost; }
+  }
+  out[0] = best_mt != 0; out[1] = BN; out[2] = best_mt; out[3] = best_R; out[4] = best_p.PW; out[5] = best_p.WC; out[6] = best_p.wchunks;
+  const long long tq = best_mt ? (best_p.P + best_mt * 128 - 1) / (best_mt * 128) : 0;
+  out[7] = (int)(((a->ldy + BN - 1) / (BN ? BN : 1)) * tq * best_p.wchunks * a->N * best_p.To);
+  out[8] = flex; out[9] = remapped;
+  return B2_OK;
+}
 /* debug knobs of the small-M path: layers with M <= maxm take the dense-M kernel (0 = never); force_s > 0 caps the cluster size */
+int b2_debug_set_slab_mt(int mt) { g_slab_force_mt = mt < 0 ? 0 : mt; return B2_OK; }
 int b2_debug_set_densem(int maxm, int force_s) { g_densem_maxm = maxm < 0 ? -2 : maxm; g_densem_force_s = force_s; return B2_OK; }
 const char* b2_last_error(void) { return g_err; }
 uint64_t b2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -323,20 +323,33 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
             sh[c] = s_shift[c0 + c];
           }
         }
+        // residual rows are requested one M tile AHEAD of their use (two register sets): the loads are independent of the MMAs,
+        // and issued load -> use per tile each exposed ~1 us of HBM latency to the epilogue warps (73% of their stall samples on
+        // the temporal convolutions of R(2+1)D, profiles/ncu_r02)
+        uint4 rres[2][4];
+        auto load_res = [&](int j) {
+          if (p.residual && j < w.mt_valid && ok[j]) {
+            const __half* rrow = p.residual + row[j] * p.ldr + c0;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8)
+              if (jc * 32 + c8 * 8 < ncols_here) rres[j & 1][c8] = __ldg(reinterpret_cast<const uint4*>(rrow + c8 * 8));
+          }
+        };
+        load_res(0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (j < w.mt_valid) {                            // warp-uniform
+            if (j + 1 < 4) load_res(j + 1);
             uint32_t v[32];
             tmem_ld32(acc + j * accs + jc * 32, v);        // warp-collective: outside the `ok` branch
             tmem_ld_wait();
             if (ok[j]) {
               __half* yrow = p.y + row[j] * p.ldy + c0;
               if (p.residual) {                              // uniform: residual added in fp32 before the single rounding
-                const __half* rrow = p.residual + row[j] * p.ldr + c0;
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                   if (jc * 32 + c8 * 8 < ncols_here) {
-                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + c8 * 8));
+                    const uint4 rv = rres[j & 1][c8];
                     const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
                     uint32_t o[4];
 #pragma unroll

@@ -11,7 +11,10 @@ lib = _lib.load()
 lib.b2_debug_set_densem.restype = ctypes.c_int
 lib.b2_debug_set_densem.argtypes = [ctypes.c_int, ctypes.c_int]
 specs = [l.split() for l in open(sys.argv[1]) if l.strip() and not l.startswith("#")]
+# a setting is "maxm:force_s" (dense-M path: -1 = default rule, 0 = off) optionally followed by ":mt" (slab M tiles per item, 0 = cost model)
 settings = [tuple(int(v) for v in s.split(":")) for s in sys.argv[2:]] or [(0, 0), (1 << 30, 0)]
+lib.b2_debug_set_slab_mt.restype = ctypes.c_int
+lib.b2_debug_set_slab_mt.argtypes = [ctypes.c_int]
 dev = torch.device("cuda:0")
 REP = 20
 for sp in specs:
@@ -33,8 +36,11 @@ for sp in specs:
         M = want.data.shape[0]
         fl = 2.0 * M * K * Cin * kt * kh * kw
         out = ["%-44s M=%-7d" % (" ".join(sp[:12]) + (" +res" if with_res else ""), M)]
-        for maxm, fs in settings:
+        for st in settings:
+            maxm, fs = st[0], st[1]
+            mt = st[2] if len(st) > 2 else 0
             lib.b2_debug_set_densem(maxm, fs)
+            lib.b2_debug_set_slab_mt(mt)
             for _ in range(2):
                 y = engine.conv_bn_act(conv, bn, x, residual=res, relu=True)
             torch.cuda.synchronize()
@@ -50,6 +56,6 @@ for sp in specs:
                 g.replay()
             e1.record(); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / (3 * REP) * 1e3
-            out.append("[%s:%d] %7.1f us %6.0f TF/s %s" % ("dm" if maxm else "slab", fs, us, fl / us / 1e6, "" if err < 2e-3 else "ERR %.1e" % err))
+            out.append("[%s] %7.1f us %6.0f TF/s %s" % (":".join(map(str, st)), us, fl / us / 1e6, "" if err < 2e-3 else "ERR %.1e" % err))
             del g
         print("  ".join(out), flush=True)
