@@ -309,12 +309,10 @@ static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out,
     const long long items = (long long)ntn * tq * planes * p.wchunks * (p.up ? 4 : 1);
     const double rounds = (double)((items + sm_count() - 1) / sm_count());
     const double tiles_per_item = (double)((p.P + 127) / 128) / (double)tq;          // average (the last item of a plane is short)
-    // the issuing warp spends ~650 cycles per weight tile (barrier wait, descriptor arithmetic, commits: measured on the
-    // (1,3,3) C64->144 layer of R(2+1)D, profiles/ncu_r02) -- with one M tile per item and a narrow N that, not the tensor pipe,
-    // is the floor; more tiles per item amortise it
-    const double mma_work = tiles_per_item * p.kt * taps_hw * ksteps * (40.0 + 0.5 * BN);
-    const double issue_floor = (double)p.kt * taps_hw * p.cchunks * 650.0;
-    const double mma = mma_work > issue_floor ? mma_work : issue_floor;
+    // (A per-weight-tile issue floor of ~650 cycles was tried here after profiles/ncu_r02 showed the issuing warp, not the tensor
+    // pipe, pacing one-tile items with a narrow N; it moved the (1,3,3) C64->144 layer from MT = 1 with two accumulator sets to MT = 2
+    // with one, which measured 59 us instead of 44 us -- losing the epilogue overlap costs more than the amortised issue work gains.)
+    const double mma = tiles_per_item * p.kt * taps_hw * ksteps * (40.0 + 0.5 * BN);
     const double load = (double)p.kt * p.n_sub * p.cchunks * slab_b / 48.0 + (double)p.kt * taps_hw * p.cchunks * w_stage / 48.0;
     const double epi = (MT * acc_stride <= 256) ? 0.0 : tiles_per_item * ((BN + 31) / 32) * 250.0;
     const double cost = rounds * ((mma > load ? mma : load) + epi + 1500.0);
