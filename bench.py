@@ -201,7 +201,10 @@ def run_reference_arm(args, spec, rank):
 # ------------------------------------------------------------------------------------------------
 # GPU arm, video / image classifiers
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, spec, rank, world, local):
+def run_ours(args, spec, rank, world, local, secondary=False):
+    """All GPU work of one classifier workload.  Returns the JSON line (rank 0; None elsewhere) WITHOUT its cpu_baseline: the CPU
+    legs run in main() after the process group is gone, so that no rank sits in an NCCL barrier while rank 0 times the host.
+    ``secondary``: a compact measurement riding on the default line (no fp16 / uint8 e2e variants, no nested workloads)."""
     import torch
     import torch.distributed as dist
     from pretorched_x_b200 import ops, parallel, _lib
@@ -317,11 +320,13 @@ def run_ours(args, spec, rank, world, local):
         return total * args.steps / sec, sec
 
     e2e_fp32, sec32 = run_e2e(host_in, x_dev)
-    host_in16 = [h.half().pin_memory() for h in host_in]
-    e2e_fp16, _ = run_e2e(host_in16, x_dev.half())
+    e2e_fp16 = e2e_u8 = None
+    if not secondary:
+        host_in16 = [h.half().pin_memory() for h in host_in]
+        e2e_fp16, _ = run_e2e(host_in16, x_dev.half())
+        del host_in16
     # decoded uint8 frames (3 bytes per pixel over PCIe), normalised on the device by ClipToStemInput (video workloads)
-    e2e_u8 = None
-    if len(spec["sample"]) == 4:
+    if len(spec["sample"]) == 4 and not secondary:
         import pretorched_x_b200 as P
         from pretorched_x_b200.transforms import ClipToStemInput
         tf = ClipToStemInput(P.pretrained_settings["resnet3d50"]["kinetics-400"])
@@ -329,18 +334,29 @@ def run_ours(args, spec, rank, world, local):
         host_u8 = [torch.randint(0, 256, (B, T_, H_, W_, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
         e2e_u8, _ = run_e2e(host_u8, host_u8[0].to(dev), fwd=lambda u8: model(tf(u8)))
 
-    # ---- second half of BASELINE.json's metric on the same ranks (images/sec, BigGAN-deep-256) ----
-    second = None
-    if args.workload == DEFAULT_WORKLOAD and not args.no_biggan:
-        torch.cuda.empty_cache()
-        try:
-            second = run_biggan(args, rank, world, local, emit=False, steps=max(5, min(args.steps, 20)))
-        except Exception as exc:          # the contract's line must survive a failure of the secondary workload
-            second = {"error": "%s: %s" % (type(exc).__name__, exc)}
-            print("secondary BigGAN measurement failed: %s" % second["error"], file=sys.stderr)
-        torch.cuda.empty_cache()
+    # ---- the other BASELINE.json configs on the same ranks, as compact sub-lines of the default line: BigGAN-deep-256 (the
+    #      second half of the metric, configs[4]), R(2+1)D-34 (configs[2], strong scaling) and the non-local net (configs[3]) ----
+    others = {}
+    if args.workload == DEFAULT_WORKLOAD and not secondary:
+        del host_in
+        x_keep = x_dev
+        sub_steps = max(5, min(args.steps, 20))
+        todo = ([] if args.no_biggan else ["biggan256"]) + ([] if args.no_others else ["r2plus1d34", "nonlocal50"])
+        for name in todo:
+            torch.cuda.empty_cache()
+            try:
+                if name == "biggan256":
+                    others[name] = run_biggan(args, rank, world, local, emit=False, steps=sub_steps)
+                else:
+                    sub = argparse.Namespace(**dict(vars(args), workload=name, batch=0, steps=sub_steps, layers=False))
+                    others[name] = run_ours(sub, WORKLOADS[name], rank, world, local, secondary=True)
+            except Exception as exc:      # the contract's line must survive a failure of a secondary workload
+                others[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                print("secondary %s measurement failed: %s" % (name, others[name]["error"]), file=sys.stderr)
+            torch.cuda.empty_cache()
+        x_dev = x_keep
     if rank != 0:
-        return
+        return None
 
     # ---- per-launch profile (eager, CUDA events on the launching stream) -> roofline of the dominant kernel ----
     peaks = load_peaks()
@@ -376,11 +392,6 @@ def run_ours(args, spec, rank, world, local):
     if args.layers:
         print_layers(rows, nrep, all_ms, ms_total / args.steps)
 
-    cpu = None
-    if not args.no_cpu:
-        cb = time_cpu(spec, steps=3, warmup=1)
-        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-
     line = {
         "metric": spec["metric"], "value": value, "unit": spec["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": spec["scaling"], "vs_baseline": None,
@@ -405,13 +416,13 @@ def run_ours(args, spec, rank, world, local):
         "gpu_launches": int(launches_per_fwd * args.steps),
         "parity": parity,
         "roofline": roofline,
-        "cpu_baseline": cpu,
+        "cpu_baseline": None,           # filled in by main() once the process group is gone
     }
-    if second is not None:
-        line["biggan256"] = second if "error" in second else {
-            k: second[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "e2e", "gpu_launches", "roofline",
-                                   "cpu_baseline", "config", "parity")}
-    print(json.dumps(line), flush=True)
+    keep = ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "e2e", "gpu_launches", "roofline", "cpu_baseline", "config", "parity")
+    for name, sub in others.items():
+        if sub is not None:
+            line[name] = sub if "error" in sub else {k: sub[k] for k in keep if k in sub}
+    return line
 
 
 def print_layers(rows, nrep, all_ms, step_ms):
@@ -517,7 +528,7 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
     graphed = GraphedForward(model, (z_dev, l_dev), warmup=1, out_dtype=torch.float16)
 
     parity = None
-    if rank == 0 and not args.no_check and emit:
+    if rank == 0 and not args.no_check:
         # the timed generator's first images against the CPU restatement and its fp16-storage twin (tests/test_gpu_biggan.py's bound)
         k = 2
         with torch.no_grad():
@@ -612,10 +623,6 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
     })
     if args.layers:
         print_layers(rows, 1, all_ms, ms_total / steps)
-    cpu = None
-    if not args.no_cpu:
-        cb = biggan_cpu(steps=2 if not emit else 3, warmup=1)
-        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = ({
         "metric": BIGGAN_METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
@@ -629,9 +636,7 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "input": "fp32 z + int64 class ids in pinned host memory; fp16 NCHW images copied back to pinned host memory every step"},
-        "gpu_launches": int(launches_per_fwd * steps), "parity": parity, "roofline": roofline, "cpu_baseline": cpu})
-    if emit:
-        print(json.dumps(line), flush=True)
+        "gpu_launches": int(launches_per_fwd * steps), "parity": parity, "roofline": roofline, "cpu_baseline": None})
     return line
 
 
@@ -689,6 +694,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-check", action="store_true", help="skip the in-bench parity check against the CPU oracle")
     ap.add_argument("--no-biggan", action="store_true", help="skip the secondary BigGAN-deep-256 measurement of the default line")
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary r2plus1d34 / nonlocal50 measurements of the default line")
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(WORKLOADS) + ["biggan256"],
                     help="which BASELINE.json config to time (default resnet3d50 = configs[1], the contract's line)")
     args = ap.parse_args()
@@ -711,13 +717,24 @@ def main():
         from pretorched_x_b200 import parallel
         parallel.init_from_env(backend="nccl")
     if args.workload == "biggan256":
-        run_biggan(args, rank, world, local)
+        line = run_biggan(args, rank, world, local)
     else:
-        run_ours(args, spec, rank, world, local)
+        line = run_ours(args, spec, rank, world, local)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        dist.destroy_process_group()          # every rank but 0 is done: nobody spins on a GPU while the host legs run
+    if rank != 0 or line is None:
+        return
+    if not args.no_cpu:
+        def cpu_of(name, steps):
+            cb = biggan_cpu(steps=steps, warmup=1) if name == "biggan256" else time_cpu(WORKLOADS[name], steps=steps, warmup=1)
+            return {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = cpu_of(args.workload, 3)
+        for name in ("biggan256", "r2plus1d34", "nonlocal50"):
+            if isinstance(line.get(name), dict) and "error" not in line[name]:
+                line[name]["cpu_baseline"] = cpu_of(name, 2)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -401,7 +401,7 @@ static int launch_stem(const b2_conv_args* a, cudaStream_t stream) {
   }
   p.w_bytes = a->kh * BN * 64;
   p.stage_bytes = ((p.rows * kStemPitch + p.w_bytes) + 127) / 128 * 128;
-  const int tail_bytes = 128 + 2048 + 512 + 256;      // barriers, scale / shift, W-pool exchange slots
+  const int tail_bytes = 128 + 2048 + 1024 + 256;     // barriers, scale / shift, W-pool exchange slots
   p.nstages = (227 * 1024 - tail_bytes) / p.stage_bytes;
   if (p.nstages > kStemMaxStages) p.nstages = kStemMaxStages;
   if (p.nstages < 1) return set_error(B2_ERR_UNSUPPORTED, "stem slab does not fit in shared memory (kh=%d)", a->kh);

@@ -21,14 +21,14 @@
 //
 // Persistent CTAs (one per SM) walk (plane, row-group, column-tile) work items; TMEM holds two accumulator sets
 // so the epilogue of item i (BN + ReLU -> fp16 NDHWC) overlaps the MMAs of item i+1.
-// Warps 0-3: epilogue, warp 4: TMA/bulk-copy producer, warp 5: MMA issuer.
+// Warps 0-3 and 6-9: epilogue (the two warpgroups split the 32-column chunks), warp 4: TMA/bulk-copy producer, warp 5: MMA issuer.
 #pragma once
 
 #include "b2_ptx.cuh"
 
 namespace b2 {
 
-constexpr int kStemThreads = 192;
+constexpr int kStemThreads = 320;       // warps 0-3 and 6-9: epilogue (even / odd 32-column chunks), 4: producer, 5: MMA issuer
 constexpr int kStemPitch = 2048;        // bytes per slab row: 256 pixels [2*w0-4, 2*w0+252) of 8 bytes
 constexpr int kStemRowPx = 256;         // TMA box width (the maximum box extent), one 8-byte element per pixel
 constexpr int kStemTileW = 120;         // output columns per item: rows r < 124 of the 128-row MMA tile see complete runs
@@ -112,7 +112,7 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_scale = reinterpret_cast<float*>(tail + 128);       // [256] (ntiles_n * BN <= 256 is enforced by the host)
   float* s_shift = s_scale + 256;
-  uint32_t* s_xchg = reinterpret_cast<uint32_t*>(s_shift + 256);   // [2][4][16]: lane 31 of each epilogue warp, for the W pool
+  uint32_t* s_xchg = reinterpret_cast<uint32_t*>(s_shift + 256);   // [2 groups][2][4][16]: lane 31 of each epilogue warp, for the W pool
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int slab_bytes = p.rows * kStemPitch;
@@ -120,7 +120,7 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
 
   if (tid == 128) {
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
   }
@@ -198,8 +198,11 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
     }
   } else {
     // ================================ epilogue ==========================================
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    for (int c = 0; c < 512; c += 32) tmem_st32_zero(tmem_base + lane_off + c);   // both accumulator sets start at zero
+    // a warp may only touch TMEM lanes 32*(warp%4)..+31: pixel (row) index of this thread, and its warpgroup's column chunks
+    const int ew = warp & 3, egroup = warp >= 6 ? 1 : 0;
+    const int erow = ew * 32 + (tid & 31);
+    const uint32_t lane_off = static_cast<uint32_t>(ew * 32) << 16;
+    for (int c = egroup * 32; c < 512; c += 64) tmem_st32_zero(tmem_base + lane_off + c);   // both accumulator sets start at zero
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(&acc_empty[0]);
@@ -211,9 +214,9 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
       const int ab = lt & 1;
       const int n0 = w.ntile * BN;
       const int ncols_here = min(BN, p.ldy - n0);
-      const int wo = p.pair ? (tid & 63) : w.w0 + tid;
-      const int plane_out = p.pair ? 2 * w.plane_o + (tid >> 6) : w.plane_o;
-      const bool col_ok = p.pair ? (wo < p.Wo && plane_out < p.planes_total) : ((tid < kStemTileW) && (wo < p.Wo));
+      const int wo = p.pair ? (erow & 63) : w.w0 + erow;
+      const int plane_out = p.pair ? 2 * w.plane_o + (erow >> 6) : w.plane_o;
+      const bool col_ok = p.pair ? (wo < p.Wo && plane_out < p.planes_total) : ((erow < kStemTileW) && (wo < p.Wo));
       mbar_wait(&acc_full[ab], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + lane_off + ab * kAccCols;
@@ -225,10 +228,10 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
         const int lane = tid & 31;
         int xit = 0;
         for (int g = 0; g < g_valid; ++g) {
-          const size_t prow = (static_cast<size_t>(w.plane_o) * p.Ho + (w.ho0 + g)) * p.Wp + (tid >> 1);
+          const size_t prow = (static_cast<size_t>(w.plane_o) * p.Ho + (w.ho0 + g)) * p.Wp + (erow >> 1);
           __half* yrow = p.y + prow * p.ldy + n0;
 #pragma unroll 1
-          for (int jc = 0; jc < BN / 32; ++jc, ++xit) {
+          for (int jc = egroup; jc < BN / 32; jc += 2, ++xit) {
             uint32_t v[32];
             tmem_ld32(acc + g * BN + jc * 32, v);
             tmem_ld_wait();
@@ -240,23 +243,24 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
               const float a1 = fmaxf(__uint_as_float(v[e * 2 + 1]) * s_scale[ci + 1] + s_shift[ci + 1], 0.f);
               h[e] = col_ok ? pack_half2(a0, a1) : 0u;
             }
-            uint32_t* xb = s_xchg + ((xit & 1) * 4 + warp) * 16;
+            uint32_t* xb = s_xchg + (((egroup * 2 + (xit & 1)) * 4) + ew) * 16;
             if (lane == 31) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) xb[e] = h[e];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps (double-buffered slots: one barrier per chunk)
+            if (egroup) asm volatile("bar.sync 2, 128;" ::: "memory");       // the four warps of this warpgroup (double-buffered slots:
+            else asm volatile("bar.sync 1, 128;" ::: "memory");             // one barrier per chunk)
             uint32_t m[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               uint32_t l = __shfl_up_sync(0xffffffffu, h[e], 1);
               const uint32_t r = __shfl_down_sync(0xffffffffu, h[e], 1);
-              if (lane == 0) l = (warp > 0) ? (xb - 16)[e] : 0u;       // lane 31 of the previous warp; column -1 does not exist
+              if (lane == 0) l = (ew > 0) ? (xb - 16)[e] : 0u;         // lane 31 of the previous warp; column -1 does not exist
               __half2 mm = __hmax2(*reinterpret_cast<const __half2*>(&h[e]), *reinterpret_cast<const __half2*>(&l));
               mm = __hmax2(mm, *reinterpret_cast<const __half2*>(&r));
               m[e] = *reinterpret_cast<const uint32_t*>(&mm);
             }
-            if (col_ok && (tid & 1) == 0) {
+            if (col_ok && (erow & 1) == 0) {
 #pragma unroll
               for (int c8 = 0; c8 < 4; ++c8) {
                 const int col = jc * 32 + c8 * 8;
@@ -271,7 +275,7 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
         const size_t row = (static_cast<size_t>(plane_out) * p.Ho + (w.ho0 + g)) * p.Wo + wo;
         __half* yrow = p.y + row * p.ldy + n0;
 #pragma unroll 1
-        for (int jc = 0; jc < BN / 32; ++jc) {
+        for (int jc = egroup; jc < BN / 32; jc += 2) {
           uint32_t v[32];
           tmem_ld32(acc + g * BN + jc * 32, v);
           tmem_ld_wait();
@@ -295,7 +299,7 @@ stemconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as 8-byte pi
           }
         }
       }
-      for (int c = 0; c < kAccCols; c += 32) tmem_st32_zero(acc + c);        // hand the set back zeroed
+      for (int c = egroup * 32; c < kAccCols; c += 64) tmem_st32_zero(acc + c);   // hand the set back zeroed (this group's chunks)
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
