@@ -90,6 +90,13 @@ typedef struct b2_conv_args {
                            Wp = (Wo - 1) / 2 + 1 columns per output row ([N*To*Ho*Wp][ldy]); the H / T directions of the pool
                            are a second b2_maxpool3d_ndhwc call with kernel (kt, kh, 1) -- max-pooling is separable -- over a
                            tensor half the size.  Output rows of at most 120 columns                                   */
+  const float* in_scale; /* nullable.  Per-SAMPLE affine + ReLU applied to the INPUT of a 1x1 stride-1 convolution on its way to the
+                            tensor core: the convolution sees relu(x * in_scale[n][c] + in_shift[n][c]) -- the class-conditional
+                            BatchNorm + ReLU that opens a GBlock, without a stand-alone pass over x (x itself stays untouched in
+                            memory: the block's skip path reads it raw).  fp32 [N][in_aff_ld], 16-byte aligned, in_aff_ld % 4 == 0,
+                            To*Ho*Wo % 128 == 0                                                                           */
+  const float* in_shift;
+  int32_t in_aff_ld;
 } b2_conv_args;
 
 int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream);

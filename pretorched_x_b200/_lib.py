@@ -37,6 +37,7 @@ class ConvArgs(ctypes.Structure):
         ("pt", c_i32), ("ph", c_i32), ("pw", c_i32),
         ("relu", c_i32), ("out_f32", c_i32), ("accumulate", c_i32), ("mode", c_i32), ("aff_ld", c_i32), ("upsample", c_i32), ("residual_up", c_i32), ("residual_pre", c_i32),
         ("y2", c_void_p), ("scale2", c_void_p), ("shift2", c_void_p), ("aff2_ld", c_i32), ("pool_w", c_i32),
+        ("in_scale", c_void_p), ("in_shift", c_void_p), ("in_aff_ld", c_i32),
     ]
 
 

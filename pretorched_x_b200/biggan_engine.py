@@ -54,6 +54,10 @@ def _sn_weight(mod, eps):
     return mod.weight.detach().double() / _sn_sigma(mod.weight, mod.u0, eps)
 
 
+import os
+FUSE_BN1 = os.environ.get("B2_GAN_FUSE_BN1", "1") != "0"      # A/B switch (tools, tests)
+
+
 class _NS:
     pass
 
@@ -229,12 +233,16 @@ def _gblock_body(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None):
     ``fuse_output_bn`` (last block only): returns relu(bn_out(h)) instead, see ``_pack``."""
     bp = pk.blocks[id(blk)]
     up = 2 if blk.upsample else 1
+    in_aff = None
     if pre is None:
         s1, t1 = _aff(aff, bp.bn[0])
-        pre = ops.ccbn_act(a, s1, t1)                                        # relu(bn1(x))
+        if bp.fuse2 and (a.H * a.W) % 128 == 0 and a.ld % 64 == 0 and FUSE_BN1:
+            in_aff, pre = (s1, t1), a            # bn1 + ReLU applied to conv1's A operand inside the GEMM: no stand-alone pass
+        else:
+            pre = ops.ccbn_act(a, s1, t1)                                    # relu(bn1(x))
     t = pre
     if bp.fuse2:
-        t = ops.conv(t, bp.conv[0], relu=True, sample_affine=_aff(aff, bp.bn[1]))     # relu(bn2(conv1(.)))
+        t = ops.conv(t, bp.conv[0], relu=True, sample_affine=_aff(aff, bp.bn[1]), in_affine=in_aff)     # relu(bn2(conv1(relu(bn1(x)))))
     else:
         t = ops.conv(t, bp.conv[0])                                          # conv1 + bias
         s2, t2 = _aff(aff, bp.bn[1])

@@ -593,6 +593,7 @@ static int launch_densem(const IgemmLaunch& L, cudaStream_t stream) {
 
 // does the dense-M kernel take this launch?  (plain per-column affine, no generator extras, few output positions)
 static bool densem_applies(const IgemmParams& p, int k2) {
+  if (p.in_scale) return false;
   const bool gather = p.amode != AMODE_TMA;
   const int taps = gather ? p.kt * p.kh * p.kw : 1;
   const bool strided = gather && (p.st > 1 || p.sh > 1 || p.sw > 1);
@@ -644,9 +645,10 @@ static int launch_pgemm(const IgemmLaunch& L, cudaStream_t stream) {
   p.res_ld = ip.ldr; p.Wh = up_W; p.Hh = ip.up_H > 0 ? ip.up_H : 2; p.res_rows = res_rows;
   p.fd_Wh = make_fastdiv(p.Wh); p.fd_Hh = make_fastdiv(p.Hh);
   p.res_pre = ip.res_pre;
+  p.in_scale = GAN ? ip.in_scale : nullptr; p.in_shift = ip.in_shift; p.in_ld = ip.in_ld; p.in_rows = ip.in_rows > 0 ? ip.in_rows : 128;
   p.dual = ip.y2 != nullptr; p.scale2 = ip.scale2; p.shift2 = ip.shift2; p.aff2_ld = ip.aff2_ld; p.aff2_rows = ip.aff2_rows > 0 ? ip.aff2_rows : 128;
   const int grid = p.tiles_total < sm_count() ? p.tiles_total : sm_count();
-  B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN, GAN>, dim3(grid), dim3(kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, tmC2, p));
+  B2_CHECK_CUDA(launch_pdl(pgemm_kernel<BN, GAN>, dim3(grid), dim3(GAN ? kPgThreadsGan : kPgThreads), S::kTotal, stream, tmA, tmB, tmA2, tmB2, tmC, tmR, tmC2, p));
   B2_CHECK_LAUNCH("pgemm_kernel");
   return B2_OK;
 }
@@ -655,14 +657,14 @@ static int dispatch_igemm(const IgemmLaunch& L, cudaStream_t stream) {
   if (g_gemm_algo == 0 && densem_applies(L.p, L.k2)) return launch_densem(L, stream);
   if (g_gemm_algo == 0 && L.p.amode == AMODE_TMA && L.p.epi == EPI_TMA_F16 && !L.p.per_row) {
     if (L.p.y2) return launch_pgemm<64, 1>(L, stream);       // second output: the 64-wide instance has a second staging tile
-    if (L.p.res_up || L.p.res_pre)
+    if (L.p.res_up || L.p.res_pre || L.p.in_scale)
       return L.p.ldy <= 64 ? launch_pgemm<64, 1>(L, stream) : launch_pgemm<128, 1>(L, stream);
     return L.p.ldy <= 64 ? launch_pgemm<64, 0>(L, stream) : launch_pgemm<128, 0>(L, stream);
   }
   if (L.p.aff_ld)
     return set_error(B2_ERR_UNSUPPORTED, "per-sample affine is implemented by the slab convolution and the persistent GEMM only");
-  if (L.p.res_up || L.p.res_pre || L.p.y2)
-    return set_error(B2_ERR_UNSUPPORTED, "upsampled / pre-scale residuals and second outputs are implemented by the persistent GEMM (1x1 convolutions, fp16) only");
+  if (L.p.res_up || L.p.res_pre || L.p.y2 || L.p.in_scale)
+    return set_error(B2_ERR_UNSUPPORTED, "upsampled / pre-scale residuals, second outputs and input affines are implemented by the persistent GEMM (1x1 convolutions, fp16) only");
   // 64-wide tiles for narrow outputs, 128 otherwise
   const int width = (L.p.epi == EPI_TMA_F16) ? L.p.ldy : L.p.Ncols;
   if (width <= 64) return launch_igemm<64>(L, stream);
@@ -769,7 +771,7 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   const long long M_out = (long long)a->N * conv_out_dim(a->T, a->kt, a->st, a->pt) * conv_out_dim(a->H, a->kh, a->sh, a->ph) *
                           conv_out_dim(a->W, a->kw, a->sw, a->pw);
   const bool small_m = a->mode == B2_CONV_AUTO && !a->upsample && !a->aff_ld && !a->out_f32 && !a->y2 && !a->residual_up &&
-                       !a->residual_pre && g_gemm_algo == 0 &&
+                       !a->residual_pre && !a->in_scale && g_gemm_algo == 0 &&
                        densem_wanted(M_out, a->kt * a->kh * a->kw, a->st > 1 || a->sh > 1 || a->sw > 1);
   rc = small_m ? 0 : try_slab(a, reinterpret_cast<cudaStream_t>(stream));
   if (rc != 0) return rc < 0 ? rc : B2_OK;
@@ -804,6 +806,16 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
                  "second output needs scale2 / shift2 (fp32 [N][aff2_ld >= K]) and a 1x1 convolution with fp16 output");
     if (p.aff2_rows % 128 != 0)
       return set_error(B2_ERR_UNSUPPORTED, "second output with a per-sample affine needs To*Ho*Wo %% 128 == 0 (got %d)", p.aff2_rows);
+  }
+  if (a->in_scale) {
+    B2_CHECK_ARG(a->in_shift && a->in_aff_ld >= a->C && (a->in_aff_ld & 3) == 0 && !a->out_f32 && a->kt * a->kh * a->kw == 1 && a->st == 1 &&
+                     a->sh == 1 && a->sw == 1 && (reinterpret_cast<uintptr_t>(a->in_scale) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->in_shift) & 15) == 0,
+                 "input affine needs in_shift, a 16-byte aligned fp32 [N][in_aff_ld >= C] pair (pitch %% 4 == 0) and a 1x1 stride-1 convolution with fp16 output");
+    if ((p.To * p.Ho * p.Wo) % 128 != 0 || a->C % 64 != 0)
+      return set_error(B2_ERR_UNSUPPORTED, "input affine needs To*Ho*Wo %% 128 == 0 and a channel pitch that is a multiple of 64 (got %d, %d)",
+                       p.To * p.Ho * p.Wo, a->C);
+    p.in_scale = a->in_scale; p.in_shift = a->in_shift; p.in_ld = a->in_aff_ld; p.in_rows = p.To * p.Ho * p.Wo;
   }
   p.aff_rows = p.To * p.Ho * p.Wo;
   if (a->aff_ld && p.aff_rows % 128 != 0)

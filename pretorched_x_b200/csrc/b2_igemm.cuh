@@ -57,6 +57,9 @@ struct IgemmParams {
   const float* scale2;
   const float* shift2;
   int aff2_ld, aff2_rows;
+  const float* in_scale;   // persistent GEMM (generator instance) only: per-sample affine + ReLU on the A operand, see PgemmParams
+  const float* in_shift;
+  int in_ld, in_rows;
 };
 
 template <int BN>

@@ -25,6 +25,8 @@ namespace b2 {
 
 constexpr int kPgEpiWarps = 8;                       // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int kPgThreads = (kPgEpiWarps + 2) * 32;
+constexpr int kPgXformWarps = 4;                     // generator instance only: A-operand transform warps (see PgemmParams::in_scale)
+constexpr int kPgThreadsGan = (kPgEpiWarps + 2 + kPgXformWarps) * 32;
 constexpr int kPgStages = 3;
 
 struct PgemmParams {
@@ -54,6 +56,14 @@ struct PgemmParams {
   const float* scale2;
   const float* shift2;
   int aff2_ld, aff2_rows;
+  // Input-side per-sample affine + ReLU (pgemm_kernel<BN, 1>): the A operand becomes relu(a * in_scale[m / in_rows][k] + in_shift[...])
+  // -- the class-conditional BatchNorm + ReLU that OPENS a GBlock, applied to the raw block input on its way to the tensor core
+  // instead of in a stand-alone read + write pass over the tensor.  Four transform warps rewrite each A tile in place in shared
+  // memory (one 128-byte row per thread, fp32 arithmetic) between the TMA landing and the MMA; the tile loop is HBM-bound, so
+  // the ~280 instructions per K block per thread ride in issue slots that were idle.  First operand pair only; in_rows % 128 == 0.
+  const float* in_scale;
+  const float* in_shift;
+  int in_ld, in_rows;
 };
 
 template <int BN>
@@ -72,8 +82,8 @@ struct PgemmSmem {
   static constexpr int kTotal = kAffOff + 4 * BN * 4 + 1024;
 };
 
-template <int BN, int GAN>   // GAN = 1: instance with the generator extras (res_up gather, res_pre); 0: the classic epilogue
-__global__ void __launch_bounds__(kPgThreads, 1)
+template <int BN, int GAN>   // GAN = 1: instance with the generator extras (res_up gather, res_pre, A transform); 0: the classic epilogue
+__global__ void __launch_bounds__(GAN ? kPgThreadsGan : kPgThreads, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -88,11 +98,13 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* res_full = acc_empty + 2;                                // [2]
   uint64_t* res_empty = res_full + 2;                                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
+  uint64_t* xf_full = reinterpret_cast<uint64_t*>(smem + S::kBarOff + 128);   // [3] A tile transformed (generator instance)
+  const bool xform = GAN && p.in_scale != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5;
 
   if (tid == kPgEpiWarps * 32) {
-    for (int s = 0; s < kPgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kPgStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xf_full[s], kPgXformWarps * 32); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPgEpiWarps * 32);
       mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], kPgEpiWarps * 32);
@@ -163,7 +175,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int nkb_all = p.nkb + p.nkb2;
       for (int kb = 0; kb < nkb_all; ++kb, ++it) {
         const int s = it % kPgStages;
-        mbar_wait(&full[s], (it / kPgStages) & 1);
+        if (xform && kb < p.nkb) mbar_wait(&xf_full[s], (it / kPgStages) & 1);     // operands landed AND the A tile was rewritten
+        else mbar_wait(&full[s], (it / kPgStages) & 1);
         tc_fence_after();
         const uint32_t a_lo = sw128_desc_lo(ring + s * S::kStage);
         const uint32_t b_lo = sw128_desc_lo(ring + s * S::kStage + S::kABytes);
@@ -176,6 +189,46 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (kb == nkb_all - 1) umma_commit(&acc_full[ab]);
         }
         __syncwarp();
+      }
+    }
+  } else if (GAN && warp >= kPgEpiWarps + 2) {
+    // ================================ A-operand transform (generator instance) ==========
+    if (xform) {
+      // thread t owns logical 8-channel chunk j = t & 7 (its 8 scale + 8 shift values stay in registers for the K block) of the
+      // rows (t >> 3) + 16 i, i = 0..7.  The eight threads of a quarter-warp cover one 128-byte row: conflict-free; all loads of a K
+      // block are issued before the first use and all stores after the last (one row per thread with load -> store per chunk
+      // serialised on shared-memory latency: 2x slower layers than the stand-alone pass it replaces).
+      const int t = tid - (kPgEpiWarps + 2) * 32;
+      const int j = t & 7, r0 = t >> 3;
+      const uint32_t coff = (static_cast<uint32_t>(j) ^ static_cast<uint32_t>(r0 & 7)) << 4;     // (r0 + 16 i) & 7 == r0 & 7
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+        const int m0 = (tile / p.tiles_n) * 128;
+        const size_t arow = static_cast<size_t>(m0 / p.in_rows) * p.in_ld;   // a 128-row tile never straddles two samples
+        for (int kb = 0; kb < p.nkb + p.nkb2; ++kb, ++it) {
+          if (kb >= p.nkb) continue;
+          const int s = it % kPgStages;
+          const float4* sc4 = reinterpret_cast<const float4*>(p.in_scale + arow + kb * 64 + j * 8);
+          const float4* sh4 = reinterpret_cast<const float4*>(p.in_shift + arow + kb * 64 + j * 8);
+          const float4 s0 = __ldg(sc4), s1 = __ldg(sc4 + 1), t0 = __ldg(sh4), t1 = __ldg(sh4 + 1);   // before the wait: independent of the tile
+          mbar_wait(&full[s], (it / kPgStages) & 1);
+          uint8_t* base = smem + s * S::kStage + r0 * 128 + coff;
+          uint4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(base + i * (16 * 128));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 x0 = unpack_half2(v[i].x), x1 = unpack_half2(v[i].y), x2 = unpack_half2(v[i].z), x3 = unpack_half2(v[i].w);
+            v[i].x = pack_half2(fmaxf(fmaf(x0.x, s0.x, t0.x), 0.f), fmaxf(fmaf(x0.y, s0.y, t0.y), 0.f));
+            v[i].y = pack_half2(fmaxf(fmaf(x1.x, s0.z, t0.z), 0.f), fmaxf(fmaf(x1.y, s0.w, t0.w), 0.f));
+            v[i].z = pack_half2(fmaxf(fmaf(x2.x, s1.x, t1.x), 0.f), fmaxf(fmaf(x2.y, s1.y, t1.y), 0.f));
+            v[i].w = pack_half2(fmaxf(fmaf(x3.x, s1.z, t1.z), 0.f), fmaxf(fmaf(x3.y, s1.w, t1.w), 0.f));
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(base + i * (16 * 128)) = v[i];
+          fence_proxy_async();                        // generic-proxy writes -> visible to tcgen05.mma's shared-memory reads
+          mbar_arrive(&xf_full[s]);
+        }
       }
     }
   } else {

@@ -213,7 +213,7 @@ def _out_dim(i, k, s, p):
 # convolution / dense
 # ---------------------------------------------------------------------------------------------
 def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, residual_up=False, residual_pre=False,
-         next_affine=None, pool_w=False):
+         next_affine=None, pool_w=False, in_affine=None):
     """nn.Conv3d -> BatchNorm3d -> (+residual) -> ReLU in one kernel
     (resnet3D.py:91-106, 125-143, 176-185; r2plus1d.py:85-88; torchvision_models.py:449-451).
 
@@ -264,6 +264,11 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     args.relu, args.out_f32, args.accumulate, args.mode = int(relu), 0, 0, pc.mode
     args.upsample = int(pc.up)
     args.pool_w = int(pool_w)
+    if in_affine is not None:         # relu(x * scale[n] + shift[n]) on the A operand of a 1x1 convolution (GBlock bn1 + ReLU)
+        isc, ish = in_affine
+        if simt or isc.shape != ish.shape or isc.shape[0] != a.N or isc.stride(0) != ish.stride(0) or isc.shape[1] < a.C:
+            raise ValueError("input affine must be two fp32 [N][>=C] views with the same pitch")
+        args.in_scale, args.in_shift, args.in_aff_ld = _ptr(isc), _ptr(ish), isc.stride(0)
     if pc.up and simt:
         raise ValueError("the CUDA-core cross-check has no fused upsampling")
     if sample_affine is not None:
@@ -277,8 +282,9 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     flops = 2.0 * (a.N * To * Ho * Wconv) * pc.K * pc.Cin * taps        # algorithmic (padding taps included)
     res_rows = 0 if residual is None else (M // 4 if residual_up else M)
     nbytes = 2.0 * (a.M * a.C + M * pc.K * (2 if y2 is not None else 1) + res_rows * pc.K + pc.K * pc.Cin * taps)
-    desc = "conv %dx%dx%d s%s C%d->%d M=%d%s%s%s" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, a.N * To * Ho * Wconv,
-                                                    " up2" if pc.up else "", " +next" if y2 is not None else "", " +poolW" if pool_w else "")
+    desc = "conv %dx%dx%d s%s C%d->%d M=%d%s%s%s%s" % (kt, kh, kw, "".join(map(str, pc.s)), pc.Cin, pc.K, a.N * To * Ho * Wconv,
+                                                      " up2" if pc.up else "", " +next" if y2 is not None else "", " +poolW" if pool_w else "",
+                                                      " bn1(A)" if in_affine is not None else "")
     with _timed("conv", desc, flops, nbytes):
         _lib.check(fn(ctypes.byref(args), _stream()), "b2_conv_ndhwc_fprop")
     out = Act(y, a.N, To, Ho, Wo, pc.K)
