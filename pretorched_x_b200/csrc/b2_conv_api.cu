@@ -10,6 +10,7 @@
 #include "b2_densem.cuh"
 #include "b2_pgemm.cuh"
 #include "b2_slabconv.cuh"
+#include "b2_slabts.cuh"
 #include "b2_stemconv.cuh"
 
 namespace b2 {
@@ -371,6 +372,59 @@ static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
   int rc = flex ? launch_slab<0>(a, p, best_mt, best_R, stream)
                 : (BN == 64) ? launch_slab<64>(a, p, best_mt, best_R, stream) : launch_slab<128>(a, p, best_mt, best_R, stream);
   return rc == B2_OK ? 1 : rc;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// temporal-group slab kernel (b2_slabts.cuh): 3 x kh x kw stride-1 "same" convolutions with <= 64 output channels
+// ------------------------------------------------------------------------------------------
+static int g_slabts = -1;     // B2_SLABTS=0 disables (A/B measurements)
+static int try_slabts(const b2_conv_args* a, cudaStream_t stream) {
+  if (g_slabts < 0) { const char* e = getenv("B2_SLABTS"); g_slabts = (e && e[0] == '0') ? 0 : 1; }
+  if (!g_slabts || g_conv_algo != 0) return 0;
+  if (a->mode != B2_CONV_AUTO || a->out_f32 || a->upsample || a->aff_ld || a->y2 || a->residual_up || a->residual_pre || a->in_scale) return 0;
+  if (a->kt != 3 || a->st != 1 || a->pt != 1 || a->sh != 1 || a->sw != 1 || a->ldy > 64 || a->T < 3) return 0;
+  SlabParams p;
+  if (!slab_geometry(a, &p, 0) || p.n_sub != 1) return 0;
+  int MT = p.P > 128 ? 2 : 1, R = 0;
+  long long smem = 0;
+  for (; MT >= 1; --MT) {
+    R = slab_rows(MT, p.PW, p.reach, p.P);
+    const long long slab_b = ((long long)R * p.PW * 128 + 1023) / 1024 * 1024;
+    smem = kSlabSStages * slab_b + kSlabWStages * kTsWBytes + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
+    if (R <= 256 && smem <= 227 * 1024) break;
+  }
+  if (MT < 1) return 0;
+  p.R = R;
+  p.slab_bytes = ((R * p.PW * 128) + 1023) / 1024 * 1024;
+  p.MT = MT; p.nacc = 1; p.bn = kTsBN; p.wbytes = kTsWBytes; p.accs = kTsBN;
+  p.Ncols = a->K;
+  p.scale = a->scale; p.shift = a->shift;
+  p.residual = reinterpret_cast<const __half*>(a->residual);
+  p.ldr = a->ldr;
+  p.y = reinterpret_cast<__half*>(a->y);
+  p.ldy = a->ldy;
+  p.relu = a->relu;
+  p.naff = slab_naff(a->ldy);
+  p.tiles_n = 1;
+  p.tiles_q = (p.P + MT * 128 - 1) / (MT * 128);
+  const int groups = (p.To + kTsGroup - 1) / kTsGroup;
+  const long long items = (long long)p.tiles_q * p.wchunks * a->N * groups;
+  if (items >= (1ll << 31)) return 0;
+  p.items_total = (int)items;
+  p.fd_tiles_n = make_fastdiv(1); p.fd_tiles_q = make_fastdiv(p.tiles_q); p.fd_wchunks = make_fastdiv(p.wchunks);
+  p.fd_To = make_fastdiv(groups); p.fd_PW = make_fastdiv(p.PW);
+  B2_OPT_IN_SMEM(slabts_kernel, 227 * 1024);
+  CUtensorMap tmX, tmB;
+  int rc;
+  const int taps = a->kt * a->kh * a->kw;
+  if ((rc = make_tmap_ndhwc_slab(&tmX, a->x, (uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N * a->T, (uint32_t)p.PW,
+                                 (uint32_t)R, 1u)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)taps * a->C, (uint64_t)a->K, (uint64_t)taps * a->C, 64, kTsBN, true)) != B2_OK) return rc;
+  const int grid = p.items_total < sm_count() ? p.items_total : sm_count();
+  B2_CHECK_CUDA(launch_pdl(slabts_kernel, dim3(grid), dim3(kSlabThreads), (size_t)smem, stream, tmX, tmB, p));
+  B2_CHECK_LAUNCH("slabts_kernel");
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -773,6 +827,8 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   const bool small_m = a->mode == B2_CONV_AUTO && !a->upsample && !a->aff_ld && !a->out_f32 && !a->y2 && !a->residual_up &&
                        !a->residual_pre && !a->in_scale && g_gemm_algo == 0 &&
                        densem_wanted(M_out, a->kt * a->kh * a->kw, a->st > 1 || a->sh > 1 || a->sw > 1);
+  rc = small_m ? 0 : try_slabts(a, reinterpret_cast<cudaStream_t>(stream));
+  if (rc != 0) return rc < 0 ? rc : B2_OK;
   rc = small_m ? 0 : try_slab(a, reinterpret_cast<cudaStream_t>(stream));
   if (rc != 0) return rc < 0 ? rc : B2_OK;
   if (a->upsample) return set_error(B2_ERR_UNSUPPORTED, "fused upsampling needs the slab kernel, which does not take this shape");

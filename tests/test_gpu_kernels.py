@@ -83,6 +83,12 @@ CONV_CASES = [
     ("densem_temporal_1152_512_res", 5, 1152, 2, 4, 4, 512, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
     ("densem_3x3x3_s2_odd_200ch", 3, 200, 3, 9, 9, 328, (3, 3, 3), (2, 2, 2), (1, 1, 1), True, True, False, True),
     ("densem_tiny_m_3", 3, 256, 1, 1, 1, 96, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, False, True, False),
+    # temporal-group slab kernel (3 x kh x kw, Cout <= 64): frame groups 3 + 2, 3 + 3 + 1, clip boundaries, residual, odd widths, 2 K chunks
+    ("slabts_c64_t5_res", 2, 64, 5, 20, 20, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), True, True, False, True),
+    ("slabts_c32_to_48_t7_odd", 1, 32, 7, 13, 19, 48, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    ("slabts_c128_to_64_t3", 2, 128, 3, 24, 24, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, False, False, True),
+    ("slabts_temporal_3x1x1_to_64", 2, 144, 6, 28, 28, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
+    ("slabts_wide_rows_chunked", 1, 64, 4, 5, 300, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
 ]
 
 
