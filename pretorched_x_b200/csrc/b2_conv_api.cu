@@ -384,6 +384,12 @@ static int try_slabts(const b2_conv_args* a, cudaStream_t stream) {
   if (!g_slabts || g_conv_algo != 0) return 0;
   if (a->mode != B2_CONV_AUTO || a->out_f32 || a->upsample || a->aff_ld || a->y2 || a->residual_up || a->residual_pre || a->in_scale) return 0;
   if (a->kt != 3 || a->st != 1 || a->pt != 1 || a->sh != 1 || a->sw != 1 || a->ldy > 64 || a->T < 3) return 0;
+  // Measured (CUDA-graph replays, profiles/README_r02.md): 180 vs 186 us on the 3x3x3 C64->64 layer of resnet3d50 -- the operand
+  // traffic it saves in shared memory comes back as 2.5x more weight bytes per output tile from L2 (one 24 KB stack per tap and input
+  // frame, two M tiles per item) -- and it LOSES where the single accumulator set exposes a residual read (243 vs 190 us) or the
+  // in-plane filter is 1x1 (the (3,1,1) convolutions of R(2+1)D: 64 vs 31 us against the frames-as-rows remap).  So: true 3-D
+  // filters without a residual only.
+  if (a->kh * a->kw < 9 || a->residual) return 0;
   SlabParams p;
   if (!slab_geometry(a, &p, 0) || p.n_sub != 1) return 0;
   int MT = p.P > 128 ? 2 : 1, R = 0;
