@@ -121,3 +121,58 @@ def test_shard_bounds_cover_batch_exactly():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_slab_tiling_plan_is_host_logic():
+    """The slab kernel's tiling decision (N tile, M tiles per item, slab rows, W chunking) is pure host code behind a debug entry
+    point: the shapes of the BASELINE nets must be accepted with a plan that fits TMEM (MT * N <= 512 columns)."""
+    import ctypes
+    from pretorched_x_b200 import _lib
+    lib = _lib.load()
+    lib.b2_debug_slab_plan.argtypes = [ctypes.POINTER(_lib.ConvArgs), ctypes.POINTER(ctypes.c_int)]
+
+    def plan(N, C, T, H, W, K, k, s=(1, 1, 1)):
+        a = _lib.ConvArgs()
+        a.N, a.T, a.H, a.W, a.C, a.K = N, T, H, W, (C + 7) // 8 * 8, K
+        a.ldy = (K + 7) // 8 * 8
+        a.kt, a.kh, a.kw = k
+        a.st, a.sh, a.sw = s
+        a.pt, a.ph, a.pw = k[0] // 2, k[1] // 2, k[2] // 2
+        out = (ctypes.c_int * 10)()
+        assert lib.b2_debug_slab_plan(ctypes.byref(a), out) == 0
+        return dict(zip("applies BN MT R PW WC wchunks items flex remap".split(), list(out)))
+
+    p = plan(32, 64, 8, 56, 56, 64, (3, 3, 3))                     # resnet3d50 layer1 conv2
+    assert p["applies"] and p["BN"] == 64 and 1 <= p["MT"] <= 4 and p["PW"] == 58 and p["wchunks"] == 1
+    p = plan(16, 64, 16, 28, 28, 144, (1, 3, 3))                   # R(2+1)D layer1 spatial: runtime N tile of 144 columns
+    assert p["applies"] and p["flex"] and p["BN"] == 144 and p["MT"] * 160 <= 512
+    p = plan(16, 144, 16, 28, 28, 64, (3, 1, 1))                   # temporal conv: remapped to frames x positions, 64-wide chunks
+    assert p["applies"] and p["remap"] and p["WC"] <= 64 and p["wchunks"] >= 13
+    p = plan(1, 64, 1, 6, 300, 64, (1, 3, 3))                      # rows longer than a TMA box are cut into W chunks
+    assert p["applies"] and p["wchunks"] >= 2 and p["PW"] <= 256
+    assert not plan(2, 64, 4, 8, 8, 256, (1, 1, 1))["applies"]     # 1x1x1: persistent GEMM, not the slab kernel
+
+
+def test_library_abi_is_pinned(monkeypatch):
+    from pretorched_x_b200 import _lib
+    assert _lib.load().b2_version() == _lib.EXPECTED_ABI
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "EXPECTED_ABI", _lib.EXPECTED_ABI + 1)
+    with pytest.raises(RuntimeError, match="stale library"):
+        _lib.load()
+    monkeypatch.undo()
+    assert _lib.load().b2_version() == _lib.EXPECTED_ABI
+
+
+def test_cache_invalidation_hooks():
+    """Packed-weight caches are dropped on train()/eval(), _apply and on request (engine.CacheOwner)."""
+    m = P.resnet3d10(num_classes=3)
+    m.layer1[0].conv1.__dict__["_b2_cache"] = {"pc": ("sig", "packed")}
+    m.eval()
+    assert "_b2_cache" not in m.layer1[0].conv1.__dict__
+    m.layer1[0].conv1.__dict__["_b2_cache"] = {"pc": ("sig", "packed")}
+    m.invalidate()
+    assert "_b2_cache" not in m.layer1[0].conv1.__dict__
+    m.layer1[0].conv1.__dict__["_b2_cache"] = {"pc": ("sig", "packed")}
+    m.float()
+    assert "_b2_cache" not in m.layer1[0].conv1.__dict__
