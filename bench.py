@@ -50,6 +50,12 @@ WORKLOADS = {
     "resnet18": dict(arch="resnet18", kwargs=dict(num_classes=1000), sample=(3, 224, 224), batch=256, scaling="weak",
                      gflop=3.63, classes=1000, unit="images/s", metric="images/sec resnet18 224x224 forward",
                      config="configs[0]", check_clips=4, cpu_sample=16, act_elems=4.7e6),
+    # the TRN wrapper as `trn()` builds it (trn.py:345-355: class defaults => consensus 'HTRN', which
+    # degenerates to one 8-frame Relation) on the 2-D ResNet-50 backbone; 8 frames of 224x224 per clip.
+    "trn": dict(arch="trn", builder="trn", kwargs=dict(num_classes=339, num_segments=8, arch="resnet50", pretrained=None),
+                sample=(8, 3, 224, 224), batch=32, scaling="weak", gflop=8 * 8.18 + 0.036, classes=339, unit="clips/s",
+                metric="clips/sec TRN (resnet50 backbone, 8 segments) forward", config="SURVEY.md 8a rows a10-a12",
+                check_clips=1, cpu_sample=2, act_elems=8 * 22.2e6),
 }
 DEFAULT_WORKLOAD = "resnet3d50"
 
@@ -65,25 +71,53 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region.  NVML (a ~1 ms query, sampled every 5 ms) when the
+    bindings are importable -- a 20-step timed region is ~80 ms, which an `nvidia-smi` subprocess (~100 ms per call) samples once
+    at best; that subprocess is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda bit: "Active" if mask & bit else "Not Active"
+        return [str(sm), str(self.max_sm), str(n.nvmlDeviceGetPowerUsage(self.handle) / 1e3), flag(n.nvmlClocksThrottleReasonHwSlowdown),
+                flag(n.nvmlClocksThrottleReasonHwThermalSlowdown), flag(n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                flag(n.nvmlClocksThrottleReasonSwPowerCap)]
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 7:
+                        self.rows.append(parts)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.005 if self.nvml is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()
@@ -96,7 +130,8 @@ class ClockSampler(threading.Thread):
             if any(r[3 + i].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -119,8 +154,20 @@ def build_ours(spec):
     import pretorched_x_b200 as P
     torch.manual_seed(0)
     arch = spec["arch"]
-    m = getattr(P, arch)(**spec["kwargs"]) if arch.startswith("r2plus1d") else getattr(P, arch)(pretrained=None, **spec["kwargs"])
+    if spec.get("builder") == "trn":
+        m = P.TRN(**spec["kwargs"])
+    else:
+        m = getattr(P, arch)(**spec["kwargs"]) if arch.startswith("r2plus1d") else getattr(P, arch)(pretrained=None, **spec["kwargs"])
     return condition_(m, spec).eval()
+
+
+def oracle_forward(spec, x, sd):
+    """The CPU checker's forward for a workload (oracle/functional.py restatements, pinned to reference outputs)."""
+    from oracle import functional as OF
+    if spec.get("builder") == "trn":
+        k = spec["kwargs"]
+        return OF.trn_forward(x, sd, k["arch"], "HTRN", k["num_segments"]).reshape(x.shape[0], -1)
+    return OF.forward(x, sd, spec["arch"])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -133,6 +180,11 @@ def cpu_forward_fn(spec):
     from oracle import functional as OF
     from oracle import reference_loader as RL
     arch = spec["arch"]
+    if spec.get("builder") == "trn":
+        # upstream's TRN cannot be constructed offline (its backbone factory must download a checkpoint): the CPU
+        # leg is the oracle restatement of TRN.forward (pinned by the trn_* fixtures), on the same seeded weights
+        sd = build_ours(spec).state_dict()
+        return (lambda x: oracle_forward(spec, x, sd)), "port"
     if RL.available():
         RL.load()
         torch.manual_seed(0)
@@ -251,8 +303,8 @@ def run_ours(args, spec, rank, world, local, secondary=False):
         k = min(spec["check_clips"], B)
         sd = {n_: v.detach().cpu() for n_, v in model.state_dict().items()}
         with torch.no_grad():
-            want = OF.forward(host_in[0][:k], sd, spec["arch"])
-            got = graphed()[:k].float().cpu()
+            want = oracle_forward(spec, host_in[0][:k], sd)
+            got = graphed()[:k].float().cpu().reshape(k, -1)
         scale = want.abs().max().item()
         err = (got.double() - want.double()).abs().max().item() / scale
         agree = bool((got.argmax(1) == want.argmax(1)).all())
@@ -326,7 +378,7 @@ def run_ours(args, spec, rank, world, local, secondary=False):
         e2e_fp16, _ = run_e2e(host_in16, x_dev.half())
         del host_in16
     # decoded uint8 frames (3 bytes per pixel over PCIe), normalised on the device by ClipToStemInput (video workloads)
-    if len(spec["sample"]) == 4 and not secondary:
+    if len(spec["sample"]) == 4 and not secondary and not spec.get("builder"):
         import pretorched_x_b200 as P
         from pretorched_x_b200.transforms import ClipToStemInput
         tf = ClipToStemInput(P.pretrained_settings["resnet3d50"]["kinetics-400"])

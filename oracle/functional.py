@@ -44,6 +44,8 @@ ARCHS = {
                                nonlocal_blocks=[0, 2, 3, 0]),
     # torchvision_models.py:484-492 (torchvision BasicBlock body)
     'resnet18': dict(family='resnet2d', block='basic', layers=[2, 2, 2, 2], shortcut='B'),
+    # torchvision Bottleneck body (stride on the 3x3 conv, v1.5) behind `resnet50` torchvision_models.py:494-532: the TRN backbone
+    'resnet50': dict(family='resnet2d', block='bottleneck', layers=[3, 4, 6, 3], shortcut='B'),
     # pre_act_resnet3D.py:100-139 (ResNet3D subclass: default shortcut 'B', head `fc`)
     'preact_resnet3d18': dict(family='resnet3d', block='preact_basic', layers=[2, 2, 2, 2], shortcut='B'),
     'preact_resnet3d50': dict(family='resnet3d', block='preact_bottleneck', layers=[3, 4, 6, 3], shortcut='B'),

@@ -32,6 +32,7 @@ MODEL_CASES = {
     "r2plus1d34_b1_t8_64": ("r2plus1d34", dict(num_classes=400), (1, 3, 8, 64, 64)),
     "nonlocalresnet3d50_b1_t16_96": ("nonlocalresnet3d50", dict(), (1, 3, 16, 96, 96)),
     "resnet18_b2_64": ("resnet18", dict(num_classes=1000), (2, 3, 64, 64)),
+    "resnet50_b2_64": ("resnet50", dict(num_classes=1000), (2, 3, 64, 64)),       # 2-D bottleneck body: the TRN backbone (trn.py:210)
     # same net with theta/phi rescaled into a trained-like logit regime (oracle.functional.calibrate_nonlocal_)
     "nonlocalresnet3d50_tamed_b1_t16_96": ("nonlocalresnet3d50", dict(), (1, 3, 16, 96, 96)),
     # ---- the BASELINE.json clip sizes themselves (configs[1], [2], [3]): what bench.py times.  Same recipe, the
