@@ -126,6 +126,7 @@ int make_tmap_ndhwc_slab(CUtensorMap* out, const void* base, uint64_t C, uint64_
 // slab convolution launcher (stride 1, "same" padding)
 // ------------------------------------------------------------------------------------------
 static int g_conv_algo = 0;   // 0 auto, 1 force gather (debug / A-B comparisons)
+static int g_slab_wide = -1;       // 256-column N tiles for channel counts that are multiples of 256: -1 rule below, 0 never, 1 always (tuning)
 static int g_slab_force_mt = -1;   // M tiles per slab work item: -1 read B2_SLAB_MT once, 0 cost model, > 0 forced (tuning)
 
 static int slab_naff(int ldy) { return (ldy + 31) / 32 * 32 + 256; }   // chunk reads may run past ldy inside the last N tile
@@ -266,7 +267,7 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
 
 // Picks the N tile (fixed 64 / 128 or runtime), the M tiles per work item and the slab rows for a geometry; *best_mt == 0
 // when no configuration fits in shared memory.
-static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out, bool* flex_out, int* best_mt_out, int* best_R_out) {
+static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out, bool* flex_out, int* best_mt_out, int* best_R_out, bool wide = false) {
   int BN = (a->ldy <= 64) ? 64 : 128;
   const int planes = a->N * p.To;
   int ntn = (a->ldy + BN - 1) / BN;
@@ -276,7 +277,7 @@ static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out,
   if (a->ldy > 128) {
     const int tn = (a->ldy + 255) / 256;
     const int bn = (((a->ldy + tn - 1) / tn) + 15) / 16 * 16;
-    if ((long long)bn * tn * 21 <= (long long)ntn * 128 * 20) {
+    if ((long long)bn * tn * 21 <= (long long)ntn * 128 * 20 || ((wide || g_slab_wide == 1) && a->ldy % 256 == 0)) {
       flex = true; BN = bn; ntn = tn;
       p.bn = bn; p.wbytes = (bn * 128 + 1023) / 1024 * 1024; p.accs = (bn + 31) / 32 * 32;
     }
@@ -363,7 +364,22 @@ static int try_slab(const b2_conv_args* a_in, cudaStream_t stream) {
     if (g_conv_algo == 2 && q.ss != 1) return 0;              // debug: strided convs through the gather kernel
     int bn_c = 0, mt_c = 0, r_c = 0;
     bool flex_c = false;
-    const double cost = slab_pick_tiles(a, q, &bn_c, &flex_c, &mt_c, &r_c);
+    double cost = slab_pick_tiles(a, q, &bn_c, &flex_c, &mt_c, &r_c);
+    if (g_slab_wide < 0 && a->ldy % 256 == 0 && !flex_c) {
+      // 256-column N tiles (one A read per 256 output channels instead of per 128): measured with tools/conv_sweep.py
+      // (profiles/slab_wide_sweep_r02.txt) they win by 5-35% wherever at least 64 work items of at least two M tiles remain, and lose
+      // when halving the number of N tiles leaves SMs idle (M = 6272: 33 -> 41 us) or an item is a single tile (7x7 planes: 23 -> 29 us)
+      SlabParams qw = q;
+      int bn_w = 0, mt_w = 0, r_w = 0;
+      bool flex_w = false;
+      const double cost_w = slab_pick_tiles(a, qw, &bn_w, &flex_w, &mt_w, &r_w, true);
+      if (mt_w != 0 && flex_w) {
+        const long long tq = (qw.P + mt_w * 128 - 1) / (mt_w * 128);
+        const long long items_w = (long long)((a->ldy + bn_w - 1) / bn_w) * tq * a->N * qw.To * qw.wchunks * (qw.up ? 4 : 1);
+        const double tiles_per_item = (double)((qw.P + 127) / 128) / (double)tq;
+        if (items_w >= 64 && tiles_per_item >= 2.0) { q = qw; bn_c = bn_w; flex_c = flex_w; mt_c = mt_w; r_c = r_w; cost = cost_w * 0.8; }
+      }
+    }
     if (mt_c == 0) continue;
     if (best_mt == 0 || cost < best_cost) { best_p = q; BN = bn_c; flex = flex_c; best_mt = mt_c; best_R = r_c; best_cost = cost; }
   }
@@ -777,6 +793,7 @@ int b2_debug_slab_plan(const b2_conv_args* a_in, int* out) {
   return B2_OK;
 }
 /* debug knobs of the small-M path: layers with M <= maxm take the dense-M kernel (0 = never); force_s > 0 caps the cluster size */
+int b2_debug_set_slab_wide(int on) { g_slab_wide = on; return B2_OK; }   /* -1 rule, 0 never, 1 always */
 int b2_debug_set_slab_mt(int mt) { g_slab_force_mt = mt < 0 ? 0 : mt; return B2_OK; }
 int b2_debug_set_densem(int maxm, int force_s) { g_densem_maxm = maxm < 0 ? -2 : maxm; g_densem_force_s = force_s; return B2_OK; }
 const char* b2_last_error(void) { return g_err; }

@@ -15,6 +15,8 @@ specs = [l.split() for l in open(sys.argv[1]) if l.strip() and not l.startswith(
 settings = [tuple(int(v) for v in s.split(":")) for s in sys.argv[2:]] or [(0, 0), (1 << 30, 0)]
 lib.b2_debug_set_slab_mt.restype = ctypes.c_int
 lib.b2_debug_set_slab_mt.argtypes = [ctypes.c_int]
+lib.b2_debug_set_slab_wide.restype = ctypes.c_int
+lib.b2_debug_set_slab_wide.argtypes = [ctypes.c_int]          # 4th field of a setting: 256-column N tiles 1 = always, 0 = never, -1 / absent = the library's rule
 dev = torch.device("cuda:0")
 REP = 20
 for sp in specs:
@@ -41,6 +43,7 @@ for sp in specs:
             mt = st[2] if len(st) > 2 else 0
             lib.b2_debug_set_densem(maxm, fs)
             lib.b2_debug_set_slab_mt(mt)
+            lib.b2_debug_set_slab_wide(st[3] if len(st) > 3 else -1)
             for _ in range(2):
                 y = engine.conv_bn_act(conv, bn, x, residual=res, relu=True)
             torch.cuda.synchronize()
