@@ -102,7 +102,7 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 }
 
 int make_tmap_ndhwc_slab(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t planes,
-                         uint32_t box_w, uint32_t box_h, uint32_t stride_hw) {
+                         uint32_t box_w, uint32_t box_h, uint32_t stride_hw, uint32_t box_planes) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return set_error(B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(B2_ERR_INVALID, "tensor base not 16-byte aligned");
@@ -110,7 +110,7 @@ int make_tmap_ndhwc_slab(CUtensorMap* out, const void* base, uint64_t C, uint64_
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
   // with element strides the box is given in traversed (full-resolution) elements; smem receives every
   // stride_hw-th pixel / row, i.e. box_w x box_h dense pixels
-  cuuint32_t box[4] = {64, stride_hw * (box_w - 1) + 1, stride_hw * (box_h - 1) + 1, 1};
+  cuuint32_t box[4] = {64, stride_hw * (box_w - 1) + 1, stride_hw * (box_h - 1) + 1, box_planes};
   cuuint32_t estr[4] = {1, stride_hw, stride_hw, 1};
   if (box[1] > 256 || box[2] > 256) return set_error(B2_ERR_UNSUPPORTED, "slab box %ux%u exceeds the TMA box limit", box[1], box[2]);
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -228,7 +228,9 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   if (BNT) { p.bn = BNT; p.wbytes = BNT * 128; p.accs = BNT; }
   const int BN = p.bn;
   p.R = R;
-  p.slab_bytes = ((R * p.PW * 128) + 1023) / 1024 * 1024;
+  p.planes_total = a->N * p.To;
+  p.plane_stride = R * p.PW * 128;
+  p.slab_bytes = ((R * p.PW * 128 * (p.mp > 1 ? p.mp : 1)) + 1023) / 1024 * 1024;
   p.MT = MT;
   p.nacc = (MT * p.accs <= 256) ? 2 : 1;
   p.Ncols = a->K;
@@ -241,8 +243,9 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   p.aff_ld = a->aff_ld;
   p.naff = slab_naff(a->ldy);
   p.tiles_n = (a->ldy + BN - 1) / BN;
-  p.tiles_q = (p.P + MT * 128 - 1) / (MT * 128);
-  const long long items = (long long)p.tiles_n * p.tiles_q * p.wchunks * a->N * p.To * (p.up ? 4 : 1);
+  p.tiles_q = p.mp > 1 ? 1 : (p.P + MT * 128 - 1) / (MT * 128);
+  const long long plane_items = p.mp > 1 ? ((long long)a->N * p.To + p.mp - 1) / p.mp : (long long)a->N * p.To;
+  const long long items = (long long)p.tiles_n * p.tiles_q * p.wchunks * plane_items * (p.up ? 4 : 1);
   if (items >= (1ll << 31)) return set_error(B2_ERR_INVALID, "slab problem too large");
   p.items_total = (int)items;
   p.fd_tiles_n = make_fastdiv(p.tiles_n); p.fd_tiles_q = make_fastdiv(p.tiles_q); p.fd_wchunks = make_fastdiv(p.wchunks);
@@ -255,7 +258,7 @@ static int launch_slab(const b2_conv_args* a, SlabParams& p, int MT, int R, cuda
   int rc;
   const int taps = p.up ? 16 : a->kt * a->kh * a->kw;
   if ((rc = make_tmap_ndhwc_slab(&tmX, a->x, (uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->N * a->T,
-                                 (uint32_t)p.PW, (uint32_t)R, (uint32_t)p.ss)) != B2_OK)
+                                 (uint32_t)p.PW, (uint32_t)R, (uint32_t)p.ss, (uint32_t)(p.mp > 1 ? p.mp : 1))) != B2_OK)
     return rc;
   if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)taps * a->C, (uint64_t)a->K, (uint64_t)taps * a->C, 64, BN, true)) != B2_OK)
     return rc;
@@ -300,22 +303,33 @@ static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out,
   for (int cc = 0; cc < p.cchunks; ++cc) { const int k = (a->C - cc * 64 + 15) / 16; ksteps += k > 4 ? 4 : k; }
   int taps_hw = 0;
   for (int sidx = 0; sidx < p.n_sub; ++sidx) taps_hw += p.sub_ntaps[sidx];
+  // planes of at most one M tile whose temporal taps do not differ from plane to plane: the MT accumulators of an item are MT
+  // consecutive PLANES (SlabParams::mp), see b2_slabconv.cuh
+  static int mp_env = -1;
+  if (mp_env < 0) { const char* e = getenv("B2_SLAB_MP"); mp_env = (e && e[0] == '0') ? 0 : 1; }
+  const bool mp_ok = mp_env && p.P <= 128 && (a->kt == 1 || a->T == 1) && p.ss == 1 && !p.up && p.wchunks == 1 && planes > 1 &&
+                     !a->aff_ld;      // (a per-sample affine is read once per item: its tiles must belong to one image)
+  p.mp = 0;
   for (int MT = 512 / acc_stride > 4 ? 4 : 512 / acc_stride; MT >= 1; --MT) {
     if (force_mt > 0 && MT != force_mt && MT != 1) continue;
-    const int R = slab_rows(MT, p.PW, p.reach, p.P);
+    // (multi-plane: rows one plane's positions and taps can touch -- slab_rows assumes a full 128-position tile)
+    const int R = mp_ok ? (p.P - 1 + p.reach) / p.PW + (p.reach + p.PW - 1) / p.PW + 1 : slab_rows(MT, p.PW, p.reach, p.P);
     if (p.ss * (R - 1) + 1 > 256) continue;
-    const long long slab_b = ((long long)R * p.PW * 128 + 1023) / 1024 * 1024;
+    const long long slab_b = ((long long)R * p.PW * 128 * (mp_ok ? MT : 1) + 1023) / 1024 * 1024;
     const long long smem = 2ll * slab_b + kSlabWStages * w_stage + 256 + 2 * slab_naff(a->ldy) * 4 + 1024;
     if (smem > 227 * 1024) continue;
-    const long long tq = (p.P + MT * 128 - 1) / (MT * 128);
-    const long long items = (long long)ntn * tq * planes * p.wchunks * (p.up ? 4 : 1);
+    const long long tq = mp_ok ? 1 : (p.P + MT * 128 - 1) / (MT * 128);
+    const long long items = (long long)ntn * tq * (mp_ok ? (planes + MT - 1) / MT : planes) * p.wchunks * (p.up ? 4 : 1);
     const double rounds = (double)((items + sm_count() - 1) / sm_count());
-    const double tiles_per_item = (double)((p.P + 127) / 128) / (double)tq;          // average (the last item of a plane is short)
+    const double tiles_per_item = mp_ok ? (double)MT : (double)((p.P + 127) / 128) / (double)tq;   // average (the last item of a plane is short)
     // (A per-weight-tile issue floor of ~650 cycles was tried here after profiles/ncu_r02 showed the issuing warp, not the tensor
     // pipe, pacing one-tile items with a narrow N; it moved the (1,3,3) C64->144 layer from MT = 1 with two accumulator sets to MT = 2
     // with one, which measured 59 us instead of 44 us -- losing the epilogue overlap costs more than the amortised issue work gains.)
     const double mma = tiles_per_item * p.kt * taps_hw * ksteps * (40.0 + 0.5 * BN);
-    const double load = (double)p.kt * p.n_sub * p.cchunks * slab_b / 48.0 + (double)p.kt * taps_hw * p.cchunks * w_stage / 48.0;
+    // small planes: every SM streams the whole filter per item at the same time, and what bounds that is the aggregate L2 -> SM rate
+    // (~7 TB/s = 26 B/cycle/SM: 192 items x 884 KB in 25 us on the 7x7 C256->576 layer), not one SM's TMA rate
+    const double bpc = mp_ok ? 26.0 : 48.0;
+    const double load = (double)p.kt * p.n_sub * p.cchunks * slab_b / bpc + (double)p.kt * taps_hw * p.cchunks * w_stage / bpc;
     const double epi = (MT * acc_stride <= 256) ? 0.0 : tiles_per_item * ((BN + 31) / 32) * 250.0;
     const double cost = rounds * ((mma > load ? mma : load) + epi + 1500.0);
     if (force_mt == -1) {                                   // previous rule (A/B): largest power-of-two MT with >= 2 rounds of items
@@ -327,6 +341,14 @@ static double slab_pick_tiles(const b2_conv_args* a, SlabParams& p, int* BN_out,
     if (best_mt == 0 || cost < best_cost || (force_mt > 0 && MT == force_mt)) { best_mt = MT; best_R = R; best_cost = cost; }
     if (force_mt > 0 && MT == force_mt) break;
   }
+  if (mp_ok && best_mt >= 2 && best_mt < 4 && force_mt <= 0 && 4 * acc_stride <= 512) {
+    // measured (profiles/slab_mp_sweep_r02.txt): four planes per item beat two by ~10% as long as a full wave of items remains
+    const int R4 = (p.P - 1 + p.reach) / p.PW + (p.reach + p.PW - 1) / p.PW + 1;
+    const long long slab4 = ((long long)R4 * p.PW * 128 * 4 + 1023) / 1024 * 1024;
+    const long long items4 = (long long)ntn * ((planes + 3) / 4);
+    if (2ll * slab4 + kSlabWStages * w_stage + 256 + 2 * slab_naff(a->ldy) * 4 + 1024 <= 227 * 1024 && items4 >= sm_count()) { best_mt = 4; best_R = R4; }
+  }
+  p.mp = (mp_ok && best_mt > 1) ? best_mt : 0;
   *BN_out = BN; *flex_out = flex; *best_mt_out = best_mt; *best_R_out = best_R;
   return best_cost;
 }
@@ -418,7 +440,9 @@ static int try_slabts(const b2_conv_args* a, cudaStream_t stream) {
   }
   if (MT < 1) return 0;
   p.R = R;
-  p.slab_bytes = ((R * p.PW * 128) + 1023) / 1024 * 1024;
+  p.planes_total = a->N * p.To;
+  p.plane_stride = R * p.PW * 128;
+  p.slab_bytes = ((R * p.PW * 128 * (p.mp > 1 ? p.mp : 1)) + 1023) / 1024 * 1024;
   p.MT = MT; p.nacc = 1; p.bn = kTsBN; p.wbytes = kTsWBytes; p.accs = kTsBN;
   p.Ncols = a->K;
   p.scale = a->scale; p.shift = a->shift;

@@ -63,7 +63,7 @@ int make_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 // 4-D fp16 tensor map over an NDHWC activation viewed as (C, W, H, N*T); smem box = (64, box_w, box_h, 1) pixels
 // taken every stride_hw-th column / row (TMA elementStrides), SWIZZLE_128B.  Negative / out-of-range box coordinates read zeros (halo columns, rows above/below the image).
 int make_tmap_ndhwc_slab(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t planes,
-                         uint32_t box_w, uint32_t box_h, uint32_t stride_hw);
+                         uint32_t box_w, uint32_t box_h, uint32_t stride_hw, uint32_t box_planes = 1);
 
 int require_sm100();
 

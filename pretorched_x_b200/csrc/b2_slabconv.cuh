@@ -79,6 +79,11 @@ struct SlabParams {
   // uses the tap table row sub_*[ph] (4 taps, weights [K][ph*4 + i][C]) and writes output pixel (2h + py, 2w + px) of a
   // (2 Ho) x (2 Wo) plane.  n_sub stays 1: all phases read the same slab.
   int up;
+  // Multi-plane items (mp >= 2, planes of at most 128 padded positions, no temporal taps that differ between planes): the MT accumulators
+  // of an item belong to mp CONSECUTIVE PLANES instead of consecutive tiles of one plane, so small planes (7x7: one 38%-full tile)
+  // share every weight tile mp ways -- these layers stream their whole filter per work item and are bound by that L2 traffic.  One
+  // 4-D TMA box brings the mp slabs ([plane][R][PW] in shared memory); tile j's A operand starts j * plane_stride bytes further.
+  int mp, plane_stride, planes_total;
   FastDiv fd_tiles_n, fd_tiles_q, fd_wchunks, fd_To, fd_PW;   // dividers of the item decode (set by launch_slab)
 };
 
@@ -98,6 +103,7 @@ __device__ __forceinline__ SlabItem slab_item(const SlabParams& p, int item, int
   const int tq = item - t * p.tiles_q; item = t;
   w.plane_o = fdiv(item, p.fd_wchunks);
   w.wc = item - w.plane_o * p.wchunks;
+  if (p.mp > 1) w.plane_o *= p.mp;                  // first plane of the group
   w.n0 = tn * BN;
   w.q0 = tq * (p.MT * 128);
   const int n = fdiv(w.plane_o, p.fd_To), to = w.plane_o - n * p.To;
@@ -111,6 +117,7 @@ __device__ __forceinline__ SlabItem slab_item(const SlabParams& p, int item, int
   w.n_slabs = p.cchunks * w.n_dt * p.n_sub;
   const int mv = (p.P - w.q0 + 127) / 128;          // M tiles that contain at least one position of the plane
   w.mt_valid = mv > p.MT ? p.MT : mv;
+  if (p.mp > 1) w.mt_valid = min(p.mp, p.planes_total - w.plane_o);   // planes of the group that exist
   return w;
 }
 
@@ -179,7 +186,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
         const int s = sg % kSlabSStages;
         mbar_wait(&slab_empty[s], ((sg / kSlabSStages) & 1) ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&slab_full[s], static_cast<uint32_t>(p.R * p.PW * 128));
+          mbar_expect_tx(&slab_full[s], static_cast<uint32_t>(p.R * p.PW * 128 * (p.mp > 1 ? p.mp : 1)));
           tma_load_4d(slab_base + s * p.slab_bytes, &tmX, &slab_full[s], cc * 64,
                       p.sub_w0[sub] + p.ss * nxt.wc * p.WC, p.ss * nxt.r_lo + p.sub_h0[sub], nxt.plane_i0 + dt);
         }
@@ -220,6 +227,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
     const uint32_t idesc = make_idesc_f16(128, bn, 0);
     const uint32_t tm = warp_uniform(tmem_base);
     const uint32_t slab0 = smem_u32(slab_base), w0s = smem_u32(w_base);
+    const uint32_t tile_stride16 = (p.mp > 1 ? static_cast<uint32_t>(p.plane_stride) : 128u * 128u) >> 4;   // A start of tile j, in 16-byte units
     int wit = 0, sg = 0, lt = 0;
     for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
       const SlabItem w = slab_item(p, item, bn);
@@ -246,7 +254,7 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
           const uint32_t a_lo0 = sw128_desc_lo(slab_addr + static_cast<uint32_t>(pix0) * 128u);
           if (elect_one()) {
             for (int j = 0; j < w.mt_valid; ++j) {
-              const uint32_t a_lo = a_lo0 + j * (128u * 128u >> 4);
+              const uint32_t a_lo = a_lo0 + j * tile_stride16;
               const uint32_t d = acc + j * accs;
               umma_f16(d, desc_from(kSw128DescHi, a_lo), desc_from(kSw128DescHi, b_lo), idesc, wl != 0 ? 1u : 0u);
               if (ksteps == 4) {
@@ -285,12 +293,13 @@ slabconv_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, W, H,
       bool ok[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int q = w.q0 + j * 128 + erow;
+        const int q = p.mp > 1 ? erow : w.q0 + j * 128 + erow;          // multi-plane items: tile j is plane plane_o + j
         const int h = fdiv(q, p.fd_PW), wp = q - h * p.PW;
         const int wo = w.wc * p.WC + wp - p.halo_l;       // output column
         ok[j] = (j < w.mt_valid) && (q < p.P) && (wp >= p.halo_l) && (wp < p.halo_l + p.WC) && (wo < p.Wo);
-        row[j] = p.up ? (static_cast<size_t>(w.plane_o) * (2 * p.Ho) + 2 * h + (w.phase >> 1)) * (2 * p.Wo) + 2 * wo + (w.phase & 1)
-                      : (static_cast<size_t>(w.plane_o) * p.Ho + h) * p.Wo + wo;
+        const size_t plane = static_cast<size_t>(w.plane_o) + (p.mp > 1 ? j : 0);
+        row[j] = p.up ? (plane * (2 * p.Ho) + 2 * h + (w.phase >> 1)) * (2 * p.Wo) + 2 * wo + (w.phase & 1)
+                      : (plane * p.Ho + h) * p.Wo + wo;
       }
 #pragma unroll 1
       for (int jc = egroup; jc * 32 < ncols_here; jc += 2) {

@@ -99,7 +99,9 @@ def test_embed_concat_and_tanh(dev):
 
 
 @pytest.mark.parametrize("shape", [(3, 64, 12, 20, 64), (2, 128, 16, 16, 128), (5, 32, 4, 4, 32), (2, 16, 40, 40, 8),
-                                   (2, 64, 20, 256, 64), (1, 128, 9, 256, 3), (2, 128, 12, 128, 128)])
+                                   (2, 64, 20, 256, 64), (1, 128, 9, 256, 3), (2, 128, 12, 128, 128),
+                                   # many small planes: items must never span two samples' affine rows
+                                   (300, 64, 8, 8, 64), (320, 128, 4, 4, 256)])
 def test_conv3x3_with_per_sample_affine(dev, shape):
     N, C, H, W, K = shape
     g = torch.Generator().manual_seed(7)

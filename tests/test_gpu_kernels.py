@@ -89,6 +89,11 @@ CONV_CASES = [
     ("slabts_c128_to_64_t3", 2, 128, 3, 24, 24, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, False, False, True),
     ("slabts_temporal_3x1x1_to_64", 2, 144, 6, 28, 28, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
     ("slabts_wide_rows_chunked", 1, 64, 4, 5, 300, 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    # multi-plane items of the slab kernel (small planes share each weight tile): odd plane counts (partial last group), residual,
+    # runtime N tile, T == 1 with a 3-tap temporal filter (only the centre tap is ever valid)
+    ("slab_multiplane_7x7_192", 9, 128, 3, 7, 7, 192, (1, 3, 3), (1, 1, 1), (0, 1, 1), True, True, False, True),
+    ("slab_multiplane_7x7_T1_3x3x3", 23, 128, 1, 7, 7, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, True, False, True),
+    ("slab_multiplane_5x6_c512_256wide", 41, 512, 1, 5, 6, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1), False, True, False, True),
 ]
 
 
