@@ -217,16 +217,17 @@ def _next_affine(nxt, a_out_hw, aff, pk):
     return _aff(aff, pk.blocks[id(nxt)].bn[0])
 
 
-def run_gblock(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None):
+def run_gblock(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None, out=None):
     """One GBlock through its torch.autograd.Function (functions.GBlockFunction: forward = the launch sequence of
-    ``_gblock_body``, outputs non-differentiable).  Returns (block output, relu(bn1_next(output)) or None)."""
+    ``_gblock_body``, outputs non-differentiable).  Returns (block output, relu(bn1_next(output)) or None).  ``out``:
+    preallocated rows for the block output (written by conv4's epilogue)."""
     from .functions import GBlockFunction
     d0, g0, d1, g1 = GBlockFunction.apply(a.data, (a.N, a.T, a.H, a.W, a.C), blk, aff, pk,
-                                          dict(fuse_output_bn=fuse_output_bn, pre=pre, nxt=nxt))
+                                          dict(fuse_output_bn=fuse_output_bn, pre=pre, nxt=nxt, out=out))
     return Act(d0, *g0), (Act(d1, *g1) if d1 is not None else None)
 
 
-def _gblock_body(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None):
+def _gblock_body(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None, out=None):
     """One GBlock: h = conv4(relu(bn4(conv3(relu(bn3(conv2(up(relu(bn2(conv1(relu(bn1(x))))))))))))) + up(x[:, :out]).
     ``pre``: relu(bn1(x)) when the previous kernel already produced it; ``nxt``: the module that consumes the result --
     if it is a GBlock its opening ccbn + ReLU is written as a second output of conv4 (returned as the second value).
@@ -253,12 +254,12 @@ def _gblock_body(blk, a, aff, pk, fuse_output_bn=False, pre=None, nxt=None):
     # conv4 + skip: the skip path x[:, :out] (channel drop = residual pitch) is read at LOW resolution by the epilogue and
     # upsampled on the fly, so up(x) is never written; the last block also carries the output BN + ReLU (see _pack)
     if fuse_output_bn:
-        return ops.conv(t, pk.out_conv4, residual=a, relu=True, residual_up=up == 2, residual_pre=True)
+        return ops.conv(t, pk.out_conv4, residual=a, relu=True, residual_up=up == 2, residual_pre=True, out=out)
     nxt_aff = _next_affine(nxt, t.H * t.W, aff, pk)
-    return ops.conv(t, bp.conv[3], residual=a, residual_up=up == 2, next_affine=nxt_aff)    # Act, or (Act, Act) with nxt_aff
+    return ops.conv(t, bp.conv[3], residual=a, residual_up=up == 2, next_affine=nxt_aff, out=out)    # Act, or (Act, Act) with nxt_aff
 
 
-def run_attention(att, a, aff, pk, nxt=None):
+def run_attention(att, a, aff, pk, nxt=None, out=None):
     """SAGAN self-attention with 2x2 max-pooled keys / values: gamma * o(softmax(theta^T phi) g) + x.  Returns (result,
     relu(bn1_next(result)) or None) like ``run_gblock``."""
     ap = pk.att[id(att)]
@@ -273,8 +274,47 @@ def run_attention(att, a, aff, pk, nxt=None):
         z, z2 = ops.gemm(o, ap.wo, ap.gamma, ap.zeros[:C], M, C, ap.dv, residual=a.data,
                          next_affine=(nxt_aff[0], nxt_aff[1], a.H * a.W))
         return Act(z, a.N, 1, a.H, a.W, C), Act(z2, a.N, 1, a.H, a.W, C)
-    z = ops.gemm(o, ap.wo, ap.gamma, ap.zeros[:C], M, C, ap.dv, residual=a.data)
+    if out is not None:
+        ops._out_rows(out, M, _round_up(C, 8))
+    z = ops.gemm(o, ap.wo, ap.gamma, ap.zeros[:C], M, C, ap.dv, residual=a.data, out=out)
     return Act(z, a.N, 1, a.H, a.W, C), None
+
+
+_DFS_SPEC = os.environ.get("B2_GAN_DFS", "auto")
+_DFS_AUTO = "64:32,128:8,256:4"       # measured rule for B >= 64 (tools/dfs_sweep.py biggan256); see dfs_plan
+
+
+def set_dfs(spec):
+    """Schedule of the generator's high-resolution tail: ``"off"``, ``"auto"`` or ``"res:images,res:images"`` -- modules whose OUTPUT
+    resolution is at least ``res`` (up to the next listed resolution) run depth-first on chunks of ``images``."""
+    global _DFS_SPEC
+    _DFS_SPEC = str(spec)
+
+
+def dfs_plan(model, B, mods):
+    """[(first module, end module, images per chunk)] covering a suffix of ``mods`` (empty = whole batch everywhere)."""
+    spec = _DFS_SPEC.strip().lower()
+    if spec in ("0", "off", "none", ""):
+        return []
+    if spec == "auto":
+        spec = _DFS_AUTO
+    levels = sorted(tuple(int(v) for v in part.split(":")) for part in spec.split(","))
+    res, out_res = model.bottom_width, []
+    for _, blk in mods:
+        if hasattr(blk, 'conv4') and blk.upsample:
+            res *= 2
+        out_res.append(res)
+    plan = []
+    for li, (r0, chunk) in enumerate(levels):
+        r1 = levels[li + 1][0] if li + 1 < len(levels) else 1 << 30
+        js = [j for j, r in enumerate(out_res) if r0 <= r < r1]
+        if not js or chunk >= B:
+            if plan:              # a whole-batch level after a chunked one: keep the suffix contiguous by chunking it by B
+                if js:
+                    plan.append((js[0], js[-1] + 1, B))
+            continue
+        plan.append((js[0], js[-1] + 1, chunk))
+    return plan
 
 
 def generator_forward(model, z, y, out_dtype=torch.float32, stages=None, fuse_output_bn=True, split_head=True,
@@ -299,25 +339,69 @@ def generator_forward(model, z, y, out_dtype=torch.float32, stages=None, fuse_ou
     a = Act(h.view(B * bw * bw, C0), B, 1, bw, bw, C0)
     if stages is not None:
         stages['linear'] = a
-    fused_tail = False
     mods = [(i, blk) for i, stage in enumerate(model.blocks) for blk in stage]
-    pre = None                                  # relu(bn1(a)) of the upcoming GBlock when its producer already wrote it
-    for j, (i, blk) in enumerate(mods):
-        nxt = mods[j + 1][1] if (j + 1 < len(mods) and dual_output) else None
-        if hasattr(blk, 'conv4'):
-            fused_tail = fuse_output_bn and blk is pk.last_block
-            a, pre = run_gblock(blk, a, aff, pk, fuse_output_bn=fused_tail, pre=pre, nxt=nxt)
-        else:
-            a, pre = run_attention(blk, a, aff, pk, nxt=nxt)
-        if stages is not None and not fused_tail and (j + 1 == len(mods) or mods[j + 1][0] != i):
-            stages['stage%d' % i] = a
-    t = a if fused_tail else ops.ccbn_act(a, pk.out_scale, pk.out_shift)
-    if stages is not None:
-        stages['out_act'] = t
-    if split_head and pk.head_w is not None:
-        part = ops.gemm(t.data, pk.head_w, pk.head_ones, pk.head_zeros, t.M, 40, t.ld)      # per-tap partial products
-        return ops.rgb_head(part, pk.head_bias, t.N, t.H, t.W, pk.head_k, out_dtype)        # gather + bias + tanh + NCHW
-    t = ops.conv(t, pk.out_conv)
-    if stages is not None:
-        stages['pre_tanh'] = t
-    return ops.tanh_to_nchw(t, out_dtype)
+
+    def run_mods(a, aff, j0, j1, out=None):
+        """Modules j0 .. j1-1 on the activation ``a`` (whole batch or a chunk of images, ``aff`` sliced alike)."""
+        fused_tail, pre = False, None           # pre: relu(bn1(a)) of the upcoming GBlock when its producer already wrote it
+        for j in range(j0, j1):
+            i, blk = mods[j]
+            nxt = mods[j + 1][1] if (j + 1 < len(mods) and dual_output) else None
+            o = out if j == j1 - 1 else None
+            if hasattr(blk, 'conv4'):
+                fused_tail = fuse_output_bn and blk is pk.last_block
+                a, pre = run_gblock(blk, a, aff, pk, fuse_output_bn=fused_tail, pre=pre, nxt=nxt, out=o)
+            else:
+                a, pre = run_attention(blk, a, aff, pk, nxt=nxt, out=o)
+            if stages is not None and not fused_tail and (j + 1 == len(mods) or mods[j + 1][0] != i):
+                stages['stage%d' % i] = a
+        return a, fused_tail
+
+    def run_tail(a, fused_tail, out=None):
+        t = a if fused_tail else ops.ccbn_act(a, pk.out_scale, pk.out_shift)
+        if stages is not None:
+            stages['out_act'] = t
+        if split_head and pk.head_w is not None:
+            part = ops.gemm(t.data, pk.head_w, pk.head_ones, pk.head_zeros, t.M, 40, t.ld)      # per-tap partial products
+            return ops.rgb_head(part, pk.head_bias, t.N, t.H, t.W, pk.head_k, out_dtype, out=out)   # gather + bias + tanh + NCHW
+        t = ops.conv(t, pk.out_conv)
+        if stages is not None:
+            stages['pre_tanh'] = t
+        return ops.tanh_to_nchw(t, out_dtype, out=out)
+
+    # Depth-first tail (see engine.run_trunk): from the resolution where a whole-batch tensor outgrows L2 the remaining modules run
+    # on chunks of images, every intermediate a write-then-read inside L2; chunk outputs land in their slice of the next segment's
+    # input (or of the image tensor).  Not with ``stages`` (whole-batch stage tensors wanted) or ``dual_output``.
+    plan = [] if (stages is not None or dual_output) else dfs_plan(model, B, mods)
+    j_first = plan[0][0] if plan else len(mods)
+    a, fused_tail = run_mods(a, aff, 0, j_first)
+    images = None
+    for j0, j1, chunk in plan:
+        last = j1 == len(mods)
+        if chunk >= B:                              # a whole-batch level behind a chunked one
+            a, fused_tail = run_mods(a, aff, j0, j1)
+            continue
+        buf = None
+        r = a.positions
+        for n0 in range(0, B, chunk):
+            n1 = min(B, n0 + chunk)
+            ca, caff = Act(a.data[n0 * r:n1 * r], n1 - n0, 1, a.H, a.W, a.C), aff[n0:n1]
+            if last:                                # ... through the RGB head: the chunk's images go straight into the batch tensor
+                y, ft = run_mods(ca, caff, j0, j1)
+                if images is None:
+                    K = pk.head_k if (split_head and pk.head_w is not None) else pk.out_conv.K
+                    images = torch.empty((B, K, y.H, y.W), dtype=out_dtype, device=dev)
+                run_tail(y, ft, out=images[n0:n1])
+                continue
+            o = buf.data[n0 * buf.positions:n1 * buf.positions] if buf is not None else None
+            y, _ = run_mods(ca, caff, j0, j1, out=o)
+            if buf is None:                         # the first chunk shows the segment's output geometry
+                buf = Act(torch.empty((B * y.positions, y.ld), dtype=torch.float16, device=dev), B, 1, y.H, y.W, y.C)
+                o = buf.data[:y.M]
+            if y.data.data_ptr() != o.data_ptr():
+                o.copy_(y.data)
+        if not last:
+            a = buf
+    if images is not None:
+        return images
+    return run_tail(a, fused_tail)

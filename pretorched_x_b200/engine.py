@@ -117,18 +117,18 @@ def _is_stem_shape(conv):
     return w.shape[1] <= 4 and kw == 7 and stride[2] == 2 and padding[2] == 3
 
 
-def _st_conv_body(conv, bn, a, residual, relu, simt):
+def _st_conv_body(conv, bn, a, residual, relu, simt, out=None):
     """(2+1)D factorised conv (r2plus1d.py:85-88): spatial conv + its own BN + ReLU, then the temporal conv whose
     epilogue carries the *outer* BN / residual / ReLU."""
     mid = conv_bn_act(conv.spatial_conv, conv.bn, a, relu=True, simt=simt)
-    return conv_bn_act(conv.temporal_conv, bn, mid, residual=residual, relu=relu, simt=simt)
+    return conv_bn_act(conv.temporal_conv, bn, mid, residual=residual, relu=relu, simt=simt, out=out)
 
 
-def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False, pool_w=False):
+def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False, pool_w=False, out=None):
     """Run ``conv`` (Conv3d / Conv2d / SpatioTemporalConv-like) -> ``bn`` -> (+residual) -> (ReLU).  ``pool_w``: stem only, see
-    ``_stem_body``."""
+    ``_stem_body``.  ``out``: preallocated output rows (``ops.conv``)."""
     if hasattr(conv, "spatial_conv") and hasattr(conv, "temporal_conv"):
-        return Fn.SpatioTemporalConvFunction.run(conv, a, bn, residual, relu, simt)
+        return Fn.SpatioTemporalConvFunction.run(conv, a, bn, residual, relu, simt, out)
     stem = a.ld == 4
     if stem and not _is_stem_shape(conv):
         raise NotImplementedError("NDHWC4 inputs are only supported by 7-wide stride-2 stem convolutions")
@@ -141,9 +141,9 @@ def conv_bn_act(conv, bn, a, residual=None, relu=False, simt=False, pool_w=False
         # once (1/s^3 of the input) and the projection becomes a plain HBM-bound GEMM on the persistent kernel
         sub = ops.shortcut_a(a, stride[0], a.C)
         pc = packed_conv(conv, bn, sub.ld, stride=(1, 1, 1))
-        return ops.conv(sub, pc, residual=residual, relu=relu)
+        return ops.conv(sub, pc, residual=residual, relu=relu, out=out)
     pc = packed_conv(conv, bn, a.ld, stem=stem)
-    return ops.conv(a, pc, residual=residual, relu=relu, simt=simt, pool_w=pool_w)
+    return ops.conv(a, pc, residual=residual, relu=relu, simt=simt, pool_w=pool_w, out=out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -160,16 +160,15 @@ def _shortcut(block, a, simt):
     raise NotImplementedError("unsupported downsample %r" % (ds,))
 
 
-def run_basic(block, a, simt=False):
+def run_basic(block, a, simt=False, out=None):
     """conv-BN-ReLU-conv-BN-(+shortcut)-ReLU (resnet3D.py:91-106)."""
-    return Fn.BasicBlockFunction.run(block, a, simt)
+    return Fn.BasicBlockFunction.run(block, a, simt, out)
 
 
-def _basic_body(block, a, simt=False):
+def _basic_body(block, a, simt=False, out=None):
     res = _shortcut(block, a, simt)
-    out = conv_bn_act(block.conv1, block.bn1, a, relu=True, simt=simt)
-    out = conv_bn_act(block.conv2, block.bn2, out, residual=res, relu=True, simt=simt)
-    return out
+    h = conv_bn_act(block.conv1, block.bn1, a, relu=True, simt=simt)
+    return conv_bn_act(block.conv2, block.bn2, h, residual=res, relu=True, simt=simt, out=out)
 
 
 def _plain_1x1(conv):
@@ -177,7 +176,7 @@ def _plain_1x1(conv):
             and all(p == 0 for p in _conv_geometry(conv)[1]))
 
 
-def _fused_close_with_projection(block, a, h):
+def _fused_close_with_projection(block, a, h, out=None):
     """conv3 + bn3 + (downsample conv + bn)(x) + ReLU as ONE two-operand GEMM (resnet3D.py:136-143 with the type-B
     shortcut of resnet3D.py:176-185): both BatchNorm scales are folded into the fp16 weight matrices, both products
     accumulate in the same TMEM tile, and the projected shortcut never goes through HBM."""
@@ -202,28 +201,29 @@ def _fused_close_with_projection(block, a, h):
                *_bn_tensors(ds_bn)) + (h.ld, xs.ld)
     w3, wd, ones, shift = _cached(block, "close2", sig, build)
     K = w3.shape[0]
-    y = ops.gemm(h.data, w3, ones, shift, h.M, K, h.ld, relu=True, second=(xs.data, wd, xs.ld))
+    if out is not None:
+        ops._out_rows(out, h.M, ops._round_up(K, 8))
+    y = ops.gemm(h.data, w3, ones, shift, h.M, K, h.ld, relu=True, second=(xs.data, wd, xs.ld), out=out)
     return Act(y, h.N, h.T, h.H, h.W, K)
 
 
-def run_bottleneck(block, a, simt=False):
+def run_bottleneck(block, a, simt=False, out=None):
     """1x1x1-BN-ReLU, 3x3x3(stride)-BN-ReLU, 1x1x1-BN-(+shortcut)-ReLU (resnet3D.py:125-143)."""
-    return Fn.BottleneckFunction.run(block, a, simt)
+    return Fn.BottleneckFunction.run(block, a, simt, out)
 
 
-def _bottleneck_body(block, a, simt=False):
+def _bottleneck_body(block, a, simt=False, out=None):
     ds = block.downsample
     if (not simt and isinstance(ds, nn.Sequential) and len(ds) == 2 and _plain_1x1(ds[0]) and _plain_1x1(block.conv3)
             and not ds[1].training and len(set(_conv_geometry(ds[0])[0])) == 1 and (a.T > 1 or _conv_geometry(ds[0])[0][0] == 1)
             and isinstance(ds[0], nn.Conv3d)):
-        out = conv_bn_act(block.conv1, block.bn1, a, relu=True)
-        out = conv_bn_act(block.conv2, block.bn2, out, relu=True)
-        return _fused_close_with_projection(block, a, out)
+        h = conv_bn_act(block.conv1, block.bn1, a, relu=True)
+        h = conv_bn_act(block.conv2, block.bn2, h, relu=True)
+        return _fused_close_with_projection(block, a, h, out)
     res = _shortcut(block, a, simt)
-    out = conv_bn_act(block.conv1, block.bn1, a, relu=True, simt=simt)
-    out = conv_bn_act(block.conv2, block.bn2, out, relu=True, simt=simt)
-    out = conv_bn_act(block.conv3, block.bn3, out, residual=res, relu=True, simt=simt)
-    return out
+    h = conv_bn_act(block.conv1, block.bn1, a, relu=True, simt=simt)
+    h = conv_bn_act(block.conv2, block.bn2, h, relu=True, simt=simt)
+    return conv_bn_act(block.conv3, block.bn3, h, residual=res, relu=True, simt=simt, out=out)
 
 
 def _bn_relu(bn, a):
@@ -236,7 +236,7 @@ def _bn_relu(bn, a):
     return Act(flat.data, a.N, a.T, a.H, a.W, a.C)
 
 
-def _preact_body(block, a, simt=False):
+def _preact_body(block, a, simt=False, out=None):
     """PreActivationBasicBlock / PreActivationBottleneck (pre_act_resnet3D.py:41-57, 76-96):
     out = conv1(relu(bn1(x))); out = conv2(relu(bn2(out))); [out = conv3(relu(bn3(out)))]; out += shortcut(x); no ReLU.
     bn_{k+1} + ReLU run in conv_k's epilogue; the last convolution's epilogue adds the shortcut of the RAW x."""
@@ -245,19 +245,23 @@ def _preact_body(block, a, simt=False):
     h = conv_bn_act(block.conv1, block.bn2, h, relu=True, simt=simt)
     if hasattr(block, "conv3"):
         h = conv_bn_act(block.conv2, block.bn3, h, relu=True, simt=simt)
-        return conv_bn_act(block.conv3, None, h, residual=res, relu=False, simt=simt)
-    return conv_bn_act(block.conv2, None, h, residual=res, relu=False, simt=simt)
+        return conv_bn_act(block.conv3, None, h, residual=res, relu=False, simt=simt, out=out)
+    return conv_bn_act(block.conv2, None, h, residual=res, relu=False, simt=simt, out=out)
 
 
-def run_block(block, a, simt=False):
-    if getattr(block, "preactivation", False):
-        out = Fn.PreActBlockFunction.run(block, a, simt)
-    else:
-        out = run_bottleneck(block, a, simt) if hasattr(block, "conv3") else run_basic(block, a, simt)
+def run_block(block, a, simt=False, out=None):
+    """One residual block (+ its non-local block).  ``out``: preallocated rows for the block's result (the last kernel writes there)."""
     nl = getattr(block, "nonlocalblock", None)
-    if nl is not None and getattr(block, "nonlocal_layer", True):
-        out = run_nonlocal(nl, out, simt=simt)
-    return out
+    if nl is not None and not getattr(block, "nonlocal_layer", True):
+        nl = None
+    bout = out if nl is None else None
+    if getattr(block, "preactivation", False):
+        y = Fn.PreActBlockFunction.run(block, a, simt, bout)
+    else:
+        y = run_bottleneck(block, a, simt, bout) if hasattr(block, "conv3") else run_basic(block, a, simt, bout)
+    if nl is not None:
+        y = run_nonlocal(nl, y, simt=simt, out=out)
+    return y
 
 
 # ---------------------------------------------------------------------------------------------
@@ -280,11 +284,11 @@ def _pad_cols(x2d, cols):
     return y
 
 
-def run_nonlocal(nl, a, simt=False):
-    return Fn.NonLocalFunction.run(nl, a, simt)
+def run_nonlocal(nl, a, simt=False, out=None):
+    return Fn.NonLocalFunction.run(nl, a, simt, out)
 
 
-def _nonlocal_body(nl, a, simt=False):
+def _nonlocal_body(nl, a, simt=False, out=None):
     """z = W(y) + x with y = softmax(theta^T phi) g  (embedded gaussian, nonlocalnet.py:143-166),
     y = softmax(x^T phi(x)) g (gaussian, :168-190), y = (theta^T phi / N) g (dot product, :192-211) or
     y = (relu(w . [theta_i ; phi_j]) / N) g (concatenation, :213-243); phi and g are max-pooled when ``sub_sample``
@@ -397,7 +401,9 @@ def _nonlocal_body(nl, a, simt=False):
         kvp = ops.maxpool3d(Act(kv, a.N, a.T, a.H, a.W, 2 * dp), pool, pool, (0, 0, 0))   # ... max-pooled together
         y = ops.attention(q, kvp.data, kvp.data[:, dp:], dp, dp, B, Nq, kvp.positions, mode=amode)
     # W (1x1 conv with bias) + BN + residual x, no ReLU
-    z = ops.gemm(y, wo, so, bo, a.M, C, dp, residual=a.data)
+    if out is not None:
+        ops._out_rows(out, a.M, ops._round_up(C, 8))
+    z = ops.gemm(y, wo, so, bo, a.M, C, dp, residual=a.data, out=out)
     return Act(z, a.N, a.T, a.H, a.W, C)
 
 
@@ -413,13 +419,13 @@ def _pool_args(mp):
     return _triple(mp.kernel_size), _triple(mp.stride), _triple(mp.padding)
 
 
-def run_stem(model, x, simt=False):
+def run_stem(model, x, simt=False, out=None):
     """conv1 -> bn1 -> relu -> maxpool (torchvision_models.py:449-452)."""
     a = x if isinstance(x, Act) else ops.from_ncdhw(x)
-    return Fn.StemFunction.run(model, a, simt)
+    return Fn.StemFunction.run(model, a, simt, out)
 
 
-def _stem_body(model, a, simt=False):
+def _stem_body(model, a, simt=False, out=None):
     """conv1 -> bn1 -> ReLU -> maxpool.  When the stem runs on the Toeplitz kernel and the pool is the usual 3-wide / stride-2 /
     pad-1 window along W, that direction of the pool is taken in the convolution's epilogue (max-pooling is separable, so this is
     exact): the stem writes half of its output and the remaining (kt, kh, 1) pool reads half as much."""
@@ -429,17 +435,176 @@ def _stem_body(model, a, simt=False):
     if (plain and not simt and a.ld == 4 and _is_stem_shape(conv) and (k[2], s[2], p[2]) == (3, 2, 1)
             and ops._out_dim(a.W, 7, 2, 3) <= 120 and os.environ.get("B2_STEM_POOLW", "1") != "0"):
         a = conv_bn_act(conv, model.bn1, a, relu=True, pool_w=True)
-        return ops.maxpool3d(a, (k[0], k[1], 1), (s[0], s[1], 1), (p[0], p[1], 0))
+        return ops.maxpool3d(a, (k[0], k[1], 1), (s[0], s[1], 1), (p[0], p[1], 0), out=out)
     a = conv_bn_act(conv, model.bn1, a, relu=True, simt=simt)
-    return ops.maxpool3d(a, k, s, p)
+    return ops.maxpool3d(a, k, s, p, out=out)
+
+
+# ---------------------------------------------------------------------------------------------
+# trunk schedule: breadth-first (one launch per layer over the whole batch) or depth-first in L2-sized clip chunks
+# ---------------------------------------------------------------------------------------------
+# Clips are independent in every layer (eval-mode BN, per-clip attention), so the trunk may be walked in any clip order.  At the
+# BASELINE batch sizes the early stages move far more bytes than the 126 MB L2 holds (resnet3d50, 32 clips of 16x224^2: every
+# layer1 tensor is 411 MB), and their 1x1x1 convolutions, pooling and layout passes run at the HBM copy rate.  Walking the first
+# stages DEPTH-first -- a chunk of a few clips goes through stem, pool and a run of residual blocks before the next chunk starts
+# -- makes every intermediate tensor of the chunk a write-then-read inside L2 (the allocator hands the next chunk the same
+# addresses, so dirty lines are overwritten in place rather than written back), and only the segment's first input and last
+# output cross HBM.  Later stages, whose whole-batch tensors fit L2 anyway, stay breadth-first so that their launches keep
+# enough tiles for 148 SMs.  Same kernels, same arithmetic per output element: results are bit-identical to the breadth-first walk.
+_DFS_SPEC = os.environ.get("B2_DFS", "auto")
+_DFS_L2_BYTES = 126 << 20            # B200 L2 capacity (B300_MICROARCH.md "L2 cache"; same die pair on sm_100a)
+_DFS_TUNE = dict(full=0.80, chunk=0.45, min_rows=128 * 148)   # see dfs_plan
+
+
+def set_dfs(spec=None, **tune):
+    """Trunk schedule: ``"auto"`` (rule in ``dfs_plan``), ``"off"`` (breadth-first), or an explicit ``"units:clips,units:clips"``
+    list -- consecutive segments of trunk units (unit 0 = stem + pool, then the residual blocks in order), each walked depth-first
+    in chunks of ``clips``; units not covered run breadth-first.  Keyword arguments override the rule's constants (tuning)."""
+    global _DFS_SPEC
+    if spec is not None:
+        _DFS_SPEC = str(spec)
+    _DFS_TUNE.update(tune)
+
+
+def _trunk_units(model):
+    units = [("stem", model)]
+    for name in ("layer1", "layer2", "layer3", "layer4"):
+        units += [("block", blk) for blk in getattr(model, name)]
+    return units
+
+
+def _conv_out_geom(conv, g):
+    """((T, H, W, C) after ``conv``, bytes per clip of the tensors it writes) for a plain or (2+1)D-factorised convolution;
+    ``(None, 0)`` for anything else."""
+    if hasattr(conv, "spatial_conv") and hasattr(conv, "temporal_conv"):
+        mid, b1 = _conv_out_geom(conv.spatial_conv, g)
+        if mid is None:
+            return None, 0
+        q, b2 = _conv_out_geom(conv.temporal_conv, mid)
+        return q, b1 + b2
+    if not isinstance(conv, (nn.Conv3d, nn.Conv2d)):
+        return None, 0
+    k = _triple(conv.kernel_size)
+    s, p = _conv_geometry(conv)
+    q = tuple(ops._out_dim(g[i], k[i], s[i], p[i]) for i in range(3)) + (conv.out_channels,)
+    return q, q[0] * q[1] * q[2] * ops._round_up(q[3], 8) * 2
+
+
+def _unit_bytes(kind, m, g):
+    """Rough per-clip byte footprint of one trunk unit -- input + output + the intermediates alive in between -- and its output
+    geometry.  Only steers the schedule (never correctness); unknown module shapes return (None, None) and end the depth-first part."""
+    px = lambda q: q[0] * q[1] * q[2]
+    if kind == "stem":
+        c, cb = _conv_out_geom(m.conv1, g)
+        if c is None:
+            return None, None
+        k, s, p = _pool_args(m.maxpool)
+        o = tuple(ops._out_dim(c[i], k[i], s[i], p[i]) for i in range(3)) + (c[3],)
+        # fp32 NCDHW input + NDHWC4 copy + conv output(s) (the Toeplitz stem writes its output W-pooled: half) + pooled output
+        return px(g) * (4 * g[3] + 8) + cb // (2 if (o[2] < c[2] and isinstance(m.conv1, (nn.Conv3d, nn.Conv2d))) else 1) + px(o) * o[3] * 2, o
+    convs = [getattr(m, n) for n in ("conv1", "conv2", "conv3") if hasattr(m, n)]
+    if not convs:
+        return None, None
+    q, total = g, px(g) * g[3] * 2
+    for c in convs:
+        q, cb = _conv_out_geom(c, q)
+        if q is None:
+            return None, None
+        total += cb
+    nl = getattr(m, "nonlocalblock", None)
+    if nl is not None and getattr(m, "nonlocal_layer", True):
+        total += px(q) * (3 * ops._round_up(nl.inter_channels, 64) + nl.inter_channels + q[3]) * 2    # theta|phi|g, y, z
+    return total, q
+
+
+def dfs_plan(model, N, geom):
+    """[(units, clips per chunk)] for ``run_trunk`` -- ``geom`` = (T, H, W, C) of one input clip.
+
+    Rule (``auto``): walk the units in order; a unit whose whole-batch footprint N * bytes(unit) is at most ``full`` x L2 ends the
+    depth-first part (tensors only shrink with depth).  Otherwise the unit wants the largest power of two of clips whose footprint
+    stays within ``chunk`` x L2.  It joins the running segment (whose chunk becomes the minimum of its units' wishes) as long as its
+    launches keep ``min_rows`` rows -- one 128-row tile per SM; smaller launches lose more to tile quantisation than L2 residency
+    gains -- and otherwise opens a new segment with a chunk raised to ``min_rows``.  Long segments matter: a segment boundary is a
+    whole-batch tensor that goes through HBM."""
+    spec = _DFS_SPEC.strip().lower()
+    if spec in ("0", "off", "none", ""):
+        return []
+    if spec != "auto":
+        return [tuple(int(v) for v in part.split(":")) for part in spec.split(",")]
+    plan, g = [], tuple(geom)
+    budget = _DFS_TUNE["chunk"] * _DFS_L2_BYTES
+    for kind, m in _trunk_units(model):
+        rows = g[0] * g[1] * g[2] if kind != "stem" else 0      # rows the unit's first (widest) launches work on, per clip
+        nbytes, g = _unit_bytes(kind, m, g)
+        if kind == "stem" and g is not None:
+            rows = g[0] * g[1] * g[2] * 4                        # the stem convolution's output rows (before the pool), roughly
+        if nbytes is None or N * nbytes <= _DFS_TUNE["full"] * _DFS_L2_BYTES:
+            break
+        want = 1
+        while want * 2 * nbytes <= budget:
+            want *= 2
+        # join the running segment (chunk = minimum of its units' wishes) while launches stay large enough; a unit that needs the
+        # segment's current chunk just to reach min_rows joins as well (a new segment would pick the same chunk)
+        need = want
+        while need * rows < _DFS_TUNE["min_rows"] and need < N:
+            need *= 2
+        if plan and min(plan[-1][1], want) * rows >= _DFS_TUNE["min_rows"]:
+            plan[-1] = (plan[-1][0] + 1, min(plan[-1][1], want))
+        elif plan and plan[-1][1] == need:
+            plan[-1] = (plan[-1][0] + 1, need)
+        elif need >= N:
+            break
+        else:
+            plan.append((1, need))
+    return plan
+
+
+def _slice_clips(x, n0, n1):
+    if isinstance(x, Act):
+        r = x.positions
+        return Act(x.data[n0 * r:n1 * r], n1 - n0, x.T, x.H, x.W, x.C)
+    return x[n0:n1]
+
+
+def _run_units(units, a, simt, out=None):
+    for j, (kind, m) in enumerate(units):
+        o = out if j == len(units) - 1 else None
+        a = run_stem(m, a, simt=simt, out=o) if kind == "stem" else run_block(m, a, simt=simt, out=o)
+    return a
+
+
+def _run_segment(units, x, N, clips, simt):
+    """Depth-first walk of ``units`` in chunks of ``clips``; the last kernel of each chunk writes straight into its row range of the
+    segment's whole-batch output (allocated once the first chunk has shown the output geometry)."""
+    buf = None
+    for n0 in range(0, N, clips):
+        n1 = min(N, n0 + clips)
+        o = buf.data[n0 * buf.positions:n1 * buf.positions] if buf is not None else None
+        y = _run_units(units, _slice_clips(x, n0, n1), simt, out=o)
+        if buf is None:
+            buf = Act(torch.empty((N * y.positions, y.ld), dtype=torch.float16, device=y.data.device), N, y.T, y.H, y.W, y.C)
+            o = buf.data[:y.M]
+        if y.data.data_ptr() != o.data_ptr():      # first chunk, or a unit whose last kernel takes no ``out``
+            o.copy_(y.data)
+    return buf
 
 
 def run_trunk(model, x, simt=False):
-    a = run_stem(model, x, simt=simt)
-    for name in ("layer1", "layer2", "layer3", "layer4"):
-        for block in getattr(model, name):
-            a = run_block(block, a, simt=simt)
-    return a
+    units = _trunk_units(model)
+    if isinstance(x, Act):
+        N, geom = x.N, (x.T, x.H, x.W, x.C)
+    else:
+        N = x.shape[0]
+        geom = (1,) + tuple(x.shape[2:]) + (x.shape[1],) if x.dim() == 4 else tuple(x.shape[2:]) + (x.shape[1],)
+    plan = [] if simt else dfs_plan(model, N, geom)
+    a, ui = x, 0
+    for n_units, clips in plan:
+        seg = units[ui:ui + n_units]
+        if not seg:
+            break
+        ui += len(seg)
+        a = _run_segment(seg, a, N, clips, simt) if 0 < clips < N else _run_units(seg, a, simt)
+    return _run_units(units[ui:], a, simt) if ui < len(units) else a
 
 
 def run_head(model, a, head):

@@ -15,6 +15,8 @@ Two kinds:
   head can be trained on engine features without leaving the library.
 
 Tensors cross a Function boundary as the raw ``[N*T*H*W][ld]`` fp16 matrix of an ``ops.Act`` plus its geometry tuple.
+``out`` (optional, last argument of the block bodies): a preallocated ``[rows][ld]`` fp16 row range the body's LAST kernel writes
+its result into -- how the depth-first trunk schedule (``engine.run_trunk``) assembles a full-batch tensor chunk by chunk.
 """
 import torch
 
@@ -50,48 +52,48 @@ class StemFunction(_FrozenFunction):
     """conv1 -> bn1 -> relu -> maxpool (torchvision_models.py:449-452).  ``x`` is the NDHWC4 / NDHWC input matrix."""
 
     @staticmethod
-    def forward(ctx, x2d, geom, model, simt=False):
+    def forward(ctx, x2d, geom, model, simt=False, out=None):
         from . import engine
-        return StemFunction._finish(ctx, engine._stem_body(model, Act(x2d, *geom), simt))
+        return StemFunction._finish(ctx, engine._stem_body(model, Act(x2d, *geom), simt, out))
 
 
 class BottleneckFunction(_FrozenFunction):
     @staticmethod
-    def forward(ctx, x2d, geom, block, simt=False):
+    def forward(ctx, x2d, geom, block, simt=False, out=None):
         from . import engine
-        return BottleneckFunction._finish(ctx, engine._bottleneck_body(block, Act(x2d, *geom), simt))
+        return BottleneckFunction._finish(ctx, engine._bottleneck_body(block, Act(x2d, *geom), simt, out))
 
 
 class BasicBlockFunction(_FrozenFunction):
     @staticmethod
-    def forward(ctx, x2d, geom, block, simt=False):
+    def forward(ctx, x2d, geom, block, simt=False, out=None):
         from . import engine
-        return BasicBlockFunction._finish(ctx, engine._basic_body(block, Act(x2d, *geom), simt))
+        return BasicBlockFunction._finish(ctx, engine._basic_body(block, Act(x2d, *geom), simt, out))
 
 
 class PreActBlockFunction(_FrozenFunction):
     """Pre-activation residual blocks (pre_act_resnet3D.py:27-96)."""
 
     @staticmethod
-    def forward(ctx, x2d, geom, block, simt=False):
+    def forward(ctx, x2d, geom, block, simt=False, out=None):
         from . import engine
-        return PreActBlockFunction._finish(ctx, engine._preact_body(block, Act(x2d, *geom), simt))
+        return PreActBlockFunction._finish(ctx, engine._preact_body(block, Act(x2d, *geom), simt, out))
 
 
 class SpatioTemporalConvFunction(_FrozenFunction):
     """(1,k,k) conv -> BN -> ReLU -> (k,1,1) conv [-> outer BN -> +residual -> ReLU] (r2plus1d.py:85-88)."""
 
     @staticmethod
-    def forward(ctx, x2d, geom, conv, bn=None, residual=None, relu=False, simt=False):
+    def forward(ctx, x2d, geom, conv, bn=None, residual=None, relu=False, simt=False, out=None):
         from . import engine
-        return SpatioTemporalConvFunction._finish(ctx, engine._st_conv_body(conv, bn, Act(x2d, *geom), residual, relu, simt))
+        return SpatioTemporalConvFunction._finish(ctx, engine._st_conv_body(conv, bn, Act(x2d, *geom), residual, relu, simt, out))
 
 
 class NonLocalFunction(_FrozenFunction):
     @staticmethod
-    def forward(ctx, x2d, geom, nl, simt=False):
+    def forward(ctx, x2d, geom, nl, simt=False, out=None):
         from . import engine
-        return NonLocalFunction._finish(ctx, engine._nonlocal_body(nl, Act(x2d, *geom), simt))
+        return NonLocalFunction._finish(ctx, engine._nonlocal_body(nl, Act(x2d, *geom), simt, out))
 
 
 class GBlockFunction(_FrozenFunction):

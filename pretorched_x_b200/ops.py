@@ -212,8 +212,17 @@ def _out_dim(i, k, s, p):
 # ---------------------------------------------------------------------------------------------
 # convolution / dense
 # ---------------------------------------------------------------------------------------------
+def _out_rows(out, M, ld):
+    """Validate a caller-provided output row range (``out=``): fp16 [M][ld], dense rows, 16-byte aligned."""
+    if (out.dtype != torch.float16 or out.dim() != 2 or tuple(out.shape) != (M, ld) or out.stride(1) != 1 or out.stride(0) != ld
+            or out.data_ptr() % 16):
+        raise ValueError("out= must be a dense fp16 [%d][%d] row range, got %s %s strides %s" % (M, ld, out.dtype, tuple(out.shape),
+                                                                                                  tuple(out.stride())))
+    return out
+
+
 def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, residual_up=False, residual_pre=False,
-         next_affine=None, pool_w=False, in_affine=None):
+         next_affine=None, pool_w=False, in_affine=None, out=None):
     """nn.Conv3d -> BatchNorm3d -> (+residual) -> ReLU in one kernel
     (resnet3D.py:91-106, 125-143, 176-185; r2plus1d.py:85-88; torchvision_models.py:449-451).
 
@@ -223,7 +232,8 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     first K channels are used: the GBlock's channel drop); ``residual_pre``: the residual joins before the affine,
     y = act(scale * (conv + residual) + shift).  ``next_affine=(scale2, shift2)`` (fp32 [N][pitch] views): also return
     relu(y * scale2[n] + shift2[n]) -- the ccbn + ReLU that opens the next GBlock -- as a second Act, written by the same
-    kernel.  All three: 1x1 convolutions only."""
+    kernel.  All three: 1x1 convolutions only.  ``out``: preallocated fp16 [M][round_up(K, 8)] rows to write instead of a
+    fresh tensor (a row range of a larger batch buffer: the depth-first trunk schedule)."""
     if a.ld != pc.C:
         raise ValueError("activation pitch %d != packed filter pitch %d" % (a.ld, pc.C))
     kt, kh, kw = pc.k
@@ -238,7 +248,7 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
         Wo = (Wo - 1) // 2 + 1
     M = a.N * To * Ho * Wo
     ldy = _round_up(pc.K, 8)
-    y = torch.empty((M, ldy), dtype=torch.float16, device=a.data.device)
+    y = _out_rows(out, M, ldy) if out is not None else torch.empty((M, ldy), dtype=torch.float16, device=a.data.device)
     args = ConvArgs()
     args.x, args.w, args.scale, args.shift = _ptr(a.data), _ptr(pc.w), _ptr(pc.scale), _ptr(pc.shift)
     args.residual = _ptr(residual.data if residual is not None else None)
@@ -356,13 +366,14 @@ def linear(x2d, pl, relu=False, out_f32=False, out=None, accumulate=False):
 # ---------------------------------------------------------------------------------------------
 # pooling / shortcuts / casts
 # ---------------------------------------------------------------------------------------------
-def maxpool3d(a, kernel, stride, padding):
-    """nn.MaxPool3d (resnet3D.py:156; executed at torchvision_models.py:452)."""
+def maxpool3d(a, kernel, stride, padding, out=None):
+    """nn.MaxPool3d (resnet3D.py:156; executed at torchvision_models.py:452).  ``out``: see ``conv``."""
     kt, kh, kw = kernel
     st, sh, sw = stride
     pt, ph, pw = padding
     To, Ho, Wo = _out_dim(a.T, kt, st, pt), _out_dim(a.H, kh, sh, ph), _out_dim(a.W, kw, sw, pw)
-    y = torch.empty((a.N * To * Ho * Wo, a.ld), dtype=torch.float16, device=a.data.device)
+    My = a.N * To * Ho * Wo
+    y = _out_rows(out, My, a.ld) if out is not None else torch.empty((My, a.ld), dtype=torch.float16, device=a.data.device)
     with _timed("maxpool", "maxpool C%d M=%d->%d" % (a.C, a.M, y.shape[0]), 0.0, 2.0 * a.C * (a.M + y.shape[0])):
         _lib.check(_lib.load().b2_maxpool3d_ndhwc(_ptr(a.data), _ptr(y), a.N, a.T, a.H, a.W, a.ld, kt, kh, kw, st, sh, sw,
                                                  pt, ph, pw, _stream()), "b2_maxpool3d_ndhwc")
@@ -508,11 +519,19 @@ def ccbn_act(a, scale=None, shift=None, channels=None, up=1, relu=True):
     return Act(y, a.N, 1, a.H * up, a.W * up, C)
 
 
-def tanh_to_nchw(a, out_dtype=torch.float32):
-    """torch.tanh + channels-last -> NCHW: the generator's image write (fp32 like the public model, or fp16)."""
+def _out_images(out, shape, dtype):
+    if tuple(out.shape) != tuple(shape) or out.dtype != dtype or not out.is_contiguous():
+        raise ValueError("out= must be a contiguous %s %s tensor, got %s %s" % (dtype, tuple(shape), out.dtype, tuple(out.shape)))
+    return out
+
+
+def tanh_to_nchw(a, out_dtype=torch.float32, out=None):
+    """torch.tanh + channels-last -> NCHW: the generator's image write (fp32 like the public model, or fp16).  ``out``: a
+    preallocated image range to write (a batch slice of a larger NCHW tensor)."""
     if out_dtype not in (torch.float32, torch.float16):
         raise ValueError("images are written as fp32 or fp16")
-    y = torch.empty((a.N, a.C, a.H, a.W), dtype=out_dtype, device=a.data.device)
+    shape = (a.N, a.C, a.H, a.W)
+    y = _out_images(out, shape, out_dtype) if out is not None else torch.empty(shape, dtype=out_dtype, device=a.data.device)
     S = a.T * a.H * a.W
     with _timed("tanh", "tanh->nchw C%d px=%d" % (a.C, a.M), 0.0, a.M * (2.0 * a.ld + y.element_size() * a.C)):
         _lib.check(_lib.load().b2_tanh_nhwc_to_nchw(_ptr(a.data), a.ld, _ptr(y), a.N, a.C, S, int(out_dtype == torch.float32),
@@ -520,12 +539,12 @@ def tanh_to_nchw(a, out_dtype=torch.float32):
     return y
 
 
-def rgb_head(partial, bias, N, H, W, K=3, out_dtype=torch.float32):
+def rgb_head(partial, bias, N, H, W, K=3, out_dtype=torch.float32, out=None):
     """Second half of the split RGB head: gather the per-tap partial products of the 1x1 GEMM (fp16 [N*H*W][>=36], column
-    tap*4 + k), add the bias, tanh, write NCHW images (see b2_rgb_head_gather_tanh)."""
+    tap*4 + k), add the bias, tanh, write NCHW images (see b2_rgb_head_gather_tanh).  ``out``: see ``tanh_to_nchw``."""
     if out_dtype not in (torch.float32, torch.float16):
         raise ValueError("images are written as fp32 or fp16")
-    y = torch.empty((N, K, H, W), dtype=out_dtype, device=partial.device)
+    y = _out_images(out, (N, K, H, W), out_dtype) if out is not None else torch.empty((N, K, H, W), dtype=out_dtype, device=partial.device)
     M = N * H * W
     with _timed("tanh", "rgb gather+tanh px=%d" % M, 0.0, M * (2.0 * 36 + y.element_size() * K)):
         _lib.check(_lib.load().b2_rgb_head_gather_tanh(_ptr(partial), partial.stride(0), _ptr(bias), _ptr(y), N, H, W, K,

@@ -170,3 +170,27 @@ def test_stacked_ccbn_gemm_algebra(monkeypatch):
         h = (y.half().double() @ pk.lin_w.double()[:, :256].t() + pk.lin_b.double()).view(B, 16, C0).permute(0, 2, 1).reshape(B, C0, 4, 4)
         want_h = torch.nn.functional.linear(y, OB.sn_weight(sd, "linear"), sd["linear.bias"]).view(B, C0, 4, 4)
         assert ((h - want_h.double()).abs().max() / want_h.abs().max()).item() <= 2e-3
+
+
+def test_generator_dfs_plan_levels():
+    """biggan_engine.dfs_plan: modules are grouped by OUTPUT resolution into a contiguous suffix of depth-first levels."""
+    import pretorched_x_b200 as P
+    from pretorched_x_b200 import biggan_engine as be
+    m = P.biggan_deep(256, G_ch=16, n_classes=10).eval()
+    mods = [(i, blk) for i, stage in enumerate(m.blocks) for blk in stage]
+    assert len(mods) == 13                                    # 6 stages x 2 GBlocks + attention at 64x64
+    try:
+        be.set_dfs("off")
+        assert be.dfs_plan(m, 256, mods) == []
+        be.set_dfs("256:4")
+        assert be.dfs_plan(m, 256, mods) == [(12, 13, 4)]
+        be.set_dfs("64:16,128:8,256:4")
+        assert be.dfs_plan(m, 256, mods) == [(7, 10, 16), (10, 12, 8), (12, 13, 4)]
+        be.set_dfs("64:8,128:300,256:4")                      # a whole-batch level behind a chunked one stays in the suffix
+        assert be.dfs_plan(m, 256, mods) == [(7, 10, 8), (10, 12, 256), (12, 13, 4)]
+        be.set_dfs("128:300,256:4")                           # ... in front of it: part of the whole-batch prefix
+        assert be.dfs_plan(m, 256, mods) == [(12, 13, 4)]
+        be.set_dfs("256:4")
+        assert be.dfs_plan(m, 4, mods) == []                  # batch no larger than the chunk
+    finally:
+        be.set_dfs("auto")

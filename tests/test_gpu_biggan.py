@@ -291,3 +291,33 @@ def test_full_size_biggan_deep_256(dev):
     with torch.no_grad():
         emb = model(z.to(dev), model.shared.weight[labels.to(dev)])
     assert torch.equal(emb, got)
+
+
+@pytest.mark.parametrize("res,ch,specs", [(128, 16, ["64:2", "16:3,64:1", "8:2,32:7,128:2"]), (256, 16, ["128:2,256:1", "256:3"])])
+def test_depth_first_tail_matches_whole_batch(dev, res, ch, specs):
+    """The generator's high-resolution tail walked depth-first on chunks of images (biggan_engine.dfs_plan; ragged last chunk,
+    whole-batch level behind a chunked one, fp32 and fp16 images) equals the whole-batch walk to rounding -- a chunk may move a
+    layer across a kernel-dispatch boundary (different fp32 summation order), as for a batch of one in the full-size test."""
+    from pretorched_x_b200.graph import GraphedForward
+    model, sd, z, labels = OB.build_case(P.biggan_deep, res, ch, 10, 5, init="ortho")
+    model = model.to(dev)
+    z, labels = z.to(dev), labels.to(dev)
+    try:
+        biggan_engine.set_dfs("off")
+        with torch.no_grad():
+            want = model(z, labels)
+        for spec in specs:
+            biggan_engine.set_dfs(spec)
+            with torch.no_grad():
+                got = model(z, labels)
+                half = model(z, labels, out_dtype=torch.float16)
+            assert got.shape == want.shape and got.dtype == want.dtype
+            assert (got - want).abs().max().item() <= 1e-2, spec
+            assert (got - want).pow(2).mean().sqrt().item() <= 1e-3, spec
+            assert (half.float() - got).abs().max().item() <= 1e-3, spec
+        g = GraphedForward(model, (z, labels))
+        with torch.no_grad():
+            eager = model(z, labels)
+        assert torch.equal(g((z, labels)), eager)
+    finally:
+        biggan_engine.set_dfs("auto")

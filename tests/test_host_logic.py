@@ -176,3 +176,90 @@ def test_cache_invalidation_hooks():
     m.layer1[0].conv1.__dict__["_b2_cache"] = {"pc": ("sig", "packed")}
     m.float()
     assert "_b2_cache" not in m.layer1[0].conv1.__dict__
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# depth-first trunk schedule (engine.run_trunk): plan rule and chunk assembly, on CPU stand-ins for the kernels
+# ---------------------------------------------------------------------------------------------------------------
+def test_dfs_plan_rule():
+    from pretorched_x_b200 import engine
+    engine.set_dfs("auto")
+    m = P.resnet3d50(num_classes=400, pretrained=None).eval()
+    plan = engine.dfs_plan(m, 32, (16, 224, 224, 3))                 # BASELINE configs[1]: every layer1 tensor is 411 MB
+    assert plan and plan[0][0] >= 4 and plan[0][1] <= 4, plan        # stem + layer1 (+ layer2.0) in chunks of a few clips
+    assert all(c < 32 for _, c in plan) and sum(u for u, _ in plan) <= 17
+    assert engine.dfs_plan(m, 2, (8, 64, 64, 3)) == []               # small problems stay breadth-first
+    assert engine.dfs_plan(m, 1, (16, 224, 224, 3)) == []            # one clip: nothing to chunk
+    try:
+        engine.set_dfs("off")
+        assert engine.dfs_plan(m, 32, (16, 224, 224, 3)) == []
+        engine.set_dfs("5:2,4:8")
+        assert engine.dfs_plan(m, 32, (16, 224, 224, 3)) == [(5, 2), (4, 8)]
+    finally:
+        engine.set_dfs("auto")
+    # footprints follow the tensors: layer1 blocks of resnet3d50 hold ~30 MB per 16x224x224 clip
+    g = (16, 224, 224, 3)
+    sizes = []
+    for kind, mod in engine._trunk_units(m):
+        b, g = engine._unit_bytes(kind, mod, g)
+        sizes.append(b)
+    assert g == (1, 7, 7, 2048) and 25e6 < sizes[2] < 40e6 and sizes[-1] < 1e6
+
+
+def test_dfs_segments_assemble_the_breadth_first_result(monkeypatch):
+    """run_trunk with the kernels replaced by CPU stand-ins: chunked segments (ragged last chunk, units that honour ``out`` and
+    units that do not) reproduce the whole-batch walk, and every unit sees only its chunk."""
+    from pretorched_x_b200 import engine
+    from pretorched_x_b200.ops import Act
+    seen = []
+
+    def fake_stem(model, x, simt=False, out=None):
+        n = x.shape[0]
+        seen.append(("stem", n))
+        rows = x.reshape(n, 3, -1).permute(0, 2, 1).reshape(-1, 3)            # [n * px][3]
+        y = torch.zeros((rows.shape[0], 8), dtype=torch.float16)
+        y[:, :3] = rows.half()
+        if out is not None:
+            out.copy_(y)
+            y = out
+        return Act(y, n, 1, x.shape[2], x.shape[3], 3)
+
+    def fake_block(block, a, simt=False, out=None):
+        seen.append((block.tag, a.N))
+        y = a.data * 2 + block.tag
+        y[:, a.C:] = 0
+        if out is not None and block.tag % 2 == 0:      # odd blocks ignore ``out``: the scheduler must copy
+            out.copy_(y)
+            y = out
+        return Act(y, a.N, a.T, a.H, a.W, a.C)
+
+    class Blk(nn.Module):
+        def __init__(self, tag):
+            super().__init__()
+            self.tag = tag
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layer1 = nn.Sequential(Blk(1), Blk(2))
+            self.layer2 = nn.Sequential(Blk(3))
+            self.layer3 = nn.Sequential(Blk(4), Blk(5))
+            self.layer4 = nn.Sequential(Blk(6))
+
+    monkeypatch.setattr(engine, "run_stem", fake_stem)
+    monkeypatch.setattr(engine, "run_block", fake_block)
+    net = Net()
+    x = torch.randn(7, 3, 4, 5)
+    try:
+        engine.set_dfs("off")
+        want = engine.run_trunk(net, x)
+        for spec in ("3:2", "1:3,2:2,2:4", "7:3", "2:7", "4:1,3:5"):
+            seen.clear()
+            engine.set_dfs(spec)
+            got = engine.run_trunk(net, x)
+            assert (got.N, got.H, got.W, got.C) == (want.N, want.H, want.W, want.C) and torch.equal(got.data, want.data), spec
+            first_chunk = int(spec.split(",")[0].split(":")[1])
+            assert seen[0] == ("stem", min(first_chunk, 7)), (spec, seen[:3])
+            assert len(seen) > 7 or first_chunk >= 7
+    finally:
+        engine.set_dfs("auto")
