@@ -259,7 +259,7 @@ def run_ours(args, spec, rank, world, local, secondary=False):
     ``secondary``: a compact measurement riding on the default line (no fp16 / uint8 e2e variants, no nested workloads)."""
     import torch
     import torch.distributed as dist
-    from pretorched_x_b200 import ops, parallel, _lib
+    from pretorched_x_b200 import ops, parallel, _lib, engine
     from pretorched_x_b200.graph import GraphedForward, PipelinedForward
     from oracle import functional as OF           # checker (parity) + cpu_baseline leg only; never on the timed path
 
@@ -295,6 +295,12 @@ def run_ours(args, spec, rank, world, local, secondary=False):
         launches_per_fwd = _lib.launch_count() - c0
 
     graphed = GraphedForward(model, x_dev, warmup=2)
+    # trunk schedule of the timed forward (engine.run_trunk): [(units, clips per chunk)] walked depth-first, the rest breadth-first
+    schedule = None
+    if hasattr(model, "layer1") and hasattr(model, "conv1"):
+        plan = engine.dfs_plan()
+        schedule = {"depth_first": [list(p_) for p_ in plan], "units": "0 = stem + pool, then the residual blocks in order",
+                    "set_by": "B2_DFS=%s" % os.environ.get("B2_DFS")} if plan else "breadth-first (one launch per layer over the whole batch)"
 
     # ---- parity of the timed configuration itself (outside the timed region): the graph's logits for the first clips of the
     #      timed batch against the CPU oracle (pinned bit-exact to the reference, tests/test_oracle_golden.py) ----
@@ -454,6 +460,7 @@ def run_ours(args, spec, rank, world, local, secondary=False):
                    "global_batch": total, "parallelism": "dp%d" % world,
                    "l2": "input (%.0f MB fp32) and the activations of one step (%.0f MB) exceed the 126 MB L2; no flush needed"
                          % (h2d_bytes / 1e6, spec["act_elems"] * 2 * B / 1e6),
+                   "schedule": schedule,
                    "timing": "CUDA events around %d CUDA-graph replays, max over ranks" % args.steps},
         "clocks": clocks,
         "e2e": {"value": e2e_fp32, "unit": spec["unit"], "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
@@ -548,7 +555,7 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
     import torch
     import torch.distributed as dist
     import pretorched_x_b200 as P
-    from pretorched_x_b200 import ops, parallel, _lib
+    from pretorched_x_b200 import ops, parallel, _lib, biggan_engine
     from pretorched_x_b200.graph import GraphedForward, PipelinedForward
     from oracle import biggan as OB                 # standing-statistics conditioning, checker, cpu_baseline leg only
 
@@ -578,6 +585,9 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
         torch.cuda.synchronize()
         launches_per_fwd = _lib.launch_count() - c0
     graphed = GraphedForward(model, (z_dev, l_dev), warmup=1, out_dtype=torch.float16)
+    gplan = biggan_engine.dfs_plan(model, B, [(i, blk) for i, stage in enumerate(model.blocks) for blk in stage])
+    schedule = {"depth_first": [list(p_) for p_ in gplan], "levels": "(first module, end module, images per chunk) by output resolution",
+                "set_by": "B2_GAN_DFS=%s" % os.environ.get("B2_GAN_DFS")} if gplan else "whole batch per launch"
 
     parity = None
     if rank == 0 and not args.no_check:
@@ -684,6 +694,7 @@ def run_biggan(args, rank, world, local, emit=True, steps=None):
                                "oracle/biggan.py (unpinned)" % (gflop, B),
                    "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "activations of one step (tens of GB) exceed the 126 MB L2; no flush needed",
+                   "schedule": schedule,
                    "timing": "CUDA events around %d CUDA-graph replays, max over ranks" % steps},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,

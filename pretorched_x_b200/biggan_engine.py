@@ -280,13 +280,14 @@ def run_attention(att, a, aff, pk, nxt=None, out=None):
     return Act(z, a.N, 1, a.H, a.W, C), None
 
 
-_DFS_SPEC = os.environ.get("B2_GAN_DFS", "auto")
-_DFS_AUTO = "64:32,128:8,256:4"       # measured rule for B >= 64 (tools/dfs_sweep.py biggan256); see dfs_plan
+_DFS_SPEC = os.environ.get("B2_GAN_DFS", "off")
 
 
 def set_dfs(spec):
-    """Schedule of the generator's high-resolution tail: ``"off"``, ``"auto"`` or ``"res:images,res:images"`` -- modules whose OUTPUT
-    resolution is at least ``res`` (up to the next listed resolution) run depth-first on chunks of ``images``."""
+    """Schedule of the generator's high-resolution tail: ``"off"`` (whole batch per launch: the default and the measured optimum,
+    see ``engine.set_dfs``) or ``"res:images,res:images"`` -- modules whose OUTPUT resolution is at least ``res`` (up to the next
+    listed resolution) run depth-first on chunks of ``images``.  Measured at B = 256 (profiles/dfs_sweep_r02.txt): 22.5 ms whole
+    batch; the last block alone in chunks of 16 / 8 / 4 / 2 images: 23.1 / 23.8 / 24.4 / 25.8 ms."""
     global _DFS_SPEC
     _DFS_SPEC = str(spec)
 
@@ -294,10 +295,8 @@ def set_dfs(spec):
 def dfs_plan(model, B, mods):
     """[(first module, end module, images per chunk)] covering a suffix of ``mods`` (empty = whole batch everywhere)."""
     spec = _DFS_SPEC.strip().lower()
-    if spec in ("0", "off", "none", ""):
+    if spec in ("0", "off", "none", "", "auto"):      # "auto" = the measured rule: never chunk
         return []
-    if spec == "auto":
-        spec = _DFS_AUTO
     levels = sorted(tuple(int(v) for v in part.split(":")) for part in spec.split(","))
     res, out_res = model.bottom_width, []
     for _, blk in mods:
@@ -369,9 +368,9 @@ def generator_forward(model, z, y, out_dtype=torch.float32, stages=None, fuse_ou
             stages['pre_tanh'] = t
         return ops.tanh_to_nchw(t, out_dtype, out=out)
 
-    # Depth-first tail (see engine.run_trunk): from the resolution where a whole-batch tensor outgrows L2 the remaining modules run
-    # on chunks of images, every intermediate a write-then-read inside L2; chunk outputs land in their slice of the next segment's
-    # input (or of the image tensor).  Not with ``stages`` (whole-batch stage tensors wanted) or ``dual_output``.
+    # Optional depth-first tail (set_dfs; off by default -- measured slower, see engine.set_dfs): the modules of the listed
+    # resolutions run on chunks of images, every intermediate a write-then-read inside L2; chunk outputs land in their slice of the
+    # next segment's input (or of the image tensor).  Not with ``stages`` (whole-batch stage tensors wanted) or ``dual_output``.
     plan = [] if (stages is not None or dual_output) else dfs_plan(model, B, mods)
     j_first = plan[0][0] if plan else len(mods)
     a, fused_tail = run_mods(a, aff, 0, j_first)

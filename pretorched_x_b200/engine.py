@@ -441,29 +441,28 @@ def _stem_body(model, a, simt=False, out=None):
 
 
 # ---------------------------------------------------------------------------------------------
-# trunk schedule: breadth-first (one launch per layer over the whole batch) or depth-first in L2-sized clip chunks
+# trunk schedule: breadth-first (default) or, on request, depth-first in clip chunks
 # ---------------------------------------------------------------------------------------------
-# Clips are independent in every layer (eval-mode BN, per-clip attention), so the trunk may be walked in any clip order.  At the
-# BASELINE batch sizes the early stages move far more bytes than the 126 MB L2 holds (resnet3d50, 32 clips of 16x224^2: every
-# layer1 tensor is 411 MB), and their 1x1x1 convolutions, pooling and layout passes run at the HBM copy rate.  Walking the first
-# stages DEPTH-first -- a chunk of a few clips goes through stem, pool and a run of residual blocks before the next chunk starts
-# -- makes every intermediate tensor of the chunk a write-then-read inside L2 (the allocator hands the next chunk the same
-# addresses, so dirty lines are overwritten in place rather than written back), and only the segment's first input and last
-# output cross HBM.  Later stages, whose whole-batch tensors fit L2 anyway, stay breadth-first so that their launches keep
-# enough tiles for 148 SMs.  Same kernels, same arithmetic per output element: results are bit-identical to the breadth-first walk.
-_DFS_SPEC = os.environ.get("B2_DFS", "auto")
-_DFS_L2_BYTES = 126 << 20            # B200 L2 capacity (B300_MICROARCH.md "L2 cache"; same die pair on sm_100a)
-_DFS_TUNE = dict(full=0.80, chunk=0.45, min_rows=128 * 148)   # see dfs_plan
+# Clips are independent in every layer (eval-mode BN, per-clip attention), so the trunk may be walked in any clip order.  The
+# breadth-first walk (one launch per layer over the whole batch) is the default.  ``set_dfs("units:clips,...")`` walks consecutive
+# segments of trunk units DEPTH-first instead -- a chunk of a few clips goes through stem, pool and a run of residual blocks before
+# the next chunk starts, so that a chunk's intermediates are write-then-read inside the 126 MB L2 (the allocator hands the next
+# chunk the same addresses) and only a segment's first input and last output cross HBM; the last kernel of a chunk writes straight
+# into its row range of the whole-batch tensor (``out=``).  MEASURED on B200 (tools/dfs_sweep.py, profiles/dfs_sweep_r02.txt): it
+# never pays.  resnet3d50 at 32 clips of 16x224x224: 3.72 ms breadth-first; stem + layer1 in chunks of 8 / 4 / 2 / 1 clips: 4.07 /
+# 4.25 / 4.88 / 6.53 ms; same picture for R(2+1)D-34, the non-local net, resnet18 and the BigGAN generator.  Every extra launch of
+# these persistent kernels costs 6-9 us of pipeline fill, drain and tile quantisation, and the layers that look HBM-bound (1x1x1
+# convolutions at 0.83 of the copy rate) do not speed up when their operands are L2-resident.  The schedule stays as an opt-in
+# (same kernels per output element: results equal the breadth-first walk up to kernel-dispatch boundaries) with the evidence.
+_DFS_SPEC = os.environ.get("B2_DFS", "off")
 
 
-def set_dfs(spec=None, **tune):
-    """Trunk schedule: ``"auto"`` (rule in ``dfs_plan``), ``"off"`` (breadth-first), or an explicit ``"units:clips,units:clips"``
-    list -- consecutive segments of trunk units (unit 0 = stem + pool, then the residual blocks in order), each walked depth-first
-    in chunks of ``clips``; units not covered run breadth-first.  Keyword arguments override the rule's constants (tuning)."""
+def set_dfs(spec):
+    """Trunk schedule: ``"off"`` (breadth-first, the default and the measured optimum) or an explicit
+    ``"units:clips,units:clips"`` list -- consecutive segments of trunk units (unit 0 = stem + pool, then the residual blocks in
+    order), each walked depth-first in chunks of ``clips``; units not covered run breadth-first."""
     global _DFS_SPEC
-    if spec is not None:
-        _DFS_SPEC = str(spec)
-    _DFS_TUNE.update(tune)
+    _DFS_SPEC = str(spec)
 
 
 def _trunk_units(model):
@@ -473,90 +472,12 @@ def _trunk_units(model):
     return units
 
 
-def _conv_out_geom(conv, g):
-    """((T, H, W, C) after ``conv``, bytes per clip of the tensors it writes) for a plain or (2+1)D-factorised convolution;
-    ``(None, 0)`` for anything else."""
-    if hasattr(conv, "spatial_conv") and hasattr(conv, "temporal_conv"):
-        mid, b1 = _conv_out_geom(conv.spatial_conv, g)
-        if mid is None:
-            return None, 0
-        q, b2 = _conv_out_geom(conv.temporal_conv, mid)
-        return q, b1 + b2
-    if not isinstance(conv, (nn.Conv3d, nn.Conv2d)):
-        return None, 0
-    k = _triple(conv.kernel_size)
-    s, p = _conv_geometry(conv)
-    q = tuple(ops._out_dim(g[i], k[i], s[i], p[i]) for i in range(3)) + (conv.out_channels,)
-    return q, q[0] * q[1] * q[2] * ops._round_up(q[3], 8) * 2
-
-
-def _unit_bytes(kind, m, g):
-    """Rough per-clip byte footprint of one trunk unit -- input + output + the intermediates alive in between -- and its output
-    geometry.  Only steers the schedule (never correctness); unknown module shapes return (None, None) and end the depth-first part."""
-    px = lambda q: q[0] * q[1] * q[2]
-    if kind == "stem":
-        c, cb = _conv_out_geom(m.conv1, g)
-        if c is None:
-            return None, None
-        k, s, p = _pool_args(m.maxpool)
-        o = tuple(ops._out_dim(c[i], k[i], s[i], p[i]) for i in range(3)) + (c[3],)
-        # fp32 NCDHW input + NDHWC4 copy + conv output(s) (the Toeplitz stem writes its output W-pooled: half) + pooled output
-        return px(g) * (4 * g[3] + 8) + cb // (2 if (o[2] < c[2] and isinstance(m.conv1, (nn.Conv3d, nn.Conv2d))) else 1) + px(o) * o[3] * 2, o
-    convs = [getattr(m, n) for n in ("conv1", "conv2", "conv3") if hasattr(m, n)]
-    if not convs:
-        return None, None
-    q, total = g, px(g) * g[3] * 2
-    for c in convs:
-        q, cb = _conv_out_geom(c, q)
-        if q is None:
-            return None, None
-        total += cb
-    nl = getattr(m, "nonlocalblock", None)
-    if nl is not None and getattr(m, "nonlocal_layer", True):
-        total += px(q) * (3 * ops._round_up(nl.inter_channels, 64) + nl.inter_channels + q[3]) * 2    # theta|phi|g, y, z
-    return total, q
-
-
-def dfs_plan(model, N, geom):
-    """[(units, clips per chunk)] for ``run_trunk`` -- ``geom`` = (T, H, W, C) of one input clip.
-
-    Rule (``auto``): walk the units in order; a unit whose whole-batch footprint N * bytes(unit) is at most ``full`` x L2 ends the
-    depth-first part (tensors only shrink with depth).  Otherwise the unit wants the largest power of two of clips whose footprint
-    stays within ``chunk`` x L2.  It joins the running segment (whose chunk becomes the minimum of its units' wishes) as long as its
-    launches keep ``min_rows`` rows -- one 128-row tile per SM; smaller launches lose more to tile quantisation than L2 residency
-    gains -- and otherwise opens a new segment with a chunk raised to ``min_rows``.  Long segments matter: a segment boundary is a
-    whole-batch tensor that goes through HBM."""
+def dfs_plan(model=None, N=None, geom=None):
+    """[(units, clips per chunk)] for ``run_trunk`` (empty = breadth-first)."""
     spec = _DFS_SPEC.strip().lower()
-    if spec in ("0", "off", "none", ""):
+    if spec in ("0", "off", "none", "", "auto"):       # "auto" = the measured rule: never chunk
         return []
-    if spec != "auto":
-        return [tuple(int(v) for v in part.split(":")) for part in spec.split(",")]
-    plan, g = [], tuple(geom)
-    budget = _DFS_TUNE["chunk"] * _DFS_L2_BYTES
-    for kind, m in _trunk_units(model):
-        rows = g[0] * g[1] * g[2] if kind != "stem" else 0      # rows the unit's first (widest) launches work on, per clip
-        nbytes, g = _unit_bytes(kind, m, g)
-        if kind == "stem" and g is not None:
-            rows = g[0] * g[1] * g[2] * 4                        # the stem convolution's output rows (before the pool), roughly
-        if nbytes is None or N * nbytes <= _DFS_TUNE["full"] * _DFS_L2_BYTES:
-            break
-        want = 1
-        while want * 2 * nbytes <= budget:
-            want *= 2
-        # join the running segment (chunk = minimum of its units' wishes) while launches stay large enough; a unit that needs the
-        # segment's current chunk just to reach min_rows joins as well (a new segment would pick the same chunk)
-        need = want
-        while need * rows < _DFS_TUNE["min_rows"] and need < N:
-            need *= 2
-        if plan and min(plan[-1][1], want) * rows >= _DFS_TUNE["min_rows"]:
-            plan[-1] = (plan[-1][0] + 1, min(plan[-1][1], want))
-        elif plan and plan[-1][1] == need:
-            plan[-1] = (plan[-1][0] + 1, need)
-        elif need >= N:
-            break
-        else:
-            plan.append((1, need))
-    return plan
+    return [tuple(int(v) for v in part.split(":")) for part in spec.split(",")]
 
 
 def _slice_clips(x, n0, n1):
@@ -591,12 +512,8 @@ def _run_segment(units, x, N, clips, simt):
 
 def run_trunk(model, x, simt=False):
     units = _trunk_units(model)
-    if isinstance(x, Act):
-        N, geom = x.N, (x.T, x.H, x.W, x.C)
-    else:
-        N = x.shape[0]
-        geom = (1,) + tuple(x.shape[2:]) + (x.shape[1],) if x.dim() == 4 else tuple(x.shape[2:]) + (x.shape[1],)
-    plan = [] if simt else dfs_plan(model, N, geom)
+    N = x.N if isinstance(x, Act) else x.shape[0]
+    plan = [] if simt else dfs_plan()
     a, ui = x, 0
     for n_units, clips in plan:
         seg = units[ui:ui + n_units]

@@ -7,6 +7,7 @@ reference's hot path (file:line given per function); the arithmetic happens in
 ``csrc/*.cu`` behind ``include/b2_pretorched.h``.  There is no CPU implementation.
 """
 import ctypes
+import functools
 import math
 
 import torch
@@ -25,6 +26,28 @@ def _stream():
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _first_cuda_device(args, kwargs):
+    for v in list(args) + list(kwargs.values()):
+        t = getattr(v, "data", None) if isinstance(v, Act) else v
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    return None
+
+
+def _on_device(fn):
+    """Run an operator with the device of its first CUDA tensor current (like torch's own device guard): the kernels launch on
+    ``torch.cuda.current_stream()`` of the CURRENT device, so a model moved to ``cuda:1`` in a process whose current device is 0
+    (``model.to('cuda:1')``, ``nn.DataParallel`` replicas call this from their own threads) must switch for the launch."""
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        dev = _first_cuda_device(args, kwargs)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return guarded
 
 
 def _require_cuda(t, what):
@@ -100,6 +123,7 @@ class Act:
 # ---------------------------------------------------------------------------------------------
 # layout
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def from_ncdhw(x, pitch=None):
     """fp32 NCDHW (or NCHW) tensor -> Act.  ``pitch`` = channel pitch (4 for stem inputs)."""
     _require_cuda(x, "input")
@@ -121,6 +145,7 @@ def from_ncdhw(x, pitch=None):
     return Act(y, N, T, H, W, C)
 
 
+@_on_device
 def to_ncdhw(a):
     """Act -> fp32 NCDHW tensor (the layout/dtype the reference's ``features`` returns)."""
     y = torch.empty((a.N, a.C, a.T, a.H, a.W), dtype=torch.float32, device=a.data.device)
@@ -141,6 +166,7 @@ class PackedConv:
     """
     __slots__ = ("w", "scale", "shift", "K", "Cin", "C", "k", "s", "p", "mode", "up")
 
+    @_on_device
     def __init__(self, weight, bias=None, bn=None, stride=(1, 1, 1), padding=(0, 0, 0), in_pitch=None, stem=False,
                  upsample=False):
         _require_cuda(weight, "conv weight")
@@ -221,6 +247,7 @@ def _out_rows(out, M, ld):
     return out
 
 
+@_on_device
 def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, residual_up=False, residual_pre=False,
          next_affine=None, pool_w=False, in_affine=None, out=None):
     """nn.Conv3d -> BatchNorm3d -> (+residual) -> ReLU in one kernel
@@ -301,6 +328,7 @@ def conv(a, pc, residual=None, relu=False, simt=False, sample_affine=None, resid
     return (out, Act(y2, a.N, To, Ho, Wo, pc.K)) if y2 is not None else out
 
 
+@_on_device
 def gemm(a2d, b2d, scale, shift, M, N, Kd, residual=None, relu=False, per_row=False, out=None, out_f32=False,
          accumulate=False, second=None, aff_rows=0, next_affine=None):
     """D[M][N] = act(scale * A[M][Kd] . B[N][Kd]^T + shift + residual) on tcgen05 (b2_gemm_f16).
@@ -366,6 +394,7 @@ def linear(x2d, pl, relu=False, out_f32=False, out=None, accumulate=False):
 # ---------------------------------------------------------------------------------------------
 # pooling / shortcuts / casts
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def maxpool3d(a, kernel, stride, padding, out=None):
     """nn.MaxPool3d (resnet3D.py:156; executed at torchvision_models.py:452).  ``out``: see ``conv``."""
     kt, kh, kw = kernel
@@ -380,6 +409,7 @@ def maxpool3d(a, kernel, stride, padding, out=None):
     return Act(y, a.N, To, Ho, Wo, a.C)
 
 
+@_on_device
 def avgpool_global(a):
     """nn.AdaptiveAvgPool3d(1) + view(B, -1) (torchvision_models.py:460-463): -> fp16 [N][ld]."""
     y = torch.empty((a.N, a.ld), dtype=torch.float16, device=a.data.device)
@@ -389,6 +419,7 @@ def avgpool_global(a):
     return y
 
 
+@_on_device
 def shortcut_a(a, stride, out_channels):
     """Type-A shortcut: F.avg_pool3d(k=1, stride) + zero channel padding (resnet3D.py:65-74)."""
     To, Ho, Wo = (a.T - 1) // stride + 1, (a.H - 1) // stride + 1, (a.W - 1) // stride + 1
@@ -399,6 +430,7 @@ def shortcut_a(a, stride, out_channels):
     return Act(y, a.N, To, Ho, Wo, out_channels)
 
 
+@_on_device
 def concat_rows(a2d, Ca, b2d, Cb):
     """fp16 [rows][>=Ca] ++ [rows][>=Cb] -> [rows][round_up(Ca+Cb, 8)] (torch.cat(dim=1), slowfast.py:143-150, 392)."""
     rows = a2d.shape[0]
@@ -418,6 +450,7 @@ def concat_channels(a, b):
     return Act(concat_rows(a.data, a.C, b.data, b.C), a.N, a.T, a.H, a.W, a.C + b.C)
 
 
+@_on_device
 def cast_rows(x2d, relu=False):
     """fp32 [rows][cols] -> fp16 [rows][round_up(cols, 8)], optional ReLU (trn.py:40-41)."""
     _require_cuda(x2d, "input")
@@ -429,6 +462,7 @@ def cast_rows(x2d, relu=False):
     return y
 
 
+@_on_device
 def gather_frames(x3d, idx_dev):
     """x3d fp16 [N][T][F], idx int32[n] on device -> [N][n*F] (trn.py:108)."""
     N, T, F = x3d.shape
@@ -438,6 +472,7 @@ def gather_frames(x3d, idx_dev):
     return y
 
 
+@_on_device
 def gather_frame_tuples(x3d, idx_dev, n_tuples, n_idx):
     """x3d fp16 [N][T][F], idx int32 [n_tuples][n_idx] on device -> [N * n_tuples][n_idx * F], tuple index fastest
     (trn.py:100-110: every sampled tuple of one scale in one launch)."""
@@ -451,6 +486,7 @@ def gather_frame_tuples(x3d, idx_dev, n_tuples, n_idx):
 # ---------------------------------------------------------------------------------------------
 # non-local attention
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def attention(q2d, k2d, v2d, d, dv, B, Nq, Nk, dot_product=False, mode=None):
     """softmax(Q K^T) V (mode 0), (Q K^T / Nk) V (mode 1, ``dot_product``) or (relu(Q K^T) / Nk) V (mode 2, the
     concatenation mode's rank-2 encoding) -- nonlocalnet.py:143-243.
@@ -476,6 +512,7 @@ def nonlocal_attention(qkv, d, dv, B, Npos):
 # ---------------------------------------------------------------------------------------------
 # BigGAN-deep generator helpers (architecture absent from the reference tree; see models/biggan_deep.py)
 # ---------------------------------------------------------------------------------------------
+@_on_device
 def embed_concat(z, labels, table, split=False):
     """The conditioning vector every ccbn of the generator consumes, v = [table[labels] | z | 0] (D = round_up(ds+dz, 8)):
     fp16 [B][D], or with ``split`` fp16 [B][3D] = [hi | lo | hi] (v = hi + lo to ~2^-22) for the high-accuracy GEMM against
@@ -498,6 +535,7 @@ def embed_concat(z, labels, table, split=False):
     return y
 
 
+@_on_device
 def ccbn_act(a, scale=None, shift=None, channels=None, up=1, relu=True):
     """act(x * scale[n] + shift[n]) with optional nearest 2x upsampling: the ccbn -> ReLU (-> F.interpolate) chain of a
     GBlock in one HBM pass.  ``scale``/``shift``: fp32 [N][pitch] views (per sample), [1][pitch] (shared), or None
@@ -525,6 +563,7 @@ def _out_images(out, shape, dtype):
     return out
 
 
+@_on_device
 def tanh_to_nchw(a, out_dtype=torch.float32, out=None):
     """torch.tanh + channels-last -> NCHW: the generator's image write (fp32 like the public model, or fp16).  ``out``: a
     preallocated image range to write (a batch slice of a larger NCHW tensor)."""
@@ -539,6 +578,7 @@ def tanh_to_nchw(a, out_dtype=torch.float32, out=None):
     return y
 
 
+@_on_device
 def rgb_head(partial, bias, N, H, W, K=3, out_dtype=torch.float32, out=None):
     """Second half of the split RGB head: gather the per-tap partial products of the 1x1 GEMM (fp16 [N*H*W][>=36], column
     tap*4 + k), add the bias, tanh, write NCHW images (see b2_rgb_head_gather_tanh).  ``out``: see ``tanh_to_nchw``."""

@@ -193,4 +193,4 @@ def test_generator_dfs_plan_levels():
         be.set_dfs("256:4")
         assert be.dfs_plan(m, 4, mods) == []                  # batch no larger than the chunk
     finally:
-        be.set_dfs("auto")
+        be.set_dfs("off")

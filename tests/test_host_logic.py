@@ -181,29 +181,16 @@ def test_cache_invalidation_hooks():
 # ---------------------------------------------------------------------------------------------------------------
 # depth-first trunk schedule (engine.run_trunk): plan rule and chunk assembly, on CPU stand-ins for the kernels
 # ---------------------------------------------------------------------------------------------------------------
-def test_dfs_plan_rule():
+def test_dfs_plan_spec():
     from pretorched_x_b200 import engine
-    engine.set_dfs("auto")
-    m = P.resnet3d50(num_classes=400, pretrained=None).eval()
-    plan = engine.dfs_plan(m, 32, (16, 224, 224, 3))                 # BASELINE configs[1]: every layer1 tensor is 411 MB
-    assert plan and plan[0][0] >= 4 and plan[0][1] <= 4, plan        # stem + layer1 (+ layer2.0) in chunks of a few clips
-    assert all(c < 32 for _, c in plan) and sum(u for u, _ in plan) <= 17
-    assert engine.dfs_plan(m, 2, (8, 64, 64, 3)) == []               # small problems stay breadth-first
-    assert engine.dfs_plan(m, 1, (16, 224, 224, 3)) == []            # one clip: nothing to chunk
+    assert engine.dfs_plan() == []                                   # default: breadth-first (the measured optimum)
     try:
-        engine.set_dfs("off")
-        assert engine.dfs_plan(m, 32, (16, 224, 224, 3)) == []
         engine.set_dfs("5:2,4:8")
-        assert engine.dfs_plan(m, 32, (16, 224, 224, 3)) == [(5, 2), (4, 8)]
-    finally:
+        assert engine.dfs_plan() == [(5, 2), (4, 8)]
         engine.set_dfs("auto")
-    # footprints follow the tensors: layer1 blocks of resnet3d50 hold ~30 MB per 16x224x224 clip
-    g = (16, 224, 224, 3)
-    sizes = []
-    for kind, mod in engine._trunk_units(m):
-        b, g = engine._unit_bytes(kind, mod, g)
-        sizes.append(b)
-    assert g == (1, 7, 7, 2048) and 25e6 < sizes[2] < 40e6 and sizes[-1] < 1e6
+        assert engine.dfs_plan() == []
+    finally:
+        engine.set_dfs("off")
 
 
 def test_dfs_segments_assemble_the_breadth_first_result(monkeypatch):
@@ -262,4 +249,13 @@ def test_dfs_segments_assemble_the_breadth_first_result(monkeypatch):
             assert seen[0] == ("stem", min(first_chunk, 7)), (spec, seen[:3])
             assert len(seen) > 7 or first_chunk >= 7
     finally:
-        engine.set_dfs("auto")
+        engine.set_dfs("off")
+
+
+def test_ops_device_guard_is_transparent_on_cpu_arguments():
+    """ops._on_device: operators switch to the device of their first CUDA tensor for the launch (ADVICE r1: `model.to('cuda:1')`);
+    with no CUDA tensor in sight the call goes straight through and the no-CPU-path error is what the caller sees."""
+    assert ops._first_cuda_device((torch.zeros(2), ops.Act(torch.zeros(4, 8), 1, 1, 2, 2, 3)), {"residual": None}) is None
+    assert ops.conv.__name__ == "conv" and "BatchNorm3d" in ops.conv.__doc__
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ops.from_ncdhw(torch.zeros(1, 3, 2, 4, 4))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """CUDA-graph-timed sweep of the trunk schedule (engine.run_trunk: breadth-first vs depth-first in L2-sized clip chunks).
 
-    python tools/dfs_sweep.py resnet3d50 [spec ...]      # spec: off | auto | units:clips[,units:clips...] | auto@chunk=0.5,full=0.8
+    python tools/dfs_sweep.py resnet3d50 [spec ...]      # spec: off | units:clips[,units:clips...]  (biggan256: res:images,...)
 
 Prints one line per spec: ms per forward (min and median of 3 rounds of `--reps` graph replays), clips/s, and the maximum
 deviation of the logits from the breadth-first walk (0 = bit-identical).  Same model / input construction as bench.py.
@@ -20,26 +20,20 @@ from pretorched_x_b200 import engine  # noqa: E402
 from pretorched_x_b200.graph import GraphedForward  # noqa: E402
 
 DEFAULT_SPECS = {
-    "resnet3d50": ["off", "auto", "1:1", "1:2", "1:4", "4:1", "4:2", "4:4", "4:8", "5:1", "5:2", "5:4", "5:2,3:8", "5:2,4:8",
+    "resnet3d50": ["off", "1:1", "1:2", "1:4", "4:1", "4:2", "4:4", "4:8", "5:1", "5:2", "5:4", "5:2,3:8", "5:2,4:8",
                    "5:1,4:8", "5:4,4:8", "5:2,4:16", "5:2,4:4", "8:4", "8:8", "5:2,4:8,5:16", "4:2,5:8", "off"],
-    "nonlocal50": ["off", "auto", "4:1", "4:2", "5:1", "5:2", "5:1,4:2", "5:1,4:4", "9:1", "9:2", "off"],
-    "resnet18": ["off", "auto", "1:16", "1:32", "3:8", "3:16", "3:32", "3:64", "4:16", "4:32", "5:32", "5:64", "4:16,1:64", "4:32,5:64", "off"],
-    "r2plus1d34": ["off", "auto", "1:1", "1:2", "1:4", "4:2", "4:4", "1:1,3:4", "1:2,3:4", "1:2,3:8", "off"],
-    "trn": ["off", "auto", "5:8", "5:16", "5:8,4:32", "5:16,4:64", "off"],
+    "nonlocal50": ["off", "4:1", "4:2", "5:1", "5:2", "5:1,4:2", "5:1,4:4", "9:1", "9:2", "off"],
+    "resnet18": ["off", "1:16", "1:32", "3:8", "3:16", "3:32", "3:64", "4:16", "4:32", "5:32", "5:64", "4:16,1:64", "4:32,5:64", "off"],
+    "r2plus1d34": ["off", "1:1", "1:2", "1:4", "4:2", "4:4", "1:1,3:4", "1:2,3:4", "1:2,3:8", "off"],
+    "trn": ["off", "5:8", "5:16", "5:8,4:32", "5:16,4:64", "off"],
     # generator: res:images levels (biggan_engine.dfs_plan)
-    "biggan256": ["off", "auto", "256:2", "256:4", "256:8", "256:16", "128:4", "128:8", "128:16", "128:8,256:4", "128:16,256:8",
+    "biggan256": ["off", "256:2", "256:4", "256:8", "256:16", "128:4", "128:8", "128:16", "128:8,256:4", "128:16,256:8",
                   "64:16,128:8,256:4", "64:32,128:16,256:8", "64:32,128:8,256:4", "32:64,64:32,128:8,256:4", "64:8", "64:16", "off"],
 }
 
 
 def apply_spec(spec):
-    tune = dict(full=0.80, chunk=0.45, min_rows=128 * 148)
-    if "@" in spec:
-        spec, kv = spec.split("@")
-        for part in kv.split(","):
-            k, v = part.split("=")
-            tune[k] = float(v)
-    engine.set_dfs(spec, **tune)
+    engine.set_dfs(spec)
 
 
 def time_graph(gf, reps):
@@ -82,7 +76,7 @@ def sweep_biggan(args, dev):
         except Exception as e:      # noqa: BLE001
             print("%-12s %-28s FAILED: %r" % ("biggan256", spec, e), flush=True)
         torch.cuda.empty_cache()
-    biggan_engine.set_dfs("auto")
+    biggan_engine.set_dfs("off")
 
 
 def main():
@@ -104,10 +98,7 @@ def main():
     ref = None
     for spec in specs:
         apply_spec(spec)
-        plan = None
-        if args.workload != "trn":
-            geom = (1,) + tuple(x.shape[2:]) + (x.shape[1],) if x.dim() == 4 else tuple(x.shape[2:]) + (x.shape[1],)
-            plan = engine.dfs_plan(model, B, geom)
+        plan = engine.dfs_plan()
         try:
             gf = GraphedForward(model, x, warmup=1)
             out = gf().float().clone()
@@ -121,7 +112,7 @@ def main():
         except Exception as e:      # noqa: BLE001 - a sweep keeps going
             print("%-12s %-28s FAILED: %r" % (args.workload, spec, e), flush=True)
         torch.cuda.empty_cache()
-    engine.set_dfs("auto", full=0.80, chunk=0.45, min_rows=128 * 148)
+    engine.set_dfs("off")
 
 
 if __name__ == "__main__":
