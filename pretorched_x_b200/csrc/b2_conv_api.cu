@@ -11,6 +11,7 @@
 #include "b2_pgemm.cuh"
 #include "b2_slabconv.cuh"
 #include "b2_slabts.cuh"
+#include "b2_tstack.cuh"
 #include "b2_stemconv.cuh"
 
 namespace b2 {
@@ -474,6 +475,52 @@ static int try_slabts(const b2_conv_args* a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------
+// temporal stack kernel (b2_tstack.cuh): (kt,1,1) stride-1 "same" convolutions with <= 64 output channels, resident filter
+// ------------------------------------------------------------------------------------------
+static int g_last_conv_path = 0;   // which launcher took the last b2_conv_ndhwc_fprop call: 0 generic, 1 tstack (tests pin the dispatch)
+static int g_tstack = -2;     // -2: read B2_TSTACK once (0 = never); -1 rule below, 0 never, 1 whenever the shape is eligible (tests / sweeps)
+static int try_tstack(const b2_conv_args* a, cudaStream_t stream) {
+  if (g_tstack == -2) { const char* e = getenv("B2_TSTACK"); g_tstack = (e && e[0] == '0') ? 0 : -1; }
+  if (g_tstack == 0 || g_conv_algo != 0) return 0;
+  if (a->mode != B2_CONV_AUTO || a->out_f32 || a->upsample || a->aff_ld || a->y2 || a->residual_up || a->residual_pre || a->in_scale) return 0;
+  if (a->kh != 1 || a->kw != 1 || a->kt < 3 || !(a->kt & 1) || a->st != 1 || a->sh != 1 || a->sw != 1 || a->pt != a->kt / 2 || a->ph != 0 ||
+      a->pw != 0 || a->ldy > 64 || a->T < 2)
+    return 0;
+  const int cchunks = (a->C + 63) / 64;
+  const long long wbytes = (long long)cchunks * a->kt * kTkWBlock;
+  if (wbytes > 144 * 1024) return 0;                         // the filter must stay resident next to the A ring
+  const long long HW = (long long)a->H * a->W;
+  if (HW >= (1ll << 24)) return 0;
+  TstackParams p;
+  p.T = a->T; p.HW = (int)HW; p.C = a->C;
+  p.kt = a->kt; p.pt = a->pt;
+  p.cchunks = cchunks;
+  p.groups = (a->T + kTkG - 1) / kTkG;
+  p.tiles_q = (int)((HW + 127) / 128);
+  const long long items = (long long)a->N * p.groups * p.tiles_q;
+  if (items >= (1ll << 31)) return 0;
+  // Below one work item per SM the frames-as-rows form of the slab kernel (more, smaller items) keeps more SMs busy.
+  if (g_tstack < 0 && items < sm_count()) return 0;
+  p.items_total = (int)items;
+  p.Ncols = a->K; p.ldy = a->ldy; p.ldr = a->ldr; p.relu = a->relu;
+  p.scale = a->scale; p.shift = a->shift;
+  p.residual = reinterpret_cast<const __half*>(a->residual);
+  p.y = reinterpret_cast<__half*>(a->y);
+  p.fd_tiles_q = make_fastdiv(p.tiles_q); p.fd_groups = make_fastdiv(p.groups);
+  const size_t smem = 1024 + (size_t)kTkStages * kTkABytes + (size_t)wbytes + 128 + 512 + 64;
+  B2_OPT_IN_SMEM(tstack_kernel, 227 * 1024);
+  CUtensorMap tmX, tmB;
+  int rc;
+  if ((rc = make_tmap_ndhwc_slab(&tmX, a->x, (uint64_t)a->C, (uint64_t)HW, 1, (uint64_t)a->N * a->T, 128u, 1u, 1u)) != B2_OK) return rc;
+  if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)a->kt * a->C, (uint64_t)a->K, (uint64_t)a->kt * a->C, 64, 64, true)) != B2_OK) return rc;
+  const int grid = p.items_total < sm_count() ? p.items_total : sm_count();
+  B2_CHECK_CUDA(launch_pdl(tstack_kernel, dim3(grid), dim3(kTkThreads), smem, stream, tmX, tmB, p));
+  B2_CHECK_LAUNCH("tstack_kernel");
+  g_last_conv_path = 1;
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // stem convolution launcher (Toeplitz-descriptor kernel)
 // ------------------------------------------------------------------------------------------
 template <int BN>
@@ -818,6 +865,8 @@ int b2_debug_slab_plan(const b2_conv_args* a_in, int* out) {
 }
 /* debug knobs of the small-M path: layers with M <= maxm take the dense-M kernel (0 = never); force_s > 0 caps the cluster size */
 int b2_debug_set_slab_wide(int on) { g_slab_wide = on; return B2_OK; }   /* -1 rule, 0 never, 1 always */
+int b2_debug_last_conv_path(void) { return g_last_conv_path; }   /* 1: the temporal stack kernel took the last convolution */
+int b2_debug_set_tstack(int mode) { g_tstack = mode < -1 ? -1 : (mode > 1 ? 1 : mode); return B2_OK; }   /* temporal stack kernel: -1 rule, 0 never, 1 whenever eligible */
 int b2_debug_set_slab_mt(int mt) { g_slab_force_mt = mt < 0 ? 0 : mt; return B2_OK; }
 int b2_debug_set_densem(int maxm, int force_s) { g_densem_maxm = maxm < 0 ? -2 : maxm; g_densem_force_s = force_s; return B2_OK; }
 const char* b2_last_error(void) { return g_err; }
@@ -874,6 +923,9 @@ int b2_conv_ndhwc_fprop(const b2_conv_args* a, void* stream) {
   const bool small_m = a->mode == B2_CONV_AUTO && !a->upsample && !a->aff_ld && !a->out_f32 && !a->y2 && !a->residual_up &&
                        !a->residual_pre && !a->in_scale && g_gemm_algo == 0 &&
                        densem_wanted(M_out, a->kt * a->kh * a->kw, a->st > 1 || a->sh > 1 || a->sw > 1);
+  g_last_conv_path = 0;
+  rc = small_m ? 0 : try_tstack(a, reinterpret_cast<cudaStream_t>(stream));
+  if (rc != 0) return rc < 0 ? rc : B2_OK;
   rc = small_m ? 0 : try_slabts(a, reinterpret_cast<cudaStream_t>(stream));
   if (rc != 0) return rc < 0 ? rc : B2_OK;
   rc = small_m ? 0 : try_slab(a, reinterpret_cast<cudaStream_t>(stream));

@@ -100,6 +100,47 @@ CONV_CASES = [
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 @pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "simt_crosscheck"])
 def test_conv_bn_act_matches_oracle(dev, case, simt):
+    check_conv_case(dev, case, simt)
+
+
+# temporal stack kernel (b2_tstack.cuh: (kt,1,1) filters, Cout <= 64, resident filter, 4 output frames per item, two accumulator
+# sets): forced on shapes below its one-item-per-SM rule.  Frame groups 4 + 4, 4 + 1, 4 + 2 + ..., a single group of 2 or 3 frames
+# (T < kt: taps that never see a valid frame), clip boundaries between samples, ragged position tiles (HW % 128 != 0, HW < 128),
+# residual / no residual / no ReLU / bias without BN, 1 - 3 channel chunks with ragged tails, K < 64 (zero pad columns), kt = 3, 5, 7.
+TSTACK_CASES = [
+    ("tstack_3_c144_to_64_t8_28x28_res", 2, 144, 8, 28, 28, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
+    ("tstack_3_c144_to_64_t5_res", 3, 144, 5, 14, 14, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
+    ("tstack_7_c110_to_64_t16_56x56", 1, 110, 16, 56, 56, 64, (7, 1, 1), (1, 1, 1), (3, 0, 0), False, False, False, True),
+    ("tstack_7_c110_to_64_t6_clips", 3, 110, 6, 20, 20, 64, (7, 1, 1), (1, 1, 1), (3, 0, 0), False, True, False, True),
+    ("tstack_7_t3_taps_outside", 2, 64, 3, 24, 24, 64, (7, 1, 1), (1, 1, 1), (3, 0, 0), True, True, False, True),
+    ("tstack_5_c64_to_42_t9_ragged", 2, 64, 9, 9, 11, 42, (5, 1, 1), (1, 1, 1), (2, 0, 0), True, False, True, False),
+    ("tstack_3_c200_to_48_t2", 5, 200, 2, 12, 12, 48, (3, 1, 1), (1, 1, 1), (1, 0, 0), False, True, False, True),
+    ("tstack_3_c24_to_64_t13_tiny_planes", 4, 24, 13, 5, 5, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), True, True, False, True),
+]
+
+
+@pytest.mark.parametrize("case", TSTACK_CASES, ids=[c[0] for c in TSTACK_CASES])
+def test_temporal_stack_kernel_matches_oracle(dev, case):
+    from pretorched_x_b200 import _lib
+    lib = _lib.load()
+    lib.b2_debug_set_tstack(1)
+    try:
+        check_conv_case(dev, case, False)
+        assert lib.b2_debug_last_conv_path() == 1          # the temporal stack kernel, not the slab kernel, produced the result
+    finally:
+        lib.b2_debug_set_tstack(-1)
+
+
+def test_temporal_stack_kernel_many_items_per_cta(dev):
+    """More work items than SMs x 2 (every CTA walks several items: ring phases, both accumulator sets, re-zeroed accumulators),
+    taken by the library's own rule (no forcing) -- the layer1 temporal convolution of R(2+1)D-34 on 6 clips."""
+    from pretorched_x_b200 import _lib
+    check_conv_case(dev, ("tstack_rule_c144_to_64_t16_28x28_res", 6, 144, 16, 28, 28, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0),
+                          True, True, False, True), False)
+    assert _lib.load().b2_debug_last_conv_path() == 1
+
+
+def check_conv_case(dev, case, simt):
     from pretorched_x_b200 import ops, engine
     name, N, Cin, T, H, W, K, k, s, p, res, relu, bias, bn = case
     g = torch.Generator().manual_seed(seed_of(name))

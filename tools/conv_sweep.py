@@ -17,6 +17,8 @@ lib.b2_debug_set_slab_mt.restype = ctypes.c_int
 lib.b2_debug_set_slab_mt.argtypes = [ctypes.c_int]
 lib.b2_debug_set_slab_wide.restype = ctypes.c_int
 lib.b2_debug_set_slab_wide.argtypes = [ctypes.c_int]          # 4th field of a setting: 256-column N tiles 1 = always, 0 = never, -1 / absent = the library's rule
+lib.b2_debug_set_tstack.restype = ctypes.c_int
+lib.b2_debug_set_tstack.argtypes = [ctypes.c_int]             # 5th field: temporal stack kernel 1 = whenever eligible, 0 = never, -1 / absent = the library's rule
 dev = torch.device("cuda:0")
 REP = 20
 for sp in specs:
@@ -44,6 +46,7 @@ for sp in specs:
             lib.b2_debug_set_densem(maxm, fs)
             lib.b2_debug_set_slab_mt(mt)
             lib.b2_debug_set_slab_wide(st[3] if len(st) > 3 else -1)
+            lib.b2_debug_set_tstack(st[4] if len(st) > 4 else -1)
             for _ in range(2):
                 y = engine.conv_bn_act(conv, bn, x, residual=res, relu=True)
             torch.cuda.synchronize()

@@ -1,4 +1,6 @@
-"""Turn gpurun_out/ev2/ (written by tools/evidence_r02.sh on the GPU box) into the tracked profiles/*_r02.* files.
+"""Turn gpurun_out/ev2/ (written by tools/evidence_r02.sh, or its refresh tools/evidence_r02b.sh, on the GPU box) into the tracked
+profiles/*_r02.* files.  The refresh does not repeat the `ncu --set full` captures: when gpurun_out/ev2 holds none, the committed
+profiles/ncu_top_r02.csv / ncu_traffic_r02.json are kept and quoted as they are.
 usage: python tools/evidence_summary_r02.py"""
 import collections, csv, json, os, shutil
 
@@ -6,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EV = os.path.join(ROOT, "gpurun_out", "ev2")
 PR = os.path.join(ROOT, "profiles")
 TAG = "r02"
-WORKLOADS = ("resnet3d50", "r2plus1d34", "nonlocal50", "resnet18", "biggan256")
+WORKLOADS = ("resnet3d50", "r2plus1d34", "nonlocal50", "resnet18", "biggan256", "trn")
 
 
 def last_json_line(path):
@@ -68,11 +70,14 @@ def main():
     shutil.copy(os.path.join(EV, "pytest_gpu.txt"), os.path.join(PR, "pytest_gpu_%s.txt" % TAG))
     lines = {}
     for w in WORKLOADS:
+        if not os.path.exists(os.path.join(EV, "line_%s.json" % w)):
+            continue
         shutil.copy(os.path.join(EV, "layers_%s.txt" % w), os.path.join(PR, "layers_%s_%s.txt" % (w, TAG)))
         lines[w] = last_json_line(os.path.join(EV, "line_%s.json" % w))
     with open(os.path.join(PR, "workloads_%s.jsonl" % TAG), "w") as f:
         for w in WORKLOADS:
-            f.write(json.dumps(lines[w]) + "\n")
+            if w in lines:
+                f.write(json.dumps(lines[w]) + "\n")
 
     # ---- launch lists: the second forward of tools/fwd_once.py (per-kernel device time, cold cache, serialised) ----
     launch_txt = []
@@ -112,8 +117,19 @@ def main():
         ("ncu_gan_conv64", "slabconv<64> BigGAN conv 3x3 C64->64 at 256x256, 64 images, per-sample affine", None, 2 * 64 * 65536 * 64 * 2.0),
     ]
     top_lines, traffic = [], {}
-    with open(os.path.join(PR, "ncu_top_%s.csv" % TAG), "w") as f:
-        f.write("capture," + ",".join(k for k, _ in want) + ",algorithmic_MB\n")
+    have_caps = any(os.path.exists(os.path.join(EV, fn + ".raw.csv")) for fn, _, _, _ in captures)
+    if not have_caps:          # refresh without new captures: quote the committed summary
+        with open(os.path.join(PR, "ncu_top_%s.csv" % TAG)) as f:
+            rd = csv.DictReader(f)
+            for d in rd:
+                top_lines.append("%-100s %8.1f us  dram R %7.1f + W %7.1f MB vs %7.1f algorithmic (dram %4.1f%%)  tensor-pipe %4.1f%%  L2 %4.1f%%  regs %3d" % (
+                    d["capture"], float(d["duration_us"]), float(d["dram_read_MB"]), float(d["dram_write_MB"]), float(d["algorithmic_MB"]),
+                    float(d["dram_pct"]), float(d["tensor_pipe_active_pct"]), float(d["l2_throughput_pct"]), int(float(d["regs"]))))
+    with open(os.path.join(PR, "ncu_top_%s.csv" % TAG), "w" if have_caps else "a") as f:
+        if not have_caps:
+            captures = []
+        else:
+            f.write("capture," + ",".join(k for k, _ in want) + ",algorithmic_MB\n")
         for fn, label, desc, alg in captures:
             path = os.path.join(EV, fn + ".raw.csv")
             if not os.path.exists(path) or os.path.getsize(path) < 100:
@@ -127,16 +143,20 @@ def main():
                 d["l2_throughput_pct"], int(d["regs"])))
             traffic[label] = {"dram_bytes": int((d["dram_read_MB"] + d["dram_write_MB"]) * 1e6), "algorithmic_bytes": int(alg),
                               "bench_desc": desc}
-    json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full --clock-control none` captures "
+    if have_caps:
+      json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full --clock-control none` captures "
                            "(tools/evidence_r02.sh); bench.py leaves roofline.traffic null because DRAM counters cannot be read in an "
                            "un-profiled run -- this file is the ncu measurement of the same kernels at the same shapes",
                "captures": traffic}, open(os.path.join(PR, "ncu_traffic_%s.json" % TAG), "w"), indent=1)
 
     out = ["# profiles/ -- round 2 evidence (B200, sm_100a)\n",
-           "Produced by `tools/evidence_r02.sh` on a fresh `gpurun` B200 box, summarised by `tools/evidence_summary_r02.py`.  No throughput "
-           "number was taken under a profiler.\n",
+           "Produced by `tools/evidence_r02.sh` (ncu --set full captures) and its refresh `tools/evidence_r02b.sh` (tests, bench lines, layer "
+           "tables, launch lists, sanitizer passes with the final kernels) on fresh `gpurun` B200 boxes, summarised by "
+           "`tools/evidence_summary_r02.py`.  No throughput number was taken under a profiler.\n",
            "## Bench lines (`python bench.py [--workload W]`, N = 1)\n"]
     for w in WORKLOADS:
+        if w not in lines:
+            continue
         ln = lines[w]
         e2e = ln["e2e"]
         out.append("* **%s** (%s): **%.0f %s** device-resident (%.3f ms per step); e2e from fp32 pinned host input %.0f%s; parity vs the CPU oracle: %s; "
@@ -149,6 +169,28 @@ def main():
                % (TAG, bench["value"], bench["e2e"]["value"], "%.2f" % bench["cpu_baseline"]["value"] if bench.get("cpu_baseline") else "n/a",
                   bench["cpu_baseline"]["cores"] if bench.get("cpu_baseline") else "?", bench["cpu_baseline"]["kind"] if bench.get("cpu_baseline") else "?",
                   ", ".join("%s %.0f %s" % (k, bench[k]["value"], bench[k]["unit"]) for k in ("biggan256", "r2plus1d34", "nonlocal50") if isinstance(bench.get(k), dict) and "value" in bench[k])))
+    # ---- sanitizer passes (tools/sanitize.sh all) ----
+    san_dir = os.path.join(ROOT, "gpurun_out", "sanitizer")
+    san = []
+    for tool in ("memcheck", "synccheck", "initcheck", "racecheck"):
+        logp, outp = os.path.join(san_dir, tool + ".log"), os.path.join(san_dir, tool + ".out")
+        if not os.path.exists(logp):
+            continue
+        log = open(logp).read().strip().splitlines()
+        summary = [l_ for l_ in log if "ERROR SUMMARY" in l_ or "RACECHECK SUMMARY" in l_]
+        cases = [l_ for l_ in open(outp).read().splitlines() if l_.strip() and not l_.startswith("=")] if os.path.exists(outp) else []
+        san.append("== compute-sanitizer --tool %s  (kernels of namespace b2 only): %s" % (tool, summary[-1].replace("=========", "").strip() if summary else "no summary line"))
+        san += ["   " + c_ for c_ in cases]
+        extra = [l_ for l_ in log if l_.startswith("=========") and ("Error" in l_ or "Warning" in l_ or "hazard" in l_.lower() or "Uninitialized" in l_)]
+        seen = collections.Counter(" ".join(e.replace("=========", "").split()[:12]) for e in extra)
+        san += ["   finding x%d: %s" % (n, k) for k, n in seen.most_common(12)]
+    if san:
+        open(os.path.join(PR, "sanitizer_%s.txt" % TAG), "w").write("\n".join(san) + "\n")
+        out.append("## compute-sanitizer (`sanitizer_%s.txt`, tools/sanitize.sh)\n" % TAG)
+        out.append("```\n" + "\n".join(l_ for l_ in san if l_.startswith("==") or "finding" in l_) + "\n```\n")
+    out.append("## Trunk schedule sweep (`dfs_sweep_%s.txt`, tools/dfs_sweep.py)\n" % TAG)
+    out.append("Depth-first (L2-resident) walks of the early stages in clip chunks against the breadth-first walk, CUDA-graph-timed: every "
+               "chunked schedule is slower on every workload (DESIGN.md section 3c); breadth-first is the default.\n")
     out.append("## ncu launch lists (`launches_*_%s.csv`)\n" % TAG)
     out.append("```\n" + "\n".join(launch_txt) + "\n```\n")
     out.append("## ncu --set full captures (`ncu_top_%s.csv`, `ncu_traffic_%s.json`)\n" % (TAG, TAG))
