@@ -507,19 +507,13 @@ static int try_tstack(const b2_conv_args* a, cudaStream_t stream) {
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.y = reinterpret_cast<__half*>(a->y);
   p.fd_tiles_q = make_fastdiv(p.tiles_q); p.fd_groups = make_fastdiv(p.groups);
-  int stages = (int)((227 * 1024 - 2048 - wbytes) / kTkABytes);       // bytes in flight cover the load latency: as deep as fits
-  stages = stages > kTkMaxStages ? kTkMaxStages : stages;
-  if (stages < 4) return 0;
-  p.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * kTkABytes + (size_t)wbytes + 256 + 512 + 64;
+  const size_t smem = 1024 + (size_t)kTkStages * kTkABytes + (size_t)wbytes + 128 + 512 + 64;
   B2_OPT_IN_SMEM(tstack_kernel, 227 * 1024);
   CUtensorMap tmX, tmB;
   int rc;
   if ((rc = make_tmap_ndhwc_slab(&tmX, a->x, (uint64_t)a->C, (uint64_t)HW, 1, (uint64_t)a->N * a->T, 128u, 1u, 1u)) != B2_OK) return rc;
   if ((rc = make_tmap_2d_f16(&tmB, a->w, (uint64_t)a->kt * a->C, (uint64_t)a->K, (uint64_t)a->kt * a->C, 64, 64, true)) != B2_OK) return rc;
-  int grid = p.items_total < sm_count() ? p.items_total : sm_count();
-  p.items_per_cta = (p.items_total + grid - 1) / grid;
-  grid = (p.items_total + p.items_per_cta - 1) / p.items_per_cta;      // no CTA without an item
+  const int grid = p.items_total < sm_count() ? p.items_total : sm_count();
   B2_CHECK_CUDA(launch_pdl(tstack_kernel, dim3(grid), dim3(kTkThreads), smem, stream, tmX, tmB, p));
   B2_CHECK_LAUNCH("tstack_kernel");
   g_last_conv_path = 1;

@@ -17,7 +17,7 @@
 // (no halo, rows past the end of a frame zero-filled), and with one M tile per item TWO accumulator sets (2 x 256 TMEM columns) let
 // the epilogue of item i -- residual rows requested before the accumulators are even complete -- overlap the MMAs of item i + 1.
 //
-//   warp 4   TMA producer: resident weights once, then the A tiles of (item, input frame, channel chunk) through a 4..8-stage ring
+//   warp 4   TMA producer: resident weights once, then the A tiles of (item, input frame, channel chunk) through a 4-stage ring
 //   warp 5   MMA issuer: per input frame one MMA of N = 64 x slots per K step into accumulator set (item & 1); all MMAs accumulate
 //            (the epilogue hands accumulators back zeroed, tcgen05.st, so slots may start from different input frames)
 //   warps 0-3, 6-9   epilogue: thread = one position (TMEM lane) x 32 channels; affine (+ residual) (+ ReLU), 16-byte stores
@@ -28,7 +28,7 @@
 namespace b2 {
 
 constexpr int kTkThreads = 320;
-constexpr int kTkMaxStages = 8;              // A-tile ring depth: as many 16 KB stages as fit beside the resident filter (4 .. 8)
+constexpr int kTkStages = 4;                 // A-tile ring depth
 constexpr int kTkABytes = 128 * 128;         // one A tile: 128 positions x 64 fp16 channels, SWIZZLE_128B
 constexpr int kTkG = 4;                      // output frames (accumulator slots) per work item
 constexpr int kTkSetCols = kTkG * 64;        // TMEM columns of one accumulator set
@@ -41,10 +41,6 @@ struct TstackParams {
   int groups;              // ceil(T / kTkG) frame groups per clip
   int tiles_q;             // ceil(HW / 128) position tiles per frame
   int items_total;         // N * groups * tiles_q
-  int items_per_cta;       // CTA b owns the items [b * items_per_cta, (b + 1) * items_per_cta): frame group fastest, so that consecutive
-                           // items of a CTA are consecutive groups of one (clip, position tile) and re-read the kt - 1 frames they
-                           // share from L2 (tile-fastest round-robin sent those re-reads, 1.5x - 2.5x of the input, to HBM)
-  int stages;              // A-tile ring depth
   int Ncols, ldy, ldr, relu;
   const float* scale;
   const float* shift;
@@ -63,10 +59,9 @@ struct TstackItem {
 
 __device__ __forceinline__ TstackItem tstack_item(const TstackParams& p, int item) {
   TstackItem w;
-  const int pq = fdiv(item, p.fd_groups);             // (clip, position tile); frame group fastest
-  const int g = item - pq * p.groups;
-  const int n = fdiv(pq, p.fd_tiles_q);
-  w.q0 = (pq - n * p.tiles_q) * 128;
+  const int pg = fdiv(item, p.fd_tiles_q);            // (clip, frame group); position tile fastest
+  w.q0 = (item - pg * p.tiles_q) * 128;
+  const int n = fdiv(pg, p.fd_groups), g = pg - n * p.groups;
   const int to0 = g * kTkG;
   w.nf = min(kTkG, p.T - to0);
   w.plane_o0 = n * p.T + to0;
@@ -83,21 +78,18 @@ tstack_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, HW, 1, 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align<1024>(smem_raw);
   uint8_t* a_base = smem;
-  const int kTkStages = p.stages;
   uint8_t* w_base = smem + kTkStages * kTkABytes;
   uint8_t* tail = w_base + p.cchunks * p.kt * kTkWBlock;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* a_empty = a_full + kTkMaxStages;
-  uint64_t* w_full = a_empty + kTkMaxStages;          // [1]
+  uint64_t* a_empty = a_full + kTkStages;
+  uint64_t* w_full = a_empty + kTkStages;             // [1]
   uint64_t* acc_full = w_full + 1;                    // [2]
   uint64_t* acc_empty = acc_full + 2;                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* s_scale = reinterpret_cast<float*>(tail + 256);   // barriers + TMEM slot occupy the first 172 bytes
+  float* s_scale = reinterpret_cast<float*>(tail + 128);   // barriers + TMEM slot occupy the first 108 bytes
   float* s_shift = s_scale + 64;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int item_lo = blockIdx.x * p.items_per_cta;
-  const int item_hi = min(p.items_total, item_lo + p.items_per_cta);
 
   if (tid == 128) {
     for (int s = 0; s < kTkStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -134,7 +126,7 @@ tstack_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, HW, 1, 
   if (warp == 4) {
     // ================================ TMA producer ======================================
     int it = 0;
-    for (int item = item_lo; item < item_hi; ++item) {
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
       const TstackItem w = tstack_item(p, item);
       for (int fr = w.fr_lo; fr <= w.fr_hi; ++fr) {
         for (int cc = 0; cc < p.cchunks; ++cc, ++it) {
@@ -156,7 +148,7 @@ tstack_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, HW, 1, 
     mbar_wait(&w_full[0], 0);
     tc_fence_after();
     int it = 0, lt = 0;
-    for (int item = item_lo; item < item_hi; ++item, ++lt) {
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
       const TstackItem w = tstack_item(p, item);
       const int ab = lt & 1;
       mbar_wait(&acc_empty[ab], (lt >> 1) & 1);            // the epilogue has drained AND re-zeroed this accumulator set
@@ -201,7 +193,7 @@ tstack_kernel(const __grid_constant__ CUtensorMap tmX,   // input as (C, HW, 1, 
     for (int c = 0; c < 32; ++c) { sc[c] = s_scale[c0 + c]; sh[c] = s_shift[c0 + c]; }
     const int ncols_here = min(64, p.ldy);
     int lt = 0;
-    for (int item = item_lo; item < item_hi; ++item, ++lt) {
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x, ++lt) {
       const TstackItem w = tstack_item(p, item);
       const int ab = lt & 1;
       const bool ok = w.q0 + erow < p.HW;
