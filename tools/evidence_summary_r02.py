@@ -195,6 +195,11 @@ def main():
     out.append("## Trunk schedule sweep (`dfs_sweep_%s.txt`, tools/dfs_sweep.py)\n" % TAG)
     out.append("Depth-first (L2-resident) walks of the early stages in clip chunks against the breadth-first walk, CUDA-graph-timed: every "
                "chunked schedule is slower on every workload (DESIGN.md section 3c); breadth-first is the default.\n")
+    out.append("## Temporal stack kernel (`tstack_sweep_%s.txt`, tools/conv_sweep.py)\n" % TAG)
+    out.append("(kt,1,1) Cout = 64 layers of R(2+1)D-34, CUDA-graph-timed: (7,1,1) C110->64 on 16 clips 263.6 -> 167.8 us, (3,1,1) C144->64 "
+               "+ residual 39.3 -> 32.2 us; whole network 7307 -> 7889 clips/s.  The r2plus1d34 line and layer table above are from the run "
+               "with the kernel; the `r2plus1d34` sub-line inside `bench_%s.json` and `launches_r2plus1d34_%s.csv` were taken just before it "
+               "was added (slab kernel on those 13 launches).\n" % (TAG, TAG))
     out.append("## ncu launch lists (`launches_*_%s.csv`)\n" % TAG)
     out.append("```\n" + "\n".join(launch_txt) + "\n```\n")
     out.append("## ncu --set full captures (`ncu_top_%s.csv`, `ncu_traffic_%s.json`)\n" % (TAG, TAG))
