@@ -479,18 +479,17 @@ static int try_slabts(const b2_conv_args* a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 static int g_last_conv_path = 0;   // which launcher took the last b2_conv_ndhwc_fprop call: 0 generic, 1 tstack (tests pin the dispatch)
 static int g_tstack = -2;     // -2: read B2_TSTACK once (0 = never); -1 rule below, 0 never, 1 whenever the shape is eligible (tests / sweeps)
-static int try_tstack(const b2_conv_args* a, cudaStream_t stream) {
-  if (g_tstack == -2) { const char* e = getenv("B2_TSTACK"); g_tstack = (e && e[0] == '0') ? 0 : -1; }
-  if (g_tstack == 0 || g_conv_algo != 0) return 0;
-  if (a->mode != B2_CONV_AUTO || a->out_f32 || a->upsample || a->aff_ld || a->y2 || a->residual_up || a->residual_pre || a->in_scale) return 0;
+// Shape test + work decomposition (host only).  Returns false when the kernel does not take the convolution.
+static bool tstack_plan(const b2_conv_args* a, TstackParams* out, size_t* smem_out) {
+  if (a->mode != B2_CONV_AUTO || a->out_f32 || a->upsample || a->aff_ld || a->y2 || a->residual_up || a->residual_pre || a->in_scale) return false;
   if (a->kh != 1 || a->kw != 1 || a->kt < 3 || !(a->kt & 1) || a->st != 1 || a->sh != 1 || a->sw != 1 || a->pt != a->kt / 2 || a->ph != 0 ||
       a->pw != 0 || a->ldy > 64 || a->T < 2)
-    return 0;
+    return false;
   const int cchunks = (a->C + 63) / 64;
   const long long wbytes = (long long)cchunks * a->kt * kTkWBlock;
-  if (wbytes > 144 * 1024) return 0;                         // the filter must stay resident next to the A ring
+  if (wbytes > 144 * 1024) return false;                     // the filter must stay resident next to the A ring
   const long long HW = (long long)a->H * a->W;
-  if (HW >= (1ll << 24)) return 0;
+  if (HW >= (1ll << 24)) return false;
   TstackParams p;
   p.T = a->T; p.HW = (int)HW; p.C = a->C;
   p.kt = a->kt; p.pt = a->pt;
@@ -498,16 +497,28 @@ static int try_tstack(const b2_conv_args* a, cudaStream_t stream) {
   p.groups = (a->T + kTkG - 1) / kTkG;
   p.tiles_q = (int)((HW + 127) / 128);
   const long long items = (long long)a->N * p.groups * p.tiles_q;
-  if (items >= (1ll << 31)) return 0;
-  // Below one work item per SM the frames-as-rows form of the slab kernel (more, smaller items) keeps more SMs busy.
-  if (g_tstack < 0 && items < sm_count()) return 0;
+  if (items >= (1ll << 31)) return false;
+  // Below one work item per SM the frames-as-rows form of the slab kernel (more, smaller items) keeps more SMs busy
+  // (2 clips of the (3,1,1) C144 layer, 56 items: 9.6 vs 11.0 us, profiles/tstack_sweep_r02.txt).
+  if (g_tstack < 0 && items < sm_count()) return false;
   p.items_total = (int)items;
   p.Ncols = a->K; p.ldy = a->ldy; p.ldr = a->ldr; p.relu = a->relu;
   p.scale = a->scale; p.shift = a->shift;
   p.residual = reinterpret_cast<const __half*>(a->residual);
   p.y = reinterpret_cast<__half*>(a->y);
   p.fd_tiles_q = make_fastdiv(p.tiles_q); p.fd_groups = make_fastdiv(p.groups);
-  const size_t smem = 1024 + (size_t)kTkStages * kTkABytes + (size_t)wbytes + 128 + 512 + 64;
+  *out = p;
+  *smem_out = 1024 + (size_t)kTkStages * kTkABytes + (size_t)wbytes + 128 + 512 + 64;
+  return true;
+}
+
+static int try_tstack(const b2_conv_args* a, cudaStream_t stream) {
+  if (g_tstack == -2) { const char* e = getenv("B2_TSTACK"); g_tstack = (e && e[0] == '0') ? 0 : -1; }
+  if (g_tstack == 0 || g_conv_algo != 0) return 0;
+  TstackParams p;
+  size_t smem = 0;
+  if (!tstack_plan(a, &p, &smem)) return 0;
+  const long long HW = p.HW;
   B2_OPT_IN_SMEM(tstack_kernel, 227 * 1024);
   CUtensorMap tmX, tmB;
   int rc;
@@ -865,6 +876,18 @@ int b2_debug_slab_plan(const b2_conv_args* a_in, int* out) {
 }
 /* debug knobs of the small-M path: layers with M <= maxm take the dense-M kernel (0 = never); force_s > 0 caps the cluster size */
 int b2_debug_set_slab_wide(int on) { g_slab_wide = on; return B2_OK; }   /* -1 rule, 0 never, 1 always */
+/* host-only view of the temporal stack kernel's decision for a convolution (no launch, no GPU needed): out = {applies, items, frame
+   groups per clip, position tiles per frame, channel chunks, resident filter bytes, dynamic shared memory bytes} */
+int b2_debug_tstack_plan(const b2_conv_args* a, int* out) {
+  if (g_tstack == -2) { const char* e = getenv("B2_TSTACK"); g_tstack = (e && e[0] == '0') ? 0 : -1; }
+  TstackParams p;
+  size_t smem = 0;
+  memset(&p, 0, sizeof(p));
+  const bool ok = g_tstack != 0 && tstack_plan(a, &p, &smem);
+  out[0] = ok; out[1] = ok ? p.items_total : 0; out[2] = p.groups; out[3] = p.tiles_q; out[4] = p.cchunks;
+  out[5] = ok ? p.cchunks * p.kt * kTkWBlock : 0; out[6] = ok ? (int)smem : 0;
+  return B2_OK;
+}
 int b2_debug_last_conv_path(void) { return g_last_conv_path; }   /* 1: the temporal stack kernel took the last convolution */
 int b2_debug_set_tstack(int mode) { g_tstack = mode < -1 ? -1 : (mode > 1 ? 1 : mode); return B2_OK; }   /* temporal stack kernel: -1 rule, 0 never, 1 whenever eligible */
 int b2_debug_set_slab_mt(int mt) { g_slab_force_mt = mt < 0 ? 0 : mt; return B2_OK; }

@@ -153,6 +153,48 @@ def test_slab_tiling_plan_is_host_logic():
     assert not plan(2, 64, 4, 8, 8, 256, (1, 1, 1))["applies"]     # 1x1x1: persistent GEMM, not the slab kernel
 
 
+def test_temporal_stack_plan_is_host_logic():
+    """Which convolutions the temporal stack kernel (b2_tstack.cuh) takes, and with what decomposition: pure host code behind a debug
+    entry point.  The 64-wide temporal halves of R(2+1)D-34 at the BASELINE batch are taken with the filter resident; launches with
+    less than one work item per SM, wider outputs, strided / spatial filters and filters too big to stay resident are not."""
+    import ctypes
+    from pretorched_x_b200 import _lib
+    lib = _lib.load()
+    lib.b2_debug_tstack_plan.argtypes = [ctypes.POINTER(_lib.ConvArgs), ctypes.POINTER(ctypes.c_int)]
+
+    def plan(N, C, T, H, W, K, k, s=(1, 1, 1), pad=None):
+        a = _lib.ConvArgs()
+        a.N, a.T, a.H, a.W, a.C, a.K = N, T, H, W, (C + 7) // 8 * 8, K
+        a.ldy = (K + 7) // 8 * 8
+        a.kt, a.kh, a.kw = k
+        a.st, a.sh, a.sw = s
+        a.pt, a.ph, a.pw = pad if pad is not None else (k[0] // 2, k[1] // 2, k[2] // 2)
+        out = (ctypes.c_int * 7)()
+        assert lib.b2_debug_tstack_plan(ctypes.byref(a), out) == 0
+        return dict(zip("applies items groups tiles cchunks wbytes smem".split(), list(out)))
+
+    lib.b2_debug_set_tstack(-1)
+    p = plan(16, 110, 32, 56, 56, 64, (7, 1, 1))                   # R(2+1)D stem, temporal half: 8 groups of 4 frames x 25 tiles x 16 clips
+    assert p["applies"] and (p["items"], p["groups"], p["tiles"], p["cchunks"]) == (3200, 8, 25, 2)
+    assert p["wbytes"] == 2 * 7 * 8192 and p["smem"] <= 227 * 1024
+    p = plan(16, 144, 16, 28, 28, 64, (3, 1, 1))                   # layer1 temporal halves: 3 channel chunks, 72 KB filter
+    assert p["applies"] and (p["items"], p["groups"], p["tiles"], p["cchunks"], p["wbytes"]) == (448, 4, 7, 3, 73728)
+    assert not plan(2, 144, 16, 28, 28, 64, (3, 1, 1))["applies"]   # 56 items < one per SM: the slab kernel keeps more SMs busy
+    assert not plan(16, 288, 8, 14, 14, 128, (3, 1, 1))["applies"]  # 128 output channels: N = 128 MMAs are balanced already
+    assert not plan(16, 64, 16, 28, 28, 64, (3, 3, 3))["applies"]   # in-plane taps: slab / slabts
+    assert not plan(16, 230, 8, 14, 14, 64, (3, 1, 1), s=(2, 1, 1))["applies"]   # temporal stride
+    assert not plan(16, 64, 16, 28, 28, 64, (3, 1, 1), pad=(0, 0, 0))["applies"]  # not "same"-padded
+    assert not plan(64, 1024, 8, 14, 14, 64, (3, 1, 1))["applies"]  # 16 chunks x 3 taps x 8 KB = 384 KB: cannot stay resident
+    assert not plan(64, 64, 1, 56, 56, 64, (3, 1, 1))["applies"]    # a single frame: only the centre tap ever sees data
+    try:
+        lib.b2_debug_set_tstack(1)                                 # forced (tests): eligibility without the one-item-per-SM rule
+        assert plan(2, 144, 16, 28, 28, 64, (3, 1, 1))["applies"]
+        lib.b2_debug_set_tstack(0)
+        assert not plan(16, 110, 32, 56, 56, 64, (7, 1, 1))["applies"]
+    finally:
+        lib.b2_debug_set_tstack(-1)
+
+
 def test_library_abi_is_pinned(monkeypatch):
     from pretorched_x_b200 import _lib
     assert _lib.load().b2_version() == _lib.EXPECTED_ABI
