@@ -248,6 +248,23 @@ def test_depth_first_schedule_at_baseline_clip_size(dev):
     assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item()
 
 
+def test_model_on_a_second_device_with_device_0_current():
+    """`model.to('cuda:1')` in a process whose current device is 0 -- every operator switches to its tensors' device for
+    the launch (ops._on_device), kernel attributes / SM counts are cached per device ordinal.  Needs two GPUs (skipped otherwise)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    fx = torch.load([p for p in MODEL_FIX if os.path.basename(p) == "resnet3d50_b2_t8_64.pt"][0], weights_only=False)
+    x = OF.seeded_input(fx["input_shape"], fx["seeds"]["input"])
+    torch.cuda.set_device(0)
+    m0 = build(fx, torch.device("cuda:0"))
+    m1 = build(fx, torch.device("cuda:1"))
+    with torch.no_grad():
+        y0 = m0(x.to("cuda:0"))
+        y1 = m1(x.to("cuda:1"))            # current device is still 0
+    assert torch.cuda.current_device() == 0 and y1.device.index == 1
+    assert torch.equal(y0.cpu(), y1.cpu())
+
+
 SF_FIX = [g for g in GOLDEN if torch.load(g, weights_only=False)["kind"] == "slowfast"]
 
 
