@@ -66,6 +66,24 @@ def test_spectral_norm_sigma():
     assert abs(OB.sn_sigma(q, torch.randn(1, 16)) - 1.0) < 1e-5
 
 
+def test_spectral_norm_sigma_equals_torch_spectral_norm_power_step():
+    """The restatement's sigma (one power-iteration step from the stored u0, eval semantics of the published generator) is the
+    sigma torch.nn.utils.spectral_norm -- an independent, third-party implementation of the same estimator -- computes in its first
+    training-mode forward from the same start vector, for a Linear and for a 3x3 convolution."""
+    import torch.nn as nn
+    torch.manual_seed(11)
+    for mod, x in ((nn.Linear(40, 24, bias=False), torch.zeros(1, 40)), (nn.Conv2d(6, 10, 3, bias=False), torch.zeros(1, 6, 5, 5))):
+        sn = torch.nn.utils.spectral_norm(mod, n_power_iterations=1)
+        u0 = sn.weight_u.detach().clone()
+        w = sn.weight_orig.detach().clone()
+        sn.train()
+        sn(x)                                                  # one power iteration from u0; module.weight = weight_orig / sigma
+        sigma_torch = (w.norm() / sn.weight.detach().norm()).item()
+        ours = OB.sn_sigma(w, u0.view(1, -1)).item()
+        assert abs(ours - sigma_torch) <= 1e-5 * sigma_torch, (ours, sigma_torch)
+        assert torch.allclose(w / ours, sn.weight.detach(), rtol=1e-5, atol=1e-7)
+
+
 def test_mac_count_matches_hooked_restatement(monkeypatch):
     res, ch, ncls, B = 128, 16, 10, 1
     _, sd, z, labels = OB.build_case(P.biggan_deep, res, ch, ncls, B)
