@@ -34,6 +34,8 @@ How the pieces map:
   2x2 max-pool of phi|g, the fused softmax(theta^T phi) g kernel, and the output 1x1 GEMM with gamma as its scale and x
   as its residual.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -54,7 +56,6 @@ def _sn_weight(mod, eps):
     return mod.weight.detach().double() / _sn_sigma(mod.weight, mod.u0, eps)
 
 
-import os
 FUSE_BN1 = os.environ.get("B2_GAN_FUSE_BN1", "1") != "0"      # A/B switch (tools, tests)
 
 

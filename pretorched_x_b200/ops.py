@@ -8,7 +8,6 @@ reference's hot path (file:line given per function); the arithmetic happens in
 """
 import ctypes
 import functools
-import math
 
 import torch
 
