@@ -195,6 +195,40 @@ def test_temporal_stack_plan_is_host_logic():
         lib.b2_debug_set_tstack(-1)
 
 
+def test_temporal_stack_slot_algebra():
+    """The frame-group / slot / stacked-filter arithmetic of b2_tstack.cuh (tstack_item and the MMA issuer's s_lo, s_hi, r0), transcribed
+    and run on scalars for every clip length 2..21 and kt = 3, 5, 7, 9: each output frame must receive exactly the taps of a zero-padded
+    temporal convolution, each through the stack block that holds W(dt), every issued MMA must cover a contiguous block range inside
+    the stack and at most 4 slots.  (The GPU tests cover a handful of (T, kt); this pins the index algebra for all of them.)"""
+    G = 4
+    for kt in (3, 5, 7, 9):
+        pt = kt // 2
+        w = torch.arange(1, kt + 1, dtype=torch.float64) * 0.37 + 1.0          # W(dt), distinct values
+        for T in range(2, 22):
+            x = torch.arange(1, T + 1, dtype=torch.float64) ** 1.5
+            want = torch.nn.functional.conv1d(x.view(1, 1, T), w.view(1, 1, kt), padding=pt).view(T)
+            got = torch.zeros(T, dtype=torch.float64)
+            groups = (T + G - 1) // G
+            for g in range(groups):
+                to0 = g * G
+                nf = min(G, T - to0)
+                fr_lo = max(0, pt - to0)
+                fr_hi = min(nf + kt - 2, T - 1 - to0 + pt)
+                assert fr_lo <= fr_hi
+                for fr in range(fr_lo, fr_hi + 1):
+                    f = to0 - pt + fr                                            # absolute input frame (plane_i0 + fr)
+                    assert 0 <= f < T
+                    s_lo, s_hi = max(0, fr - (kt - 1)), min(nf - 1, fr)
+                    nslots = s_hi - s_lo + 1
+                    assert 1 <= nslots <= 4                                      # N = 64 * nslots <= 256
+                    r0 = kt - 1 - (fr - s_lo)                                    # first block of the stack [W(kt-1); ...; W(0)]
+                    assert 0 <= r0 and r0 + nslots - 1 <= kt - 1
+                    for j in range(nslots):
+                        dt = kt - 1 - (r0 + j)                                   # block r holds W(dt = kt-1-r)
+                        got[to0 + s_lo + j] += x[f] * w[dt]
+            assert torch.allclose(got, want, rtol=1e-12, atol=1e-9), (kt, T)
+
+
 def test_library_abi_is_pinned(monkeypatch):
     from pretorched_x_b200 import _lib
     assert _lib.load().b2_version() == _lib.EXPECTED_ABI
